@@ -1,0 +1,235 @@
+/*
+ * microclimf_b200 — C ABI of the B200-native grid solver (the drop-in boundary).
+ *
+ * This header is what the reference's Rcpp glue would bind for its hot path.  Each entry point
+ * replaces one family of `.Call` symbols of the reference (ilyamaclean/microclimf v2.0.0):
+ *
+ *   mcf_runmicro    <- _microclimf_runmicro{1,2,3,4}Cpp    src/RcppExports.cpp:248-349,
+ *                      R/RcppExports.R:72-86, drivers src/microclimfCpp.cpp:2052, 2340, 2624, 2926
+ *   mcf_runbioclim  <- _microclimf_runbioclim{1,2,3,4}Cpp  src/RcppExports.cpp:350-465,
+ *                      R/RcppExports.R:88-102, drivers src/microclimfCpp.cpp:3457-3700
+ *
+ * Plain pointers and sizes only.  All arrays are R layout (column-major, FP64):
+ *   matrix [rows, cols]        : idx = i + rows*j
+ *   array  [rows, cols, n]     : idx = i + rows*j + rows*cols*k     (cells contiguous per slice)
+ * so for a fixed hour k the cells are contiguous ("cell-major"), which is exactly the layout the
+ * kernels read and write coalesced.
+ *
+ * There is NO CPU fallback: every compute entry point returns MCF_ERR_CUDA when no sm_100 device
+ * is usable.  INTEGRATION.md shows the Rcpp-side stub that forwards the SEXPs to these calls.
+ */
+#ifndef MICROCLIMF_B200_H
+#define MICROCLIMF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCF_ABI_VERSION 1
+
+/* status codes (the Rcpp stub maps non-zero to Rcpp::stop(err), cf. BEGIN_RCPP/END_RCPP
+ * src/RcppExports.cpp:251-271) */
+#define MCF_OK 0
+#define MCF_ERR_ARG 1    /* bad argument (NULL where data is required, bad mode, bad dfsel span ...) */
+#define MCF_ERR_CUDA 2   /* CUDA runtime failure / no usable device */
+#define MCF_ERR_NOMEM 3  /* the problem does not fit the device even after chunking */
+
+/* the 10 outputs of runmicroNCpp, in the order of its `out` logical vector
+ * (src/microclimfCpp.cpp:2131-2140, 2325-2336) */
+enum {
+    MCF_OUT_TZ = 0,
+    MCF_OUT_TLEAF = 1,
+    MCF_OUT_RELHUM = 2,
+    MCF_OUT_SOILM = 3,
+    MCF_OUT_WINDSPEED = 4,
+    MCF_OUT_RDIRDOWN = 5,
+    MCF_OUT_RDIFDOWN = 6,
+    MCF_OUT_RLWDOWN = 7,
+    MCF_OUT_RSWUP = 8,
+    MCF_OUT_RLWUP = 9,
+    MCF_NOUT = 10
+};
+#define MCF_NBIO 19 /* bio1..bio19, src/microclimfCpp.cpp:3539-3559 */
+
+/* R's NA_real_ bit pattern: outputs of skipped cells / never-computed hours carry it, as the
+ * reference's NumericVector(n, NA_REAL) prefill does (src/microclimfCpp.cpp:2131). */
+#define MCF_NA_REAL_BITS 0x7FF00000000007A2ULL
+
+/*
+ * One grid-model problem = the argument list of runmicroNCpp, flattened.
+ *
+ * mode 1: static vegetation, data.frame climate   (runmicro1Cpp, src/microclimfCpp.cpp:2052)
+ * mode 2: static vegetation, array climate        (runmicro2Cpp, :2340)
+ * mode 3: layered vegetation, data.frame climate  (runmicro3Cpp, :2624)
+ * mode 4: layered vegetation, array climate       (runmicro4Cpp, :2926)
+ *
+ * Climate / point-model series have length `tsteps` in modes 1/3 and rows*cols*tsteps in modes 2/4
+ * (`winddir` is always a length-tsteps vector, src/microclimfCpp.cpp:2359).  Vegetation fields have
+ * rows*cols*nlyr elements (nlyr = 1 in modes 1/2).  Soil fields are [rows, cols]; `wsa` is
+ * [rows, cols, 8] and `hor` is [rows, cols, 24].
+ */
+typedef struct mcf_problem {
+    int32_t mode;     /* 1..4 */
+    int32_t rows;     /* fast spatial axis */
+    int32_t cols;     /* slow spatial axis: bands for multi-GPU sharding are column ranges */
+    int32_t tsteps;   /* hours; only floor(tsteps/24) whole days are computed in modes 1/2 */
+    int32_t nlyr;     /* vegetation layers (modes 3/4), else 1 */
+    int32_t complete; /* `complete` flag: all hours of the year present (below-ground branch) */
+
+    double reqhgt, zref;
+    double lat, lon;      /* modes 1/3 */
+    double Sminp, Smaxp;  /* accepted and ignored, as in soildCppm (src/microclimfCpp.cpp:975) */
+    double tfact, mat;
+
+    /* dfsel (modes 3/4): 0-based inclusive hour spans per layer, src/microclimfCpp.cpp:2629-2639 */
+    const int32_t* lyr_st;
+    const int32_t* lyr_ed;
+
+    /* obstime */
+    const int32_t* year;
+    const int32_t* month;
+    const int32_t* day;
+    const double* hour;
+
+    /* climdata: temp|tc, es, ea, tdew, pres|pk, swdown, difrad, lwdown, windspeed, winddir */
+    const double* temp;
+    const double* es;
+    const double* ea;
+    const double* tdew;
+    const double* pres;
+    const double* swdown;
+    const double* difrad;
+    const double* lwdown;
+    const double* windspeed;
+    const double* winddir;
+
+    /* pointm: soilm, Tg, Tbp, G|Gp, umu, kp, muGp, dtrp  (T0p, DDp, Tc are never read by the grid
+     * drivers; Tg/Tbp only when reqhgt < 0 and may be NULL otherwise) */
+    const double* p_soilm;
+    const double* p_Tg;
+    const double* p_Tbp;
+    const double* p_G;
+    const double* p_umu;
+    const double* p_kp;
+    const double* p_muGp;
+    const double* p_dtrp;
+
+    /* vegp */
+    const double* hgt;
+    const double* pai;
+    const double* x;
+    const double* gsmax;
+    const double* leafr;
+    const double* leaft;
+    const double* clump;
+    const double* leafd;
+    const double* paia;
+    const double* leafden;
+
+    /* soilc */
+    const double* Smin;
+    const double* Smax;
+    const double* gref;
+    const double* soilb;
+    const double* Psie;
+    const double* Vq;
+    const double* Vm;
+    const double* Mc;
+    const double* rho;
+    const double* slope;
+    const double* aspect;
+    const double* twi;
+    const double* svfa;
+    const double* wsa; /* [rows, cols, 8]  */
+    const double* hor; /* [rows, cols, 24] */
+
+    /* modes 2/4: per-cell latitude / longitude matrices */
+    const double* lats;
+    const double* lons;
+
+    /* Band sharding (multi-GPU): when this process holds only a column band of the raster, the
+     * whole-raster mean of log(twi)/tfact that soildCppm subtracts (src/microclimfCpp.cpp:993-1004)
+     * must be supplied by the caller (all-reduce of mcf_twi_partial over the bands). */
+    int32_t has_twi_mean;
+    double twi_mean;
+} mcf_problem;
+
+/* ------------------------------------------------------------------------------------------- */
+/* Host-buffer entry points: what the Rcpp stub calls.  Inputs and outputs are HOST memory; the
+ * library uploads the static layers once, streams the time axis through the device in chunks and
+ * copies the results back (pinned staging, copy/compute overlap).                               */
+/* ------------------------------------------------------------------------------------------- */
+
+/* out[v] == NULL  <=>  out[v] FALSE in the reference call.  Each non-NULL buffer holds
+ * rows*cols*tsteps doubles and is completely overwritten (NA_REAL where the reference leaves its
+ * prefill).  Returns MCF_OK or an error code with a message in err (NUL-terminated, truncated). */
+int mcf_runmicro(const mcf_problem* prob, double* const out[MCF_NOUT], char* err, size_t errlen);
+
+/* runbioclimNCpp: tsteps must be 336 (14 days).  wetq/dryq/hotq/colq are 0-based hour indices
+ * (src/microclimfCpp.cpp:3317-3360); `air` selects Tz (1) or tleaf (0).  bio[b] == NULL <=> out[b]
+ * FALSE; each non-NULL buffer holds rows*cols doubles.  bio3 and bio7 are derived from bio2/5/6
+ * computed internally, whether or not those outputs are requested. */
+int mcf_runbioclim(const mcf_problem* prob, const int32_t* wetq, int32_t nwetq, const int32_t* dryq,
+                   int32_t ndryq, const int32_t* hotq, int32_t nhotq, const int32_t* colq,
+                   int32_t ncolq, int32_t air, double* const bio[MCF_NBIO], char* err, size_t errlen);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Device-buffer entry points: every pointer in `prob` and `out` is DEVICE memory on the current
+ * device (scalars and the lyr_st/lyr_ed/year/month/day arrays stay on the HOST).  Used by the
+ * throughput benchmark (inputs resident in HBM) and by callers that keep rasters on the GPU.    */
+/* ------------------------------------------------------------------------------------------- */
+
+/* A time window: compute day-blocks [block0, block0 + nblocks) of the problem (a day-block is one
+ * 24-hour block; modes 1/2: block b = hours 24b..24b+23; modes 3/4: the blocks of layer 0, then
+ * layer 1, ... which must be ascending and non-overlapping).  Hour k of the problem is written to
+ * time slot ((k - hour0) mod ring_hours) of each output buffer, whose slot stride is rows*cols;
+ * ring_hours >= 24 lets a caller reuse a small buffer as a ring (the output sink for rasters whose
+ * full [rows, cols, tsteps] result exceeds HBM).  Window {0, -1, 0, tsteps} = the whole problem. */
+typedef struct mcf_window {
+    int32_t block0;
+    int32_t nblocks; /* -1 = all remaining blocks */
+    int64_t hour0;
+    int64_t ring_hours;
+} mcf_window;
+
+/* reqhgt >= 0 only when the window is partial (the below-ground pass needs every hour of a cell).
+ * `stream` is a cudaStream_t (NULL = default stream); the call is asynchronous on that stream
+ * unless `err` reporting requires otherwise (launch errors are reported synchronously). */
+int mcf_runmicro_dev(const mcf_problem* prob, double* const out[MCF_NOUT], const mcf_window* win,
+                     void* stream, char* err, size_t errlen);
+
+int mcf_runbioclim_dev(const mcf_problem* prob, const int32_t* wetq, int32_t nwetq,
+                       const int32_t* dryq, int32_t ndryq, const int32_t* hotq, int32_t nhotq,
+                       const int32_t* colq, int32_t ncolq, int32_t air, double* const bio[MCF_NBIO],
+                       void* stream, char* err, size_t errlen);
+
+/* sum and count of log(twi)/tfact over the non-NaN cells of a HOST twi buffer holding n cells
+ * (the two numbers the bands all-reduce before calling with has_twi_mean = 1). */
+int mcf_twi_partial(const double* twi, int64_t n, double tfact, double* sum, int64_t* count,
+                    char* err, size_t errlen);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Device management and instrumentation                                                          */
+/* ------------------------------------------------------------------------------------------- */
+int mcf_abi_version(void);
+int mcf_device_count(void);
+int mcf_set_device(int device);
+/* kernels launched by this library in this process since the last reset (bench.py's gpu_launches) */
+int64_t mcf_launch_count(void);
+void mcf_launch_count_reset(void);
+/* Device time (ms, CUDA events on the launching stream) and number of grid-kernel launches
+ * accumulated since the last reset: the dominant kernel's average launch duration for the roofline. */
+int mcf_kernel_time(double* total_ms, int64_t* launches);
+void mcf_kernel_time_reset(void);
+void mcf_kernel_timing_enable(int on);
+/* DFMA micro-benchmark: measured non-tensor FP64 peak of the current device, TFLOP/s
+ * (2 flop per DFMA); the FP64 roofline denominator that MEASURED_PEAKS.json does not carry. */
+int mcf_fp64_peak(double* tflops, char* err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MICROCLIMF_B200_H */

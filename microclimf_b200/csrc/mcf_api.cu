@@ -1,0 +1,858 @@
+// microclimf_b200 — C ABI (include/microclimf_b200.h): host orchestration around the kernels.
+//
+//   mcf_runmicro_dev : prepare (hour table / calendar, twi mean, day-block list) -> grid kernel over the
+//                      requested window -> (reqhgt < 0) below-ground kernel, all on one stream.
+//   mcf_runmicro     : host buffers.  Statics and forcing are uploaded once; the time axis is streamed
+//                      through two device output chunks so the device->host copy of chunk i overlaps the
+//                      kernels of chunk i+1 (outputs of large rasters do not fit HBM).
+//   mcf_runbioclim*  : runmicro with outm = {Tz|tleaf, soilm} into device scratch, then the 19 reductions.
+//
+// No CPU compute path exists here: without a usable CUDA device every entry point fails.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "mcf_kernels.cuh"
+#include "microclimf_b200.h"
+
+using namespace mcf;
+
+namespace {
+
+std::atomic<int64_t> g_launches{0};
+std::mutex g_time_mu;
+bool g_timing = false;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_events;
+double g_time_ms = 0.0;
+int64_t g_time_n = 0;
+
+struct Err {
+    int code = MCF_OK;
+    std::string msg;
+};
+
+int report(const Err& e, char* err, size_t errlen) {
+    if (err && errlen) std::snprintf(err, errlen, "%s", e.msg.c_str());
+    return e.code;
+}
+Err make_err(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    std::vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    Err e;
+    e.code = code;
+    e.msg = buf;
+    return e;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t _e = (call);                                                                              \
+        if (_e != cudaSuccess)                                                                                \
+            return make_err(_e == cudaErrorMemoryAllocation ? MCF_ERR_NOMEM : MCF_ERR_CUDA, "%s failed: %s",  \
+                            #call, cudaGetErrorString(_e));                                                   \
+    } while (0)
+#define TRY(expr)                       \
+    do {                                \
+        Err _r = (expr);                \
+        if (_r.code != MCF_OK) return _r; \
+    } while (0)
+
+// stream-ordered scratch allocations, released when the holder dies
+struct Scratch {
+    cudaStream_t stream;
+    std::vector<void*> ptrs;
+    explicit Scratch(cudaStream_t s) : stream(s) {}
+    ~Scratch() {
+        for (void* p : ptrs) cudaFreeAsync(p, stream);
+    }
+    template <class T> cudaError_t alloc(T** p, size_t n) {
+        void* q = nullptr;
+        cudaError_t e = cudaMallocAsync(&q, std::max<size_t>(n, 1) * sizeof(T), stream);
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *p = (T*)q;
+        return e;
+    }
+};
+
+const double* const* clim_ptrs(const mcf_problem* p, const double* out[10]) {
+    out[0] = p->temp; out[1] = p->es; out[2] = p->ea; out[3] = p->tdew; out[4] = p->pres;
+    out[5] = p->swdown; out[6] = p->difrad; out[7] = p->lwdown; out[8] = p->windspeed; out[9] = p->winddir;
+    return out;
+}
+
+Err validate(const mcf_problem* p) {
+    if (!p) return make_err(MCF_ERR_ARG, "problem is NULL");
+    if (p->mode < 1 || p->mode > 4) return make_err(MCF_ERR_ARG, "mode must be 1..4 (got %d)", p->mode);
+    if (p->rows <= 0 || p->cols <= 0 || p->tsteps <= 0) return make_err(MCF_ERR_ARG, "rows, cols, tsteps must be > 0");
+    if ((int64_t)p->rows * p->cols > INT32_MAX - 256) return make_err(MCF_ERR_ARG, "rows*cols exceeds 2^31");
+    const bool layered = p->mode >= 3;
+    const bool arr = (p->mode == 2 || p->mode == 4);
+    const void* req[] = {p->year, p->month, p->day, p->hour, p->temp, p->es, p->ea, p->tdew, p->pres, p->swdown,
+                         p->difrad, p->lwdown, p->windspeed, p->winddir, p->p_soilm, p->p_G, p->p_umu, p->p_kp,
+                         p->p_muGp, p->p_dtrp, p->hgt, p->pai, p->x, p->gsmax, p->leafr, p->leaft, p->clump,
+                         p->leafd, p->paia, p->leafden, p->Smin, p->Smax, p->gref, p->soilb, p->Psie, p->Vq, p->Vm,
+                         p->Mc, p->rho, p->slope, p->aspect, p->twi, p->svfa, p->wsa, p->hor};
+    for (const void* q : req)
+        if (!q) return make_err(MCF_ERR_ARG, "a required input pointer is NULL");
+    if (p->reqhgt < 0 && (!p->p_Tg || !p->p_Tbp) && !p->complete)
+        return make_err(MCF_ERR_ARG, "reqhgt < 0 with an incomplete series needs pointm Tg and Tbp");
+    if (arr && (!p->lats || !p->lons)) return make_err(MCF_ERR_ARG, "modes 2/4 need lats and lons");
+    if (layered) {
+        if (p->nlyr < 1 || !p->lyr_st || !p->lyr_ed) return make_err(MCF_ERR_ARG, "modes 3/4 need nlyr >= 1 and dfsel");
+    }
+    return Err();
+}
+
+// day-block list (ref :2194 for modes 1/2; :2629-2639 + :2770-2800 for modes 3/4)
+Err build_blocks(const mcf_problem* p, std::vector<DayBlock>& blocks) {
+    blocks.clear();
+    if (p->mode <= 2) {
+        const int nd = p->tsteps / 24;
+        for (int d = 0; d < nd; ++d) blocks.push_back(DayBlock{24 * d, 0});
+        return Err();
+    }
+    int prev_end = 0;
+    for (int l = 0; l < p->nlyr; ++l) {
+        const int span = p->lyr_ed[l] - p->lyr_st[l] + 1;
+        if (span < 24) // the reference's Rcpp::stop (src/microclimfCpp.cpp:2636-2637)
+            return make_err(MCF_ERR_ARG, "Too many layers in vegp. Max layers must be <= max days");
+        const int nd = span / 24;
+        if (p->lyr_st[l] < prev_end)
+            return make_err(MCF_ERR_ARG, "dfsel layers must be ascending and non-overlapping (layer %d)", l + 1);
+        if (p->lyr_st[l] + 24 * nd > p->tsteps)
+            return make_err(MCF_ERR_ARG, "dfsel layer %d runs past the end of the series", l + 1);
+        for (int d = 0; d < nd; ++d) blocks.push_back(DayBlock{p->lyr_st[l] + 24 * d, l});
+        prev_end = p->lyr_st[l] + 24 * nd;
+    }
+    return Err();
+}
+
+int rq_of(double reqhgt) { return reqhgt > 0.0 ? RQ_ABOVE : (reqhgt == 0.0 ? RQ_SURFACE : RQ_BELOW); }
+
+bool kernel_writes(int rq, int v) {
+    switch (v) {
+    case MCF_OUT_TZ: return true;
+    case MCF_OUT_TLEAF:
+    case MCF_OUT_RELHUM: return rq == RQ_ABOVE;
+    case MCF_OUT_RLWDOWN:
+    case MCF_OUT_RLWUP: return rq != RQ_BELOW;
+    default: return true;
+    }
+}
+
+int g_sm_count = 0;
+Err device_info() {
+    if (g_sm_count) return Err();
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return make_err(MCF_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name,
+                        prop.major, prop.minor);
+    g_sm_count = prop.multiProcessorCount;
+    return Err();
+}
+
+void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// A prepared problem on the device: everything a window launch needs.
+struct Plan {
+    const mcf_problem* p = nullptr;
+    bool arr = false;
+    int rq = RQ_ABOVE;
+    int ncells = 0;
+    std::vector<DayBlock> blocks;
+    DayBlock* d_blocks = nullptr;
+    HourRec* d_hours = nullptr;
+    HourCal* d_cal = nullptr;
+    double* d_scal = nullptr;      // [0] mxtc, [1] twi sum, [2] twi count, then reduction scratch
+    double* d_mxtc_cell = nullptr;
+    double* d_stash = nullptr;
+    int grid = 0;
+};
+
+Err plan_prepare(Plan& pl, const mcf_problem* p, Scratch& sc, cudaStream_t st) {
+    TRY(validate(p));
+    TRY(device_info());
+    pl.p = p;
+    pl.arr = (p->mode == 2 || p->mode == 4);
+    pl.rq = rq_of(p->reqhgt);
+    pl.ncells = p->rows * p->cols;
+    TRY(build_blocks(p, pl.blocks));
+    const int T = p->tsteps;
+    CU(sc.alloc(&pl.d_blocks, pl.blocks.size()));
+    if (!pl.blocks.empty())
+        CU(cudaMemcpyAsync(pl.d_blocks, pl.blocks.data(), pl.blocks.size() * sizeof(DayBlock), cudaMemcpyHostToDevice, st));
+    CU(sc.alloc(&pl.d_scal, 4 + 2 * 256 + 2));
+    // calendar ints are host arrays by contract: stage them
+    int32_t* d_cal3 = nullptr;
+    CU(sc.alloc(&d_cal3, (size_t)3 * T));
+    CU(cudaMemcpyAsync(d_cal3, p->year, T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_cal3 + T, p->month, T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_cal3 + 2 * T, p->day, T * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    if (pl.arr) CU(sc.alloc(&pl.d_cal, T));
+    else CU(sc.alloc(&pl.d_hours, T));
+    const double* clim[10];
+    clim_ptrs(p, clim);
+    const double* pnt[6] = {p->p_soilm, p->p_G, p->p_umu, p->p_kp, p->p_muGp, p->p_dtrp};
+    CU(launch_prep_hours(d_cal3, d_cal3 + T, d_cal3 + 2 * T, p->hour, clim, pnt, p->lat, p->lon, T, pl.arr, pl.d_hours,
+                         pl.d_cal, pl.d_scal, st));
+    count_launch();
+    if (pl.arr) {
+        CU(sc.alloc(&pl.d_mxtc_cell, pl.ncells));
+        CU(launch_mxtc_cell(p->temp, pl.ncells, T, pl.d_mxtc_cell, st));
+        count_launch();
+    }
+    if (!p->has_twi_mean) {
+        CU(launch_twi_sum(p->twi, pl.ncells, p->tfact, pl.d_scal + 1, st));
+        count_launch(2);
+    }
+    pl.grid = g_sm_count * grid_blocks_per_sm(pl.arr, pl.rq);
+    CU(sc.alloc(&pl.d_stash, (size_t)pl.grid * 24 * kStashVars * kTile));
+    return Err();
+}
+
+void fill_common(const Plan& pl, GridArgs& a) {
+    const mcf_problem* p = pl.p;
+    std::memset(&a, 0, sizeof a);
+    a.ncells = pl.ncells;
+    a.tsteps = p->tsteps;
+    a.nlyr = p->mode >= 3 ? p->nlyr : 1;
+    a.reqhgt2 = p->reqhgt < 0.00001 ? 0.00001 : p->reqhgt;
+    a.zref = p->zref;
+    a.lat = p->lat;
+    a.tfact = p->tfact;
+    a.has_tadd_mean = p->has_twi_mean;
+    a.tadd_mean = p->twi_mean;
+    a.dscal = pl.d_scal;
+    a.hours = pl.d_hours;
+    const double* clim[10];
+    clim_ptrs(p, clim);
+    for (int i = 0; i < 9; ++i) a.clim[i] = clim[i];
+    a.pnt[0] = p->p_soilm; a.pnt[1] = p->p_G; a.pnt[2] = p->p_umu; a.pnt[3] = p->p_kp; a.pnt[4] = p->p_muGp;
+    a.pnt[5] = p->p_dtrp;
+    a.lats = p->lats;
+    a.lons = p->lons;
+    a.mxtc_cell = pl.d_mxtc_cell;
+    a.cal = pl.d_cal;
+    const double* veg[10] = {p->hgt, p->pai, p->x, p->gsmax, p->leafr, p->leaft, p->clump, p->leafd, p->paia, p->leafden};
+    for (int i = 0; i < 10; ++i) a.veg[i] = veg[i];
+    const double* soil[13] = {p->Smin, p->Smax, p->gref, p->soilb, p->Psie, p->Vq, p->Vm, p->Mc, p->rho, p->slope,
+                              p->aspect, p->twi, p->svfa};
+    for (int i = 0; i < 13; ++i) a.soil[i] = soil[i];
+    a.wsa = p->wsa;
+    a.hor = p->hor;
+    a.blocks = pl.d_blocks;
+    a.stash = pl.d_stash;
+}
+
+Err timed_grid_launch(const GridArgs& a, bool arr, int rq, int grid, cudaStream_t st) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_timing) {
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, st));
+    }
+    CU(launch_grid(a, arr, rq, grid, st));
+    count_launch();
+    if (g_timing) {
+        CU(cudaEventRecord(e1, st));
+        std::lock_guard<std::mutex> lk(g_time_mu);
+        g_events.emplace_back(e0, e1);
+    }
+    return Err();
+}
+
+// Run day-blocks [b0, b0+nb) into out[] (device).  rq != RQ_BELOW.
+Err plan_run_window(const Plan& pl, double* const out[MCF_NOUT], int b0, int nb, long long hour0, long long ring,
+                    Scratch& sc, cudaStream_t st) {
+    if (nb <= 0) return Err();
+    GridArgs a;
+    fill_common(pl, a);
+    a.cell_begin = 0;
+    a.cell_end = pl.ncells;
+    a.block0 = b0;
+    a.nblocks = nb;
+    a.hour0 = hour0;
+    a.ring_hours = ring;
+    a.outmask = 0;
+    for (int v = 0; v < MCF_NOUT; ++v) {
+        a.out[v] = out[v];
+        if (out[v] && kernel_writes(pl.rq, v)) a.outmask |= 1u << v;
+    }
+    unsigned int* ctr = nullptr;
+    CU(sc.alloc(&ctr, 1));
+    CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+    a.tile_counter = ctr;
+    const int ntiles = (pl.ncells + kTile - 1) / kTile;
+    return timed_grid_launch(a, pl.arr, pl.rq, std::min(pl.grid, ntiles), st);
+}
+
+// Whole series for reqhgt < 0: grid kernel writes Tg into scratch per cell chunk, then the time-axis pass.
+Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cudaStream_t st) {
+    const mcf_problem* p = pl.p;
+    const int T = p->tsteps;
+    const int numDays = T / 24;
+    size_t freeb = 0, totalb = 0;
+    CU(cudaMemGetInfo(&freeb, &totalb));
+    const size_t budget = std::max<size_t>(freeb / 4, (size_t)64 << 20);
+    long long wmax = (long long)(budget / ((size_t)T * sizeof(double)));
+    wmax = std::max<long long>(kTile, (wmax / kTile) * kTile);
+    const int W = (int)std::min<long long>(wmax, ((pl.ncells + kTile - 1) / kTile) * kTile);
+    double *tg = nullptr, *dds = nullptr, *daily = nullptr;
+    CU(sc.alloc(&tg, (size_t)T * W));
+    CU(sc.alloc(&dds, W));
+    CU(sc.alloc(&daily, (size_t)2 * std::max(numDays, 1) * W));
+    const int nchunks = (pl.ncells + W - 1) / W;
+    unsigned int* ctr = nullptr;
+    CU(sc.alloc(&ctr, nchunks));
+    CU(cudaMemsetAsync(ctr, 0, nchunks * sizeof(unsigned int), st));
+    int hiy = 365 * 24;
+    if (p->year[0] % 4 == 0) hiy = 366 * 24; // ref :2171-2172
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int c0 = ch * W, c1 = std::min(pl.ncells, c0 + W);
+        // uncovered hours keep Tg = 0, DD = 0, as the reference's zero-initialised vectors (:2192-2193)
+        CU(cudaMemsetAsync(tg, 0, (size_t)T * (c1 - c0) * sizeof(double), st));
+        CU(cudaMemsetAsync(dds, 0, (size_t)(c1 - c0) * sizeof(double), st));
+        GridArgs a;
+        fill_common(pl, a);
+        a.cell_begin = c0;
+        a.cell_end = c1;
+        a.block0 = 0;
+        a.nblocks = (int)pl.blocks.size();
+        a.hour0 = 0;
+        a.ring_hours = T;
+        a.outmask = 0;
+        for (int v = 0; v < MCF_NOUT; ++v) {
+            a.out[v] = out[v];
+            if (out[v] && v != MCF_OUT_TZ && kernel_writes(pl.rq, v)) a.outmask |= 1u << v;
+        }
+        a.tile_counter = ctr + ch;
+        a.tg_scratch = tg;
+        a.dd_sum = dds;
+        const int ntiles = (c1 - c0 + kTile - 1) / kTile;
+        if (a.nblocks > 0) TRY(timed_grid_launch(a, pl.arr, pl.rq, std::min(pl.grid, ntiles), st));
+        if (out[MCF_OUT_TZ]) {
+            BelowArgs b;
+            std::memset(&b, 0, sizeof b);
+            b.width = c1 - c0;
+            b.ncells = pl.ncells;
+            b.cell_begin = c0;
+            b.tsteps = T;
+            b.arr = pl.arr ? 1 : 0;
+            b.complete = p->complete;
+            b.hiy = hiy;
+            b.reqhgt = p->reqhgt;
+            b.mat = p->mat;
+            b.tg = tg;
+            b.dd_sum = dds;
+            b.Tgp = p->p_Tg;
+            b.Tbp = p->p_Tbp;
+            b.hgt = p->hgt;
+            b.daily = daily;
+            b.Tz = out[MCF_OUT_TZ];
+            CU(launch_below(b, st));
+            count_launch();
+        }
+    }
+    return Err();
+}
+
+// NA prefill of whatever the kernels will not write in a whole-series run
+Err prefill_whole(const Plan& pl, double* const out[MCF_NOUT], cudaStream_t st) {
+    const int T = pl.p->tsteps;
+    std::vector<char> covered(T, 0);
+    for (const DayBlock& b : pl.blocks)
+        for (int h = 0; h < 24; ++h) covered[b.k0 + h] = 1;
+    bool gaps = false;
+    for (int k = 0; k < T; ++k) gaps |= !covered[k];
+    for (int v = 0; v < MCF_NOUT; ++v) {
+        if (!out[v]) continue;
+        const bool written = kernel_writes(pl.rq, v);
+        const bool all_hours = (pl.rq == RQ_BELOW && v == MCF_OUT_TZ); // the time-axis pass writes every hour
+        if (!written || (gaps && !all_hours)) {
+            CU(launch_fill_na(out[v], (int64_t)T * pl.ncells, st));
+            count_launch();
+        }
+    }
+    return Err();
+}
+
+Err run_dev(const mcf_problem* p, double* const out[MCF_NOUT], const mcf_window* win, cudaStream_t st) {
+    Scratch sc(st);
+    Plan pl;
+    TRY(plan_prepare(pl, p, sc, st));
+    const int nblk = (int)pl.blocks.size();
+    int b0 = 0, nb = nblk;
+    long long hour0 = 0, ring = p->tsteps;
+    bool whole = true;
+    if (win) {
+        b0 = win->block0;
+        nb = win->nblocks < 0 ? nblk - b0 : win->nblocks;
+        hour0 = win->hour0;
+        ring = win->ring_hours;
+        if (b0 < 0 || nb < 0 || b0 + nb > nblk) return make_err(MCF_ERR_ARG, "window outside the %d day-blocks", nblk);
+        if (ring < 24) return make_err(MCF_ERR_ARG, "ring_hours must be >= 24");
+        whole = (b0 == 0 && nb == nblk && hour0 == 0 && ring >= p->tsteps);
+    }
+    if (pl.rq == RQ_BELOW) {
+        if (!whole) return make_err(MCF_ERR_ARG, "reqhgt < 0 needs the whole series in one window");
+        TRY(prefill_whole(pl, out, st));
+        return plan_run_below(pl, out, sc, st);
+    }
+    if (whole) TRY(prefill_whole(pl, out, st));
+    return plan_run_window(pl, out, b0, nb, hour0, ring, sc, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-buffer path
+// ------------------------------------------------------------------------------------------------
+struct DevCopy { // device mirror of a host problem; owns the allocations
+    std::vector<void*> ptrs;
+    ~DevCopy() {
+        for (void* q : ptrs) cudaFree(q);
+    }
+    Err up(const double* h, size_t n, const double** d) {
+        *d = nullptr;
+        if (!h) return Err();
+        void* q = nullptr;
+        CU(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(double)));
+        ptrs.push_back(q);
+        CU(cudaMemcpy(q, h, n * sizeof(double), cudaMemcpyHostToDevice));
+        *d = (const double*)q;
+        return Err();
+    }
+    Err dalloc(double** d, size_t n) {
+        void* q = nullptr;
+        CU(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(double)));
+        ptrs.push_back(q);
+        *d = (double*)q;
+        return Err();
+    }
+};
+
+Err upload_problem(const mcf_problem* h, mcf_problem* d, DevCopy& dc) {
+    *d = *h;
+    const bool arr = (h->mode == 2 || h->mode == 4);
+    const size_t nc = (size_t)h->rows * h->cols, T = h->tsteps;
+    const size_t ns = arr ? nc * T : T;
+    const size_t nv = nc * (h->mode >= 3 ? h->nlyr : 1);
+    TRY(dc.up(h->hour, T, &d->hour));
+    TRY(dc.up(h->temp, ns, &d->temp));
+    TRY(dc.up(h->es, ns, &d->es));
+    TRY(dc.up(h->ea, ns, &d->ea));
+    TRY(dc.up(h->tdew, ns, &d->tdew));
+    TRY(dc.up(h->pres, ns, &d->pres));
+    TRY(dc.up(h->swdown, ns, &d->swdown));
+    TRY(dc.up(h->difrad, ns, &d->difrad));
+    TRY(dc.up(h->lwdown, ns, &d->lwdown));
+    TRY(dc.up(h->windspeed, ns, &d->windspeed));
+    TRY(dc.up(h->winddir, T, &d->winddir));
+    TRY(dc.up(h->p_soilm, ns, &d->p_soilm));
+    TRY(dc.up(h->reqhgt < 0 ? h->p_Tg : nullptr, ns, &d->p_Tg));
+    TRY(dc.up(h->reqhgt < 0 ? h->p_Tbp : nullptr, ns, &d->p_Tbp));
+    TRY(dc.up(h->p_G, ns, &d->p_G));
+    TRY(dc.up(h->p_umu, ns, &d->p_umu));
+    TRY(dc.up(h->p_kp, ns, &d->p_kp));
+    TRY(dc.up(h->p_muGp, ns, &d->p_muGp));
+    TRY(dc.up(h->p_dtrp, ns, &d->p_dtrp));
+    TRY(dc.up(h->hgt, nv, &d->hgt));
+    TRY(dc.up(h->pai, nv, &d->pai));
+    TRY(dc.up(h->x, nv, &d->x));
+    TRY(dc.up(h->gsmax, nv, &d->gsmax));
+    TRY(dc.up(h->leafr, nv, &d->leafr));
+    TRY(dc.up(h->leaft, nv, &d->leaft));
+    TRY(dc.up(h->clump, nv, &d->clump));
+    TRY(dc.up(h->leafd, nv, &d->leafd));
+    TRY(dc.up(h->paia, nv, &d->paia));
+    TRY(dc.up(h->leafden, nv, &d->leafden));
+    TRY(dc.up(h->Smin, nc, &d->Smin));
+    TRY(dc.up(h->Smax, nc, &d->Smax));
+    TRY(dc.up(h->gref, nc, &d->gref));
+    TRY(dc.up(h->soilb, nc, &d->soilb));
+    TRY(dc.up(h->Psie, nc, &d->Psie));
+    TRY(dc.up(h->Vq, nc, &d->Vq));
+    TRY(dc.up(h->Vm, nc, &d->Vm));
+    TRY(dc.up(h->Mc, nc, &d->Mc));
+    TRY(dc.up(h->rho, nc, &d->rho));
+    TRY(dc.up(h->slope, nc, &d->slope));
+    TRY(dc.up(h->aspect, nc, &d->aspect));
+    TRY(dc.up(h->twi, nc, &d->twi));
+    TRY(dc.up(h->svfa, nc, &d->svfa));
+    TRY(dc.up(h->wsa, nc * 8, &d->wsa));
+    TRY(dc.up(h->hor, nc * 24, &d->hor));
+    TRY(dc.up(arr ? h->lats : nullptr, nc, &d->lats));
+    TRY(dc.up(arr ? h->lons : nullptr, nc, &d->lons));
+    return Err();
+}
+
+struct StreamGuard {
+    cudaStream_t s = nullptr;
+    ~StreamGuard() {
+        if (s) cudaStreamDestroy(s);
+    }
+};
+struct EventGuard {
+    cudaEvent_t e = nullptr;
+    ~EventGuard() {
+        if (e) cudaEventDestroy(e);
+    }
+};
+struct PinGuard { // cudaHostRegister of caller buffers so device->host copies run asynchronously
+    std::vector<void*> pinned;
+    ~PinGuard() {
+        for (void* q : pinned) cudaHostUnregister(q);
+    }
+    void pin(void* q, size_t bytes) {
+        if (cudaHostRegister(q, bytes, cudaHostRegisterDefault) == cudaSuccess) pinned.push_back(q);
+        else (void)cudaGetLastError(); // not fatal: the copy is then staged by the runtime
+    }
+};
+
+void host_fill_na(double* p, size_t n) {
+    const uint64_t bits = MCF_NA_REAL_BITS;
+    uint64_t* q = reinterpret_cast<uint64_t*>(p);
+    for (size_t i = 0; i < n; ++i) q[i] = bits;
+}
+
+Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
+    TRY(validate(hp));
+    TRY(device_info());
+    DevCopy dc;
+    mcf_problem dp;
+    TRY(upload_problem(hp, &dp, dc));
+    StreamGuard cs, xs;
+    CU(cudaStreamCreateWithFlags(&cs.s, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&xs.s, cudaStreamNonBlocking));
+    const size_t nc = (size_t)hp->rows * hp->cols;
+    const int T = hp->tsteps;
+    int nreq = 0;
+    for (int v = 0; v < MCF_NOUT; ++v) nreq += out[v] != nullptr;
+    if (nreq == 0) return Err();
+    size_t freeb = 0, totalb = 0;
+    CU(cudaMemGetInfo(&freeb, &totalb));
+    const int rq = rq_of(hp->reqhgt);
+    const size_t per_hour = (size_t)nreq * nc * sizeof(double);
+    {
+        Scratch sc(cs.s);
+        Plan pl;
+        TRY(plan_prepare(pl, &dp, sc, cs.s));
+        const int nblk = (int)pl.blocks.size();
+        const bool fits = (double)per_hour * T < 0.55 * (double)freeb;
+        if (fits || rq == RQ_BELOW) {
+            if (!fits) return make_err(MCF_ERR_NOMEM, "reqhgt < 0 on a raster whose outputs exceed device memory: "
+                                                      "split the raster into column bands (has_twi_mean)");
+            double* dout[MCF_NOUT] = {nullptr};
+            for (int v = 0; v < MCF_NOUT; ++v)
+                if (out[v]) TRY(dc.dalloc(&dout[v], nc * T));
+            TRY(prefill_whole(pl, dout, cs.s));
+            if (rq == RQ_BELOW) TRY(plan_run_below(pl, dout, sc, cs.s));
+            else TRY(plan_run_window(pl, dout, 0, nblk, 0, T, sc, cs.s));
+            for (int v = 0; v < MCF_NOUT; ++v)
+                if (out[v]) CU(cudaMemcpyAsync(out[v], dout[v], nc * T * sizeof(double), cudaMemcpyDeviceToHost, cs.s));
+            CU(cudaStreamSynchronize(cs.s));
+        } else {
+            // stream the time axis through two device chunks; D2H of chunk i overlaps kernels of chunk i+1
+            long long chunk_blocks = (long long)((0.45 * (double)freeb) / (2.0 * 24.0 * (double)per_hour));
+            if (chunk_blocks < 1) return make_err(MCF_ERR_NOMEM, "one day of outputs does not fit device memory");
+            chunk_blocks = std::min<long long>(chunk_blocks, nblk);
+            const long long chunk_hours = chunk_blocks * 24;
+            double* dout[2][MCF_NOUT] = {{nullptr}, {nullptr}};
+            for (int s = 0; s < 2; ++s)
+                for (int v = 0; v < MCF_NOUT; ++v)
+                    if (out[v]) TRY(dc.dalloc(&dout[s][v], nc * chunk_hours));
+            PinGuard pin;
+            for (int v = 0; v < MCF_NOUT; ++v)
+                if (out[v]) pin.pin(out[v], nc * T * sizeof(double));
+            EventGuard done_k[2], done_c[2];
+            for (int s = 0; s < 2; ++s) {
+                CU(cudaEventCreateWithFlags(&done_k[s].e, cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&done_c[s].e, cudaEventDisableTiming));
+            }
+            // hours no day-block covers, and outputs this reqhgt never writes, are NA (host side)
+            std::vector<char> covered(T, 0);
+            for (const DayBlock& b : pl.blocks)
+                for (int h = 0; h < 24; ++h) covered[b.k0 + h] = 1;
+            for (int v = 0; v < MCF_NOUT; ++v) {
+                if (!out[v]) continue;
+                if (!kernel_writes(rq, v)) { host_fill_na(out[v], nc * T); continue; }
+                for (int k = 0; k < T; ++k)
+                    if (!covered[k]) host_fill_na(out[v] + (size_t)k * nc, nc);
+            }
+            int w = 0;
+            for (int b0 = 0; b0 < nblk; b0 += (int)chunk_blocks, ++w) {
+                const int s = w & 1;
+                int nb = (int)std::min<long long>(chunk_blocks, nblk - b0);
+                // a chunk must cover a contiguous hour range to be copied back in one piece per output
+                for (int i = 1; i < nb; ++i)
+                    if (pl.blocks[b0 + i].k0 != pl.blocks[b0 + i - 1].k0 + 24) { nb = i; break; }
+                if (w >= 2) CU(cudaStreamWaitEvent(cs.s, done_c[s].e, 0)); // chunk buffer s is free again
+                const long long h0 = pl.blocks[b0].k0;
+                TRY(plan_run_window(pl, dout[s], b0, nb, h0, chunk_hours, sc, cs.s));
+                CU(cudaEventRecord(done_k[s].e, cs.s));
+                CU(cudaStreamWaitEvent(xs.s, done_k[s].e, 0));
+                for (int v = 0; v < MCF_NOUT; ++v)
+                    if (out[v] && kernel_writes(rq, v))
+                        CU(cudaMemcpyAsync(out[v] + (size_t)h0 * nc, dout[s][v], nc * 24 * nb * sizeof(double),
+                                           cudaMemcpyDeviceToHost, xs.s));
+                CU(cudaEventRecord(done_c[s].e, xs.s));
+                if (nb < chunk_blocks) b0 -= (int)chunk_blocks - nb; // shortened chunk: resume right after it
+            }
+            CU(cudaStreamSynchronize(xs.s));
+            CU(cudaStreamSynchronize(cs.s));
+        }
+    }
+    CU(cudaStreamSynchronize(cs.s));
+    return Err();
+}
+
+// ------------------------------------------------------------------------------------------------
+// bioclim
+// ------------------------------------------------------------------------------------------------
+// runbioclim3/4Cpp hard-code 14 one-day vegetation layers (ref :3635-3646) and complete = true (:3576-3577)
+struct BioPatch {
+    mcf_problem pp;
+    int32_t st14[14], ed14[14];
+    Err apply(const mcf_problem* p) {
+        if (!p) return make_err(MCF_ERR_ARG, "problem is NULL");
+        pp = *p;
+        pp.complete = 1;
+        if (p->mode >= 3) {
+            if (p->nlyr < 14) return make_err(MCF_ERR_ARG, "runbioclim3/4 need 14 vegetation layers, got %d", p->nlyr);
+            for (int i = 0; i < 14; ++i) { st14[i] = i * 24; ed14[i] = i * 24 + 23; }
+            pp.nlyr = 14;
+            pp.lyr_st = st14;
+            pp.lyr_ed = ed14;
+        }
+        return validate(&pp);
+    }
+};
+
+Err run_bioclim_dev(const mcf_problem* p, const int32_t* const q[4], const int32_t nq[4], int air,
+                    double* const bio[MCF_NBIO], cudaStream_t st) {
+    if (p->tsteps < 336) return make_err(MCF_ERR_ARG, "runbioclim needs the 14 selected days (336 hours), got %d", p->tsteps);
+    for (int i = 0; i < 4; ++i) {
+        if (nq[i] < 0 || (nq[i] > 0 && !q[i])) return make_err(MCF_ERR_ARG, "quarter index vector %d is invalid", i);
+        for (int j = 0; j < nq[i]; ++j)
+            if (q[i][j] < 0 || q[i][j] >= p->tsteps) return make_err(MCF_ERR_ARG, "quarter index out of range");
+    }
+    Scratch sc(st);
+    const mcf_problem& pp = *p;
+    Plan pl;
+    TRY(plan_prepare(pl, &pp, sc, st));
+    const int T = p->tsteps;
+    const int nc = pl.ncells;
+    double *dTz = nullptr, *dsm = nullptr;
+    CU(sc.alloc(&dTz, (size_t)T * nc));
+    CU(sc.alloc(&dsm, (size_t)T * nc));
+    double* out[MCF_NOUT] = {nullptr};
+    out[air ? MCF_OUT_TZ : MCF_OUT_TLEAF] = dTz;
+    out[MCF_OUT_SOILM] = dsm;
+    TRY(prefill_whole(pl, out, st));
+    if (pl.rq == RQ_BELOW) TRY(plan_run_below(pl, out, sc, st));
+    else TRY(plan_run_window(pl, out, 0, (int)pl.blocks.size(), 0, T, sc, st));
+    int32_t* dq = nullptr;
+    const int ntot = nq[0] + nq[1] + nq[2] + nq[3];
+    CU(sc.alloc(&dq, ntot));
+    BioArgs b;
+    std::memset(&b, 0, sizeof b);
+    int off = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (nq[i]) CU(cudaMemcpyAsync(dq + off, q[i], nq[i] * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        b.q[i] = dq + off;
+        b.nq[i] = nq[i];
+        off += nq[i];
+    }
+    b.width = nc;
+    b.tsteps = T;
+    b.Tz = dTz;
+    b.soilm = dsm;
+    b.cell_begin = 0;
+    b.mask = 0;
+    for (int v = 0; v < MCF_NBIO; ++v) {
+        b.bio[v] = bio[v];
+        if (bio[v]) b.mask |= 1u << v;
+    }
+    CU(launch_bioclim(b, st));
+    count_launch();
+    // the quarter index vectors are read from pageable host memory by the async copies above
+    CU(cudaStreamSynchronize(st));
+    return Err();
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------------------------------
+// exported C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mcf_abi_version(void) { return MCF_ABI_VERSION; }
+
+int mcf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mcf_set_device(int device) {
+    g_sm_count = 0;
+    return cudaSetDevice(device) == cudaSuccess ? MCF_OK : MCF_ERR_CUDA;
+}
+
+int64_t mcf_launch_count(void) { return g_launches.load(); }
+void mcf_launch_count_reset(void) { g_launches.store(0); }
+
+void mcf_kernel_timing_enable(int on) { g_timing = on != 0; }
+void mcf_kernel_time_reset(void) {
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    for (auto& pr : g_events) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_events.clear();
+    g_time_ms = 0.0;
+    g_time_n = 0;
+}
+int mcf_kernel_time(double* total_ms, int64_t* launches) {
+    std::lock_guard<std::mutex> lk(g_time_mu);
+    for (auto& pr : g_events) {
+        if (cudaEventSynchronize(pr.second) != cudaSuccess) return MCF_ERR_CUDA;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) != cudaSuccess) return MCF_ERR_CUDA;
+        g_time_ms += ms;
+        g_time_n += 1;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_events.clear();
+    if (total_ms) *total_ms = g_time_ms;
+    if (launches) *launches = g_time_n;
+    return MCF_OK;
+}
+
+int mcf_runmicro_dev(const mcf_problem* prob, double* const out[MCF_NOUT], const mcf_window* win, void* stream,
+                     char* err, size_t errlen) {
+    if (!out) return report(make_err(MCF_ERR_ARG, "out is NULL"), err, errlen);
+    return report(run_dev(prob, out, win, (cudaStream_t)stream), err, errlen);
+}
+
+int mcf_runmicro(const mcf_problem* prob, double* const out[MCF_NOUT], char* err, size_t errlen) {
+    if (!out) return report(make_err(MCF_ERR_ARG, "out is NULL"), err, errlen);
+    return report(run_host(prob, out), err, errlen);
+}
+
+int mcf_runbioclim_dev(const mcf_problem* prob, const int32_t* wetq, int32_t nwetq, const int32_t* dryq, int32_t ndryq,
+                       const int32_t* hotq, int32_t nhotq, const int32_t* colq, int32_t ncolq, int32_t air,
+                       double* const bio[MCF_NBIO], void* stream, char* err, size_t errlen) {
+    BioPatch bp;
+    Err e = bp.apply(prob);
+    if (e.code == MCF_OK) e = device_info();
+    if (e.code == MCF_OK) {
+        const int32_t* q[4] = {wetq, dryq, hotq, colq};
+        const int32_t nq[4] = {nwetq, ndryq, nhotq, ncolq};
+        e = run_bioclim_dev(&bp.pp, q, nq, air, bio, (cudaStream_t)stream);
+    }
+    return report(e, err, errlen);
+}
+
+int mcf_runbioclim(const mcf_problem* prob, const int32_t* wetq, int32_t nwetq, const int32_t* dryq, int32_t ndryq,
+                   const int32_t* hotq, int32_t nhotq, const int32_t* colq, int32_t ncolq, int32_t air,
+                   double* const bio[MCF_NBIO], char* err, size_t errlen) {
+    auto body = [&]() -> Err {
+        BioPatch bp;
+        TRY(bp.apply(prob));
+        TRY(device_info());
+        DevCopy dc;
+        mcf_problem dp;
+        TRY(upload_problem(&bp.pp, &dp, dc));
+        const size_t nc = (size_t)prob->rows * prob->cols;
+        double* dbio[MCF_NBIO] = {nullptr};
+        for (int v = 0; v < MCF_NBIO; ++v)
+            if (bio[v]) TRY(dc.dalloc(&dbio[v], nc));
+        StreamGuard sg;
+        CU(cudaStreamCreateWithFlags(&sg.s, cudaStreamNonBlocking));
+        const int32_t* q[4] = {wetq, dryq, hotq, colq};
+        const int32_t nq[4] = {nwetq, ndryq, nhotq, ncolq};
+        TRY(run_bioclim_dev(&dp, q, nq, air, dbio, sg.s));
+        for (int v = 0; v < MCF_NBIO; ++v)
+            if (bio[v]) CU(cudaMemcpyAsync(bio[v], dbio[v], nc * sizeof(double), cudaMemcpyDeviceToHost, sg.s));
+        CU(cudaStreamSynchronize(sg.s));
+        return Err();
+    };
+    return report(body(), err, errlen);
+}
+
+int mcf_twi_partial(const double* twi, int64_t n, double tfact, double* sum, int64_t* count, char* err,
+                    size_t errlen) {
+    auto body = [&]() -> Err {
+        if (!twi || !sum || !count || n < 0) return make_err(MCF_ERR_ARG, "bad argument");
+        TRY(device_info());
+        double* d = nullptr;
+        double* sc = nullptr;
+        CU(cudaMalloc((void**)&d, std::max<int64_t>(n, 1) * sizeof(double)));
+        cudaError_t e = cudaMalloc((void**)&sc, (2 + 2 * 256) * sizeof(double));
+        if (e != cudaSuccess) { cudaFree(d); return make_err(MCF_ERR_CUDA, "cudaMalloc failed"); }
+        double res[2] = {0, 0};
+        e = cudaMemcpy(d, twi, n * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = launch_twi_sum(d, n, tfact, sc, nullptr);
+        count_launch(2);
+        if (e == cudaSuccess) e = cudaMemcpy(res, sc, sizeof res, cudaMemcpyDeviceToHost);
+        cudaFree(d);
+        cudaFree(sc);
+        if (e != cudaSuccess) return make_err(MCF_ERR_CUDA, "twi reduction failed: %s", cudaGetErrorString(e));
+        *sum = res[0];
+        *count = (int64_t)res[1];
+        return Err();
+    };
+    return report(body(), err, errlen);
+}
+
+int mcf_fp64_peak(double* tflops, char* err, size_t errlen) {
+    auto body = [&]() -> Err {
+        if (!tflops) return make_err(MCF_ERR_ARG, "tflops is NULL");
+        TRY(device_info());
+        double* sink = nullptr;
+        CU(cudaMalloc((void**)&sink, sizeof(double)));
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        const int grid = g_sm_count * 8, iters = 4096;
+        launch_fp64_peak(sink, grid, 256, nullptr); // warm-up
+        double best = 0.0;
+        for (int rep = 0; rep < 5; ++rep) {
+            cudaEventRecord(e0, nullptr);
+            launch_fp64_peak(sink, grid, iters, nullptr);
+            cudaEventRecord(e1, nullptr);
+            cudaEventSynchronize(e1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, e0, e1);
+            const double flops = (double)grid * 256.0 * 64.0 * iters * 2.0;
+            best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        count_launch(6);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(sink);
+        CU(cudaGetLastError());
+        *tflops = best;
+        return Err();
+    };
+    return report(body(), err, errlen);
+}
+
+} // extern "C"

@@ -1,0 +1,112 @@
+// microclimf_b200 — kernel argument blocks and launch wrappers (implemented in mcf_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mcf_physics.cuh"
+
+namespace mcf {
+
+constexpr int kTile = 128;       // cells per CTA tile = threads per CTA (one thread per cell)
+constexpr int kNOut = 10;
+
+// Per-hour calendar record for the array-climate modes (solar position is per cell there).
+struct HourCal {
+    int32_t jd;     // astronomical Julian day (ref juldayCpp :28)
+    int32_t windex; // wind-shelter sector (ref :2443)
+    double lt;      // local time, decimal hours
+};
+
+// One 24-hour block of work: hours k0 .. k0+23 solved with vegetation layer `lyr`.
+struct DayBlock {
+    int32_t k0;
+    int32_t lyr;
+};
+
+enum { RQ_ABOVE = 0, RQ_SURFACE = 1, RQ_BELOW = 2 };
+
+struct GridArgs {
+    int32_t ncells;     // rows*cols of the problem = time-slot stride of every [rows, cols, n] array
+    int32_t cell_begin; // cell range solved by this launch
+    int32_t cell_end;
+    int32_t tsteps;
+    int32_t nlyr;
+    double reqhgt2; // max(reqhgt, 1e-5)   (ref :2246-2247)
+    double zref, lat;
+    double tfact;            // tadd = log(twi)/tfact - mean   (ref soildCppm :975-1019)
+    int32_t has_tadd_mean;   // caller-supplied whole-raster mean (band sharding), else dscal[1]/dscal[2]
+    double tadd_mean;
+    const double* dscal;     // device scalars written by the prep kernels: [0] series max of tc (modes 1/3,
+                             // ref :2159-2168), [1] sum and [2] count of log(twi)/tfact over non-NaN cells
+    const HourRec* hours;    // modes 1/3: [tsteps]
+    // modes 2/4: [tsteps * ncells] arrays
+    const double* clim[9]; // tc es ea tdew pk swdown difrad lwdown windspeed
+    const double* pnt[6];  // soilm G umu kp muGp dtrp
+    const double* lats;
+    const double* lons;
+    const double* mxtc_cell; // per-cell max of tc over time (ref :2467-2471)
+    const HourCal* cal;
+    // statics
+    const double* veg[10];  // hgt pai x gsmax leafr leaft clump leafd paia leafden   [nlyr * ncells]
+    const double* soil[13]; // Smin Smax gref soilb Psie Vq Vm Mc rho slope aspect twi svfa
+    const double* wsa;      // [8 * ncells]
+    const double* hor;      // [24 * ncells]
+    // work list
+    const DayBlock* blocks;
+    int32_t block0, nblocks;
+    long long hour0, ring_hours;
+    // outputs
+    double* out[kNOut];
+    uint32_t outmask;
+    // scratch
+    double* stash;          // [gridDim.x][24][kStashVars][kTile]
+    unsigned int* tile_counter;
+    double* tg_scratch;     // RQ_BELOW: [tsteps][cell_end - cell_begin] ground temperature series
+    double* dd_sum;         // RQ_BELOW: [cell_end - cell_begin] sum of damping depths
+};
+
+struct BelowArgs {
+    int32_t width;  // cells in this chunk
+    int32_t ncells; // slot stride of Tz / Tgp / Tbp arrays
+    int32_t cell_begin;
+    int32_t tsteps;
+    int32_t arr;    // Tgp/Tbp are per-cell arrays (modes 2/4) or per-hour vectors
+    int32_t complete;
+    int32_t hiy;
+    double reqhgt, mat;
+    const double* tg;     // [tsteps][width]
+    const double* dd_sum; // [width]
+    const double* Tgp;
+    const double* Tbp;
+    const double* hgt;    // first-layer vegetation height: NaN => skipped cell
+    double* daily;        // scratch [2][ndays][width]
+    double* Tz;           // [tsteps][ncells]
+};
+
+struct BioArgs {
+    int32_t width, tsteps;
+    const double* Tz;    // [tsteps][width]
+    const double* soilm; // [tsteps][width]
+    const int32_t* q[4]; // wetq dryq hotq colq (device)
+    int32_t nq[4];
+    double* bio[19];     // each [ncells], written at cell_begin + c
+    int32_t cell_begin;
+    uint32_t mask;
+};
+
+// launch wrappers (all asynchronous on `stream`)
+cudaError_t launch_prep_hours(const int32_t* year, const int32_t* month, const int32_t* day, const double* hour,
+                              const double* const clim[10], const double* const pnt[6], double lat, double lon,
+                              int tsteps, bool arr, HourRec* hours, HourCal* cal, double* mxtc_out,
+                              cudaStream_t stream);
+cudaError_t launch_mxtc_cell(const double* tc, int ncells, int tsteps, double* mxtc_cell, cudaStream_t stream);
+cudaError_t launch_twi_sum(const double* twi, int64_t n, double tfact, double* sum_count /* [2] */,
+                           cudaStream_t stream);
+cudaError_t launch_grid(const GridArgs& a, bool arr, int rq, int grid, cudaStream_t stream);
+int grid_blocks_per_sm(bool arr, int rq);
+cudaError_t launch_below(const BelowArgs& a, cudaStream_t stream);
+cudaError_t launch_bioclim(const BioArgs& a, cudaStream_t stream);
+cudaError_t launch_fill_na(double* p, int64_t n, cudaStream_t stream);
+cudaError_t launch_fp64_peak(double* sink, int grid, int iters, cudaStream_t stream);
+
+} // namespace mcf

@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes access to the two CPU checkers.
+
+  ref    : oracle/_ref/libmicroclimf_ref.so — the unmodified reference C++ behind oracle/ref_driver.cpp
+  oracle : oracle/liboracle.so              — the plain-C restatement (oracle/mcf_oracle.c)
+
+Both take the product's `mcf_problem` struct, so a GridProblem feeds either checker or the CUDA path
+unchanged.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from microclimf_b200 import _abi
+from microclimf_b200.problem import GridProblem
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_PATH = os.path.join(_HERE, "_ref", "libmicroclimf_ref.so")
+ORACLE_PATH = os.path.join(_HERE, "liboracle.so")
+_libs = {}
+
+
+def have_ref() -> bool:
+    return os.path.exists(REF_PATH)
+
+
+def have_oracle() -> bool:
+    return os.path.exists(ORACLE_PATH)
+
+
+def _lib(kind: str):
+    if kind not in _libs:
+        path = REF_PATH if kind == "ref" else ORACLE_PATH
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not built: run `make -C oracle` (or __graft_entry__.build())")
+        _libs[kind] = C.CDLL(path)
+    return _libs[kind]
+
+
+def _na_filled(n):
+    a = np.empty(n, dtype=np.float64)
+    a.view(np.uint64)[:] = 0xDEADBEEFDEADBEEF  # poison: the callee must overwrite everything
+    return a
+
+
+def runmicro(prob: GridProblem, out_mask=None, kind: str = "oracle"):
+    """Run the CPU checker; returns {name: array[rows, cols, tsteps] (Fortran order)}."""
+    lib = _lib(kind)
+    fn = getattr(lib, "ref_runmicro" if kind == "ref" else "oracle_runmicro")
+    fn.restype = C.c_int
+    s, keep = prob.as_struct()
+    out_mask = [True] * _abi.MCF_NOUT if out_mask is None else list(out_mask)
+    n = prob.ncells * prob.tsteps
+    bufs = [_na_filled(n) if m else None for m in out_mask]
+    ptrs = _abi.OutPtrs(*[b.ctypes.data_as(C.POINTER(C.c_double)) if b is not None else None for b in bufs])
+    err = C.create_string_buffer(512)
+    rc = fn(C.byref(s), ptrs, err, C.c_size_t(512))
+    if rc != 0:
+        raise RuntimeError(f"{kind} runmicro failed ({rc}): {err.value.decode()}")
+    del keep
+    return {nm: b.reshape((prob.rows, prob.cols, prob.tsteps), order="F")
+            for nm, b in zip(_abi.OUT_NAMES, bufs) if b is not None}
+
+
+def runbioclim(prob: GridProblem, quarters: dict, air: bool = True, out_mask=None, kind: str = "oracle"):
+    lib = _lib(kind)
+    fn = getattr(lib, "ref_runbioclim" if kind == "ref" else "oracle_runbioclim")
+    fn.restype = C.c_int
+    s, keep = prob.as_struct()
+    out_mask = [True] * _abi.MCF_NBIO if out_mask is None else list(out_mask)
+    bufs = [_na_filled(prob.ncells) if m else None for m in out_mask]
+    ptrs = _abi.BioPtrs(*[b.ctypes.data_as(C.POINTER(C.c_double)) if b is not None else None for b in bufs])
+    q = {k: np.ascontiguousarray(np.asarray(v, dtype=np.int32)) for k, v in quarters.items()}
+    pi = C.POINTER(C.c_int32)
+    err = C.create_string_buffer(512)
+    rc = fn(C.byref(s), q["wetq"].ctypes.data_as(pi), C.c_int32(len(q["wetq"])), q["dryq"].ctypes.data_as(pi),
+            C.c_int32(len(q["dryq"])), q["hotq"].ctypes.data_as(pi), C.c_int32(len(q["hotq"])),
+            q["colq"].ctypes.data_as(pi), C.c_int32(len(q["colq"])), C.c_int32(1 if air else 0), ptrs, err,
+            C.c_size_t(512))
+    if rc != 0:
+        raise RuntimeError(f"{kind} runbioclim failed ({rc}): {err.value.decode()}")
+    del keep
+    return {nm: b.reshape((prob.rows, prob.cols), order="F") for nm, b in zip(_abi.BIO_NAMES, bufs) if b is not None}

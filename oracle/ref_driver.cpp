@@ -1,0 +1,274 @@
+// TEST INFRASTRUCTURE ONLY — not part of the product path.
+//
+// extern "C" driver over the UNMODIFIED reference translation unit (/root/reference/src/
+// microclimfCpp.cpp, compiled in place against oracle/rcpp_shim/Rcpp.h).  It takes the same
+// `mcf_problem` description as the product C ABI (include/microclimf_b200.h), rebuilds the
+// DataFrame / List arguments the reference drivers expect (names per src/microclimfCpp.cpp:2056-2111
+// for modes 1/3 and :2344-2399 for modes 2/4) and copies the returned arrays out.
+//
+// Used by: tests/ (parity), tests/golden/make_golden.py (fixture generation), bench.py's
+// cpu_baseline / --impl reference legs.  Never by the product.
+#include <Rcpp.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "microclimf_b200.h"
+#include "microclimfheaders.h" // reference POD structs, included in place from /root/reference/src
+
+using namespace Rcpp;
+
+// prototypes of the reference entry points (defined in the reference .cpp; no header exports them)
+List runmicro1Cpp(DataFrame obstime, DataFrame climdata, DataFrame pointm, List vegp, List soilc, double reqhgt,
+                  double zref, double lat, double lon, double Sminp, double Smaxp, double tfact, bool complete,
+                  double mat, std::vector<bool> out);
+List runmicro2Cpp(DataFrame obstime, List climdata, List pointm, List vegp, List soilc, double reqhgt, double zref,
+                  NumericMatrix lats, NumericMatrix lons, double Sminp, double Smaxp, double tfact, bool complete,
+                  double mat, std::vector<bool> out);
+List runmicro3Cpp(DataFrame dfsel, DataFrame obstime, DataFrame climdata, DataFrame pointm, List vegp, List soilc,
+                  double reqhgt, double zref, double lat, double lon, double Sminp, double Smaxp, double tfact,
+                  bool complete, double mat, std::vector<bool> out);
+List runmicro4Cpp(DataFrame dfsel, DataFrame obstime, List climdata, List pointm, List vegp, List soilc,
+                  double reqhgt, double zref, NumericMatrix lats, NumericMatrix lons, double Sminp, double Smaxp,
+                  double tfact, bool complete, double mat, std::vector<bool> out);
+List runbioclim1Cpp(DataFrame obstime, DataFrame climdata, DataFrame pointm, List vegp, List soilc, double reqhgt,
+                    double zref, double lat, double lon, double Sminp, double Smaxp, double tfact, double mat,
+                    std::vector<bool> out, IntegerVector wetq, IntegerVector dryq, IntegerVector hotq,
+                    IntegerVector colq, bool air);
+List runbioclim2Cpp(DataFrame obstime, List climdata, List pointm, List vegp, List soilc, double reqhgt, double zref,
+                    NumericMatrix lats, NumericMatrix lons, double Sminp, double Smaxp, double tfact, double mat,
+                    std::vector<bool> out, IntegerVector wetq, IntegerVector dryq, IntegerVector hotq,
+                    IntegerVector colq, bool air);
+List runbioclim3Cpp(DataFrame obstime, DataFrame climdata, DataFrame pointm, List vegp, List soilc, double reqhgt,
+                    double zref, double lat, double lon, double Sminp, double Smaxp, double tfact, double mat,
+                    std::vector<bool> out, IntegerVector wetq, IntegerVector dryq, IntegerVector hotq,
+                    IntegerVector colq, bool air);
+List runbioclim4Cpp(DataFrame obstime, List climdata, List pointm, List vegp, List soilc, double reqhgt, double zref,
+                    NumericMatrix lats, NumericMatrix lons, double Sminp, double Smaxp, double tfact, double mat,
+                    std::vector<bool> out, IntegerVector wetq, IntegerVector dryq, IntegerVector hotq,
+                    IntegerVector colq, bool air);
+solmodel solpositionCpp(double lat, double lon, int year, int month, int day, double lt);
+NumericVector clearskyradCpp(IntegerVector year, IntegerVector month, IntegerVector day, NumericVector lt, double lat,
+                             double lon, NumericVector tc, NumericVector rh, NumericVector pk);
+std::vector<double> manCpp(std::vector<double> x, int n);
+double satvapCpp(double tc);
+
+namespace {
+
+NumericVector vec(const double* p, size_t n) {
+    NumericVector v(n);
+    if (p) std::memcpy(v.raw(), p, n * sizeof(double));
+    return v;
+}
+IntegerVector ivec(const int32_t* p, size_t n) {
+    IntegerVector v(n);
+    for (size_t i = 0; i < n; ++i) v[i] = p[i];
+    return v;
+}
+NumericMatrix mat2(const double* p, int r, int c) {
+    NumericMatrix m(r, c);
+    if (p) std::memcpy(m.raw(), p, (size_t)r * c * sizeof(double));
+    return m;
+}
+NumericVector arr3(const double* p, int r, int c, int n) {
+    NumericVector v((size_t)r * c * n);
+    if (p) std::memcpy(v.raw(), p, (size_t)r * c * n * sizeof(double));
+    v.set_dims({r, c, n});
+    return v;
+}
+
+struct Args {
+    DataFrame dfsel, obstime;
+    List climdata, pointm, vegp, soilc;
+    NumericMatrix lats, lons;
+};
+
+Args build(const mcf_problem* p) {
+    Args a;
+    const bool arrclim = (p->mode == 2 || p->mode == 4);
+    const bool layered = (p->mode == 3 || p->mode == 4);
+    const int R = p->rows, C = p->cols, T = p->tsteps;
+    const size_t nc = (size_t)R * C;
+    const size_t nclim = arrclim ? nc * T : (size_t)T;
+    a.obstime["year"] = ivec(p->year, T);
+    a.obstime["month"] = ivec(p->month, T);
+    a.obstime["day"] = ivec(p->day, T);
+    a.obstime["hour"] = vec(p->hour, T);
+    a.climdata[arrclim ? "tc" : "temp"] = vec(p->temp, nclim);
+    a.climdata["es"] = vec(p->es, nclim);
+    a.climdata["ea"] = vec(p->ea, nclim);
+    a.climdata["tdew"] = vec(p->tdew, nclim);
+    a.climdata[arrclim ? "pk" : "pres"] = vec(p->pres, nclim);
+    a.climdata["swdown"] = vec(p->swdown, nclim);
+    a.climdata["difrad"] = vec(p->difrad, nclim);
+    a.climdata["lwdown"] = vec(p->lwdown, nclim);
+    a.climdata["windspeed"] = vec(p->windspeed, nclim);
+    a.climdata["winddir"] = vec(p->winddir, T);
+    a.pointm["soilm"] = vec(p->p_soilm, nclim);
+    a.pointm["Tg"] = vec(p->p_Tg, nclim);
+    a.pointm["Tbp"] = vec(p->p_Tbp, nclim);
+    a.pointm[arrclim ? "Gp" : "G"] = vec(p->p_G, nclim);
+    a.pointm["umu"] = vec(p->p_umu, nclim);
+    a.pointm["kp"] = vec(p->p_kp, nclim);
+    a.pointm["muGp"] = vec(p->p_muGp, nclim);
+    a.pointm["dtrp"] = vec(p->p_dtrp, nclim);
+    // read by the reference into locals that are never used (src/microclimfCpp.cpp:2075, 2078)
+    a.pointm["T0p"] = NumericVector(nclim);
+    a.pointm["DDp"] = NumericVector(nclim);
+    const int L = layered ? p->nlyr : 1;
+    auto veg = [&](const double* q) -> NumericVector {
+        if (layered) return arr3(q, R, C, L);
+        return mat2(q, R, C);
+    };
+    a.vegp["hgt"] = veg(p->hgt);
+    a.vegp["pai"] = veg(p->pai);
+    a.vegp["x"] = veg(p->x);
+    a.vegp["gsmax"] = veg(p->gsmax);
+    a.vegp["leafr"] = veg(p->leafr);
+    a.vegp["leaft"] = veg(p->leaft);
+    a.vegp["clump"] = veg(p->clump);
+    a.vegp["leafd"] = veg(p->leafd);
+    a.vegp["paia"] = veg(p->paia);
+    a.vegp["leafden"] = veg(p->leafden);
+    a.soilc["Smin"] = mat2(p->Smin, R, C);
+    a.soilc["Smax"] = mat2(p->Smax, R, C);
+    a.soilc["gref"] = mat2(p->gref, R, C);
+    a.soilc["soilb"] = mat2(p->soilb, R, C);
+    a.soilc["Psie"] = mat2(p->Psie, R, C);
+    a.soilc["Vq"] = mat2(p->Vq, R, C);
+    a.soilc["Vm"] = mat2(p->Vm, R, C);
+    a.soilc["Mc"] = mat2(p->Mc, R, C);
+    a.soilc["rho"] = mat2(p->rho, R, C);
+    a.soilc["slope"] = mat2(p->slope, R, C);
+    a.soilc["aspect"] = mat2(p->aspect, R, C);
+    a.soilc["twi"] = mat2(p->twi, R, C);
+    a.soilc["svfa"] = mat2(p->svfa, R, C);
+    a.soilc["wsa"] = arr3(p->wsa, R, C, 8);
+    a.soilc["hor"] = arr3(p->hor, R, C, 24);
+    if (arrclim) {
+        a.lats = mat2(p->lats, R, C);
+        a.lons = mat2(p->lons, R, C);
+    }
+    if (layered) {
+        IntegerVector lyr(L);
+        for (int i = 0; i < L; ++i) lyr[i] = i + 1;
+        a.dfsel["lyr"] = lyr;
+        a.dfsel["st"] = ivec(p->lyr_st, L);
+        a.dfsel["ed"] = ivec(p->lyr_ed, L);
+    }
+    return a;
+}
+
+int fail(char* err, size_t errlen, const std::string& msg, int code) {
+    if (err && errlen) std::snprintf(err, errlen, "%s", msg.c_str());
+    return code;
+}
+
+const char* const kOutNames[MCF_NOUT] = {"Tz",       "tleaf",    "relhum",  "soilm", "windspeed",
+                                         "Rdirdown", "Rdifdown", "Rlwdown", "Rswup", "Rlwup"};
+
+} // namespace
+
+extern "C" int ref_runmicro(const mcf_problem* p, double* const out[MCF_NOUT], char* err, size_t errlen) {
+    try {
+        Args a = build(p);
+        std::vector<bool> o(MCF_NOUT);
+        for (int v = 0; v < MCF_NOUT; ++v) o[v] = out[v] != nullptr;
+        List res;
+        switch (p->mode) {
+        case 1:
+            res = runmicro1Cpp(a.obstime, a.climdata, a.pointm, a.vegp, a.soilc, p->reqhgt, p->zref, p->lat, p->lon,
+                               p->Sminp, p->Smaxp, p->tfact, p->complete != 0, p->mat, o);
+            break;
+        case 2:
+            res = runmicro2Cpp(a.obstime, a.climdata, a.pointm, a.vegp, a.soilc, p->reqhgt, p->zref, a.lats, a.lons,
+                               p->Sminp, p->Smaxp, p->tfact, p->complete != 0, p->mat, o);
+            break;
+        case 3:
+            res = runmicro3Cpp(a.dfsel, a.obstime, a.climdata, a.pointm, a.vegp, a.soilc, p->reqhgt, p->zref, p->lat,
+                               p->lon, p->Sminp, p->Smaxp, p->tfact, p->complete != 0, p->mat, o);
+            break;
+        case 4:
+            res = runmicro4Cpp(a.dfsel, a.obstime, a.climdata, a.pointm, a.vegp, a.soilc, p->reqhgt, p->zref, a.lats,
+                               a.lons, p->Sminp, p->Smaxp, p->tfact, p->complete != 0, p->mat, o);
+            break;
+        default:
+            return fail(err, errlen, "ref_runmicro: mode must be 1..4", MCF_ERR_ARG);
+        }
+        const size_t n = (size_t)p->rows * p->cols * p->tsteps;
+        for (int v = 0; v < MCF_NOUT; ++v) {
+            if (!out[v]) continue;
+            NumericVector r = res[kOutNames[v]];
+            std::memcpy(out[v], r.raw(), n * sizeof(double));
+        }
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e.what(), MCF_ERR_ARG);
+    }
+    return MCF_OK;
+}
+
+extern "C" int ref_runbioclim(const mcf_problem* p, const int32_t* wetq, int32_t nwetq, const int32_t* dryq,
+                              int32_t ndryq, const int32_t* hotq, int32_t nhotq, const int32_t* colq, int32_t ncolq,
+                              int32_t air, double* const bio[MCF_NBIO], char* err, size_t errlen) {
+    try {
+        Args a = build(p);
+        std::vector<bool> o(MCF_NBIO);
+        for (int v = 0; v < MCF_NBIO; ++v) o[v] = bio[v] != nullptr;
+        IntegerVector wq = ivec(wetq, nwetq), dq = ivec(dryq, ndryq), hq = ivec(hotq, nhotq), cq = ivec(colq, ncolq);
+        List res;
+        switch (p->mode) {
+        case 1:
+            res = runbioclim1Cpp(a.obstime, a.climdata, a.pointm, a.vegp, a.soilc, p->reqhgt, p->zref, p->lat, p->lon,
+                                 p->Sminp, p->Smaxp, p->tfact, p->mat, o, wq, dq, hq, cq, air != 0);
+            break;
+        case 2:
+            res = runbioclim2Cpp(a.obstime, a.climdata, a.pointm, a.vegp, a.soilc, p->reqhgt, p->zref, a.lats, a.lons,
+                                 p->Sminp, p->Smaxp, p->tfact, p->mat, o, wq, dq, hq, cq, air != 0);
+            break;
+        case 3:
+            res = runbioclim3Cpp(a.obstime, a.climdata, a.pointm, a.vegp, a.soilc, p->reqhgt, p->zref, p->lat, p->lon,
+                                 p->Sminp, p->Smaxp, p->tfact, p->mat, o, wq, dq, hq, cq, air != 0);
+            break;
+        case 4:
+            res = runbioclim4Cpp(a.obstime, a.climdata, a.pointm, a.vegp, a.soilc, p->reqhgt, p->zref, a.lats, a.lons,
+                                 p->Sminp, p->Smaxp, p->tfact, p->mat, o, wq, dq, hq, cq, air != 0);
+            break;
+        default:
+            return fail(err, errlen, "ref_runbioclim: mode must be 1..4", MCF_ERR_ARG);
+        }
+        const size_t n = (size_t)p->rows * p->cols;
+        for (int v = 0; v < MCF_NBIO; ++v) {
+            if (!bio[v]) continue;
+            NumericMatrix r = res["bio" + std::to_string(v + 1)];
+            std::memcpy(bio[v], r.raw(), n * sizeof(double));
+        }
+    } catch (const std::exception& e) {
+        return fail(err, errlen, e.what(), MCF_ERR_ARG);
+    }
+    return MCF_OK;
+}
+
+// Small helpers of the reference exposed for fixture generation and unit checks of the restatement.
+extern "C" void ref_clearskyrad(int32_t n, const int32_t* year, const int32_t* month, const int32_t* day,
+                                const double* lt, double lat, double lon, const double* tc, const double* rh,
+                                const double* pk, double* out) {
+    NumericVector r = clearskyradCpp(ivec(year, n), ivec(month, n), ivec(day, n), vec(lt, n), lat, lon, vec(tc, n),
+                                     vec(rh, n), vec(pk, n));
+    std::memcpy(out, r.raw(), (size_t)n * sizeof(double));
+}
+
+extern "C" void ref_solposition(double lat, double lon, int32_t year, int32_t month, int32_t day, double lt,
+                                double* zend_azid /* [2] */) {
+    solmodel s = solpositionCpp(lat, lon, year, month, day, lt);
+    zend_azid[0] = s.zend;
+    zend_azid[1] = s.azid;
+}
+
+extern "C" void ref_man(const double* x, int32_t m, int32_t n, double* out) {
+    std::vector<double> r = manCpp(std::vector<double>(x, x + m), n);
+    std::memcpy(out, r.data(), (size_t)m * sizeof(double));
+}
+
+extern "C" double ref_satvap(double tc) { return satvapCpp(tc); }
