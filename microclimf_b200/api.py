@@ -1,0 +1,168 @@
+"""Python mirror of the reference's Rcpp-exported operators for the hot path.
+
+Same names, argument order and meaning as R/RcppExports.R:72-102 (runmicro1Cpp ... runbioclim4Cpp):
+data.frames / lists become dicts of numpy arrays keyed by the reference's column names, matrices are
+[rows, cols] arrays and 3-D arrays are [rows, cols, n] (any memory order; they are packed to R's
+column-major layout here).  The return value is the reference's named list as a dict: each present
+element a float64 array of shape (rows, cols, tsteps) (Fortran order, i.e. R's memory layout).
+
+Everything runs through the C ABI (include/microclimf_b200.h) on the GPU; errors surface as McfError,
+the analogue of the R condition raised through END_RCPP (src/RcppExports.cpp:251-271).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _abi, _lib
+from .problem import GridProblem
+
+_PD = C.POINTER(C.c_double)
+_PI = C.POINTER(C.c_int32)
+
+# reference column names -> ABI field names
+_CLIM_DF = dict(temp="temp", es="es", ea="ea", tdew="tdew", pres="pres", swdown="swdown", difrad="difrad",
+                lwdown="lwdown", windspeed="windspeed", winddir="winddir")          # src/microclimfCpp.cpp:2062-2071
+_CLIM_ARR = dict(tc="temp", es="es", ea="ea", tdew="tdew", pk="pres", swdown="swdown", difrad="difrad",
+                 lwdown="lwdown", windspeed="windspeed", winddir="winddir")         # :2350-2359
+_POINT_DF = dict(soilm="p_soilm", Tg="p_Tg", Tbp="p_Tbp", G="p_G", umu="p_umu", kp="p_kp", muGp="p_muGp",
+                 dtrp="p_dtrp")                                                      # :2073-2082
+_POINT_ARR = dict(soilm="p_soilm", Tg="p_Tg", Tbp="p_Tbp", Gp="p_G", umu="p_umu", kp="p_kp", muGp="p_muGp",
+                  dtrp="p_dtrp")                                                     # :2361-2370
+_VEG = dict(hgt="hgt", pai="pai", x="x", gsmax="gsmax", leafr="leafr", leaft="leaft", clump="clump", leafd="leafd",
+            paia="paia", leafden="leafden")
+_SOIL = {n: n for n in _abi.SOIL_FIELDS}
+
+
+def _problem(mode, dfsel, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, lats, lons, Sminp, Smaxp,
+             tfact, complete, mat) -> GridProblem:
+    hgt = np.asarray(vegp["hgt"], dtype=np.float64)
+    if hgt.ndim < 2:
+        raise ValueError("vegp$hgt must be a [rows, cols] matrix or [rows, cols, nlyr] array")
+    rows, cols = hgt.shape[0], hgt.shape[1]
+    tsteps = int(np.asarray(obstime["hour"]).size)
+    layered = mode in (3, 4)
+    nlyr = hgt.shape[2] if (layered and hgt.ndim == 3) else 1
+    p = GridProblem(mode=mode, rows=rows, cols=cols, tsteps=tsteps, reqhgt=float(reqhgt), zref=float(zref),
+                    lat=float(lat), lon=float(lon), Sminp=float(Sminp), Smaxp=float(Smaxp), tfact=float(tfact),
+                    mat=float(mat), complete=bool(complete), nlyr=nlyr)
+    if layered:
+        p.lyr_st = np.asarray(dfsel["st"], dtype=np.int32)
+        p.lyr_ed = np.asarray(dfsel["ed"], dtype=np.int32)
+    for n in ("year", "month", "day", "hour"):
+        p.set(n, obstime[n])
+    arr = mode in (2, 4)
+    for table, names in ((climdata, _CLIM_ARR if arr else _CLIM_DF), (pointm, _POINT_ARR if arr else _POINT_DF),
+                         (vegp, _VEG), (soilc, _SOIL)):
+        for ref_name, abi_name in names.items():
+            if ref_name in table and table[ref_name] is not None:
+                p.set(abi_name, table[ref_name])
+    if arr:
+        p.set("lats", lats)
+        p.set("lons", lons)
+    p.validate()
+    return p
+
+
+def run_problem(p: GridProblem, out: Optional[Sequence[bool]] = None) -> Dict[str, np.ndarray]:
+    """mcf_runmicro on a host GridProblem; returns the reference's named list."""
+    L = _lib.lib()
+    out = [True] * _abi.MCF_NOUT if out is None else [bool(o) for o in out]
+    if len(out) != _abi.MCF_NOUT:
+        raise ValueError("out must have 10 logicals")
+    n = p.ncells * p.tsteps
+    bufs = [np.empty(n, dtype=np.float64) if o else None for o in out]
+    ptrs = _abi.OutPtrs(*[b.ctypes.data_as(_PD) if b is not None else None for b in bufs])
+    s, keep = p.as_struct()
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runmicro(C.byref(s), ptrs, err, 512), err)
+    del keep
+    return {nm: b.reshape((p.rows, p.cols, p.tsteps), order="F") for nm, b in zip(_abi.OUT_NAMES, bufs)
+            if b is not None}
+
+
+def run_bioclim_problem(p: GridProblem, wetq, dryq, hotq, colq, air: bool = True,
+                        out: Optional[Sequence[bool]] = None) -> Dict[str, np.ndarray]:
+    L = _lib.lib()
+    out = [True] * _abi.MCF_NBIO if out is None else [bool(o) for o in out]
+    if len(out) != _abi.MCF_NBIO:
+        raise ValueError("out must have 19 logicals")
+    bufs = [np.empty(p.ncells, dtype=np.float64) if o else None for o in out]
+    ptrs = _abi.BioPtrs(*[b.ctypes.data_as(_PD) if b is not None else None for b in bufs])
+    qs = [np.ascontiguousarray(np.asarray(q, dtype=np.int32)) for q in (wetq, dryq, hotq, colq)]
+    qargs = []
+    for q in qs:
+        qargs += [q.ctypes.data_as(_PI), C.c_int32(q.size)]
+    s, keep = p.as_struct()
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runbioclim(C.byref(s), *qargs, C.c_int32(1 if air else 0), ptrs, err, 512), err)
+    del keep
+    return {nm: b.reshape((p.rows, p.cols), order="F") for nm, b in zip(_abi.BIO_NAMES, bufs) if b is not None}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference's operators (R/RcppExports.R:72-102)
+# ---------------------------------------------------------------------------------------------------
+def runmicro1Cpp(obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, Sminp, Smaxp, tfact, complete, mat,
+                 out):
+    """src/microclimfCpp.cpp:2052 — static vegetation, data.frame climate."""
+    return run_problem(_problem(1, None, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, None, None,
+                                Sminp, Smaxp, tfact, complete, mat), out)
+
+
+def runmicro2Cpp(obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lats, lons, Sminp, Smaxp, tfact, complete, mat,
+                 out):
+    """src/microclimfCpp.cpp:2340 — static vegetation, array climate."""
+    return run_problem(_problem(2, None, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, 0.0, 0.0, lats, lons,
+                                Sminp, Smaxp, tfact, complete, mat), out)
+
+
+def runmicro3Cpp(dfsel, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, Sminp, Smaxp, tfact, complete,
+                 mat, out):
+    """src/microclimfCpp.cpp:2624 — layered vegetation, data.frame climate."""
+    return run_problem(_problem(3, dfsel, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, None, None,
+                                Sminp, Smaxp, tfact, complete, mat), out)
+
+
+def runmicro4Cpp(dfsel, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lats, lons, Sminp, Smaxp, tfact,
+                 complete, mat, out):
+    """src/microclimfCpp.cpp:2926 — layered vegetation, array climate."""
+    return run_problem(_problem(4, dfsel, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, 0.0, 0.0, lats, lons,
+                                Sminp, Smaxp, tfact, complete, mat), out)
+
+
+def _bioclim(mode, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, lats, lons, Sminp, Smaxp, tfact,
+             mat, out, wetq, dryq, hotq, colq, air):
+    dfsel = None
+    if mode in (3, 4):  # the reference hard-codes 14 one-day layers (src/microclimfCpp.cpp:3635-3646)
+        dfsel = dict(st=np.arange(14) * 24, ed=np.arange(14) * 24 + 23)
+    p = _problem(mode, dfsel, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, lats, lons, Sminp,
+                 Smaxp, tfact, True, mat)
+    return run_bioclim_problem(p, wetq, dryq, hotq, colq, air, out)
+
+
+def runbioclim1Cpp(obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, Sminp, Smaxp, tfact, mat, out,
+                   wetq, dryq, hotq, colq, air):
+    """src/microclimfCpp.cpp:3563."""
+    return _bioclim(1, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, None, None, Sminp, Smaxp, tfact,
+                    mat, out, wetq, dryq, hotq, colq, air)
+
+
+def runbioclim2Cpp(obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lats, lons, Sminp, Smaxp, tfact, mat, out,
+                   wetq, dryq, hotq, colq, air):
+    return _bioclim(2, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, 0.0, 0.0, lats, lons, Sminp, Smaxp, tfact,
+                    mat, out, wetq, dryq, hotq, colq, air)
+
+
+def runbioclim3Cpp(obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, Sminp, Smaxp, tfact, mat, out,
+                   wetq, dryq, hotq, colq, air):
+    return _bioclim(3, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lat, lon, None, None, Sminp, Smaxp, tfact,
+                    mat, out, wetq, dryq, hotq, colq, air)
+
+
+def runbioclim4Cpp(obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lats, lons, Sminp, Smaxp, tfact, mat, out,
+                   wetq, dryq, hotq, colq, air):
+    return _bioclim(4, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, 0.0, 0.0, lats, lons, Sminp, Smaxp, tfact,
+                    mat, out, wetq, dryq, hotq, colq, air)
