@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native microclimf grid solver.
+
+Metric (BASELINE.json): runmicro cell-hours/s.  Workload: configs[3], `runmicro_big` on a synthetic
+8192 x 8192 DTM / vegp / soil raster x 8760 h, column-band sharded.  Each GPU holds ONE 8192 x 1024 band
+(1/8 of the raster: static layers + the year's forcing resident in HBM) — weak scaling: at N = 8 the
+job is exactly the config-4 raster.  A "step" is one pass of the hot path over a 30-day window
+(720 h) of the band = 6.04e9 cell-hours per GPU; successive steps walk through the year's windows.
+All 10 FP64 outputs are written, into a 24-hour HBM ring (the full [rows, cols, 8760]
+result is 4.7 TB per variable and exists nowhere; the ring keeps the HBM write traffic real).
+
+  value     : device-timed whole-job cell-hours/s, inputs resident in HBM (mcf_runmicro_dev)
+  e2e       : the same metric through the host-buffer C ABI (mcf_runmicro): pinned host inputs are
+              uploaded and all outputs copied back to host inside the timed region, on a bounded tile
+  roofline  : dominant kernel (k_grid) — algorithmic HBM bytes / CUDA-event launch time vs measured
+              copy bandwidth; plus the FP64-pipe fraction (the binding roofline)
+  cpu_baseline : the UNMODIFIED reference C++ (oracle/_ref) on the host cores, bounded sample
+
+`--impl reference` times only the reference CPU path (same metric / config), rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "runmicro cell-hours/sec"
+UNIT = "cell-hours/s"
+ROWS, BAND_COLS, TSTEPS, WIN_DAYS = 8192, 1024, 8760, 30
+REQHGT = 0.05
+# algorithmic HBM bytes: 8 B x 10 outputs per cell-hour + 440 B of static layers per cell
+BYTES_PER_CELL_HOUR = 80.0
+BYTES_PER_CELL_STATIC = 440.0
+# FP64 flop per cell-hour executed by k_grid<false, RQ_ABOVE> on this workload: measured with ncu
+# (profiles/); DFMA counted as 2.
+FLOP_PER_CELL_HOUR = None  # filled from profiles/fp64_ops.json when present
+
+
+def workload_config(args):
+    return {
+        "workload": ("runmicro_big synthetic 8192x8192 raster x 8760 h, column-band sharded (BASELINE configs[3]); "
+                     f"one {args.rows}x{args.band_cols} band per GPU resident in HBM; step = {args.win_days}-day "
+                     f"window ({args.win_days * 24} h) of the band; runmicro1Cpp semantics (static veg, broadcast "
+                     f"forcing), reqhgt {REQHGT}, all 10 outputs FP64 into a 24-h HBM ring sink"),
+        "rows": args.rows, "band_cols_per_gpu": args.band_cols, "tsteps": TSTEPS, "window_hours": args.win_days * 24,
+        "outputs": 10, "reqhgt": REQHGT,
+        "l2": "per-step traffic (>= 16 GB of output + 3.7 GB static) exceeds the 126 MB L2; no flush needed",
+    }
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU reference leg (oracle/_ref = the unmodified reference C++), N worker processes over column bands
+# ----------------------------------------------------------------------------------------------------
+SAMPLE_DAYS = [15, 52, 88, 125, 161, 198, 234, 271, 307, 344]  # 10 days spread over the year (240 h)
+
+
+def _cpu_worker(idx, rows, cols, barrier, q, reps):
+    from microclimf_b200 import synth
+    from oracle import pyoracle
+
+    kind = "ref" if pyoracle.have_ref() else "oracle"
+    p = synth.make_problem(rows, cols, 240, reqhgt=REQHGT, mode=1, seed=20240321 + idx, day_list=SAMPLE_DAYS)
+    p.twi_mean = 1.0
+    times = []
+    for _ in range(reps):
+        barrier.wait()
+        t0 = time.perf_counter()
+        pyoracle.runmicro(p, kind=kind)
+        times.append(time.perf_counter() - t0)
+        barrier.wait()
+    q.put((idx, kind, times))
+
+
+def cpu_reference(nproc, rows, cols_per_proc, reps):
+    """Runs `reps` timed passes; returns (kind, [wall seconds per pass], cell-hours per pass)."""
+    import multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    barrier = ctx.Barrier(nproc + 1)
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=(i, rows, cols_per_proc, barrier, q, reps)) for i in range(nproc)]
+    for pr in procs:
+        pr.start()
+    walls = []
+    for _ in range(reps):
+        barrier.wait()
+        t0 = time.perf_counter()
+        barrier.wait()
+        walls.append(time.perf_counter() - t0)
+    res = [q.get() for _ in procs]
+    for pr in procs:
+        pr.join()
+    return res[0][1], walls, float(nproc) * rows * cols_per_proc * 240
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    nproc = host_cores()
+    rows, cpp = 128, 64  # ~2e6 cell-hours per core and pass: a few seconds
+    kind, walls, ch = cpu_reference(nproc, rows, cpp, args.warmup + args.steps)
+    timed = walls[args.warmup:]
+    total = sum(timed)
+    value = ch * len(timed) / total
+    sample = (f"{nproc} processes x ({rows}x{cpp} cells x 240 h: 10 days spread over the year), same synthetic recipe, "
+              f"reqhgt {REQHGT}, all 10 outputs; {'unmodified reference C++ (oracle/_ref, g++ -O2)' if kind == 'ref' else 'C restatement (oracle/)'}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(timed), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nproc, "kind": "reference" if kind == "ref" else "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(prefix="mcf_clocks_", suffix=".csv")
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def gpu_arm(args):
+    import numpy as np
+    import torch
+
+    from microclimf_b200 import _lib, api, bands, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the grid solver has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    L = _lib.lib()
+    if L.mcf_set_device(local_rank) != 0:
+        raise SystemExit("mcf_set_device failed")
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    # ------------------------------------------------------------------ the band problem (HBM-resident)
+    rows, cols, T = args.rows, args.band_cols, TSTEPS
+    t_gen = time.time()
+    hp = synth.make_problem(rows, cols, T, reqhgt=REQHGT, mode=1, seed=20240321 + 1000 * rank)
+    s, n = bands.twi_partial_host(hp.arrays["twi"], hp.tfact)
+    hp.twi_mean = bands.global_twi_mean(s, n)  # the one whole-raster coupling (tiny all-reduce, off the hot path)
+    dp = hp.to_device("cuda")
+    ncells = rows * cols
+    ring_hours = 24
+    outs = [torch.empty(ring_hours * ncells, dtype=torch.float64, device="cuda") for _ in range(10)]
+    t_gen = time.time() - t_gen
+    nwin = (T // 24) // args.win_days
+    cell_hours_step = float(ncells) * args.win_days * 24
+
+    def step(i):
+        b0 = (i % nwin) * args.win_days
+        api.run_problem_dev(dp, outs, window=(b0, args.win_days, b0 * 24, ring_hours))
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    L.mcf_kernel_timing_enable(1)
+    L.mcf_kernel_time_reset()
+    L.mcf_launch_count_reset()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = int(L.mcf_launch_count())
+    kms, kn = api.kernel_time(reset=True)
+    L.mcf_kernel_timing_enable(0)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = cell_hours_step * args.steps * world / (ms * 1e-3)
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    peaks, peak_src = measured_peaks()
+    k_avg_ms = kms / max(kn, 1)
+    bytes_launch = cell_hours_step * BYTES_PER_CELL_HOUR + ncells * BYTES_PER_CELL_STATIC
+    achieved = bytes_launch / (k_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_grid<false,RQ_ABOVE>", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": k_avg_ms, "launches": kn, "kernel_share_of_step": kms / ms,
+                "algorithmic_bytes_per_launch": bytes_launch}
+    prof = os.path.join(ROOT, "profiles", "kgrid_metrics.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            pm = json.load(f)
+        roofline["traffic"] = pm.get("dram_bytes_per_cell_hour", 0) * cell_hours_step or None
+        if pm.get("fp64_flop_per_cell_hour"):
+            fpk = api.fp64_peak_tflops() if rank == 0 else None
+            if fpk:
+                ach = pm["fp64_flop_per_cell_hour"] * cell_hours_step / (k_avg_ms * 1e-3) / 1e12
+                roofline["fp64"] = {"achieved": ach, "peak": fpk, "unit": "TFLOP/s", "frac": ach / fpk,
+                                    "peak_source": "mcf_fp64_peak DFMA micro-benchmark, this run",
+                                    "flop_per_cell_hour": pm["fp64_flop_per_cell_hour"],
+                                    "flop_source": pm.get("source", "profiles/")}
+
+    # ------------------------------------------------------------------ e2e through the host-buffer C ABI
+    e2e = None
+    er, ec, et = args.e2e_rows, args.e2e_cols, args.e2e_hours
+    ep = synth.make_problem(er, ec, et, reqhgt=REQHGT, mode=1, seed=777 + rank, start_doy=150)
+    ep.twi_mean = hp.twi_mean
+    h2d = 0
+    pin_keep = []
+    for nme, a in list(ep.arrays.items()):  # pinned host inputs
+        if nme in ("year", "month", "day"):
+            continue
+        tp = torch.from_numpy(a).pin_memory()
+        pin_keep.append(tp)
+        ep.arrays[nme] = tp.numpy()
+        h2d += a.nbytes
+    eouts_t = [torch.empty(er * ec * et, dtype=torch.float64).pin_memory() for _ in range(10)]
+    eouts = [t_.numpy() for t_ in eouts_t]
+    d2h = sum(o.nbytes for o in eouts)
+    esteps = max(1, min(args.steps, 5))
+    for _ in range(2):
+        api.run_problem(ep, out_buffers=eouts)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        api.run_problem(ep, out_buffers=eouts)
+    torch.cuda.synchronize()
+    e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e_s = float(t.item())
+    e2e = {"value": float(er) * ec * et * esteps * world / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "steps": esteps, "ms_per_step": 1e3 * e_s / esteps,
+           "sample": f"{er}x{ec} cells x {et} h per GPU through mcf_runmicro (pinned host buffers, all 10 outputs "
+                     f"copied back; timed with the host clock around the blocking call)"}
+    del pin_keep
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        nproc = host_cores()
+        kind, walls, ch = cpu_reference(nproc, 128, 128, 1)
+        cpu = {"value": ch / walls[0], "unit": UNIT, "cores": nproc, "kind": "reference" if kind == "ref" else "port",
+               "sample": f"{nproc} processes x (128x128 cells x 240 h: 10 days spread over the year), reqhgt {REQHGT}, "
+                         f"all 10 outputs; unmodified reference C++ built with g++ -O2 (oracle/_ref)",
+               "seconds": walls[0]}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "setup_seconds": t_gen,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--rows", type=int, default=ROWS)
+    ap.add_argument("--band-cols", dest="band_cols", type=int, default=BAND_COLS)
+    ap.add_argument("--win-days", dest="win_days", type=int, default=WIN_DAYS)
+    ap.add_argument("--e2e-rows", dest="e2e_rows", type=int, default=1024)
+    ap.add_argument("--e2e-cols", dest="e2e_cols", type=int, default=1024)
+    ap.add_argument("--e2e-hours", dest="e2e_hours", type=int, default=120)
+    ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -66,14 +66,23 @@ def _problem(mode, dfsel, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, 
     return p
 
 
-def run_problem(p: GridProblem, out: Optional[Sequence[bool]] = None) -> Dict[str, np.ndarray]:
-    """mcf_runmicro on a host GridProblem; returns the reference's named list."""
+def run_problem(p: GridProblem, out: Optional[Sequence[bool]] = None, out_buffers=None) -> Dict[str, np.ndarray]:
+    """mcf_runmicro on a host GridProblem; returns the reference's named list.  `out_buffers` optionally
+    supplies 10 caller-owned flat float64 arrays (or None) to write into, e.g. views of pinned memory."""
     L = _lib.lib()
-    out = [True] * _abi.MCF_NOUT if out is None else [bool(o) for o in out]
-    if len(out) != _abi.MCF_NOUT:
-        raise ValueError("out must have 10 logicals")
     n = p.ncells * p.tsteps
-    bufs = [np.empty(n, dtype=np.float64) if o else None for o in out]
+    if out_buffers is not None:
+        bufs = list(out_buffers)
+        if len(bufs) != _abi.MCF_NOUT:
+            raise ValueError("out_buffers must have 10 entries")
+        for b in bufs:
+            if b is not None and (b.dtype != np.float64 or b.size != n or not b.flags.c_contiguous):
+                raise ValueError("each output buffer must be a contiguous float64 array of rows*cols*tsteps")
+    else:
+        out = [True] * _abi.MCF_NOUT if out is None else [bool(o) for o in out]
+        if len(out) != _abi.MCF_NOUT:
+            raise ValueError("out must have 10 logicals")
+        bufs = [np.empty(n, dtype=np.float64) if o else None for o in out]
     ptrs = _abi.OutPtrs(*[b.ctypes.data_as(_PD) if b is not None else None for b in bufs])
     s, keep = p.as_struct()
     err = C.create_string_buffer(512)
@@ -166,3 +175,62 @@ def runbioclim4Cpp(obstime, climdata, pointm, vegp, soilc, reqhgt, zref, lats, l
                    wetq, dryq, hotq, colq, air):
     return _bioclim(4, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, 0.0, 0.0, lats, lons, Sminp, Smaxp, tfact,
                     mat, out, wetq, dryq, hotq, colq, air)
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident path (inputs already in HBM): mcf_runmicro_dev / mcf_runbioclim_dev
+# ---------------------------------------------------------------------------------------------------
+def run_problem_dev(p: GridProblem, out_tensors, window=None, stream=None) -> None:
+    """mcf_runmicro_dev.  `p` holds CUDA tensors (GridProblem.to_device); `out_tensors` is a sequence of
+    10 CUDA float64 tensors or None.  `window` = (block0, nblocks, hour0, ring_hours) or None for the
+    whole series.  Asynchronous on `stream` (a torch.cuda.Stream; default: torch's current stream)."""
+    import torch
+
+    L = _lib.lib()
+    st = torch.cuda.current_stream() if stream is None else stream
+    ptrs = _abi.OutPtrs(*[C.cast(C.c_void_p(t.data_ptr()), _PD) if t is not None else None for t in out_tensors])
+    s, keep = p.as_struct()
+    w = None
+    if window is not None:
+        w = _abi.McfWindow(int(window[0]), int(window[1]), int(window[2]), int(window[3]))
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runmicro_dev(C.byref(s), ptrs, C.byref(w) if w is not None else None,
+                                  C.c_void_p(st.cuda_stream), err, 512), err)
+    del keep
+
+
+def run_bioclim_problem_dev(p: GridProblem, wetq, dryq, hotq, colq, air, bio_tensors, stream=None) -> None:
+    import torch
+
+    L = _lib.lib()
+    st = torch.cuda.current_stream() if stream is None else stream
+    ptrs = _abi.BioPtrs(*[C.cast(C.c_void_p(t.data_ptr()), _PD) if t is not None else None for t in bio_tensors])
+    qs = [np.ascontiguousarray(np.asarray(q, dtype=np.int32)) for q in (wetq, dryq, hotq, colq)]
+    qargs = []
+    for q in qs:
+        qargs += [q.ctypes.data_as(_PI), C.c_int32(q.size)]
+    s, keep = p.as_struct()
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runbioclim_dev(C.byref(s), *qargs, C.c_int32(1 if air else 0), ptrs,
+                                    C.c_void_p(st.cuda_stream), err, 512), err)
+    del keep
+
+
+def fp64_peak_tflops() -> float:
+    L = _lib.lib()
+    v = C.c_double(0.0)
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_fp64_peak(C.byref(v), err, 512), err)
+    return v.value
+
+
+def kernel_time(reset: bool = False):
+    """(total ms, launches) of the grid kernel since the last reset (needs timing enabled)."""
+    L = _lib.lib()
+    ms, n = C.c_double(0.0), C.c_int64(0)
+    rc = L.mcf_kernel_time(C.byref(ms), C.byref(n))
+    if rc != 0:
+        raise _lib.McfError(rc, "mcf_kernel_time failed")
+    if reset:
+        L.mcf_kernel_time_reset()
+    return ms.value, n.value
