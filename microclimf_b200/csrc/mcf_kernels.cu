@@ -384,6 +384,9 @@ __global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_consta
                     phase1 ^= 1;
                 }
             }
+            // ring slot of the block's first hour; within the block the slot advances by one per hour and
+            // wraps at most once (ring_hours >= 24)
+            const long long slot0 = ((long long)blk.k0 - a.hour0) % a.ring_hours;
             if (blk.lyr != cur_lyr) {
                 cur_lyr = blk.lyr;
                 CellIn ci;
@@ -394,7 +397,8 @@ __global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_consta
             if (!active) {
                 if (valid) {
                     for (int hr = 0; hr < 24; ++hr) {
-                        const long long slot = ((long long)(blk.k0 + hr) - a.hour0) % a.ring_hours;
+                        long long slot = slot0 + hr;
+                        if (slot >= a.ring_hours) slot -= a.ring_hours;
                         const size_t o = (size_t)slot * a.ncells + cell;
 #pragma unroll
                         for (int q = 0; q < kNOut; ++q)
@@ -410,7 +414,8 @@ __global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_consta
                     HourRec hloc;
                     if (ARR) hour_from_arrays(a, k, cell, lat, lon, true, hloc);
                     const HourRec& h = ARR ? hloc : slab[buf][hr];
-                    const long long slot = ((long long)k - a.hour0) % a.ring_hours;
+                    long long slot = slot0 + hr;
+                    if (slot >= a.ring_hours) slot -= a.ring_hours;
                     const size_t o = (size_t)slot * a.ncells + cell;
                     // terrain-adjusted solar index with horizon shading (ref :2218-2223 / :2499-2504)
                     double si;
@@ -466,7 +471,8 @@ __global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_consta
                     HourRec hloc;
                     if (ARR) hour_from_arrays(a, k, cell, lat, lon, false, hloc);
                     const HourRec& h = ARR ? hloc : slab[buf][hr];
-                    const long long slot = ((long long)k - a.hour0) % a.ring_hours;
+                    long long slot = slot0 + hr;
+                    if (slot >= a.ring_hours) slot -= a.ring_hours;
                     const size_t o = (size_t)slot * a.ncells + cell;
                     const double* st = stash + (size_t)hr * (kStashVars * kTile);
                     const double radabs = st[0 * kTile];

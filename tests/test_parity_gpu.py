@@ -1,0 +1,191 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU checker on seeded synthetic inputs.
+
+Checker: oracle/_ref (the unmodified reference C++, src/microclimfCpp.cpp, compiled against the Rcpp
+stand-in) when present, else the C restatement.  Tolerance: 1e-6 abs + 1e-6 rel (tests/parity.py)."""
+import numpy as np
+import pytest
+
+import parity
+from microclimf_b200 import _abi, _lib, api, synth
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+KIND = "ref" if pyoracle.have_ref() else "oracle"
+
+
+def _check(p, out_mask=None):
+    want = pyoracle.runmicro(p, out_mask=out_mask, kind=KIND)
+    got = api.run_problem(p, out=out_mask)
+    assert set(got) == set(want)
+    ok, rows = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rows)
+    return got
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("reqhgt", [0.05, 0.0, -0.1, 1.0, 5.0, 40.0])
+def test_runmicro_modes_heights(mode, reqhgt):
+    """Every driver (ref runmicro1..4Cpp :2052/:2340/:2624/:2926) x below-canopy, surface, below-ground,
+    mid-canopy and above-canopy heights; grid with NA cells, bare cells, x == 1, clump == 0, flat cells."""
+    p = synth.make_problem(37, 29, 24 * 5, reqhgt=reqhgt, mode=mode, nlyr=3, zref=45.0 if reqhgt > 30 else 30.0)
+    _check(p)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("reqhgt", [-0.02, -0.5, -3.0])
+@pytest.mark.parametrize("complete", [True, False])
+def test_below_ground_branches(mode, reqhgt, complete):
+    """Tbelowgroundv (ref :1474-1539): n <= 48 direct window, n > 48 daily path, n >= T series mean;
+    incomplete-series blends (nb <= 1, <= 24, < hiy, >= hiy)."""
+    p = synth.make_problem(19, 23, 24 * 12, reqhgt=reqhgt, mode=mode, nlyr=2, complete=complete)
+    _check(p)
+
+
+def test_deep_soil_full_mean():
+    """n >= tsteps: every hour is the series mean (ref :1488-1493)."""
+    p = synth.make_problem(8, 8, 48, reqhgt=-2.0, mode=1)
+    _check(p)
+
+
+@pytest.mark.parametrize("tsteps", [24, 30, 47, 49, 71])
+def test_ragged_hours(tsteps):
+    """ndays = tsteps / 24 (ref :2116): trailing hours are never computed and stay NA."""
+    p = synth.make_problem(9, 7, tsteps, reqhgt=0.05, mode=1)
+    got = _check(p)
+    nd = tsteps // 24
+    assert np.isnan(got["Tz"][:, :, nd * 24:]).all()
+    p = synth.make_problem(9, 7, tsteps, reqhgt=-0.1, mode=2)
+    _check(p)
+
+
+def test_output_mask_and_na_bits():
+    """out[] gating (ref :2131-2151) and R NA_real_ payload in skipped cells."""
+    p = synth.make_problem(16, 16, 48, reqhgt=0.05, mode=1)
+    mask = [True, False, False, True, False, True, False, True, False, True]
+    got = _check(p, mask)
+    assert set(got) == {n for n, m in zip(_abi.OUT_NAMES, mask) if m}
+    hgt = p.arrays["hgt"].reshape(p.rows, p.cols, order="F")
+    na = np.isnan(hgt)
+    assert na.any()
+    bits = got["Tz"].view(np.uint64)[na]
+    assert (bits == _abi.NA_REAL_BITS).all()
+    # masks R applies for reqhgt == 0 and < 0 (R/internal.R:1159-1166)
+    _check(synth.make_problem(12, 12, 48, reqhgt=0.0, mode=1), [1, 0, 0, 1, 0, 1, 1, 1, 1, 1])
+    _check(synth.make_problem(12, 12, 48, reqhgt=-0.1, mode=1), [1, 0, 0, 1, 0, 0, 0, 0, 0, 0])
+
+
+def test_single_cell_and_single_column():
+    _check(synth.make_problem(1, 1, 48, reqhgt=0.05, mode=1, zref=30.0))
+    _check(synth.make_problem(130, 1, 24, reqhgt=0.05, mode=3, nlyr=1))
+    _check(synth.make_problem(1, 131, 24, reqhgt=1.0, mode=2))
+
+
+def test_all_na_grid():
+    p = synth.make_problem(6, 5, 24, reqhgt=0.05, mode=1)
+    p.arrays["hgt"] = np.full(p.ncells, np.nan)
+    got = _check(p)
+    assert all(np.isnan(v).all() for v in got.values())
+
+
+def test_latitude_classes_and_seasons():
+    """Stomatal classes by |lat| (ref stomparamsCpp :391-440) and polar day / night solar geometry."""
+    for lat, doy in ((10.0, 80), (-35.0, 355), (65.0, 172), (78.0, 355)):
+        p = synth.make_problem(20, 20, 72, reqhgt=0.5, mode=1, lat=lat, lon=20.0, start_doy=doy)
+        _check(p)
+    p = synth.make_problem(20, 20, 72, reqhgt=0.5, mode=2, lat=-12.0, lon=140.0, start_doy=10)
+    _check(p)
+
+
+def test_layer_spans_and_errors():
+    """dfsel spans (ref :2629-2639): uneven spans, a gap before the first layer, a trailing partial day;
+    a span shorter than a day raises like the reference's Rcpp::stop."""
+    p = synth.make_problem(10, 11, 24 * 9, reqhgt=0.05, mode=3, nlyr=3)
+    p.lyr_st = np.array([24, 72, 150], dtype=np.int32)
+    p.lyr_ed = np.array([71, 149, 215], dtype=np.int32)
+    _check(p)
+    p.lyr_ed = np.array([40, 149, 215], dtype=np.int32)
+    with pytest.raises(_lib.McfError) as ei:
+        api.run_problem(p)
+    assert ei.value.code == _abi.MCF_ERR_ARG and "Too many layers" in ei.value.msg
+    with pytest.raises(RuntimeError):
+        pyoracle.runmicro(p, kind=KIND)
+
+
+def test_year_long_series_band_equivalence():
+    """A full year for a small band, solved whole and as two column bands with the twi mean supplied
+    (the multi-GPU sharding contract): identical results."""
+    from microclimf_b200 import bands
+
+    p = synth.make_problem(8, 10, 8760, reqhgt=0.05, mode=1)
+    whole = _check(p)
+    s, n = bands.twi_partial_host(p.arrays["twi"], p.tfact)
+    parts = []
+    for c0, c1 in bands.band_ranges(p.cols, 2):
+        b = p.band(c0, c1)
+        b.twi_mean = s / n
+        parts.append(api.run_problem(b))
+    for nm in whole:
+        glued = np.concatenate([pt[nm] for pt in parts], axis=1)
+        np.testing.assert_allclose(glued, whole[nm], rtol=1e-12, atol=1e-12, equal_nan=True)
+
+
+def test_twi_partial_matches_numpy():
+    import ctypes as C
+
+    from microclimf_b200 import bands
+
+    rng = np.random.default_rng(3)
+    twi = np.exp(rng.uniform(0.5, 3.0, 100_003))
+    twi[::97] = np.nan
+    L = _lib.lib()
+    s, n = C.c_double(), C.c_int64()
+    err = C.create_string_buffer(256)
+    rc = L.mcf_twi_partial(twi.ctypes.data_as(C.POINTER(C.c_double)), twi.size, 1.5, C.byref(s), C.byref(n), err, 256)
+    assert rc == 0, err.value
+    hs, hn = bands.twi_partial_host(twi, 1.5)
+    assert n.value == hn
+    assert abs(s.value - hs) <= 1e-9 * abs(hs)
+
+
+def test_device_window_ring_matches_whole():
+    """mcf_runmicro_dev with a partial window into a 24-hour ring == the same hours of the whole run."""
+    import torch
+
+    p = synth.make_problem(33, 17, 24 * 6, reqhgt=0.05, mode=1)
+    whole = api.run_problem(p)
+    dp = p.to_device()
+    nc = p.ncells
+    outs = [torch.full((24 * nc,), -1.0, dtype=torch.float64, device="cuda") for _ in range(10)]
+    api.run_problem_dev(dp, outs, window=(2, 3, 48, 24))  # days 2..4; the ring ends up holding day 4
+    torch.cuda.synchronize()
+    for nm, t in zip(_abi.OUT_NAMES, outs):
+        ring = t.cpu().numpy().reshape(p.rows, p.cols, 24, order="F")
+        np.testing.assert_array_equal(ring, whole[nm][:, :, 96:120])
+
+
+def test_physical_ranges_wrapper_scenario():
+    """Known-range bounds in the spirit of the reference's own test (tests/testthat/
+    test-microclimatemodel_wrapper.R:40-48 parameters, 82-90 bounds), re-expressed on the grid kernels:
+    a uniform short canopy (h = 0.5, pai = 2, x = 1, clump = 0.1) at reqhgt 0.05."""
+    p = synth.make_problem(8, 8, 48, reqhgt=0.05, mode=1, zref=2.0, start_doy=79)
+    nc = p.ncells
+    hgt = np.full(nc, 0.5)
+    pai = np.full(nc, 2.0)
+    paia, leafden = synth.foliage_density(0.05, hgt, pai)
+    for k, v in dict(hgt=hgt, pai=pai, x=np.ones(nc), clump=np.full(nc, 0.1), leafr=np.full(nc, 0.4),
+                     leaft=np.full(nc, 0.2), leafd=np.full(nc, 0.05), gsmax=np.full(nc, 0.13), gref=np.full(nc, 0.15),
+                     paia=paia, leafden=leafden, slope=np.zeros(nc), aspect=np.zeros(nc), svfa=np.ones(nc),
+                     hor=np.zeros(nc * 24), wsa=np.ones(nc * 8)).items():
+        p.arrays[k] = np.ascontiguousarray(v, dtype=np.float64)
+    got = _check(p)
+    tair = p.arrays["temp"][None, None, :]
+    assert np.abs(got["Tz"] - tair).max() <= 8.0
+    assert got["relhum"].max() <= 100.0 and got["relhum"].min() > 10.0
+    ratio = got["windspeed"] / p.arrays["windspeed"][None, None, :]
+    assert ratio.min() > 0.02 and ratio.max() < 0.5
+    sw = p.arrays["swdown"][None, None, :]
+    day = sw[0, 0] > 50
+    assert (got["Rswup"][:, :, day] / sw[:, :, day]).max() < 0.3
+    lw = p.arrays["lwdown"][None, None, :]
+    r = got["Rlwdown"] / lw
+    assert r.min() > 0.9 and r.max() < 1.4
