@@ -173,7 +173,8 @@ def static_layers(rows: int, cols: int, reqhgt: float, seed: int = 20240321, nly
     # smooth DTM-like field -> slope/aspect with realistic spatial coherence
     fx, fy = 2 * np.pi / max(rows, 8), 2 * np.pi / max(cols, 8)
     dtm = 150 + 80 * np.sin(1.3 * fx * ii) * np.cos(0.9 * fy * jj) + 40 * np.sin(3.1 * fx * ii + 2.2 * fy * jj)
-    gy, gx = np.gradient(dtm, 10.0)
+    gy = np.gradient(dtm, 10.0, axis=0) if rows > 1 else np.zeros_like(dtm)
+    gx = np.gradient(dtm, 10.0, axis=1) if cols > 1 else np.zeros_like(dtm)
     slope = np.degrees(np.arctan(np.hypot(gx, gy))).clip(0, 40)
     aspect = np.mod(np.degrees(np.arctan2(-gx, gy)), 360.0)
     flat = rng.random((rows, cols)) < 0.03
