@@ -47,6 +47,8 @@ def lib() -> C.CDLL:
         L.mcf_kernel_timing_enable.restype = None
         L.mcf_fp64_peak.argtypes = [pd, C.c_char_p, C.c_size_t]
         L.mcf_fp64_peak.restype = C.c_int
+        L.mcf_math_eval.argtypes = [C.c_int, pd, pd, C.c_int64, pd, C.c_char_p, C.c_size_t]
+        L.mcf_math_eval.restype = C.c_int
         L.mcf_runmicro.argtypes = [pp, _abi.OutPtrs, C.c_char_p, C.c_size_t]
         L.mcf_runmicro.restype = C.c_int
         L.mcf_runmicro_dev.argtypes = [pp, _abi.OutPtrs, pw, C.c_void_p, C.c_char_p, C.c_size_t]

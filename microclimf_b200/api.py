@@ -234,3 +234,15 @@ def kernel_time(reset: bool = False):
     if reset:
         L.mcf_kernel_time_reset()
     return ms.value, n.value
+
+
+def math_eval(fn: int, x, y=None):
+    """mcf_math_eval: the kernels' own FP64 elementary functions, element-wise (accuracy tests)."""
+    L = _lib.lib()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    yy = None if y is None else np.ascontiguousarray(np.broadcast_to(np.asarray(y, dtype=np.float64), x.shape))
+    out = np.empty_like(x)
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_math_eval(fn, x.ctypes.data_as(_PD), yy.ctypes.data_as(_PD) if yy is not None else None,
+                               x.size, out.ctypes.data_as(_PD), err, 512), err)
+    return out

@@ -822,6 +822,25 @@ int mcf_twi_partial(const double* twi, int64_t n, double tfact, double* sum, int
     return report(body(), err, errlen);
 }
 
+int mcf_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, char* err, size_t errlen) {
+    auto body = [&]() -> Err {
+        if (!x || !out || n < 0 || fn < 0 || fn > 6) return make_err(MCF_ERR_ARG, "bad argument");
+        if ((fn == 1 || fn == 6) && !y) return make_err(MCF_ERR_ARG, "fn %d needs a second operand", fn);
+        TRY(device_info());
+        DevCopy dc;
+        const double *dx = nullptr, *dy = nullptr;
+        double* dout = nullptr;
+        TRY(dc.up(x, (size_t)n, &dx));
+        TRY(dc.up(y, (size_t)n, &dy));
+        TRY(dc.dalloc(&dout, (size_t)n));
+        CU(launch_math_eval(fn, dx, dy, n, dout, nullptr));
+        count_launch();
+        CU(cudaMemcpy(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+        return Err();
+    };
+    return report(body(), err, errlen);
+}
+
 int mcf_fp64_peak(double* tflops, char* err, size_t errlen) {
     auto body = [&]() -> Err {
         if (!tflops) return make_err(MCF_ERR_ARG, "tflops is NULL");

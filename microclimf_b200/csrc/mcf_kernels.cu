@@ -447,8 +447,8 @@ __global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_consta
                     if (om & (1u << 4)) __stcs(&a.out[4][o], w.uz);
                     // ground surface temperature with G = 0 (ref soiltempG0 :1262-1275)
                     const double radabs = r.radGsw + radGlw;
-                    const double matric = -v.psie_abs * exp(-v.soilb * log(soild / v.Smax));
-                    double surfwet = exp((0.018 * matric) / (8.31 * (h.tc + 273.15)));
+                    const double matric = -v.psie_abs * mexp(-v.soilb * mlog(soild * v.inv_Smax));
+                    double surfwet = mexp((0.018 * matric) * h.invRT);
                     if (surfwet > 1.0) surfwet = 1.0;
                     double m_unused;
                     const double Tg0 = pm_ts(h, dTmx, radabs, w.gHa, w.gHa, 0.0, surfwet, m_unused);
@@ -486,12 +486,12 @@ __global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_consta
                     const double cs = (2400 * v.rho / 2.64 + 4180.0 * soild);
                     const double ph = (v.rho * (1.0 - soild) + soild) * 1000.0;
                     const double c2 = 1.06 * v.rho * soild;
-                    const double kcon = v.c1 + c2 * soild - (v.c1 - v.c4) * exp(-pow4(v.c3 * soild));
-                    const double kap = kcon / (cs * ph);
-                    const double DD = sqrt(2.0 * kap / kOmdy);
+                    const double kcon = v.c1 + c2 * soild - (v.c1 - v.c4) * mexp(-pow4(v.c3 * soild));
+                    const double kap = mdiv(kcon, cs * ph);
+                    const double DD = msqrt(kap * (2.0 / kOmdy));
                     // ground heat flux scaled from the point model (ref soiltemp_hrCpp :1277-1296)
-                    const double dtR = dtr / h.dtrp;
-                    const double Gmu = dtR * (kcon * h.muGp) / (h.kp * DD);
+                    const double dtR = dtr * h.inv_dtrp;
+                    const double Gmu = dtR * (kcon * h.muGp_kp) * mrcp(DD);
                     double G = h.Gp * Gmu;
                     if (G > 0.6 * Rmx) G = 0.6 * Rmx;
                     if (G < -0.6 * Rmx) G = -0.6 * Rmx;
@@ -771,6 +771,34 @@ cudaError_t launch_fill_na(double* p, int64_t n, cudaStream_t stream) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_fill_na<<<(int)blocks, 256, 0, stream>>>(p, n);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// element-wise evaluation of the mcf_math.cuh functions (accuracy tests)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_math_eval(int fn, const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                            double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = x[i], b = y ? y[i] : 0.0;
+        double r;
+        switch (fn) {
+        case 0: r = mrcp(a); break;
+        case 1: r = mdiv(a, b); break;
+        case 2: r = msqrt(a); break;
+        case 3: r = mexp(a); break;
+        case 4: r = mexp2(a); break;
+        case 5: r = mlog(a); break;
+        default: r = mpow(a, b); break;
+        }
+        out[i] = r;
+    }
+}
+cudaError_t launch_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_math_eval<<<(int)blocks, 256, 0, stream>>>(fn, x, y, n, out);
     return cudaGetLastError();
 }
 

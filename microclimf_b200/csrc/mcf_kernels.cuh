@@ -107,6 +107,7 @@ int grid_blocks_per_sm(bool arr, int rq);
 cudaError_t launch_below(const BelowArgs& a, cudaStream_t stream);
 cudaError_t launch_bioclim(const BioArgs& a, cudaStream_t stream);
 cudaError_t launch_fill_na(double* p, int64_t n, cudaStream_t stream);
+cudaError_t launch_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* sink, int grid, int iters, cudaStream_t stream);
 
 } // namespace mcf

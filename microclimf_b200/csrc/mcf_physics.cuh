@@ -19,6 +19,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "mcf_math.cuh"
+
 namespace mcf {
 
 constexpr double kPi = 3.14159265358979323846;
@@ -49,9 +51,17 @@ struct __align__(16) HourRec {
     double Rem; // 0.97*sb*(tc+273.15)^4
     double la;  // latent heat of vapourisation
     int32_t sindex, windex; // horizon / wind-shelter sector (:2166-2167)
+    // hour-invariant quotients, formed once with IEEE division so that the hot loops only multiply
+    double inv_pk;    // 1 / pk
+    double invRT;     // 1 / (8.31 (tc + 273.15))                   (soiltempG0 :1268)
+    double inv_dtrp;  // 1 / dtrp                                    (soiltemp_hrCpp :1284)
+    double muGp_kp;   // muGp / kp                                   (soiltemp_hrCpp :1285)
+    double Rbeam0;    // (Rsw - Rdif) / cos(zenith), uncapped        (twostreamCpp :1122, :1152)
+    double pmmu;      // la * 43 / pk                                (TVaboveground :1456)
+    double inv_pmmu;
     double pad0, pad1;
 };
-static_assert(sizeof(HourRec) == 256, "HourRec must be 256 bytes");
+static_assert(sizeof(HourRec) == 320, "HourRec must be 320 bytes");
 
 // ---------------------------------------------------------------------------------------------
 // helpers
@@ -63,6 +73,13 @@ __device__ __forceinline__ double radem4(double tc) { return pow4(tc + 273.15); 
 // ref satvapCpp :480-490
 __device__ __forceinline__ double satvap(double tc) {
     return (tc > 0) ? 0.61078 * exp(17.27 * tc / (tc + 237.3)) : 0.61078 * exp(21.875 * tc / (tc + 265.5));
+}
+// same, through the branch-free mexp / mrcp (hot loops; tc + 237.3 and tc + 265.5 never vanish)
+__device__ __forceinline__ double satvap_m(double tc) {
+    const bool w = tc > 0;
+    const double a = w ? 17.27 : 21.875;
+    const double b = w ? 237.3 : 265.5;
+    return 0.61078 * mexp(a * tc * mrcp(tc + b));
 }
 __device__ __forceinline__ double latent(double tc) { // ref :1227-1232
     return (tc >= 0) ? 45068.7 - 42.8428 * tc : 51078.69 - 4.338 * tc - 0.06367 * tc * tc;
@@ -129,6 +146,7 @@ __device__ __forceinline__ void hour_geometry(HourRec& h, const SolPos& s) {
     h.kq_cos = cos(zq);
     h.zend = s.zend;
     h.sindex = ((int)round(s.azid / 15.0)) % 24;
+    h.Rbeam0 = (h.Rsw - h.Rdif) / h.cosz; // forcing fields are filled before the geometry
 }
 __device__ __forceinline__ void hour_airterms(HourRec& h) {
     h.De = satvap(h.tc + 0.5) - satvap(h.tc - 0.5);
@@ -136,6 +154,12 @@ __device__ __forceinline__ void hour_airterms(HourRec& h) {
     h.gr4 = (4 * kEm * kSb * (tk * tk * tk)) / 29.3;
     h.Rem = kEm * kSb * pow4(tk);
     h.la = latent(h.tc);
+    h.inv_pk = 1.0 / h.pk;
+    h.invRT = 1.0 / (8.31 * tk);
+    h.inv_dtrp = 1.0 / h.dtrp;
+    h.muGp_kp = h.muGp / h.kp;
+    h.pmmu = h.la * (43.0 / h.pk);
+    h.inv_pmmu = 1.0 / h.pmmu;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -177,6 +201,8 @@ struct CellInv {
     double leafd, leafden, nearcoef; // nearcoef = 3.047519 + 0.128642*log(pai)
     double a2h, inth_h, inth_z, zq, hmz; // rhcanopy pieces; zq = reqhgt, hmz = hgt - reqhgt
     double Hf0;           // mincondCpp's Hf for gs = 999.99 (first call in leaftemp :1348)
+    // reciprocals of cell invariants (IEEE division, once per cell)
+    double inv_rge, inv_Smax, inv_kden, inv_leafd, inv_hgt, inv_a2h;
 };
 
 // ref zeroplanedisCpp :294
@@ -352,6 +378,12 @@ static __device__ __noinline__ void cell_setup(const CellIn& c, double reqhgt2, 
     v.hmz = c.hgt - reqhgt2;
     double Hlf0 = 1.09767 * pow(1 / 999.99, 0.2672778);
     v.Hf0 = -1.0 / (1.0 + exp(2.0 - Hlf0));
+    v.inv_rge = 1.0 / v.rge;
+    v.inv_Smax = 1.0 / c.Smax;
+    v.inv_kden = 1.0 / v.kden;
+    v.inv_leafd = 1.0 / c.leafd;
+    v.inv_hgt = 1.0 / c.hgt;
+    v.inv_a2h = 1.0 / v.a2h;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -369,10 +401,10 @@ constexpr int kStashVars = 4;
 
 // ref soildCpp :1021-1032, closed form of logistic(logit(theta) + tadd)
 __device__ __forceinline__ double soil_distribute(const CellInv& v, double soilmp) {
-    double theta = (soilmp - v.Smin) / v.rge;
+    double theta = (soilmp - v.Smin) * v.inv_rge;
     if (theta > 0.9999) theta = 0.9999;
     if (theta < 0.0001) theta = 0.0001;
-    double sm = theta / (theta + (1.0 - theta) * v.Etadd);
+    double sm = mdiv(theta, theta + (1.0 - theta) * v.Etadd); // divisor in (0, max(1, Etadd)]
     return sm * v.rge + v.Smin;
 }
 
@@ -401,9 +433,9 @@ struct PM {
 __device__ __forceinline__ double pm_ts(const HourRec& h, double dTmx, double Rabs, double gHa, double gV, double G,
                                         double surfwet, double& m_out) {
     double gHr = gHa + h.gr4;
-    double m = h.la * (gV / h.pk);
+    double m = h.la * (gV * h.inv_pk);
     double L = m * (h.es - h.ea) * surfwet;
-    double dT = (Rabs - h.Rem - L - G) / (29.3 * gHr + m * h.De);
+    double dT = mdiv(Rabs - h.Rem - L - G, 29.3 * gHr + m * h.De); // divisor > 0
     if (dT > dTmx) dT = dTmx;
     if (dT > 80.0) dT = 80.0;
     double Ts = dT + h.tc;
@@ -427,20 +459,21 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
         if (v.xflag == 1) k = 1.0 / (2.0 * h.coszc);
         else if (v.xflag == 3) k = 1.0;
         else if (v.xflag == 2) k = h.tanzc;
-        else k = sqrt(v.x * v.x + h.tanzc * h.tanzc) / v.kden;
+        else k = msqrt(v.x * v.x + h.tanzc * h.tanzc) * v.inv_kden;
         if (k > 6000.0) k = 6000.0;
-        double kd = k * h.coszc / si;
+        const double isi = mrcp(si); // NaN for si == 0: both uses are replaced below, as the reference's inf is
+        double kd = k * h.coszc * isi;
         if (si == 0) kd = 1.0;
-        double Kc = 1.0 / si;
+        double Kc = isi;
         if (si == 0.0) Kc = 600.0;
         // direct-beam two-stream parameters
         const double apg = v.a + v.gma;
         double sig = kd * kd + v.gma * v.gma - apg * apg;
-        double ss = 0.5 * (v.om + v.Jdel / kd) * kd;
+        double ss = 0.5 * (v.om + v.Jdel * mrcp(kd)) * kd;
         double sstr = v.om * kd - ss;
-        double S2 = exp(-kd * v.pait);
+        double S2 = mexp(-kd * v.pait);
         double p5 = -ss * (apg - kd) - v.gma * sstr;
-        double isig = 1.0 / sig;
+        double isig = mrcp(sig);
         double p5s = p5 * isig;
         double v1 = ss - p5s * (apg + kd);
         double v2 = ss - v.gma - p5s * (v.u1 + kd);
@@ -452,13 +485,13 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
         double p9 = -v.invD2 * ((p8s * v.invS1) * (v.u2 + v.h) + v3);
         double p10 = v.invD2 * ((p8s * v.S1) * (v.u2 - v.h) + v3);
         // gap transmissions
-        double trbn = exp(Kc * v.logclump);
+        double trbn = mexp(Kc * v.logclump); // clump == 0: logclump = -inf, mexp -> 3e-308 (the reference: 0)
         if (trbn > 0.999) trbn = 0.999;
         if (trbn < 0.0) trbn = 0.0;
-        double trb = exp(Kc * v.loggi);
+        double trb = mexp(Kc * v.loggi);
         if (trb > 0.999) trb = 0.999;
         if (trb < 0.0) trb = 0.0;
-        double S2a = exp(-kd * v.paiaa);
+        double S2a = mexp(-kd * v.paiaa);
         // black-sky albedo
         double albb = (1.0 - v.trdn * trbn) * (p5s + p6 + p7) + v.trdn * trbn * v.gref;
         if (albb > v.amx) albb = v.amx;
@@ -473,7 +506,7 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
         if (Rdbdn_z > v.amx) Rdbdn_z = v.amx;
         if (Rdbdn_z < 0.0) Rdbdn_z = 0.0;
         // incident flux
-        double Rbeam = (Rsw - Rdif) / cosz;
+        double Rbeam = h.Rbeam0;
         if (Rbeam > 1352.0) Rbeam = 1352.0;
         double Rb = Rbeam * cosz;
         double trg = trb + (1 - trb) * S2;
@@ -491,7 +524,7 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
         o.Rdup = v.Rdup_z * Rds + Rdbup_z * Rb;
         o.Lhalf = 0.5 * (o.Rddown + o.Rdup + k * cosz * o.Rbdown); // ref :1142-1143
     } else {
-        o.Rbdown = (Rsw - Rdif) / cosz;
+        o.Rbdown = h.Rbeam0;
         o.Rddown = Rdif * v.svfa;
         o.Rdup = v.gref * (Rdif * v.svfa + (Rsw - Rdif));
         o.radGsw = (1.0 - v.gref) * (v.svfa * Rdif + si * o.Rbdown);
@@ -505,31 +538,32 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
 // gs2 = mu * gsmax.  Shared by the (up to) three stomcondCpp calls of one cell-hour.
 __device__ __forceinline__ double stom_gs2(const CellInv& v, double theta) {
     double thetan = v.rat * theta + (1 - v.rat) * kThetaM;
-    double Se = thetan / v.Smax;
+    double Se = thetan * v.inv_Smax;
     if (Se > 1.0) Se = 1.0;
-    double psiw = -v.psie_abs * exp(-v.soilb * log(Se)) * 0.01; // pow(Se, -b)
+    double psiw = -v.psie_abs * mexp(-v.soilb * mlog(Se)) * 0.01; // pow(Se, -b), Se in (0, 1]
     if (psiw < v.psiw0) psiw = v.psiw0;
-    double mu = 1.0 - (exp(-v.kk * psiw) - 1.0) * v.inv_stomden;
+    double mu = 1.0 - (mexp(-v.kk * psiw) - 1.0) * v.inv_stomden;
     return mu * v.gsmax;
 }
 // ref stomcondCpp :442-458 given gs2
 __device__ __forceinline__ double stomcond(const CellInv& v, double Rswabs, double gs2) {
     if (Rswabs <= 0.0) return 0.0;
     if (Rswabs > v.Rsmx) Rswabs = v.Rsmx;
-    double gs = v.gsmax * exp2(-(v.Rsmx - Rswabs) * v.inv02Rsmx);
+    double gs = v.gsmax * mexp2(-(v.Rsmx - Rswabs) * v.inv02Rsmx);
     if (gs > gs2) gs = gs2;
     return gs;
 }
 
 // ref mincondCpp :1316-1331 (second call in leaftemp, rs from gs)
-__device__ __forceinline__ double mincond(double Rnet, double gs, double leafd) {
+__device__ __forceinline__ double mincond(double Rnet, double gs, double inv_leafd) {
     double rs = 500.0;
-    if (gs > 0.0) rs = 1 / gs;
+    if (gs > 0.0) rs = mrcp(gs);
     if (rs > 500.0) rs = 500.0;
-    double Hlf = 1.09767 * pow(rs, 0.2672778);
-    double Hf = -1.0 / (1.0 + exp(2.0 - Hlf));
+    double Hlf = 1.09767 * mpow(rs, 0.2672778);
+    double Hf = -mrcp(1.0 + mexp(2.0 - Hlf));
     double H = Hf * Rnet;
-    double gmin = 0.0463 * pow(fabs(H) / leafd, 0.2);
+    // H == 0: mlog(0) ~ -709, so the power is ~1e-62 instead of 0; either way gmin takes its floor
+    double gmin = 0.0463 * mpow(fabs(H) * inv_leafd, 0.2);
     if (gmin < 0.05) gmin = 0.05;
     return gmin;
 }
@@ -544,12 +578,12 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
     Above out;
     const double tc = h.tc, ea = h.ea, Rlw = h.Rlw;
     // ground and surface wetness
-    double esTg = satvap(Tg);
+    double esTg = satvap_m(Tg);
     double eT = esTg - ea;
     if (eT < 0.001) eT = 0.001;
-    double plf = 0.8753 - 1.7126 * log(eT);
-    double gwet = 1.0 / (1.0 + exp(-plf));
-    double surfwet = (soilm - v.Smin) / (v.Smax - v.Smin);
+    double plf = 0.8753 - 1.7126 * mlog(eT);
+    double gwet = mrcp(1.0 + mexp(-plf));
+    double surfwet = (soilm - v.Smin) * v.inv_rge;
     if (surfwet > gwet) gwet = surfwet;
     // canopy conductance (ref canopycondCpp :460-477) with k from the degrees-as-radians cankCpp call
     double gV = 0.0;
@@ -560,7 +594,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         if (v.xflag == 1) kq = 1.0 / (2.0 * h.kq_cos);
         else if (v.xflag == 3) kq = 1.0;
         else if (v.xflag == 2) kq = h.kq_tan;
-        else kq = sqrt(v.x * v.x + h.kq_tan * h.kq_tan) / v.kden;
+        else kq = msqrt(v.x * v.x + h.kq_tan * h.kq_tan) * v.inv_kden;
         if (kq > 6000.0) kq = 6000.0;
         double Rshade_abs = h.Rdif * v.shade_fac; // NaN for pai == 0 (0/0), as in the reference
         double Rsun_abs = (h.Rsw - h.Rdif) * kq * (1 - v.omp) + Rshade_abs;
@@ -568,7 +602,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         if (Rshade_abs <= 0.0 && Rsun_abs <= 0.0) {
             gS = 0.0; // both stomcondCpp calls return 0
         } else {
-            double P_sun = (1.0 - exp(-kq * v.pai)) / kq;
+            double P_sun = (1.0 - mexp(-kq * v.pai)) * mrcp(kq);
             double P_shade = v.pai - P_sun;
             gs2 = stom_gs2(v, soilm);
             have_gs2 = true;
@@ -579,13 +613,13 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             else gs_shade = stomcond(v, Rshade_abs, gs2);
             gS = gs_sun * P_sun + gs_shade * P_shade;
         }
-        if (gS > 0.0) gV = 1.0 / (1.0 / w.gHa + 1 / gS);
+        if (gS > 0.0) gV = mdiv(w.gHa * gS, w.gHa + gS); // 1 / (1/gHa + 1/gS)
     }
     // canopy temperature
     double Rabs = radCsw + radClw;
     double m;
     double Tcan = pm_ts(h, dTmx, Rabs, w.gHa, gV, G, surfwet, m);
-    double esTcan = satvap(Tcan);
+    double esTcan = satvap_m(Tcan);
     double ez;
     if (v.above) {
         // ref TVabove :1298-1313 at reqhgt
@@ -602,7 +636,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
     } else {
         double pmH = 29.3 * w.gHa * (Tcan - tc);
         double pmL = m * (esTcan - ea) * surfwet;
-        double pmmu = h.la * (43.0 / h.pk);
+        double pmmu = h.pmmu;
         // ---- leaf temperature (ref leaftemp :1333-1364)
         double lwcan = kEm * kSb * radem4(Tcan);
         double lwgro = kEm * kSb * radem4(Tg);
@@ -610,9 +644,9 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         out.lwdn = v.e_paia * Rlw + (1 - v.e_paia) * lwcan;
         double lwabs = kEm * 0.5 * (out.lwup + out.lwdn);
         double leafabs = (1.0 - v.om) * Lhalf + lwabs;
-        double gh = 0.135 * sqrt(w.uz / v.leafd) * 1.4;
+        double gh = 0.135 * msqrt(w.uz * v.inv_leafd) * 1.4;
         double Rnetl = leafabs - lwcan;
-        double gmin = 0.0463 * pow(fabs(v.Hf0 * Rnetl) / v.leafd, 0.2);
+        double gmin = 0.0463 * mpow(fabs(v.Hf0 * Rnetl) * v.inv_leafd, 0.2);
         if (gmin < 0.05) gmin = 0.05;
         if (gh < gmin) gh = gmin;
         double gVl = gh;
@@ -624,13 +658,13 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
                 if (!have_gs2) gs2 = stom_gs2(v, soilm);
                 gs = stomcond(v, radLpar, gs2);
             }
-            gmin = mincond(Rnetl, gs, v.leafd);
+            gmin = mincond(Rnetl, gs, v.inv_leafd);
             if (gh < gmin) gh = gmin;
-            if (gs > 0.0) gVl = 1 / (1 / gh + 1 / gs);
+            if (gs > 0.0) gVl = mdiv(gh * gs, gh + gs); // 1 / (1/gh + 1/gs)
         }
         double ml;
         double tleaf = pm_ts(h, dTmx, leafabs, gh, gVl, 0.0, surfwet, ml);
-        double esTl = satvap(tleaf);
+        double esTl = satvap_m(tleaf);
         double lfH = 29.3 * gh * (tleaf - tc);
         double lfL = ml * (esTl - ea) * surfwet;
         out.tleaf = tleaf;
@@ -644,15 +678,16 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             eh = ea + (esTcan - ea) * surfwet;
         }
         // ---- diffusivities (ref TVbelow :1385-1390, rhcanopy :1365-1380)
-        double mu_r = w.uf / v.a2h * 1.0 / (w.uf * w.uf);
+        double mu_r = v.inv_a2h * mrcp(w.uf); // (uf / a2h) / uf^2
         double Rc = v.inth_h * mu_r;
         if (Rc < 0.001) Rc = 0.001;
         double Rz = v.inth_z * mu_r;
         if (Rz < 0.001) Rz = 0.001;
-        double Kc = v.hgt / Rc;
-        double Kg = (1.0 / Rz) / v.zq;
-        double Kh = (1.0 / (Rc - Rz)) / v.hmz;
-        double iK = 1.0 / (Kg + Kh + Kc);
+        double iKc = Rc * v.inv_hgt; // 1 / Kc
+        double Kc = mrcp(iKc);
+        double Kg = mrcp(Rz * v.zq);
+        double Kh = mrcp((Rc - Rz) * v.hmz); // Rc == Rz: NaN here, inf / inf = NaN in the reference
+        double iK = mrcp(Kg + Kh + Kc);
         // ---- temperature below canopy (ref :1447-1453)
         {
             const double cp = 29.3 * 43.0;
@@ -660,12 +695,12 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             double SH = Th * cp;
             double SG = Tg * cp;
             double mxnear = fabs(tleaf - Th) * cp;
-            double SC = SH + Flux / Kc;
+            double SC = SH + Flux * iKc;
             double farg = (Kg * SG + Kh * SH + Kc * SC) * iK;
             double nearf = v.nearcoef * (lfH * v.leafden);
             if (fabs(nearf) > mxnear) nearf = (nearf > 0.0) ? mxnear : -mxnear;
             if (isnan(nearf)) nearf = 0;
-            out.Tz = (nearf + farg) / cp;
+            out.Tz = (nearf + farg) * (1.0 / cp);
         }
         // ---- vapour pressure below canopy (ref :1455-1460)
         {
@@ -673,15 +708,15 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             double SH = eh * pmmu;
             double SG = esTg * gwet * pmmu;
             double mxnear = fabs(esTl - eh) * pmmu;
-            double SC = SH + Flux / Kc;
+            double SC = SH + Flux * iKc;
             double farg = (Kg * SG + Kh * SH + Kc * SC) * iK;
             double nearf = v.nearcoef * (lfL * v.leafden);
             if (fabs(nearf) > mxnear) nearf = (nearf > 0.0) ? mxnear : -mxnear;
             if (isnan(nearf)) nearf = 0;
-            ez = (nearf + farg) / pmmu;
+            ez = (nearf + farg) * h.inv_pmmu;
         }
     }
-    out.rh = (ez / satvap(out.Tz)) * 100.0;
+    out.rh = mdiv(ez, satvap_m(out.Tz)) * 100.0;
     if (out.rh > 100.0) out.rh = 100.0;
     // limits (ref :1467-1470; std::max/min over {tleaf, tc, Tg, Tcan} with their NaN-ignoring fold order)
     double tmx = out.tleaf;
