@@ -12,7 +12,7 @@ import os
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmicroclimf_b200.so")
+LIB_PATH = os.environ.get("MCF_LIB_PATH") or os.path.join(_HERE, "csrc", "libmicroclimf_b200.so")  # env: dev experiments
 _lib = None
 
 

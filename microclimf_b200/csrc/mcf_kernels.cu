@@ -315,7 +315,7 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
 }
 
 template <bool ARR, int RQ>
-__global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_constant__ GridArgs a) {
+__global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 : 1) : kMinBlocks) k_grid(const __grid_constant__ GridArgs a) {
     __shared__ __align__(128) HourRec slab[2][24];
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ int s_tile;
@@ -447,8 +447,8 @@ __global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_consta
                     if (om & (1u << 4)) __stcs(&a.out[4][o], w.uz);
                     // ground surface temperature with G = 0 (ref soiltempG0 :1262-1275)
                     const double radabs = r.radGsw + radGlw;
-                    const double matric = -v.psie_abs * mexp(-v.soilb * mlog(soild * v.inv_Smax));
-                    double surfwet = mexp((0.018 * matric) * h.invRT);
+                    const double matric = -v.psie_abs * mexp_nc(-v.soilb * mlog(soild * v.inv_Smax));
+                    double surfwet = mexp_lo((0.018 * matric) * h.invRT);
                     if (surfwet > 1.0) surfwet = 1.0;
                     double m_unused;
                     const double Tg0 = pm_ts(h, dTmx, radabs, w.gHa, w.gHa, 0.0, surfwet, m_unused);
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_consta
                     const double cs = (2400 * v.rho / 2.64 + 4180.0 * soild);
                     const double ph = (v.rho * (1.0 - soild) + soild) * 1000.0;
                     const double c2 = 1.06 * v.rho * soild;
-                    const double kcon = v.c1 + c2 * soild - (v.c1 - v.c4) * mexp(-pow4(v.c3 * soild));
+                    const double kcon = v.c1 + c2 * soild - (v.c1 - v.c4) * mexp_lo(-pow4(v.c3 * soild));
                     const double kap = mdiv(kcon, cs * ph);
                     const double DD = msqrt(kap * (2.0 / kOmdy));
                     // ground heat flux scaled from the point model (ref soiltemp_hrCpp :1277-1296)
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kTile, ARR ? 2 : 3) k_grid(const __grid_consta
 
 int grid_blocks_per_sm(bool arr, int rq) {
     (void)rq;
-    return arr ? 2 : 3;
+    return arr ? (kMinBlocks > 1 ? kMinBlocks - 1 : 1) : kMinBlocks;
 }
 
 cudaError_t launch_grid(const GridArgs& a, bool arr, int rq, int grid, cudaStream_t stream) {

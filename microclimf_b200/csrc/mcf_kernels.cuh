@@ -7,7 +7,14 @@
 
 namespace mcf {
 
-constexpr int kTile = 128;       // cells per CTA tile = threads per CTA (one thread per cell)
+#ifndef MCF_TILE
+#define MCF_TILE 384
+#endif
+#ifndef MCF_MINB
+#define MCF_MINB 1
+#endif
+constexpr int kTile = MCF_TILE;  // cells per CTA tile = threads per CTA (one thread per cell)
+constexpr int kMinBlocks = MCF_MINB; // resident CTAs per SM the grid kernel is compiled for
 constexpr int kNOut = 10;
 
 // Per-hour calendar record for the array-climate modes (solar position is per cell there).

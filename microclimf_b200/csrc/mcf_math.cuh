@@ -18,7 +18,7 @@
 //   * mrcp / mdiv: divisor finite, normal, non-zero.  A zero or infinite divisor yields NaN (not
 //     +-inf / 0), so it is only used where the reference's own result for that case is discarded or NaN.
 //   * mexp: any x; x < -708 returns exp(-708) ~ 3e-308 (instead of a denormal or 0), x > 709 returns
-//     exp(709); NaN propagates.
+//     exp(709); NaN propagates.  mexp_lo drops the upper clamp (x <= 700), mexp_nc both (|x| <= 700).
 //   * mlog: x > 0 finite normal; mlog(0) returns ~ -709.8 (callers that need -inf use log()).
 //   * msqrt: x >= 0 finite normal or exactly 0.
 #pragma once
@@ -64,26 +64,38 @@ __device__ __forceinline__ double msqrt(double x) {
     return (x == 0.0) ? 0.0 : g;
 }
 
-constexpr double kLn2Hi = 0.6931471675634384;      // 27 trailing zero bits: k * kLn2Hi is exact for |k| < 2^26
-constexpr double kLn2Lo = 1.2996506893889889e-08;
-constexpr double kLog2e = 1.4426950408889634;
+// Polynomial coefficients live in constant memory: ptxas then feeds them to DFMA as uniform-register
+// operands (LDCU.128 loads two at a time and keeps them across call sites) instead of materialising
+// every 64-bit immediate with two moves per use, which was ~20 % of all issued instructions.  For that
+// to work each DFMA may carry only ONE constant, hence the even/odd Horner split below (which also gives
+// two independent dependency chains).
+__constant__ double kMathC[32] = {
+    // [0..4]  exp even part c10 c8 c6 c4 c2      [5..9] exp odd part c11 c9 c7 c5 c3
+    2.763263963904103e-07, 2.4801485482328494e-05, 0.0013888888952314775, 0.0416666666664881, 0.5000000000000019,
+    2.5110037605963777e-08, 2.755724091857897e-06, 0.00019841269890047113, 0.008333333333319601, 0.1666666666666668,
+    // [10] log2(e)   [11] ln2 hi (27 trailing zero bits)   [12] ln2 lo   [13] ln2
+    1.4426950408889634, 0.6931471675634384, 1.2996506893889889e-08, 0.6931471805599453,
+    // [14..17] log P(z) even part L6 L4 L2 L0      [18..20] odd part L5 L3 L1
+    0.14643628601909797, 0.18182956608063458, 0.28571428631764334, 0.666666666666667,
+    0.15329500754204178, 0.2222221019926421, 0.39999999999886615,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
-// exp(r) for |r| <= ln2/2 (Estrin evaluation: 4 dependent levels instead of 11)
+constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52 (zero low word: encodable as a DFMA immediate)
+
+// exp(r) for |r| <= ln2/2:  1 + r + r^2 (E(r^2) + r O(r^2)), degree 11
 __device__ __forceinline__ double exp_poly(double r) {
     const double r2 = r * r;
-    const double r4 = r2 * r2;
-    const double a01 = fma(1.0, r, 1.0);
-    const double a23 = fma(0.1666666666666668, r, 0.5000000000000019);
-    const double a45 = fma(0.008333333333319601, r, 0.0416666666664881);
-    const double a67 = fma(0.00019841269890047113, r, 0.0013888888952314775);
-    const double a89 = fma(2.755724091857897e-06, r, 2.4801485482328494e-05);
-    const double aab = fma(2.5110037605963777e-08, r, 2.763263963904103e-07);
-    const double b0 = fma(a23, r2, a01);
-    const double b1 = fma(a67, r2, a45);
-    const double b2 = fma(aab, r2, a89);
-    const double r8 = r4 * r4;
-    const double c0 = fma(b1, r4, b0);
-    return fma(b2, r8, c0);
+    double e = kMathC[0], o = kMathC[5];
+    e = fma(e, r2, kMathC[1]);
+    o = fma(o, r2, kMathC[6]);
+    e = fma(e, r2, kMathC[2]);
+    o = fma(o, r2, kMathC[7]);
+    e = fma(e, r2, kMathC[3]);
+    o = fma(o, r2, kMathC[8]);
+    e = fma(e, r2, kMathC[4]);
+    o = fma(o, r2, kMathC[9]);
+    const double q = fma(o, r, e);
+    return fma(q, r2, r + 1.0);
 }
 
 // multiply p (0.5 < p < 2) by 2^k, |k| <= 1021, through the exponent field
@@ -91,26 +103,39 @@ __device__ __forceinline__ double scale2(double p, int k) {
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
 
+// exp(x) for |x| <= 700 (no range clamps: out-of-range or non-finite x gives garbage or NaN, never a trap)
+__device__ __forceinline__ double mexp_nc(double x) {
+    const double t = fma(x, kMathC[10], kMagic); // round-to-nearest integer lands in the low word
+    const int k = __double2loint(t);
+    const double kf = t - kMagic;
+    double r = fma(kf, -kMathC[11], x);
+    r = fma(kf, -kMathC[12], r);
+    return scale2(exp_poly(r), k);
+}
+// exp(x) for x <= 700: arguments below -708 (including -inf) return exp(-708) ~ 3e-308
+__device__ __forceinline__ double mexp_lo(double x) {
+    x = (x < -708.0) ? -708.0 : x;
+    return mexp_nc(x);
+}
+// exp(x), any x
 __device__ __forceinline__ double mexp(double x) {
     x = (x < -708.0) ? -708.0 : x;
     x = (x > 709.0) ? 709.0 : x;
-    const double t = fma(x, kLog2e, 6755399441055744.0); // 1.5 * 2^52: round-to-nearest integer in the low word
-    const int k = __double2loint(t);
-    const double kf = t - 6755399441055744.0;
-    double r = fma(kf, -kLn2Hi, x);
-    r = fma(kf, -kLn2Lo, r);
-    return scale2(exp_poly(r), k);
+    return mexp_nc(x);
 }
 
-// 2^x
+// 2^x for |x| <= 1000 (no clamps)
+__device__ __forceinline__ double mexp2_nc(double x) {
+    const double t = x + kMagic;
+    const int k = __double2loint(t);
+    const double kf = t - kMagic;
+    const double r = (x - kf) * kMathC[13];
+    return scale2(exp_poly(r), k);
+}
 __device__ __forceinline__ double mexp2(double x) {
     x = (x < -1021.0) ? -1021.0 : x;
     x = (x > 1023.0) ? 1023.0 : x;
-    const double t = x + 6755399441055744.0;
-    const int k = __double2loint(t);
-    const double kf = t - 6755399441055744.0;
-    const double r = (x - kf) * 0.6931471805599453;
-    return scale2(exp_poly(r), k);
+    return mexp2_nc(x);
 }
 
 __device__ __forceinline__ double mlog(double x) {
@@ -126,20 +151,21 @@ __device__ __forceinline__ double mlog(double x) {
     const double s = f * mrcp(2.0 + f);
     const double z = s * s;
     const double z2 = z * z;
-    // P(z) degree 6, Estrin
-    const double p01 = fma(0.39999999999886615, z, 0.666666666666667);
-    const double p23 = fma(0.2222221019926421, z, 0.28571428631764334);
-    const double p45 = fma(0.15329500754204178, z, 0.18182956608063458);
-    const double q0 = fma(p23, z2, p01);
-    const double q1 = fma(0.14643628601909797, z2, p45);
-    const double P = fma(q1, z2 * z2, q0);
+    // P(z) = E(z^2) + z O(z^2), degree 6
+    double pe = kMathC[14], po = kMathC[18];
+    pe = fma(pe, z2, kMathC[15]);
+    po = fma(po, z2, kMathC[19]);
+    pe = fma(pe, z2, kMathC[16]);
+    po = fma(po, z2, kMathC[20]);
+    pe = fma(pe, z2, kMathC[17]);
+    const double P = fma(po, z, pe);
     const double R = z * P;
     const double ef = (double)e;
     const double lm = f - s * (f - R);
-    return fma(ef, kLn2Hi, fma(ef, kLn2Lo, lm));
+    return fma(ef, kMathC[11], fma(ef, kMathC[12], lm));
 }
 
-// x^y for x > 0
-__device__ __forceinline__ double mpow(double x, double y) { return mexp(y * mlog(x)); }
+// x^y for x > 0, |y log x| <= 700
+__device__ __forceinline__ double mpow(double x, double y) { return mexp_nc(y * mlog(x)); }
 
 } // namespace mcf

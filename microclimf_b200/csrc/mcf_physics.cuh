@@ -79,7 +79,7 @@ __device__ __forceinline__ double satvap_m(double tc) {
     const bool w = tc > 0;
     const double a = w ? 17.27 : 21.875;
     const double b = w ? 237.3 : 265.5;
-    return 0.61078 * mexp(a * tc * mrcp(tc + b));
+    return 0.61078 * mexp_nc(a * tc * mrcp(tc + b)); // |argument| < 20 for any air / surface temperature
 }
 __device__ __forceinline__ double latent(double tc) { // ref :1227-1232
     return (tc >= 0) ? 45068.7 - 42.8428 * tc : 51078.69 - 4.338 * tc - 0.06367 * tc * tc;
@@ -471,7 +471,7 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
         double sig = kd * kd + v.gma * v.gma - apg * apg;
         double ss = 0.5 * (v.om + v.Jdel * mrcp(kd)) * kd;
         double sstr = v.om * kd - ss;
-        double S2 = mexp(-kd * v.pait);
+        double S2 = mexp_lo(-kd * v.pait);
         double p5 = -ss * (apg - kd) - v.gma * sstr;
         double isig = mrcp(sig);
         double p5s = p5 * isig;
@@ -485,13 +485,13 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
         double p9 = -v.invD2 * ((p8s * v.invS1) * (v.u2 + v.h) + v3);
         double p10 = v.invD2 * ((p8s * v.S1) * (v.u2 - v.h) + v3);
         // gap transmissions
-        double trbn = mexp(Kc * v.logclump); // clump == 0: logclump = -inf, mexp -> 3e-308 (the reference: 0)
+        double trbn = mexp_lo(Kc * v.logclump); // clump == 0: logclump = -inf, mexp -> 3e-308 (the reference: 0)
         if (trbn > 0.999) trbn = 0.999;
         if (trbn < 0.0) trbn = 0.0;
-        double trb = mexp(Kc * v.loggi);
+        double trb = mexp_lo(Kc * v.loggi);
         if (trb > 0.999) trb = 0.999;
         if (trb < 0.0) trb = 0.0;
-        double S2a = mexp(-kd * v.paiaa);
+        double S2a = mexp_lo(-kd * v.paiaa);
         // black-sky albedo
         double albb = (1.0 - v.trdn * trbn) * (p5s + p6 + p7) + v.trdn * trbn * v.gref;
         if (albb > v.amx) albb = v.amx;
@@ -540,16 +540,16 @@ __device__ __forceinline__ double stom_gs2(const CellInv& v, double theta) {
     double thetan = v.rat * theta + (1 - v.rat) * kThetaM;
     double Se = thetan * v.inv_Smax;
     if (Se > 1.0) Se = 1.0;
-    double psiw = -v.psie_abs * mexp(-v.soilb * mlog(Se)) * 0.01; // pow(Se, -b), Se in (0, 1]
+    double psiw = -v.psie_abs * mexp_nc(-v.soilb * mlog(Se)) * 0.01; // pow(Se, -b), Se in (0, 1]
     if (psiw < v.psiw0) psiw = v.psiw0;
-    double mu = 1.0 - (mexp(-v.kk * psiw) - 1.0) * v.inv_stomden;
+    double mu = 1.0 - (mexp_nc(-v.kk * psiw) - 1.0) * v.inv_stomden;
     return mu * v.gsmax;
 }
 // ref stomcondCpp :442-458 given gs2
 __device__ __forceinline__ double stomcond(const CellInv& v, double Rswabs, double gs2) {
     if (Rswabs <= 0.0) return 0.0;
     if (Rswabs > v.Rsmx) Rswabs = v.Rsmx;
-    double gs = v.gsmax * mexp2(-(v.Rsmx - Rswabs) * v.inv02Rsmx);
+    double gs = v.gsmax * mexp2_nc(-(v.Rsmx - Rswabs) * v.inv02Rsmx); // argument in [-5, 0]
     if (gs > gs2) gs = gs2;
     return gs;
 }
@@ -560,7 +560,7 @@ __device__ __forceinline__ double mincond(double Rnet, double gs, double inv_lea
     if (gs > 0.0) rs = mrcp(gs);
     if (rs > 500.0) rs = 500.0;
     double Hlf = 1.09767 * mpow(rs, 0.2672778);
-    double Hf = -mrcp(1.0 + mexp(2.0 - Hlf));
+    double Hf = -mrcp(1.0 + mexp_nc(2.0 - Hlf));
     double H = Hf * Rnet;
     // H == 0: mlog(0) ~ -709, so the power is ~1e-62 instead of 0; either way gmin takes its floor
     double gmin = 0.0463 * mpow(fabs(H) * inv_leafd, 0.2);
@@ -582,7 +582,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
     double eT = esTg - ea;
     if (eT < 0.001) eT = 0.001;
     double plf = 0.8753 - 1.7126 * mlog(eT);
-    double gwet = mrcp(1.0 + mexp(-plf));
+    double gwet = mrcp(1.0 + mexp_nc(-plf)); // plf in [-6, 13]
     double surfwet = (soilm - v.Smin) * v.inv_rge;
     if (surfwet > gwet) gwet = surfwet;
     // canopy conductance (ref canopycondCpp :460-477) with k from the degrees-as-radians cankCpp call
@@ -602,7 +602,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         if (Rshade_abs <= 0.0 && Rsun_abs <= 0.0) {
             gS = 0.0; // both stomcondCpp calls return 0
         } else {
-            double P_sun = (1.0 - mexp(-kq * v.pai)) * mrcp(kq);
+            double P_sun = (1.0 - mexp_lo(-kq * v.pai)) * mrcp(kq);
             double P_shade = v.pai - P_sun;
             gs2 = stom_gs2(v, soilm);
             have_gs2 = true;
