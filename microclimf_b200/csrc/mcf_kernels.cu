@@ -121,8 +121,6 @@ __global__ void __launch_bounds__(1024) k_prep_hours(const __grid_constant__ Pre
             hour_geometry(h, s);
             hour_airterms(h);
             h.windex = w;
-            h.pad0 = 0.0;
-            h.pad1 = 0.0;
             a.hours[k] = h;
         }
     }
@@ -308,6 +306,7 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
         double zq = (s.zend > (kPi / 2.0)) ? (kPi / 2.0) : s.zend;
         h.kq_tan = tan(zq);
         h.kq_cos = cos(zq);
+        h.kq1 = 1.0 / (2.0 * h.kq_cos);
         h.zend = s.zend;
     }
     hour_airterms(h);
@@ -407,23 +406,42 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
                 }
             } else {
                 // ------------------------------------------------------------------ pass 1
+                // Output offset of the block's first hour; it advances by one time slot per hour and wraps
+                // at most once inside the block (ring_hours >= 24).
+                const size_t o_first = (size_t)slot0 * a.ncells + cell;
+                const long long wrap_at = a.ring_hours - slot0; // hour index at which the slot wraps to 0
                 double Rmx = -999.9, tmx = -999.0, tmn = 999.0;
+                // sector layers of the coming hour are fetched one hour ahead (modes 1/3: the sector indices
+                // are in the shared hour table; modes 2/4 compute the azimuth per cell-hour)
+                double ws_n = 0.0, ha_n = 0.0;
+                if (!ARR) {
+                    ws_n = __ldg(&a.wsa[(size_t)slab[buf][0].windex * a.ncells + cell]);
+                    ha_n = __ldg(&a.hor[(size_t)slab[buf][0].sindex * a.ncells + cell]);
+                }
+                size_t o = o_first;
 #pragma unroll 1
                 for (int hr = 0; hr < 24; ++hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
                     if (ARR) hour_from_arrays(a, k, cell, lat, lon, true, hloc);
                     const HourRec& h = ARR ? hloc : slab[buf][hr];
-                    long long slot = slot0 + hr;
-                    if (slot >= a.ring_hours) slot -= a.ring_hours;
-                    const size_t o = (size_t)slot * a.ncells + cell;
+                    if (hr == wrap_at) o = cell;
+                    double ws, ha;
+                    if (ARR) {
+                        ws = __ldg(&a.wsa[(size_t)h.windex * a.ncells + cell]);
+                        ha = __ldg(&a.hor[(size_t)h.sindex * a.ncells + cell]);
+                    } else {
+                        ws = ws_n;
+                        ha = ha_n;
+                        const HourRec& hn = slab[buf][hr < 23 ? hr + 1 : 23];
+                        ws_n = __ldg(&a.wsa[(size_t)hn.windex * a.ncells + cell]);
+                        ha_n = __ldg(&a.hor[(size_t)hn.sindex * a.ncells + cell]);
+                    }
                     // terrain-adjusted solar index with horizon shading (ref :2218-2223 / :2499-2504)
                     double si;
                     if (ARR && h.zend > 90.0) si = 0.0; // shadowmask = false in modes 2/4
                     else si = h.cosz * v.cs + h.sinz * (h.cosazi * v.ssca + h.sinazi * v.sssa);
                     if (si < 0.0) si = 0.0;
-                    const double ws = __ldg(&a.wsa[(size_t)h.windex * a.ncells + cell]);
-                    const double ha = __ldg(&a.hor[(size_t)h.sindex * a.ncells + cell]);
                     if (ha > h.tan_sa) si = 0.0;
                     // distributed soil moisture
                     const double soild = soil_distribute(v, h.soilmp);
@@ -457,29 +475,43 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
                     if (Rmx < Rval) Rmx = Rval;
                     if (tmx < Tg0) tmx = Tg0;
                     if (tmn > Tg0) tmn = Tg0;
+                    // the day stash is private to the thread and re-read once: keep it out of L1 (.cg)
                     double* st = stash + (size_t)hr * (kStashVars * kTile);
-                    st[0 * kTile] = radabs;
-                    st[1 * kTile] = surfwet;
-                    st[2 * kTile] = r.radCsw;
-                    st[3 * kTile] = r.Lhalf;
+                    __stcg(&st[0 * kTile], radabs);
+                    __stcg(&st[1 * kTile], surfwet);
+                    __stcg(&st[2 * kTile], r.radCsw);
+                    __stcg(&st[3 * kTile], r.Lhalf);
+                    o += a.ncells;
                 }
                 // ------------------------------------------------------------------ pass 2
                 const double dtr = tmx - tmn;
+                o = o_first;
+                // stash and wind-sector values of the coming hour are fetched one hour ahead
+                double radabs_n = __ldcg(&stash[0 * kTile]), surfwet_n = __ldcg(&stash[1 * kTile]);
+                double radCsw_n = __ldcg(&stash[2 * kTile]), Lhalf_n = __ldcg(&stash[3 * kTile]);
+                if (!ARR) ws_n = __ldg(&a.wsa[(size_t)slab[buf][0].windex * a.ncells + cell]);
 #pragma unroll 1
                 for (int hr = 0; hr < 24; ++hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
                     if (ARR) hour_from_arrays(a, k, cell, lat, lon, false, hloc);
                     const HourRec& h = ARR ? hloc : slab[buf][hr];
-                    long long slot = slot0 + hr;
-                    if (slot >= a.ring_hours) slot -= a.ring_hours;
-                    const size_t o = (size_t)slot * a.ncells + cell;
-                    const double* st = stash + (size_t)hr * (kStashVars * kTile);
-                    const double radabs = st[0 * kTile];
-                    const double surfwet = st[1 * kTile];
-                    const double radCsw = st[2 * kTile];
-                    const double Lhalf = st[3 * kTile];
-                    const double ws = __ldg(&a.wsa[(size_t)h.windex * a.ncells + cell]);
+                    if (hr == wrap_at) o = cell;
+                    const double radabs = radabs_n, surfwet = surfwet_n, radCsw = radCsw_n, Lhalf = Lhalf_n;
+                    {
+                        const double* st = stash + (size_t)(hr < 23 ? hr + 1 : 23) * (kStashVars * kTile);
+                        radabs_n = __ldcg(&st[0 * kTile]);
+                        surfwet_n = __ldcg(&st[1 * kTile]);
+                        radCsw_n = __ldcg(&st[2 * kTile]);
+                        Lhalf_n = __ldcg(&st[3 * kTile]);
+                    }
+                    double ws;
+                    if (ARR) {
+                        ws = __ldg(&a.wsa[(size_t)h.windex * a.ncells + cell]);
+                    } else {
+                        ws = ws_n;
+                        ws_n = __ldg(&a.wsa[(size_t)slab[buf][hr < 23 ? hr + 1 : 23].windex * a.ncells + cell]);
+                    }
                     const double soild = soil_distribute(v, h.soilmp);
                     const Wind w = wind_hour(v, h.u2, h.umu, ws);
                     // soil conductivity and damping depth (ref soilcondCpp :1249-1260)
@@ -511,6 +543,7 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
                             if (om & (1u << 2)) __stcs(&a.out[2][o], tv.rh);
                         }
                     }
+                    o += a.ncells;
                 }
             }
             if (!ARR) __syncthreads(); // slab[buf] is free for the bulk copy issued two blocks from now

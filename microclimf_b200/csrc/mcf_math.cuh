@@ -5,14 +5,15 @@
 // and 64-bit immediates that more than double the instruction count and spill the loop bodies out of
 // the 32 KB L1.5 instruction cache.  These replacements are straight-line code:
 //
-//   mrcp, mdiv : MUFU.RCP64H seed (rel. err 2^-23) + one cubic Newton step         (<= 2 ulp)
-//   msqrt      : MUFU.RSQ64H seed + two coupled Newton steps                       (<= 1 ulp)
-//   mexp       : Cody-Waite reduction by ln2 (hi/lo), degree-11 polynomial         (<= 1 ulp)
+//   mrcp, mdiv : MUFU.RCP64H seed (rel. err 2^-23) + one Newton step               (<= 1.5e-14)
+//   msqrt      : MUFU.RSQ64H seed + one coupled Newton step + Heron correction     (<= 1 ulp)
+//   mexp       : Cody-Waite reduction by ln2 (hi/lo), degree-9 polynomial          (<= 8e-14)
 //   mlog       : exponent/mantissa split, log(1+f) = f - s(f - zP(z)), s = f/(2+f)  (<= 1 ulp)
 //   mpow       : exp(y log x)                                                        (~1e-14 relative)
 //
 // Coefficients come from tools/gen_math_coeffs.py (mpmath Chebyshev fits, verified there against
-// mpmath).  The parity bar is 1e-6 (tests/); these are accurate to ~1e-15.
+// mpmath).  The parity bar is 1e-6 (tests/); these are accurate to ~1e-13 or better, which leaves a
+// margin of >= 1e4 after the largest error amplification in the physics (Penman-Monteith: ~1e3).
 //
 // Domain contract (every call site in mcf_physics.cuh is annotated):
 //   * mrcp / mdiv: divisor finite, normal, non-zero.  A zero or infinite divisor yields NaN (not
@@ -40,10 +41,9 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
 
 // 1 / x
 __device__ __forceinline__ double mrcp(double x) {
-    double r = rcp_seed(x);
+    double r = rcp_seed(x);       // relative error <= 2^-23
     double e = fma(-x, r, 1.0);
-    double t = fma(e, e, e);
-    return fma(r, t, r);
+    return fma(r, e, r);          // one Newton step: <= 2^-46 ~ 1.4e-14
 }
 // a / b
 __device__ __forceinline__ double mdiv(double a, double b) { return a * mrcp(b); }
@@ -54,12 +54,9 @@ __device__ __forceinline__ double msqrt(double x) {
     double g = x * y;               // ~sqrt(x)
     double h = 0.5 * y;
     double r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
+    g = fma(g, r, g);               // ~2^-45
     h = fma(h, r, h);
-    r = fma(-h, g, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    double d = fma(-g, g, x);
+    double d = fma(-g, g, x);       // Heron correction: <= 1 ulp
     g = fma(d, h, g);
     return (x == 0.0) ? 0.0 : g;
 }
@@ -70,9 +67,11 @@ __device__ __forceinline__ double msqrt(double x) {
 // to work each DFMA may carry only ONE constant, hence the even/odd Horner split below (which also gives
 // two independent dependency chains).
 __constant__ double kMathC[32] = {
-    // [0..4]  exp even part c10 c8 c6 c4 c2      [5..9] exp odd part c11 c9 c7 c5 c3
-    2.763263963904103e-07, 2.4801485482328494e-05, 0.0013888888952314775, 0.0416666666664881, 0.5000000000000019,
-    2.5110037605963777e-08, 2.755724091857897e-06, 0.00019841269890047113, 0.008333333333319601, 0.1666666666666668,
+    // exp(r) = 1 + r + r^2 q(r), q of degree 7 (Chebyshev fit on |r| <= ln2/2, max rel. error 7.4e-14)
+    // [0..3]  even part q6 q4 q2 q0            [4..7] odd part q7 q5 q3 q1
+    2.4867870179687727e-05, 0.0013888839110572009, 0.04166666678626573, 0.4999999999995511,
+    2.7617564785876086e-06, 0.00019841224599656011, 0.00833333334420298, 0.16666666666662586,
+    0, 0,
     // [10] log2(e)   [11] ln2 hi (27 trailing zero bits)   [12] ln2 lo   [13] ln2
     1.4426950408889634, 0.6931471675634384, 1.2996506893889889e-08, 0.6931471805599453,
     // [14..17] log P(z) even part L6 L4 L2 L0      [18..20] odd part L5 L3 L1
@@ -82,18 +81,16 @@ __constant__ double kMathC[32] = {
 
 constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52 (zero low word: encodable as a DFMA immediate)
 
-// exp(r) for |r| <= ln2/2:  1 + r + r^2 (E(r^2) + r O(r^2)), degree 11
+// exp(r) for |r| <= ln2/2:  1 + r + r^2 (E(r^2) + r O(r^2)), degree 9
 __device__ __forceinline__ double exp_poly(double r) {
     const double r2 = r * r;
-    double e = kMathC[0], o = kMathC[5];
+    double e = kMathC[0], o = kMathC[4];
     e = fma(e, r2, kMathC[1]);
-    o = fma(o, r2, kMathC[6]);
+    o = fma(o, r2, kMathC[5]);
     e = fma(e, r2, kMathC[2]);
-    o = fma(o, r2, kMathC[7]);
+    o = fma(o, r2, kMathC[6]);
     e = fma(e, r2, kMathC[3]);
-    o = fma(o, r2, kMathC[8]);
-    e = fma(e, r2, kMathC[4]);
-    o = fma(o, r2, kMathC[9]);
+    o = fma(o, r2, kMathC[7]);
     const double q = fma(o, r, e);
     return fma(q, r2, r + 1.0);
 }

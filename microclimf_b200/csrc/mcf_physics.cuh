@@ -59,7 +59,8 @@ struct __align__(16) HourRec {
     double Rbeam0;    // (Rsw - Rdif) / cos(zenith), uncapped        (twostreamCpp :1122, :1152)
     double pmmu;      // la * 43 / pk                                (TVaboveground :1456)
     double inv_pmmu;
-    double pad0, pad1;
+    double k1;        // 1 / (2 coszc): cankCpp's x == 1 branch      (:111)
+    double kq1;       // 1 / (2 kq_cos): the same for the degrees-as-radians call (:1425)
 };
 static_assert(sizeof(HourRec) == 320, "HourRec must be 320 bytes");
 
@@ -144,6 +145,8 @@ __device__ __forceinline__ void hour_geometry(HourRec& h, const SolPos& s) {
     double zq = (s.zend > (kPi / 2.0)) ? (kPi / 2.0) : s.zend;
     h.kq_tan = tan(zq);
     h.kq_cos = cos(zq);
+    h.k1 = 1.0 / (2.0 * h.coszc);
+    h.kq1 = 1.0 / (2.0 * h.kq_cos);
     h.zend = s.zend;
     h.sindex = ((int)round(s.azid / 15.0)) % 24;
     h.Rbeam0 = (h.Rsw - h.Rdif) / h.cosz; // forcing fields are filled before the geometry
@@ -455,11 +458,10 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
     const double cosz = h.cosz;
     if (v.pai > 0.0) {
         // canopy extinction coefficient
-        double k;
-        if (v.xflag == 1) k = 1.0 / (2.0 * h.coszc);
-        else if (v.xflag == 3) k = 1.0;
-        else if (v.xflag == 2) k = h.tanzc;
-        else k = msqrt(v.x * v.x + h.tanzc * h.tanzc) * v.inv_kden;
+        double k = msqrt(v.x * v.x + h.tanzc * h.tanzc) * v.inv_kden; // x == inf: NaN, replaced below
+        k = (v.xflag == 1) ? h.k1 : k;
+        k = (v.xflag == 3) ? 1.0 : k;
+        k = (v.xflag == 2) ? h.tanzc : k;
         if (k > 6000.0) k = 6000.0;
         const double isi = mrcp(si); // NaN for si == 0: both uses are replaced below, as the reference's inf is
         double kd = k * h.coszc * isi;
@@ -590,11 +592,10 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
     double gs2 = 0.0;
     bool have_gs2 = false;
     if (v.pai != 0.0) { // pai == 0: Rshade_abs is 0/0 = NaN in the reference, so gS is NaN and gV stays 0
-        double kq;
-        if (v.xflag == 1) kq = 1.0 / (2.0 * h.kq_cos);
-        else if (v.xflag == 3) kq = 1.0;
-        else if (v.xflag == 2) kq = h.kq_tan;
-        else kq = msqrt(v.x * v.x + h.kq_tan * h.kq_tan) * v.inv_kden;
+        double kq = msqrt(v.x * v.x + h.kq_tan * h.kq_tan) * v.inv_kden;
+        kq = (v.xflag == 1) ? h.kq1 : kq;
+        kq = (v.xflag == 3) ? 1.0 : kq;
+        kq = (v.xflag == 2) ? h.kq_tan : kq;
         if (kq > 6000.0) kq = 6000.0;
         double Rshade_abs = h.Rdif * v.shade_fac; // NaN for pai == 0 (0/0), as in the reference
         double Rsun_abs = (h.Rsw - h.Rdif) * kq * (1 - v.omp) + Rshade_abs;
