@@ -35,18 +35,20 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         p = synth.make_problem(9, 12, 48, reqhgt=0.05, mode=2)
-        # The reference has no twi-mean argument (it always subtracts the mean of the raster it is given,
-        # src/microclimfCpp.cpp:993-1004), so for the CPU checker to stand in for the per-rank solve the two
-        # bands are given the same twi pattern: band mean == whole-raster mean.
-        twi = p.arrays["twi"].reshape(p.rows, p.cols, order="F").copy()
-        twi[:, 6:] = twi[:, :6]
-        p.arrays["twi"] = np.ascontiguousarray(twi.ravel(order="F"))
+        kind = "oracle" if po.have_oracle() else "ref"
+        if kind == "ref":
+            # The reference has no twi-mean argument (it always subtracts the mean of the raster it is given,
+            # src/microclimfCpp.cpp:993-1004), so for it to stand in for the per-rank solve the two bands are
+            # given the same twi pattern: band mean == whole-raster mean.  The C restatement honours
+            # has_twi_mean like the product and needs no such trick.
+            twi = p.arrays["twi"].reshape(p.rows, p.cols, order="F").copy()
+            twi[:, 6:] = twi[:, :6]
+            p.arrays["twi"] = np.ascontiguousarray(twi.ravel(order="F"))
         b = bands.shard(p, rank, world)
         whole_s, whole_n = bands.twi_partial_host(p.arrays["twi"], p.tfact)
         assert abs(b.twi_mean - whole_s / whole_n) < 1e-14
         c0, c1 = bands.band_ranges(p.cols, world)[rank]
         assert b.cols == c1 - c0
-        kind = "ref" if po.have_ref() else "oracle"
         out = po.runmicro(b, kind=kind)
         parts = bands.gather_bands({k: v for k, v in out.items()}, p.rows, p.cols, world)
         if rank == 0:
