@@ -215,6 +215,9 @@ int mcf_twi_partial(const double* twi, int64_t n, double tfact, double* sum, int
 /* Device management and instrumentation                                                          */
 /* ------------------------------------------------------------------------------------------- */
 int mcf_abi_version(void);
+/* The host-buffer entry points keep one grow-only device workspace between calls (allocating and
+ * freeing tens of arrays per call costs more than the solve); this releases it. */
+void mcf_release_workspace(void);
 int mcf_device_count(void);
 int mcf_set_device(int device);
 /* kernels launched by this library in this process since the last reset (bench.py's gpu_launches) */

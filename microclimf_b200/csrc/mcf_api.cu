@@ -418,25 +418,57 @@ Err run_dev(const mcf_problem* p, double* const out[MCF_NOUT], const mcf_window*
 // ------------------------------------------------------------------------------------------------
 // host-buffer path
 // ------------------------------------------------------------------------------------------------
-struct DevCopy { // device mirror of a host problem; owns the allocations
-    std::vector<void*> ptrs;
-    ~DevCopy() {
-        for (void* q : ptrs) cudaFree(q);
+// Device workspace of the host-buffer entry points: one grow-only allocation kept across calls (a
+// cudaMalloc / cudaFree pair per array and call cost more than the solve itself), carved by a bump
+// pointer.  Calls are serialised by g_ws_mu (the R caller is single-threaded anyway).
+struct Workspace {
+    void* base = nullptr;
+    size_t cap = 0;
+};
+Workspace g_ws;
+std::mutex g_ws_mu;
+
+struct DevCopy { // device mirror of a host problem, carved out of the workspace
+    size_t off = 0;
+    size_t need = 0;      // sizing pass: bytes that would have been carved
+    bool sizing = false;
+    cudaStream_t stream = nullptr;
+    static size_t pad(size_t bytes) { return (std::max<size_t>(bytes, 8) + 255) & ~(size_t)255; }
+    Err reserve(size_t bytes) {
+        if (bytes > g_ws.cap) {
+            if (g_ws.base) CU(cudaFree(g_ws.base));
+            g_ws.base = nullptr;
+            g_ws.cap = 0;
+            CU(cudaMalloc(&g_ws.base, bytes));
+            g_ws.cap = bytes;
+        }
+        off = 0;
+        return Err();
+    }
+    Err carve(void** q, size_t bytes) {
+        const size_t b = pad(bytes);
+        if (sizing) {
+            need += b;
+            *q = nullptr;
+            return Err();
+        }
+        if (off + b > g_ws.cap) return make_err(MCF_ERR_NOMEM, "internal: device workspace exhausted");
+        *q = (char*)g_ws.base + off;
+        off += b;
+        return Err();
     }
     Err up(const double* h, size_t n, const double** d) {
         *d = nullptr;
         if (!h) return Err();
         void* q = nullptr;
-        CU(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(double)));
-        ptrs.push_back(q);
-        CU(cudaMemcpy(q, h, n * sizeof(double), cudaMemcpyHostToDevice));
+        TRY(carve(&q, n * sizeof(double)));
+        if (!sizing) CU(cudaMemcpyAsync(q, h, n * sizeof(double), cudaMemcpyHostToDevice, stream));
         *d = (const double*)q;
         return Err();
     }
     Err dalloc(double** d, size_t n) {
         void* q = nullptr;
-        CU(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(double)));
-        ptrs.push_back(q);
+        TRY(carve(&q, n * sizeof(double)));
         *d = (double*)q;
         return Err();
     }
@@ -529,9 +561,7 @@ void host_fill_na(double* p, size_t n) {
 Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
     TRY(validate(hp));
     TRY(device_info());
-    DevCopy dc;
-    mcf_problem dp;
-    TRY(upload_problem(hp, &dp, dc));
+    std::lock_guard<std::mutex> ws_lock(g_ws_mu);
     StreamGuard cs, xs;
     CU(cudaStreamCreateWithFlags(&cs.s, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&xs.s, cudaStreamNonBlocking));
@@ -540,38 +570,82 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
     int nreq = 0;
     for (int v = 0; v < MCF_NOUT; ++v) nreq += out[v] != nullptr;
     if (nreq == 0) return Err();
-    size_t freeb = 0, totalb = 0;
-    CU(cudaMemGetInfo(&freeb, &totalb));
     const int rq = rq_of(hp->reqhgt);
     const size_t per_hour = (size_t)nreq * nc * sizeof(double);
+    std::vector<DayBlock> blocks;
+    TRY(build_blocks(hp, blocks));
+    const int nblk = (int)blocks.size();
+
+    // ---- sizing pass: inputs + output buffers, then one workspace reservation
+    DevCopy dc;
+    dc.stream = cs.s;
+    dc.sizing = true;
+    mcf_problem dp;
+    TRY(upload_problem(hp, &dp, dc));
+    const size_t in_bytes = dc.need;
+    size_t freeb = 0, totalb = 0;
+    CU(cudaMemGetInfo(&freeb, &totalb));
+    const size_t avail = freeb + g_ws.cap; // what a fresh reservation could use
+    const bool fits = (double)in_bytes + (double)per_hour * T + (double)nreq * 256 < 0.55 * (double)avail;
+    long long chunk_blocks = 0;
+    if (!fits) {
+        if (rq == RQ_BELOW)
+            return make_err(MCF_ERR_NOMEM, "reqhgt < 0 on a raster whose outputs exceed device memory: "
+                                           "split the raster into column bands (has_twi_mean)");
+        chunk_blocks = (long long)((0.45 * (double)avail - (double)in_bytes) / (2.0 * 24.0 * (double)per_hour));
+        if (chunk_blocks < 1) return make_err(MCF_ERR_NOMEM, "one day of outputs does not fit device memory");
+        chunk_blocks = std::min<long long>(chunk_blocks, std::max(nblk, 1));
+    }
+    const long long chunk_hours = chunk_blocks * 24;
+    const size_t out_elems = fits ? nc * (size_t)T : nc * (size_t)chunk_hours;
+    const size_t out_bytes = (size_t)nreq * (fits ? 1 : 2) * DevCopy::pad(out_elems * sizeof(double));
+    TRY(dc.reserve(in_bytes + out_bytes));
+    dc.sizing = false;
+    TRY(upload_problem(hp, &dp, dc)); // asynchronous H2D on the compute stream
     {
         Scratch sc(cs.s);
         Plan pl;
         TRY(plan_prepare(pl, &dp, sc, cs.s));
-        const int nblk = (int)pl.blocks.size();
-        const bool fits = (double)per_hour * T < 0.55 * (double)freeb;
-        if (fits || rq == RQ_BELOW) {
-            if (!fits) return make_err(MCF_ERR_NOMEM, "reqhgt < 0 on a raster whose outputs exceed device memory: "
-                                                      "split the raster into column bands (has_twi_mean)");
+        if (fits) {
             double* dout[MCF_NOUT] = {nullptr};
             for (int v = 0; v < MCF_NOUT; ++v)
-                if (out[v]) TRY(dc.dalloc(&dout[v], nc * T));
+                if (out[v]) TRY(dc.dalloc(&dout[v], out_elems));
             TRY(prefill_whole(pl, dout, cs.s));
-            if (rq == RQ_BELOW) TRY(plan_run_below(pl, dout, sc, cs.s));
-            else TRY(plan_run_window(pl, dout, 0, nblk, 0, T, sc, cs.s));
-            for (int v = 0; v < MCF_NOUT; ++v)
-                if (out[v]) CU(cudaMemcpyAsync(out[v], dout[v], nc * T * sizeof(double), cudaMemcpyDeviceToHost, cs.s));
+            if (rq == RQ_BELOW || nblk < 8) {
+                if (rq == RQ_BELOW) TRY(plan_run_below(pl, dout, sc, cs.s));
+                else TRY(plan_run_window(pl, dout, 0, nblk, 0, T, sc, cs.s));
+                for (int v = 0; v < MCF_NOUT; ++v)
+                    if (out[v])
+                        CU(cudaMemcpyAsync(out[v], dout[v], nc * T * sizeof(double), cudaMemcpyDeviceToHost, cs.s));
+            } else {
+                // Four time windows: the device->host copy of a window's hours (copy stream) overlaps the
+                // kernels of the next window (compute stream).  Window i owns the hour range from its first
+                // block to the next window's first block (the first from hour 0, the last to T), so gaps the
+                // day-blocks do not cover travel with the NA prefill.
+                const int nwin = 4;
+                EventGuard done_k[nwin];
+                for (int w = 0; w < nwin; ++w) CU(cudaEventCreateWithFlags(&done_k[w].e, cudaEventDisableTiming));
+                for (int w = 0; w < nwin; ++w) {
+                    const int b0 = (int)((long long)nblk * w / nwin), b1 = (int)((long long)nblk * (w + 1) / nwin);
+                    TRY(plan_run_window(pl, dout, b0, b1 - b0, 0, T, sc, cs.s));
+                    CU(cudaEventRecord(done_k[w].e, cs.s));
+                    CU(cudaStreamWaitEvent(xs.s, done_k[w].e, 0));
+                    const size_t h0 = (w == 0) ? 0 : (size_t)pl.blocks[b0].k0;
+                    const size_t h1 = (w == nwin - 1) ? (size_t)T : (size_t)pl.blocks[b1].k0;
+                    for (int v = 0; v < MCF_NOUT; ++v)
+                        if (out[v])
+                            CU(cudaMemcpyAsync(out[v] + h0 * nc, dout[v] + h0 * nc, (h1 - h0) * nc * sizeof(double),
+                                               cudaMemcpyDeviceToHost, xs.s));
+                }
+                CU(cudaStreamSynchronize(xs.s));
+            }
             CU(cudaStreamSynchronize(cs.s));
         } else {
             // stream the time axis through two device chunks; D2H of chunk i overlaps kernels of chunk i+1
-            long long chunk_blocks = (long long)((0.45 * (double)freeb) / (2.0 * 24.0 * (double)per_hour));
-            if (chunk_blocks < 1) return make_err(MCF_ERR_NOMEM, "one day of outputs does not fit device memory");
-            chunk_blocks = std::min<long long>(chunk_blocks, nblk);
-            const long long chunk_hours = chunk_blocks * 24;
             double* dout[2][MCF_NOUT] = {{nullptr}, {nullptr}};
             for (int s = 0; s < 2; ++s)
                 for (int v = 0; v < MCF_NOUT; ++v)
-                    if (out[v]) TRY(dc.dalloc(&dout[s][v], nc * chunk_hours));
+                    if (out[v]) TRY(dc.dalloc(&dout[s][v], out_elems));
             PinGuard pin;
             for (int v = 0; v < MCF_NOUT; ++v)
                 if (out[v]) pin.pin(out[v], nc * T * sizeof(double));
@@ -777,15 +851,21 @@ int mcf_runbioclim(const mcf_problem* prob, const int32_t* wetq, int32_t nwetq, 
         BioPatch bp;
         TRY(bp.apply(prob));
         TRY(device_info());
-        DevCopy dc;
-        mcf_problem dp;
-        TRY(upload_problem(&bp.pp, &dp, dc));
-        const size_t nc = (size_t)prob->rows * prob->cols;
-        double* dbio[MCF_NBIO] = {nullptr};
-        for (int v = 0; v < MCF_NBIO; ++v)
-            if (bio[v]) TRY(dc.dalloc(&dbio[v], nc));
+        std::lock_guard<std::mutex> ws_lock(g_ws_mu);
         StreamGuard sg;
         CU(cudaStreamCreateWithFlags(&sg.s, cudaStreamNonBlocking));
+        const size_t nc = (size_t)prob->rows * prob->cols;
+        DevCopy dc;
+        dc.stream = sg.s;
+        mcf_problem dp;
+        double* dbio[MCF_NBIO] = {nullptr};
+        for (int pass = 0; pass < 2; ++pass) { // sizing pass, then the real one
+            dc.sizing = (pass == 0);
+            TRY(upload_problem(&bp.pp, &dp, dc));
+            for (int v = 0; v < MCF_NBIO; ++v)
+                if (bio[v]) TRY(dc.dalloc(&dbio[v], nc));
+            if (pass == 0) TRY(dc.reserve(dc.need));
+        }
         const int32_t* q[4] = {wetq, dryq, hotq, colq};
         const int32_t nq[4] = {nwetq, ndryq, nhotq, ncolq};
         TRY(run_bioclim_dev(&dp, q, nq, air, dbio, sg.s));
@@ -822,20 +902,33 @@ int mcf_twi_partial(const double* twi, int64_t n, double tfact, double* sum, int
     return report(body(), err, errlen);
 }
 
+void mcf_release_workspace(void) {
+    std::lock_guard<std::mutex> ws_lock(g_ws_mu);
+    if (g_ws.base) cudaFree(g_ws.base);
+    g_ws.base = nullptr;
+    g_ws.cap = 0;
+}
+
 int mcf_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, char* err, size_t errlen) {
     auto body = [&]() -> Err {
         if (!x || !out || n < 0 || fn < 0 || fn > 6) return make_err(MCF_ERR_ARG, "bad argument");
         if ((fn == 1 || fn == 6) && !y) return make_err(MCF_ERR_ARG, "fn %d needs a second operand", fn);
         TRY(device_info());
+        std::lock_guard<std::mutex> ws_lock(g_ws_mu);
         DevCopy dc;
         const double *dx = nullptr, *dy = nullptr;
         double* dout = nullptr;
-        TRY(dc.up(x, (size_t)n, &dx));
-        TRY(dc.up(y, (size_t)n, &dy));
-        TRY(dc.dalloc(&dout, (size_t)n));
+        for (int pass = 0; pass < 2; ++pass) {
+            dc.sizing = (pass == 0);
+            TRY(dc.up(x, (size_t)n, &dx));
+            TRY(dc.up(y, (size_t)n, &dy));
+            TRY(dc.dalloc(&dout, (size_t)n));
+            if (pass == 0) TRY(dc.reserve(dc.need));
+        }
         CU(launch_math_eval(fn, dx, dy, n, dout, nullptr));
         count_launch();
-        CU(cudaMemcpy(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(out, dout, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+        CU(cudaStreamSynchronize(nullptr));
         return Err();
     };
     return report(body(), err, errlen);

@@ -5,15 +5,15 @@
 // and 64-bit immediates that more than double the instruction count and spill the loop bodies out of
 // the 32 KB L1.5 instruction cache.  These replacements are straight-line code:
 //
-//   mrcp, mdiv : MUFU.RCP64H seed (rel. err 2^-23) + one Newton step               (<= 1.5e-14)
+//   mrcp, mdiv : MUFU.RCP64H seed (~20 bits) + one Newton step                      (<= 1e-12)
 //   msqrt      : MUFU.RSQ64H seed + one coupled Newton step + Heron correction     (<= 1 ulp)
 //   mexp       : Cody-Waite reduction by ln2 (hi/lo), degree-9 polynomial          (<= 8e-14)
 //   mlog       : exponent/mantissa split, log(1+f) = f - s(f - zP(z)), s = f/(2+f)  (<= 1 ulp)
 //   mpow       : exp(y log x)                                                        (~1e-14 relative)
 //
 // Coefficients come from tools/gen_math_coeffs.py (mpmath Chebyshev fits, verified there against
-// mpmath).  The parity bar is 1e-6 (tests/); these are accurate to ~1e-13 or better, which leaves a
-// margin of >= 1e4 after the largest error amplification in the physics (Penman-Monteith: ~1e3).
+// mpmath).  The parity bar is 1e-6 (tests/); these are accurate to ~1e-12 or better, which leaves a
+// margin of >= 1e3 after the largest error amplification in the physics (Penman-Monteith: ~1e3).
 //
 // Domain contract (every call site in mcf_physics.cuh is annotated):
 //   * mrcp / mdiv: divisor finite, normal, non-zero.  A zero or infinite divisor yields NaN (not
@@ -41,9 +41,9 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
 
 // 1 / x
 __device__ __forceinline__ double mrcp(double x) {
-    double r = rcp_seed(x);       // relative error <= 2^-23
+    double r = rcp_seed(x);       // relative error ~2^-20 (the seed looks at the high word only)
     double e = fma(-x, r, 1.0);
-    return fma(r, e, r);          // one Newton step: <= 2^-46 ~ 1.4e-14
+    return fma(r, e, r);          // one Newton step: <= 2^-40 ~ 1e-12
 }
 // a / b
 __device__ __forceinline__ double mdiv(double a, double b) { return a * mrcp(b); }

@@ -194,7 +194,7 @@ def test_physical_ranges_wrapper_scenario():
 def test_kernel_math_accuracy():
     """The kernels' own branch-free exp / log / pow / division / sqrt (csrc/mcf_math.cuh) against numpy
     (glibc, < 1 ulp) over the argument ranges the physics uses.  Budgets (csrc/mcf_math.cuh): exp 1e-13
-    (degree-9 polynomial), 1/x and x/y 2e-14 (one Newton step), log 1e-14, sqrt 1 ulp, pow 2e-12."""
+    (degree-9 polynomial), 1/x and x/y 2e-12 (20-bit MUFU seed + one Newton step), log 2e-13, sqrt 1e-15, pow 5e-11."""
     rng = np.random.default_rng(11)
     n = 200_000
     x = np.concatenate([rng.uniform(-700, 700, n), rng.uniform(-2, 2, n), [-708.0, 709.0, 0.0, -1e-300]])
@@ -204,13 +204,13 @@ def test_kernel_math_accuracy():
     x = np.concatenate([rng.uniform(-1000, 1000, n), [-1021.0, 1023.0, 0.0, 0.5]])
     np.testing.assert_allclose(api.math_eval(4, x), np.exp2(x), rtol=1e-13, atol=0)
     x = np.concatenate([np.exp(rng.uniform(-300, 300, n)), rng.uniform(0.5, 2.0, n), [1.0, 2.0, 0.5, 1e-300]])
-    np.testing.assert_allclose(api.math_eval(5, x), np.log(x), rtol=1e-14, atol=1e-300)
+    np.testing.assert_allclose(api.math_eval(5, x), np.log(x), rtol=2e-13, atol=1e-300)
     x = np.exp(rng.uniform(-200, 200, n)) * rng.choice([-1.0, 1.0], n)
-    np.testing.assert_allclose(api.math_eval(0, x), 1.0 / x, rtol=2e-14, atol=0)
+    np.testing.assert_allclose(api.math_eval(0, x), 1.0 / x, rtol=2e-12, atol=0)
     y = np.exp(rng.uniform(-100, 100, n))
-    np.testing.assert_allclose(api.math_eval(1, x, y), x / y, rtol=2e-14, atol=0)
+    np.testing.assert_allclose(api.math_eval(1, x, y), x / y, rtol=2e-12, atol=0)
     x = np.concatenate([np.exp(rng.uniform(-300, 300, n)), [0.0, 1.0, 4.0]])
-    np.testing.assert_allclose(api.math_eval(2, x), np.sqrt(x), rtol=5e-16, atol=0)
+    np.testing.assert_allclose(api.math_eval(2, x), np.sqrt(x), rtol=1e-15, atol=0)
     x = np.exp(rng.uniform(-30, 10, n))
     for e in (0.2, 0.2672778, -4.5, -0.733):
-        np.testing.assert_allclose(api.math_eval(6, x, e), np.power(x, e), rtol=2e-12, atol=0)
+        np.testing.assert_allclose(api.math_eval(6, x, e), np.power(x, e), rtol=5e-11, atol=0)

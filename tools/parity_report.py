@@ -14,6 +14,7 @@ from oracle import pyoracle  # noqa: E402
 
 kind = "ref" if pyoracle.have_ref() else "oracle"
 allok = True
+worst = 0.0
 for mode in (1, 2, 3, 4):
     for rq in (0.05, 0.0, -0.1, 5.0, 1.0):
         for complete in ((True, False) if rq < 0 else (True,)):
@@ -25,7 +26,9 @@ for mode in (1, 2, 3, 4):
             t2 = time.time()
             ok, rows = parity.compare(got, want)
             allok &= ok
+            worst = max(worst, max(r[2] for r in rows))
             print(f"mode {mode} reqhgt {rq} complete {complete}: {'OK' if ok else 'FAIL'} (cpu {t1-t0:.2f}s gpu {t2-t1:.2f}s)")
             if not ok:
                 print(parity.fmt(rows))
+print(f"worst error / tolerance over the sweep: {worst:.3e}")
 print("ALL OK" if allok else "SOME FAILED")
