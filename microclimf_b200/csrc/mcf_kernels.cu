@@ -34,6 +34,9 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -314,25 +317,49 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
 }
 
 template <bool ARR, int RQ>
-__global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 : 1) : kMinBlocks) k_grid(const __grid_constant__ GridArgs a) {
-    __shared__ __align__(128) HourRec slab[2][24];
-    __shared__ __align__(8) uint64_t mbar[2];
+#ifdef MCF_MAXNREG
+#define MCF_KGRID_BOUNDS __maxnreg__(MCF_MAXNREG)
+#else
+#define MCF_KGRID_BOUNDS __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 : 1) : kMinBlocks)
+#endif
+__global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
+    // Hour-table ring (modes 1/3): kStages day slabs filled by TMA bulk copies two days ahead.  full[s]
+    // completes when the copy has landed; empty[s] completes when every warp has finished the day that
+    // used the stage.  Day number q (counted over all tiles this CTA processes) always uses stage q % kStages
+    // and is its (q / kStages)-th fill, so every thread derives stage and phase parity from q alone and the
+    // warps of a CTA may drift up to two days apart instead of meeting at a __syncthreads every day.
+    constexpr int kStages = 4, kAhead = 2;
+    __shared__ __align__(128) HourRec slab_ring[kStages][24];
+    __shared__ __align__(8) uint64_t full_bar[kStages];
+    __shared__ __align__(8) uint64_t empty_bar[kStages];
     __shared__ int s_tile;
 
     const int tid = threadIdx.x;
     const int ntiles = (a.cell_end - a.cell_begin + kTile - 1) / kTile;
     double* const stash = a.stash + (size_t)blockIdx.x * (24 * kStashVars * kTile) + tid;
-    uint32_t phase0 = 0, phase1 = 0;
+    unsigned int q0 = 0; // day number of the current tile's first day-block
 
     if (!ARR) {
         if (tid == 0) {
-            mbar_init(&mbar[0], 1);
-            mbar_init(&mbar[1], 1);
+            for (int s = 0; s < kStages; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], kTile / 32);
+            }
             mbar_fence_init();
         }
     }
     const uint32_t om = a.outmask;
     const double NA = na_real();
+
+    // producer side (thread 0): fill the stage of day q with day-block bi of the window
+    auto issue_fill = [&](unsigned int q, int bi) {
+        const int s = (int)(q % kStages);
+        const unsigned int fill = q / kStages;
+        if (fill > 0) mbar_wait(&empty_bar[s], (fill - 1) & 1u); // the previous user of the stage is done
+        const DayBlock nb = a.blocks[a.block0 + bi];
+        mbar_expect_tx(&full_bar[s], 24 * sizeof(HourRec));
+        tma_load_1d(&slab_ring[s][0], a.hours + nb.k0, 24 * sizeof(HourRec), &full_bar[s]);
+    };
 
     for (;;) {
         __syncthreads();
@@ -359,29 +386,18 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
         double ddsum = 0.0;
 
         if (!ARR) {
-            if (tid == 0) {
-                const DayBlock b0 = a.blocks[a.block0];
-                mbar_expect_tx(&mbar[0], 24 * sizeof(HourRec));
-                tma_load_1d(&slab[0][0], a.hours + b0.k0, 24 * sizeof(HourRec), &mbar[0]);
-            }
+            if (tid == 0)
+                for (int bi = 0; bi < kAhead && bi < a.nblocks; ++bi) issue_fill(q0 + bi, bi);
         }
 
         for (int bi = 0; bi < a.nblocks; ++bi) {
             const DayBlock blk = a.blocks[a.block0 + bi];
-            const int buf = bi & 1;
+            const unsigned int q = q0 + bi;
+            const int buf = (int)(q % kStages);
+            const HourRec* const slab_day = &slab_ring[buf][0];
             if (!ARR) {
-                if (tid == 0 && bi + 1 < a.nblocks) {
-                    const DayBlock nb = a.blocks[a.block0 + bi + 1];
-                    mbar_expect_tx(&mbar[buf ^ 1], 24 * sizeof(HourRec));
-                    tma_load_1d(&slab[buf ^ 1][0], a.hours + nb.k0, 24 * sizeof(HourRec), &mbar[buf ^ 1]);
-                }
-                if (buf == 0) {
-                    mbar_wait(&mbar[0], phase0);
-                    phase0 ^= 1;
-                } else {
-                    mbar_wait(&mbar[1], phase1);
-                    phase1 ^= 1;
-                }
+                if (tid == 0 && bi + kAhead < a.nblocks) issue_fill(q + kAhead, bi + kAhead);
+                mbar_wait(&full_bar[buf], (q / kStages) & 1u);
             }
             // ring slot of the block's first hour; within the block the slot advances by one per hour and
             // wraps at most once (ring_hours >= 24)
@@ -415,8 +431,8 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
                 // are in the shared hour table; modes 2/4 compute the azimuth per cell-hour)
                 double ws_n = 0.0, ha_n = 0.0;
                 if (!ARR) {
-                    ws_n = __ldg(&a.wsa[(size_t)slab[buf][0].windex * a.ncells + cell]);
-                    ha_n = __ldg(&a.hor[(size_t)slab[buf][0].sindex * a.ncells + cell]);
+                    ws_n = __ldg(&a.wsa[(size_t)slab_day[0].windex * a.ncells + cell]);
+                    ha_n = __ldg(&a.hor[(size_t)slab_day[0].sindex * a.ncells + cell]);
                 }
                 size_t o = o_first;
 #pragma unroll 1
@@ -424,7 +440,7 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
                     const int k = blk.k0 + hr;
                     HourRec hloc;
                     if (ARR) hour_from_arrays(a, k, cell, lat, lon, true, hloc);
-                    const HourRec& h = ARR ? hloc : slab[buf][hr];
+                    const HourRec& h = ARR ? hloc : slab_day[hr];
                     if (hr == wrap_at) o = cell;
                     double ws, ha;
                     if (ARR) {
@@ -433,7 +449,7 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
                     } else {
                         ws = ws_n;
                         ha = ha_n;
-                        const HourRec& hn = slab[buf][hr < 23 ? hr + 1 : 23];
+                        const HourRec& hn = slab_day[hr < 23 ? hr + 1 : 23];
                         ws_n = __ldg(&a.wsa[(size_t)hn.windex * a.ncells + cell]);
                         ha_n = __ldg(&a.hor[(size_t)hn.sindex * a.ncells + cell]);
                     }
@@ -489,13 +505,13 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
                 // stash and wind-sector values of the coming hour are fetched one hour ahead
                 double radabs_n = __ldcg(&stash[0 * kTile]), surfwet_n = __ldcg(&stash[1 * kTile]);
                 double radCsw_n = __ldcg(&stash[2 * kTile]), Lhalf_n = __ldcg(&stash[3 * kTile]);
-                if (!ARR) ws_n = __ldg(&a.wsa[(size_t)slab[buf][0].windex * a.ncells + cell]);
+                if (!ARR) ws_n = __ldg(&a.wsa[(size_t)slab_day[0].windex * a.ncells + cell]);
 #pragma unroll 1
                 for (int hr = 0; hr < 24; ++hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
                     if (ARR) hour_from_arrays(a, k, cell, lat, lon, false, hloc);
-                    const HourRec& h = ARR ? hloc : slab[buf][hr];
+                    const HourRec& h = ARR ? hloc : slab_day[hr];
                     if (hr == wrap_at) o = cell;
                     const double radabs = radabs_n, surfwet = surfwet_n, radCsw = radCsw_n, Lhalf = Lhalf_n;
                     {
@@ -510,7 +526,7 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
                         ws = __ldg(&a.wsa[(size_t)h.windex * a.ncells + cell]);
                     } else {
                         ws = ws_n;
-                        ws_n = __ldg(&a.wsa[(size_t)slab[buf][hr < 23 ? hr + 1 : 23].windex * a.ncells + cell]);
+                        ws_n = __ldg(&a.wsa[(size_t)slab_day[hr < 23 ? hr + 1 : 23].windex * a.ncells + cell]);
                     }
                     const double soild = soil_distribute(v, h.soilmp);
                     const Wind w = wind_hour(v, h.u2, h.umu, ws);
@@ -546,8 +562,12 @@ __global__ void __launch_bounds__(kTile, ARR ? (kMinBlocks > 1 ? kMinBlocks - 1 
                     o += a.ncells;
                 }
             }
-            if (!ARR) __syncthreads(); // slab[buf] is free for the bulk copy issued two blocks from now
+            if (!ARR) { // this warp is done with the stage: one arrival per warp
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&empty_bar[buf]);
+            }
         }
+        q0 += (unsigned int)a.nblocks;
         if (RQ == RQ_BELOW && active) a.dd_sum[cell - a.cell_begin] = ddsum;
     }
 }
