@@ -234,7 +234,7 @@ int mcf_fp64_peak(double* tflops, char* err, size_t errlen);
 
 /* Element-wise evaluation of the kernels' own FP64 elementary functions (csrc/mcf_math.cuh) on HOST
  * buffers, for accuracy tests: fn 0 = 1/x, 1 = x/y, 2 = sqrt(x), 3 = exp(x), 4 = 2^x, 5 = log(x),
- * 6 = x^y.  y may be NULL for the one-operand functions. */
+ * 6 = x^y, 7 = sin(x), 8 = cos(x).  y may be NULL for the one-operand functions. */
 int mcf_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, char* err, size_t errlen);
 
 #ifdef __cplusplus

@@ -911,7 +911,7 @@ void mcf_release_workspace(void) {
 
 int mcf_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, char* err, size_t errlen) {
     auto body = [&]() -> Err {
-        if (!x || !out || n < 0 || fn < 0 || fn > 6) return make_err(MCF_ERR_ARG, "bad argument");
+        if (!x || !out || n < 0 || fn < 0 || fn > 8) return make_err(MCF_ERR_ARG, "bad argument");
         if ((fn == 1 || fn == 6) && !y) return make_err(MCF_ERR_ARG, "fn %d needs a second operand", fn);
         TRY(device_info());
         std::lock_guard<std::mutex> ws_lock(g_ws_mu);

@@ -99,8 +99,13 @@ __global__ void __launch_bounds__(1024) k_prep_hours(const __grid_constant__ Pre
         w = (w + 8) % 8;
         if (a.arr) {
             HourCal c;
-            c.jd = julday(a.year[k], a.month[k], a.day[k]);
+            const int jd = julday(a.year[k], a.month[k], a.day[k]);
+            const double m = 6.24004077 + 0.01720197 * (jd - 2451545.0);
+            c.eot = -7.659 * sin(m) + 9.863 * sin(2 * m + 3.5932);
+            const double dec = (kPi * 23.5 / 180) * cos(2 * kPi * ((jd - 159.5) / 365.25));
+            sincos(dec, &c.sd, &c.cd);
             c.windex = w;
+            c.pad = 0;
             c.lt = a.hour[k];
             a.cal[k] = c;
         } else {
@@ -255,9 +260,30 @@ __device__ __forceinline__ void load_cell(const GridArgs& a, int cell, int lyr, 
 }
 
 // modes 2/4: assemble the hour record of one cell-hour from the [tsteps, ncells] arrays.
-// `full` = pass 1 (needs azimuth for the solar index and horizon sector); pass 2 only needs the zenith.
-__device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int cell, double lat, double lon, bool full,
-                                                 HourRec& h) {
+// `full` = pass 1 (needs the azimuth for the solar index and the horizon sector); pass 2 only needs the zenith.
+//
+// Solar position per cell-hour (ref solpositionCpp :48-83) without inverse trigonometry: the reference
+// forms zenith = acos(coh) and azimuth = 180 + asin-like(sazi) (+ quadrant fix) and then only ever uses
+// cos / sin / tan of those angles and the 15-degree sector of the azimuth.  Here cos(zenith) = coh,
+// sin(zenith) = sqrt((1 - coh)(1 + coh)), sin(azimuth) = -sazi, cos(azimuth) = -/+ sqrt(1 - sazi^2) by the
+// sign of the reference's cazi, and the sector comes from comparing |sin| and |cos| of the azimuth with
+// tan(7.5), tan(22.5), tan(37.5 degrees).  Identical up to rounding; sectors differ only for an azimuth
+// within rounding of a sector boundary.
+constexpr double kTanHalfPi = 1.633123935319537e+16; // tan / cos of the double nearest pi/2, as libm returns
+constexpr double kCosHalfPi = 6.123233995736766e-17;
+
+__device__ __forceinline__ int azimuth_sector(double sinazi, double cosazi) { // round(azimuth / 15) % 24
+    const double as = fabs(sinazi), ac = fabs(cosazi);
+    const bool swap = as > ac;
+    const double lo = swap ? ac : as, hi = swap ? as : ac;
+    const int j = (lo >= hi * 0.13165249758739586) + (lo >= hi * 0.41421356237309503) + (lo >= hi * 0.7673269879789604);
+    const int q = swap ? 6 - j : j; // sector within the quadrant, measured from the cos axis
+    if (cosazi >= 0.0) return (sinazi >= 0.0) ? q : (24 - q) % 24;
+    return (sinazi >= 0.0) ? 12 - q : 12 + q;
+}
+
+__device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int cell, double sl, double cl, double lon,
+                                                 bool full, HourRec& h) {
     const size_t i = (size_t)k * a.ncells + cell;
     h.tc = __ldg(&a.clim[0][i]);
     h.es = __ldg(&a.clim[1][i]);
@@ -275,44 +301,59 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
     h.muGp = __ldg(&a.pnt[4][i]);
     h.dtrp = __ldg(&a.pnt[5][i]);
     const HourCal c = a.cal[k];
-    // ref soltimeCpp :39-46, solpositionCpp :48-83 with the Julian day precomputed per hour
-    double m = 6.24004077 + 0.01720197 * (c.jd - 2451545.0);
-    double eot = -7.659 * sin(m) + 9.863 * sin(2 * m + 3.5932);
-    double st = c.lt + (4.0 * lon + eot) / 60.0;
-    double latr = lat * kPi / 180.0;
-    double tt = 0.261799 * (st - 12);
-    double dec = (kPi * 23.5 / 180) * cos(2 * kPi * ((c.jd - 159.5) / 365.25));
-    double sd, cd, sl, cl, stt, ctt;
-    sincos(dec, &sd, &cd);
-    sincos(latr, &sl, &cl);
-    sincos(tt, &stt, &ctt);
-    double coh = sd * sl + cd * cl * ctt;
-    SolPos s;
-    s.zend = acos(coh) * (180 / kPi);
-    s.zenr = s.zend * kToRad;
-    s.azid = 0.0;
+    const double st = c.lt + (4.0 * lon + c.eot) / 60.0; // ref soltimeCpp :44
+    const double tt = 0.261799 * (st - 12);
+    double stt, ctt;
+    msincos(tt, &stt, &ctt);
+    const double coh = c.sd * sl + c.cd * cl * ctt; // cos(zenith), ref :56
+    const bool up = coh > 0.0;
+    h.cosz = coh;
+    h.zend = up ? 0.0 : 180.0; // only compared with 90 (solarindexCpp, shadowmask = false)
     if (full) {
-        double hh = atan(coh / sqrt(1 - coh * coh));
-        double sazi = cd * stt / cos(hh);
-        double num = sl * cd * ctt - cl * sd;
-        double cazi = num / sqrt(sq(cd * stt) + sq(num));
-        double sqt = 1 - sazi * sazi;
-        if (sqt < 0) sqt = 0;
-        double azi = 180 + (180 * atan(sazi / sqrt(sqt))) / kPi;
-        if (cazi < 0) {
-            if (sazi < 0) azi = 180 - azi;
-            else azi = 540 - azi;
-        }
-        s.azid = azi;
-        hour_geometry(h, s);
-    } else {
-        double zq = (s.zend > (kPi / 2.0)) ? (kPi / 2.0) : s.zend;
+        const double sinz = msqrt((1.0 - coh) * (1.0 + coh));
+        const double isinz = mrcp(sinz);
+        h.sinz = sinz;
+        h.tan_sa = coh * isinz; // tan(pi/2 - zenith), ref :2504
+        h.tanzc = up ? sinz * mrcp(coh) : kTanHalfPi;
+        h.coszc = up ? coh : kCosHalfPi;
+        h.k1 = mrcp(2.0 * h.coszc);
+        double sazi = c.cd * stt * isinz; // ref :61 with cos(hh) = sin(zenith)
+        const double num = sl * c.cd * ctt - cl * c.sd; // sign of the reference's cazi (:62-64)
+        double sqt = 1.0 - sazi * sazi;
+        if (sqt < 0.0) sqt = 0.0;
+        if (sazi > 1.0) sazi = 1.0;
+        if (sazi < -1.0) sazi = -1.0;
+        const double ca = msqrt(sqt);
+        h.sinazi = -sazi;
+        h.cosazi = (num < 0.0) ? ca : -ca;
+        h.sindex = azimuth_sector(h.sinazi, h.cosazi);
+        h.Rbeam0 = mdiv(h.Rsw - h.Rdif, coh);
+    }
+    // the cankCpp call inside TVaboveground takes the zenith in DEGREES as radians (ref :1425): it clamps to
+    // pi/2 unless the sun is within 1.5708 degrees of the zenith
+    if (coh > 0.99962) {
+        const double zend = acos(coh) * (180 / kPi);
+        const double zq = (zend > (kPi / 2.0)) ? (kPi / 2.0) : zend;
         h.kq_tan = tan(zq);
         h.kq_cos = cos(zq);
         h.kq1 = 1.0 / (2.0 * h.kq_cos);
-        h.zend = s.zend;
+    } else {
+        h.kq_tan = kTanHalfPi;
+        h.kq_cos = kCosHalfPi;
+        h.kq1 = 1.0 / (2.0 * kCosHalfPi);
     }
-    hour_airterms(h);
+    // Penman-Monteith air terms and hour-invariant quotients (hour_airterms) through the fast math
+    const double tk = h.tc + 273.15;
+    h.De = satvap_m(h.tc + 0.5) - satvap_m(h.tc - 0.5);
+    h.gr4 = (4 * kEm * kSb * (tk * tk * tk)) / 29.3;
+    h.Rem = kEm * kSb * pow4(tk);
+    h.la = latent(h.tc);
+    h.inv_pk = mrcp(h.pk);
+    h.invRT = mrcp(8.31 * tk);
+    h.inv_dtrp = (h.dtrp == 0.0) ? (1.0 / h.dtrp) : mrcp(h.dtrp); // keep the reference's inf for a zero range
+    h.muGp_kp = mdiv(h.muGp, h.kp);
+    h.pmmu = h.la * (43.0 * h.inv_pk);
+    h.inv_pmmu = mrcp(h.pmmu);
     h.windex = c.windex;
 }
 
@@ -376,10 +417,12 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
         const double tmean = a.has_tadd_mean ? a.tadd_mean : a.dscal[1] / a.dscal[2];
         const double tadd = log(__ldg(&a.soil[11][cc])) / a.tfact - tmean;
         double lat = a.lat, lon = 0.0, dTmx = -0.6273 * a.dscal[0] + 49.79;
+        double sl = 0.0, cl = 1.0; // sin / cos of the cell's latitude (modes 2/4)
         if (ARR) {
             lat = __ldg(&a.lats[cc]);
             lon = __ldg(&a.lons[cc]);
             dTmx = -0.6273 * __ldg(&a.mxtc_cell[cc]) + 49.79;
+            sincos(lat * kPi / 180.0, &sl, &cl);
         }
         CellInv v;
         int cur_lyr = -1;
@@ -439,7 +482,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 for (int hr = 0; hr < 24; ++hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
-                    if (ARR) hour_from_arrays(a, k, cell, lat, lon, true, hloc);
+                    if (ARR) hour_from_arrays(a, k, cell, sl, cl, lon, true, hloc);
                     const HourRec& h = ARR ? hloc : slab_day[hr];
                     if (hr == wrap_at) o = cell;
                     double ws, ha;
@@ -510,7 +553,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 for (int hr = 0; hr < 24; ++hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
-                    if (ARR) hour_from_arrays(a, k, cell, lat, lon, false, hloc);
+                    if (ARR) hour_from_arrays(a, k, cell, sl, cl, lon, false, hloc);
                     const HourRec& h = ARR ? hloc : slab_day[hr];
                     if (hr == wrap_at) o = cell;
                     const double radabs = radabs_n, surfwet = surfwet_n, radCsw = radCsw_n, Lhalf = Lhalf_n;
@@ -842,6 +885,8 @@ __global__ void k_math_eval(int fn, const double* __restrict__ x, const double* 
         case 3: r = mexp(a); break;
         case 4: r = mexp2(a); break;
         case 5: r = mlog(a); break;
+        case 7: { double c; msincos(a, &r, &c); } break;
+        case 8: { double sn; msincos(a, &sn, &r); } break;
         default: r = mpow(a, b); break;
         }
         out[i] = r;

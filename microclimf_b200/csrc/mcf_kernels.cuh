@@ -17,11 +17,14 @@ constexpr int kTile = MCF_TILE;  // cells per CTA tile = threads per CTA (one th
 constexpr int kMinBlocks = MCF_MINB; // resident CTAs per SM the grid kernel is compiled for
 constexpr int kNOut = 10;
 
-// Per-hour calendar record for the array-climate modes (solar position is per cell there).
+// Per-hour calendar record for the array-climate modes (solar position is per cell there): everything
+// of solpositionCpp (ref :48-57) that depends on the date and time only.
 struct HourCal {
-    int32_t jd;     // astronomical Julian day (ref juldayCpp :28)
-    int32_t windex; // wind-shelter sector (ref :2443)
+    double eot;     // equation of time, minutes (ref soltimeCpp :42-43)
+    double sd, cd;  // sin / cos of the solar declination (ref :55)
     double lt;      // local time, decimal hours
+    int32_t windex; // wind-shelter sector (ref :2443)
+    int32_t pad;
 };
 
 // One 24-hour block of work: hours k0 .. k0+23 solved with vegetation layer `lyr`.

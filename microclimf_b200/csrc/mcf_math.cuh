@@ -79,6 +79,16 @@ __constant__ double kMathC[32] = {
     0.15329500754204178, 0.2222221019926421, 0.39999999999886615,
     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
+// sin / cos on |r| <= pi/4:  sin r = r + r^3 S(r^2),  cos r = 1 - r^2/2 + r^4 C(r^2), S and C of degree 5
+// (Chebyshev fits, max error 1.2e-16); highest coefficient first.
+__constant__ double kTrigC[16] = {
+    1.59153232122714e-10, -2.5051092507061385e-08, 2.755731591191116e-06, -0.00019841269836387345,
+    0.0083333333333307, -0.16666666666666666,
+    -1.1380876948169717e-11, 2.087612165887116e-09, -2.755731715246704e-07, 2.4801587298533456e-05,
+    -0.0013888888888887241, 0.041666666666666664,
+    // [12] 2/pi   [13] pi/2 hi (27 trailing zero bits)   [14] pi/2 mid   [15] pi/2 lo
+    0.6366197723675814, 1.5707963109016418, 1.5893254712295857e-08, 6.123233995736766e-17};
+
 constexpr double kMagic = 6755399441055744.0; // 1.5 * 2^52 (zero low word: encodable as a DFMA immediate)
 
 // exp(r) for |r| <= ln2/2:  1 + r + r^2 (E(r^2) + r O(r^2)), degree 9
@@ -160,6 +170,38 @@ __device__ __forceinline__ double mlog(double x) {
     const double ef = (double)e;
     const double lm = f - s * (f - R);
     return fma(ef, kMathC[11], fma(ef, kMathC[12], lm));
+}
+
+// sin(x) and cos(x) for |x| < ~1e5 (three-term Cody-Waite reduction by pi/2; no Payne-Hanek path)
+__device__ __forceinline__ void msincos(double x, double* sn, double* cs) {
+    const double t = fma(x, kTrigC[12], kMagic);
+    const int k = __double2loint(t);
+    const double kf = t - kMagic;
+    double r = fma(kf, -kTrigC[13], x);
+    r = fma(kf, -kTrigC[14], r);
+    r = fma(kf, -kTrigC[15], r);
+    const double z = r * r;
+    double ps = kTrigC[0], pc = kTrigC[6];
+    ps = fma(ps, z, kTrigC[1]);
+    pc = fma(pc, z, kTrigC[7]);
+    ps = fma(ps, z, kTrigC[2]);
+    pc = fma(pc, z, kTrigC[8]);
+    ps = fma(ps, z, kTrigC[3]);
+    pc = fma(pc, z, kTrigC[9]);
+    ps = fma(ps, z, kTrigC[4]);
+    pc = fma(pc, z, kTrigC[10]);
+    ps = fma(ps, z, kTrigC[5]);
+    pc = fma(pc, z, kTrigC[11]);
+    const double s0 = fma(r * z, ps, r);
+    const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
+    // quadrant: k mod 4 = 0: (s, c), 1: (c, -s), 2: (-s, -c), 3: (-c, s)
+    const bool swap = (k & 1) != 0;
+    double ss = swap ? c0 : s0;
+    double cc = swap ? s0 : c0;
+    if (k & 2) ss = -ss;
+    if ((k + 1) & 2) cc = -cc;
+    *sn = ss;
+    *cs = cc;
 }
 
 // x^y for x > 0, |y log x| <= 700

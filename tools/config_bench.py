@@ -1,0 +1,52 @@
+"""Device-resident throughput of the other BASELINE configs on one GPU (dev / documentation aid).
+Prints one JSON object per case: cell-hours/s with CUDA-event timing, inputs resident in HBM."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from microclimf_b200 import api, synth
+
+def timed(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+def case_runmicro(name, rows, cols, T, mode, reqhgt, nlyr=1, ring=None):
+    p = synth.make_problem(rows, cols, T, reqhgt=reqhgt, mode=mode, nlyr=nlyr)
+    dp = p.to_device()
+    nc = p.ncells
+    hours = ring or T
+    mask = [True] * 10
+    if reqhgt == 0: mask = [1, 0, 0, 1, 0, 1, 1, 1, 1, 1]
+    if reqhgt < 0: mask = [1, 0, 0, 1, 0, 0, 0, 0, 0, 0]
+    outs = [torch.empty(hours * nc, dtype=torch.float64, device="cuda") if m else None for m in mask]
+    win = None if ring is None else (0, T // 24, 0, ring)
+    ms = timed(lambda: api.run_problem_dev(dp, outs, window=win))
+    print(json.dumps({"case": name, "rows": rows, "cols": cols, "hours": T, "mode": mode, "reqhgt": reqhgt, "nlyr": nlyr,
+                      "ms": ms, "cell_hours_per_s": nc * (T // 24) * 24 / (ms * 1e-3)}), flush=True)
+    del dp, outs; torch.cuda.empty_cache()
+
+def case_bioclim(name, rows, cols, mode):
+    days, q = synth.bioclim_days()
+    p = synth.make_problem(rows, cols, 336, reqhgt=0.05, mode=mode, nlyr=14, day_list=days)
+    dp = p.to_device()
+    bio = [torch.empty(p.ncells, dtype=torch.float64, device="cuda") for _ in range(19)]
+    ms = timed(lambda: api.run_bioclim_problem_dev(dp, q["wetq"], q["dryq"], q["hotq"], q["colq"], True, bio))
+    print(json.dumps({"case": name, "rows": rows, "cols": cols, "hours": 336, "mode": mode, "ms": ms,
+                      "cell_hours_per_s": p.ncells * 336 / (ms * 1e-3)}), flush=True)
+    del dp, bio; torch.cuda.empty_cache()
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["bio", "heights", "layers", "array"]
+    if "bio" in which:
+        case_bioclim("config3 runbioclim 2048x2048 (mode 1)", 2048, 2048, 1)
+    if "heights" in which:
+        for rq in (0.05, 0.0, 5.0, -0.1, -1.0):
+            case_runmicro(f"mode1 2048x1024x240h reqhgt {rq}", 2048, 1024, 240, 1, rq)
+    if "layers" in which:
+        case_runmicro("config1-2 shape: mode 3, 12 layers, 1024x1024 x 8760 h, ring 24", 1024, 1024, 8760, 3, 0.05, nlyr=12, ring=24)
+    if "array" in which:
+        case_runmicro("config5 shape: mode 2 (array climate) 2048x1024 x 120 h", 2048, 1024, 120, 2, 0.05)
+        case_runmicro("mode 4 (array climate, 3 layers) 1024x1024 x 120 h", 1024, 1024, 120, 4, 0.05, nlyr=3)
