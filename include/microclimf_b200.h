@@ -232,6 +232,23 @@ void mcf_kernel_timing_enable(int on);
  * (2 flop per DFMA); the FP64 roofline denominator that MEASURED_PEAKS.json does not carry. */
 int mcf_fp64_peak(double* tflops, char* err, size_t errlen);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Terrain preparation (SURVEY.md NEXT-2): the pure-R stencils that produce `hor`, `svfa` and the   */
+/* wind-shelter coefficients from the DTM.  HOST buffers, R layout.                                  */
+/* ------------------------------------------------------------------------------------------- */
+
+/* .horizon (R/internal.R:909-925) for `nazi` azimuths (degrees; the grid model uses 0, 15, ..., 345,
+ * R/internal.R:1142-1145): hor is [rows, cols, nazi].  svfa (may be NULL) receives the sky-view factor
+ * 0.5 cos(2 tan(mean(atan(hor)))) + 0.5 over those azimuths (R/internal.R:1146-1148).  reso = cell size (m). */
+int mcf_horizon(const double* dtm, int32_t rows, int32_t cols, double reso, int32_t nazi, const double* azimuth_deg,
+                double* hor, double* svfa, char* err, size_t errlen);
+
+/* .windcoef (R/internal.R:949-968) for `ndir` directions: index is [rows, cols, ndir] (may be NULL).
+ * blend8 (may be NULL, needs ndir == 16) receives the 16 -> 8 direction blend of .windsheltera
+ * (R/internal.R:983-989) WITHOUT its terra aggregate/resample smoothing, which is third-party arithmetic. */
+int mcf_windcoef(const double* dsm, int32_t rows, int32_t cols, double reso, double hgt, int32_t ndir,
+                 const double* direction_deg, double* index, double* blend8, char* err, size_t errlen);
+
 /* Element-wise evaluation of the kernels' own FP64 elementary functions (csrc/mcf_math.cuh) on HOST
  * buffers, for accuracy tests: fn 0 = 1/x, 1 = x/y, 2 = sqrt(x), 3 = exp(x), 4 = 2^x, 5 = log(x),
  * 6 = x^y, 7 = sin(x), 8 = cos(x).  y may be NULL for the one-operand functions. */

@@ -47,6 +47,10 @@ def lib() -> C.CDLL:
         L.mcf_kernel_timing_enable.restype = None
         L.mcf_fp64_peak.argtypes = [pd, C.c_char_p, C.c_size_t]
         L.mcf_fp64_peak.restype = C.c_int
+        L.mcf_horizon.argtypes = [pd, C.c_int32, C.c_int32, C.c_double, C.c_int32, pd, pd, pd, C.c_char_p, C.c_size_t]
+        L.mcf_horizon.restype = C.c_int
+        L.mcf_windcoef.argtypes = [pd, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, pd, pd, pd, C.c_char_p, C.c_size_t]
+        L.mcf_windcoef.restype = C.c_int
         L.mcf_math_eval.argtypes = [C.c_int, pd, pd, C.c_int64, pd, C.c_char_p, C.c_size_t]
         L.mcf_math_eval.restype = C.c_int
         L.mcf_runmicro.argtypes = [pp, _abi.OutPtrs, C.c_char_p, C.c_size_t]

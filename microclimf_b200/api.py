@@ -246,3 +246,40 @@ def math_eval(fn: int, x, y=None):
     _lib.check(L.mcf_math_eval(fn, x.ctypes.data_as(_PD), yy.ctypes.data_as(_PD) if yy is not None else None,
                                x.size, out.ctypes.data_as(_PD), err, 512), err)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# terrain preparation (SURVEY.md NEXT-2): .horizon / sky view / .windcoef of R/internal.R on the GPU
+# ---------------------------------------------------------------------------------------------------
+def horizon(dtm, reso: float, azimuths=None, want_svf: bool = True):
+    """soilc$hor and soilc$svfa as .runmodelNCpp builds them (R/internal.R:1142-1148).  `dtm` is the
+    [rows, cols] elevation matrix (row 0 = north).  Returns (hor[rows, cols, nazi], svfa[rows, cols] | None)."""
+    L = _lib.lib()
+    d = np.asarray(dtm, dtype=np.float64)
+    rows, cols = d.shape
+    az = np.arange(24) * 15.0 if azimuths is None else np.ascontiguousarray(azimuths, dtype=np.float64)
+    flat = np.ascontiguousarray(d.ravel(order="F"))
+    hor = np.empty(rows * cols * az.size)
+    svf = np.empty(rows * cols) if want_svf else None
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_horizon(flat.ctypes.data_as(_PD), rows, cols, float(reso), int(az.size), az.ctypes.data_as(_PD),
+                             hor.ctypes.data_as(_PD), svf.ctypes.data_as(_PD) if svf is not None else None, err, 512), err)
+    return hor.reshape((rows, cols, az.size), order="F"), (svf.reshape((rows, cols), order="F") if want_svf else None)
+
+
+def windcoef(dsm, reso: float, hgt: float, directions=None, blend8: bool = False):
+    """.windcoef (R/internal.R:949-968) per direction (default: the 16 of .windsheltera) and optionally the
+    16 -> 8 blend (R/internal.R:983-989, without terra's aggregate/resample smoothing)."""
+    L = _lib.lib()
+    d = np.asarray(dsm, dtype=np.float64)
+    rows, cols = d.shape
+    dr = np.arange(16) * 22.5 if directions is None else np.ascontiguousarray(directions, dtype=np.float64)
+    flat = np.ascontiguousarray(d.ravel(order="F"))
+    idx = np.empty(rows * cols * dr.size)
+    b8 = np.empty(rows * cols * 8) if blend8 else None
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_windcoef(flat.ctypes.data_as(_PD), rows, cols, float(reso), float(hgt), int(dr.size),
+                              dr.ctypes.data_as(_PD), idx.ctypes.data_as(_PD),
+                              b8.ctypes.data_as(_PD) if b8 is not None else None, err, 512), err)
+    out = idx.reshape((rows, cols, dr.size), order="F")
+    return (out, b8.reshape((rows, cols, 8), order="F")) if blend8 else out

@@ -902,6 +902,63 @@ int mcf_twi_partial(const double* twi, int64_t n, double tfact, double* sum, int
     return report(body(), err, errlen);
 }
 
+// terrain preparation on host buffers (SURVEY.md NEXT-2).  windcoef: thr_hgt = wind height (m), else horizon.
+static Err terrain_stencil(const double* dtm, int32_t rows, int32_t cols, double reso, int32_t ndir,
+                           const double* dir_deg, bool windcoef, double hgt, double* out, double* svfa, double* blend8) {
+    if (!dtm || !dir_deg || rows <= 0 || cols <= 0 || ndir <= 0 || !(reso > 0)) return make_err(MCF_ERR_ARG, "bad argument");
+    if (blend8 && ndir != 16) return make_err(MCF_ERR_ARG, "the 16 -> 8 blend needs 16 directions");
+    TRY(device_info());
+    std::lock_guard<std::mutex> ws_lock(g_ws_mu);
+    const size_t nc = (size_t)rows * cols;
+    std::vector<double> offs((size_t)ndir * 20);
+    for (int a = 0; a < ndir; ++a) {
+        const double azi = dir_deg[a] * (3.14159265358979323846 / 180);
+        for (int s = 1; s <= 10; ++s) { // R/internal.R:921-922: 101 -/+ cos/sin(azi) * step^2
+            offs[((size_t)a * 10 + s - 1) * 2 + 0] = 101 - std::cos(azi) * (double)(s * s);
+            offs[((size_t)a * 10 + s - 1) * 2 + 1] = 101 + std::sin(azi) * (double)(s * s);
+        }
+    }
+    DevCopy dc;
+    const double *d_dtm = nullptr, *d_offs = nullptr;
+    double *d_scaled = nullptr, *d_out = nullptr, *d_svf = nullptr, *d_b8 = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        dc.sizing = (pass == 0);
+        TRY(dc.up(dtm, nc, &d_dtm));
+        TRY(dc.up(offs.data(), offs.size(), &d_offs));
+        TRY(dc.dalloc(&d_scaled, nc));
+        TRY(dc.dalloc(&d_out, nc * ndir));
+        if (svfa) TRY(dc.dalloc(&d_svf, nc));
+        if (blend8) TRY(dc.dalloc(&d_b8, nc * 8));
+        if (pass == 0) TRY(dc.reserve(dc.need));
+    }
+    CU(launch_scale_dtm(d_dtm, (int64_t)nc, reso, d_scaled, nullptr));
+    CU(launch_horizon(d_scaled, rows, cols, ndir, d_offs, hgt / reso, windcoef, d_out, nullptr));
+    count_launch(2);
+    if (svfa) {
+        CU(launch_skyview(d_out, (int64_t)nc, ndir, d_svf, nullptr));
+        count_launch();
+    }
+    if (blend8) {
+        CU(launch_blend16to8(d_out, (int64_t)nc, d_b8, nullptr));
+        count_launch();
+    }
+    if (out) CU(cudaMemcpyAsync(out, d_out, nc * ndir * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    if (svfa) CU(cudaMemcpyAsync(svfa, d_svf, nc * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    if (blend8) CU(cudaMemcpyAsync(blend8, d_b8, nc * 8 * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaStreamSynchronize(nullptr));
+    return Err();
+}
+
+int mcf_horizon(const double* dtm, int32_t rows, int32_t cols, double reso, int32_t nazi, const double* azimuth_deg,
+                double* hor, double* svfa, char* err, size_t errlen) {
+    return report(terrain_stencil(dtm, rows, cols, reso, nazi, azimuth_deg, false, 0.0, hor, svfa, nullptr), err, errlen);
+}
+
+int mcf_windcoef(const double* dsm, int32_t rows, int32_t cols, double reso, double hgt, int32_t ndir,
+                 const double* direction_deg, double* index, double* blend8, char* err, size_t errlen) {
+    return report(terrain_stencil(dsm, rows, cols, reso, ndir, direction_deg, true, hgt, index, nullptr, blend8), err, errlen);
+}
+
 void mcf_release_workspace(void) {
     std::lock_guard<std::mutex> ws_lock(g_ws_mu);
     if (g_ws.base) cudaFree(g_ws.base);

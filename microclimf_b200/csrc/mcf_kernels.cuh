@@ -117,6 +117,12 @@ int grid_blocks_per_sm(bool arr, int rq);
 cudaError_t launch_below(const BelowArgs& a, cudaStream_t stream);
 cudaError_t launch_bioclim(const BioArgs& a, cudaStream_t stream);
 cudaError_t launch_fill_na(double* p, int64_t n, cudaStream_t stream);
+// terrain preparation (mcf_terrain.cu)
+cudaError_t launch_scale_dtm(const double* dtm, int64_t n, double reso, double* out, cudaStream_t st);
+cudaError_t launch_horizon(const double* d, int rows, int cols, int ndir, const double* offs, double thr, bool windcoef,
+                           double* out, cudaStream_t st);
+cudaError_t launch_skyview(const double* hor, int64_t nc, int ndir, double* svf, cudaStream_t st);
+cudaError_t launch_blend16to8(const double* a, int64_t nc, double* out, cudaStream_t st);
 cudaError_t launch_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* sink, int grid, int iters, cudaStream_t stream);
 

@@ -550,8 +550,10 @@ __device__ __forceinline__ double stom_gs2(const CellInv& v, double theta) {
 // ref stomcondCpp :442-458 given gs2
 __device__ __forceinline__ double stomcond(const CellInv& v, double Rswabs, double gs2) {
     if (Rswabs <= 0.0) return 0.0;
-    if (Rswabs > v.Rsmx) Rswabs = v.Rsmx;
-    double gs = v.gsmax * mexp2_nc(-(v.Rsmx - Rswabs) * v.inv02Rsmx); // argument in [-5, 0]
+    // Rswabs >= Rsmx (always the case for sunlit leaves: kq is ~6000) clamps the exponent to 0 and
+    // 2^0 = 1 exactly, so the exponential is only evaluated below saturation
+    double gs = v.gsmax;
+    if (Rswabs < v.Rsmx) gs = v.gsmax * mexp2_nc(-(v.Rsmx - Rswabs) * v.inv02Rsmx); // argument in (-5, 0)
     if (gs > gs2) gs = gs2;
     return gs;
 }
@@ -603,7 +605,12 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         if (Rshade_abs <= 0.0 && Rsun_abs <= 0.0) {
             gS = 0.0; // both stomcondCpp calls return 0
         } else {
-            double P_sun = (1.0 - mexp_lo(-kq * v.pai)) * mrcp(kq);
+            // exp(-kq pai) underflows to exactly 0 in the reference once kq pai > 745 (kq is ~6000 whenever
+            // the zenith-in-degrees argument is clamped, i.e. almost always)
+            const double kp_ = kq * v.pai;
+            double esun = 0.0;
+            if (kp_ < 700.0) esun = mexp_nc(-kp_);
+            double P_sun = (1.0 - esun) * mrcp(kq);
             double P_shade = v.pai - P_sun;
             gs2 = stom_gs2(v, soilm);
             have_gs2 = true;
