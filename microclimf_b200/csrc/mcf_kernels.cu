@@ -369,7 +369,10 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
     // used the stage.  Day number q (counted over all tiles this CTA processes) always uses stage q % kStages
     // and is its (q / kStages)-th fill, so every thread derives stage and phase parity from q alone and the
     // warps of a CTA may drift up to two days apart instead of meeting at a __syncthreads every day.
-    constexpr int kStages = 4, kAhead = 2;
+#ifndef MCF_STAGES
+#define MCF_STAGES 4
+#endif
+    constexpr int kStages = MCF_STAGES, kAhead = MCF_STAGES / 2;
     __shared__ __align__(128) HourRec slab_ring[kStages][24];
     __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t empty_bar[kStages];

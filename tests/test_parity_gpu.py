@@ -217,3 +217,53 @@ def test_kernel_math_accuracy():
     x = np.exp(rng.uniform(-30, 10, n))
     for e in (0.2, 0.2672778, -4.5, -0.733):
         np.testing.assert_allclose(api.math_eval(6, x, e), np.power(x, e), rtol=5e-11, atol=0)
+
+
+def test_full_size_band_sampled_against_oracle():
+    """A bench-sized band slice (2048 x 1024 cells, device-resident, 24-hour ring) checked through
+    size-independent properties: (1) determinism: two runs are bit-identical; (2) cell independence:
+    300 randomly sampled cells, re-solved on the CPU as a 300 x 1 raster with the band's twi mean, match
+    the big run; (3) NA cells stay NA, every other value is finite."""
+    import torch
+
+    from microclimf_b200 import bands
+
+    rows, cols, T = 2048, 1024, 48
+    p = synth.make_problem(rows, cols, T, reqhgt=0.05, mode=1, seed=99)
+    s, n = bands.twi_partial_host(p.arrays["twi"], p.tfact)
+    p.twi_mean = s / n
+    dp = p.to_device()
+    nc = p.ncells
+    outs = [torch.empty(T * nc, dtype=torch.float64, device="cuda") for _ in range(10)]
+    api.run_problem_dev(dp, outs)
+    torch.cuda.synchronize()
+    first = [o.clone() for o in outs]
+    api.run_problem_dev(dp, outs)
+    torch.cuda.synchronize()
+    for a, b in zip(first, outs):
+        assert torch.equal(a.view(torch.int64), b.view(torch.int64))
+    rng = np.random.default_rng(4)
+    pick = np.sort(rng.choice(nc, 300, replace=False))
+    sub = synth.make_problem(300, 1, T, reqhgt=0.05, mode=1, seed=99)
+    for name, arr in p.arrays.items():
+        ln = p.expected_len(name)
+        if ln % nc == 0 and name not in ("year", "month", "day", "hour", "winddir") and ln >= nc and \
+                (name in _abi.VEG_FIELDS or name in _abi.SOIL_FIELDS):
+            sub.arrays[name] = np.ascontiguousarray(arr.reshape(ln // nc, nc)[:, pick].ravel())
+        else:
+            sub.arrays[name] = arr
+    sub.twi_mean = p.twi_mean
+    sub.validate()
+    kind = "oracle" if pyoracle.have_oracle() else None
+    if kind is None:
+        pytest.skip("the C restatement (honours has_twi_mean) is not built")
+    want = pyoracle.runmicro(sub, kind=kind)
+    got = {}
+    na = np.isnan(p.arrays["hgt"])
+    for nm, o in zip(_abi.OUT_NAMES, outs):
+        full = o.view(T, nc)
+        got[nm] = full[:, torch.from_numpy(pick).cuda()].cpu().numpy().T.reshape(300, 1, T)
+        v = full.cpu().numpy()
+        assert np.isnan(v[:, na]).all() and np.isfinite(v[:, ~na]).all(), nm
+    ok, rws = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rws)
