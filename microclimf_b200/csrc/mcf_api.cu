@@ -15,9 +15,11 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mcf_kernels.cuh"
@@ -541,16 +543,94 @@ struct EventGuard {
         if (e) cudaEventDestroy(e);
     }
 };
-struct PinGuard { // cudaHostRegister of caller buffers so device->host copies run asynchronously
-    std::vector<void*> pinned;
-    ~PinGuard() {
-        for (void* q : pinned) cudaHostUnregister(q);
-    }
-    void pin(void* q, size_t bytes) {
-        if (cudaHostRegister(q, bytes, cudaHostRegisterDefault) == cudaSuccess) pinned.push_back(q);
-        else (void)cudaGetLastError(); // not fatal: the copy is then staged by the runtime
-    }
+// ------------------------------------------------------------------------------------------------
+// device -> host result copies
+// ------------------------------------------------------------------------------------------------
+// A caller such as R hands us ordinary pageable memory.  cudaMemcpyAsync into pageable memory is staged by
+// the driver through one small bounce buffer at ~10 GB/s, a fifth of what PCIe gen5 delivers, and it is the
+// largest term of the host-buffer path (80 B per cell-hour).  Pageable destinations are therefore served by
+// a pool of copy threads: each owns a stream and two pinned slots, DMAs a chunk into one slot while it
+// memcpy's the previous chunk out of the other, so the DMA engine and several cores' worth of memcpy
+// bandwidth run concurrently.  Pinned (or registered) destinations are copied directly.
+struct CopyJob {
+    double* dst;
+    const double* src;
+    size_t bytes;
+    cudaEvent_t ready; // the producing kernels have completed (may be null)
 };
+
+constexpr size_t kSlotBytes = (size_t)32 << 20;
+constexpr int kMaxCopyThreads = 8;
+void* g_stage = nullptr; // kMaxCopyThreads * 2 slots of pinned memory, kept between calls (guarded by g_ws_mu)
+
+bool is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
+Err copy_back(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream) {
+    // split into pinned destinations (direct) and pageable ones (staged, chunked)
+    struct Chunk { char* dst; const char* src; size_t bytes; cudaEvent_t ready; };
+    std::vector<Chunk> chunks;
+    for (const CopyJob& j : jobs) {
+        if (!j.bytes) continue;
+        if (is_pinned(j.dst)) {
+            if (j.ready) CU(cudaStreamWaitEvent(direct_stream, j.ready, 0));
+            CU(cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDeviceToHost, direct_stream));
+        } else {
+            for (size_t off = 0; off < j.bytes; off += kSlotBytes)
+                chunks.push_back(Chunk{(char*)j.dst + off, (const char*)j.src + off, std::min(kSlotBytes, j.bytes - off), j.ready});
+        }
+    }
+    if (!chunks.empty()) {
+        int nthreads = (int)std::min<size_t>(kMaxCopyThreads, std::max(1u, std::thread::hardware_concurrency() / 2));
+        nthreads = (int)std::min<size_t>(nthreads, chunks.size());
+        if (!g_stage) CU(cudaMallocHost(&g_stage, kSlotBytes * 2 * kMaxCopyThreads));
+        int dev = 0;
+        CU(cudaGetDevice(&dev));
+        std::vector<cudaError_t> status(nthreads, cudaSuccess);
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) {
+            pool.emplace_back([&, t]() {
+                cudaError_t e = cudaSetDevice(dev);
+                cudaStream_t st = nullptr;
+                cudaEvent_t ev[2] = {nullptr, nullptr};
+                if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+                for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
+                char* slot[2] = {(char*)g_stage + kSlotBytes * (2 * t), (char*)g_stage + kSlotBytes * (2 * t + 1)};
+                // chunks t, t + nthreads, ...; DMA of chunk i+1 overlaps the memcpy of chunk i
+                std::vector<size_t> mine;
+                for (size_t c = t; c < chunks.size(); c += nthreads) mine.push_back(c);
+                auto issue = [&](size_t i) {
+                    const Chunk& c = chunks[mine[i]];
+                    if (c.ready) e = cudaStreamWaitEvent(st, c.ready, 0);
+                    if (e == cudaSuccess) e = cudaMemcpyAsync(slot[i & 1], c.src, c.bytes, cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess) e = cudaEventRecord(ev[i & 1], st);
+                };
+                if (e == cudaSuccess && !mine.empty()) issue(0);
+                for (size_t i = 0; i < mine.size() && e == cudaSuccess; ++i) {
+                    if (i + 1 < mine.size()) issue(i + 1);
+                    if (e == cudaSuccess) e = cudaEventSynchronize(ev[i & 1]);
+                    if (e == cudaSuccess) std::memcpy(chunks[mine[i]].dst, slot[i & 1], chunks[mine[i]].bytes);
+                }
+                if (st) cudaStreamSynchronize(st);
+                for (int k = 0; k < 2; ++k)
+                    if (ev[k]) cudaEventDestroy(ev[k]);
+                if (st) cudaStreamDestroy(st);
+                status[t] = e;
+            });
+        }
+        for (auto& th : pool) th.join();
+        for (cudaError_t e : status)
+            if (e != cudaSuccess) return make_err(MCF_ERR_CUDA, "staged device->host copy failed: %s", cudaGetErrorString(e));
+    }
+    CU(cudaStreamSynchronize(direct_stream));
+    return Err();
+}
 
 void host_fill_na(double* p, size_t n) {
     const uint64_t bits = MCF_NA_REAL_BITS;
@@ -586,14 +666,19 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
     size_t freeb = 0, totalb = 0;
     CU(cudaMemGetInfo(&freeb, &totalb));
     const size_t avail = freeb + g_ws.cap; // what a fresh reservation could use
-    const bool fits = (double)in_bytes + (double)per_hour * T + (double)nreq * 256 < 0.55 * (double)avail;
+    bool fits = (double)in_bytes + (double)per_hour * T + (double)nreq * 256 < 0.55 * (double)avail;
     long long chunk_blocks = 0;
+    // test hook: MCF_FORCE_STREAM_BLOCKS=n forces the streaming path with n day-blocks per device chunk
+    const char* force = std::getenv("MCF_FORCE_STREAM_BLOCKS");
+    const long long forced = (force && rq != RQ_BELOW) ? std::atoll(force) : 0;
+    if (forced > 0) fits = false;
     if (!fits) {
         if (rq == RQ_BELOW)
             return make_err(MCF_ERR_NOMEM, "reqhgt < 0 on a raster whose outputs exceed device memory: "
                                            "split the raster into column bands (has_twi_mean)");
         chunk_blocks = (long long)((0.45 * (double)avail - (double)in_bytes) / (2.0 * 24.0 * (double)per_hour));
         if (chunk_blocks < 1) return make_err(MCF_ERR_NOMEM, "one day of outputs does not fit device memory");
+        if (forced > 0) chunk_blocks = forced;
         chunk_blocks = std::min<long long>(chunk_blocks, std::max(nblk, 1));
     }
     const long long chunk_hours = chunk_blocks * 24;
@@ -611,49 +696,36 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
             for (int v = 0; v < MCF_NOUT; ++v)
                 if (out[v]) TRY(dc.dalloc(&dout[v], out_elems));
             TRY(prefill_whole(pl, dout, cs.s));
-            if (rq == RQ_BELOW || nblk < 8) {
+            // Time windows: the device->host copy of a window's hours overlaps the kernels of the next
+            // window.  Window i owns the hour range from its first block to the next window's first block
+            // (the first from hour 0, the last to T), so gaps the day-blocks do not cover travel with the NA
+            // prefill.  reqhgt < 0 needs the whole series before its time-axis pass: one window.
+            const int nwin = (rq == RQ_BELOW || nblk < 8) ? 1 : 4;
+            std::vector<EventGuard> done_k(nwin);
+            std::vector<CopyJob> jobs;
+            for (int w = 0; w < nwin; ++w) {
+                CU(cudaEventCreateWithFlags(&done_k[w].e, cudaEventDisableTiming));
+                const int b0 = (int)((long long)nblk * w / nwin), b1 = (int)((long long)nblk * (w + 1) / nwin);
                 if (rq == RQ_BELOW) TRY(plan_run_below(pl, dout, sc, cs.s));
-                else TRY(plan_run_window(pl, dout, 0, nblk, 0, T, sc, cs.s));
+                else TRY(plan_run_window(pl, dout, b0, b1 - b0, 0, T, sc, cs.s));
+                CU(cudaEventRecord(done_k[w].e, cs.s));
+                const size_t h0 = (w == 0) ? 0 : (size_t)pl.blocks[b0].k0;
+                const size_t h1 = (w == nwin - 1) ? (size_t)T : (size_t)pl.blocks[b1].k0;
                 for (int v = 0; v < MCF_NOUT; ++v)
                     if (out[v])
-                        CU(cudaMemcpyAsync(out[v], dout[v], nc * T * sizeof(double), cudaMemcpyDeviceToHost, cs.s));
-            } else {
-                // Four time windows: the device->host copy of a window's hours (copy stream) overlaps the
-                // kernels of the next window (compute stream).  Window i owns the hour range from its first
-                // block to the next window's first block (the first from hour 0, the last to T), so gaps the
-                // day-blocks do not cover travel with the NA prefill.
-                const int nwin = 4;
-                EventGuard done_k[nwin];
-                for (int w = 0; w < nwin; ++w) CU(cudaEventCreateWithFlags(&done_k[w].e, cudaEventDisableTiming));
-                for (int w = 0; w < nwin; ++w) {
-                    const int b0 = (int)((long long)nblk * w / nwin), b1 = (int)((long long)nblk * (w + 1) / nwin);
-                    TRY(plan_run_window(pl, dout, b0, b1 - b0, 0, T, sc, cs.s));
-                    CU(cudaEventRecord(done_k[w].e, cs.s));
-                    CU(cudaStreamWaitEvent(xs.s, done_k[w].e, 0));
-                    const size_t h0 = (w == 0) ? 0 : (size_t)pl.blocks[b0].k0;
-                    const size_t h1 = (w == nwin - 1) ? (size_t)T : (size_t)pl.blocks[b1].k0;
-                    for (int v = 0; v < MCF_NOUT; ++v)
-                        if (out[v])
-                            CU(cudaMemcpyAsync(out[v] + h0 * nc, dout[v] + h0 * nc, (h1 - h0) * nc * sizeof(double),
-                                               cudaMemcpyDeviceToHost, xs.s));
-                }
-                CU(cudaStreamSynchronize(xs.s));
+                        jobs.push_back(CopyJob{out[v] + h0 * nc, dout[v] + h0 * nc, (h1 - h0) * nc * sizeof(double), done_k[w].e});
             }
+            TRY(copy_back(jobs, xs.s));
             CU(cudaStreamSynchronize(cs.s));
         } else {
-            // stream the time axis through two device chunks; D2H of chunk i overlaps kernels of chunk i+1
+            // The outputs do not fit the device: stream the time axis through two device chunk buffers; the
+            // copy-back of chunk i (blocking this thread) overlaps the kernels of chunk i+1 (already queued).
             double* dout[2][MCF_NOUT] = {{nullptr}, {nullptr}};
             for (int s = 0; s < 2; ++s)
                 for (int v = 0; v < MCF_NOUT; ++v)
                     if (out[v]) TRY(dc.dalloc(&dout[s][v], out_elems));
-            PinGuard pin;
-            for (int v = 0; v < MCF_NOUT; ++v)
-                if (out[v]) pin.pin(out[v], nc * T * sizeof(double));
-            EventGuard done_k[2], done_c[2];
-            for (int s = 0; s < 2; ++s) {
-                CU(cudaEventCreateWithFlags(&done_k[s].e, cudaEventDisableTiming));
-                CU(cudaEventCreateWithFlags(&done_c[s].e, cudaEventDisableTiming));
-            }
+            EventGuard done_k[2];
+            for (int s = 0; s < 2; ++s) CU(cudaEventCreateWithFlags(&done_k[s].e, cudaEventDisableTiming));
             // hours no day-block covers, and outputs this reqhgt never writes, are NA (host side)
             std::vector<char> covered(T, 0);
             for (const DayBlock& b : pl.blocks)
@@ -664,26 +736,26 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
                 for (int k = 0; k < T; ++k)
                     if (!covered[k]) host_fill_na(out[v] + (size_t)k * nc, nc);
             }
+            std::vector<CopyJob> pending;
             int w = 0;
-            for (int b0 = 0; b0 < nblk; b0 += (int)chunk_blocks, ++w) {
+            for (int b0 = 0; b0 < nblk; ++w) {
                 const int s = w & 1;
                 int nb = (int)std::min<long long>(chunk_blocks, nblk - b0);
                 // a chunk must cover a contiguous hour range to be copied back in one piece per output
                 for (int i = 1; i < nb; ++i)
                     if (pl.blocks[b0 + i].k0 != pl.blocks[b0 + i - 1].k0 + 24) { nb = i; break; }
-                if (w >= 2) CU(cudaStreamWaitEvent(cs.s, done_c[s].e, 0)); // chunk buffer s is free again
                 const long long h0 = pl.blocks[b0].k0;
-                TRY(plan_run_window(pl, dout[s], b0, nb, h0, chunk_hours, sc, cs.s));
+                TRY(plan_run_window(pl, dout[s], b0, nb, h0, chunk_hours, sc, cs.s)); // buffer s was drained below
                 CU(cudaEventRecord(done_k[s].e, cs.s));
-                CU(cudaStreamWaitEvent(xs.s, done_k[s].e, 0));
+                if (!pending.empty()) TRY(copy_back(pending, xs.s)); // chunk w-1, overlapping the kernels of chunk w
+                pending.clear();
                 for (int v = 0; v < MCF_NOUT; ++v)
                     if (out[v] && kernel_writes(rq, v))
-                        CU(cudaMemcpyAsync(out[v] + (size_t)h0 * nc, dout[s][v], nc * 24 * nb * sizeof(double),
-                                           cudaMemcpyDeviceToHost, xs.s));
-                CU(cudaEventRecord(done_c[s].e, xs.s));
-                if (nb < chunk_blocks) b0 -= (int)chunk_blocks - nb; // shortened chunk: resume right after it
+                        pending.push_back(CopyJob{out[v] + (size_t)h0 * nc, dout[s][v], nc * 24 * (size_t)nb * sizeof(double),
+                                                  done_k[s].e});
+                b0 += nb;
             }
-            CU(cudaStreamSynchronize(xs.s));
+            if (!pending.empty()) TRY(copy_back(pending, xs.s));
             CU(cudaStreamSynchronize(cs.s));
         }
     }
@@ -964,6 +1036,8 @@ void mcf_release_workspace(void) {
     if (g_ws.base) cudaFree(g_ws.base);
     g_ws.base = nullptr;
     g_ws.cap = 0;
+    if (g_stage) cudaFreeHost(g_stage);
+    g_stage = nullptr;
 }
 
 int mcf_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, char* err, size_t errlen) {

@@ -267,3 +267,29 @@ def test_full_size_band_sampled_against_oracle():
         assert np.isnan(v[:, na]).all() and np.isfinite(v[:, ~na]).all(), nm
     ok, rws = parity.compare(got, want)
     assert ok, "\n" + parity.fmt(rws)
+
+
+def test_host_path_variants_agree(monkeypatch):
+    """mcf_runmicro's three copy-back routes give identical results: pageable destination (staged through
+    pinned slots by copy threads), pinned destination (direct), and the time-streaming path used when the
+    outputs exceed device memory (forced here with the MCF_FORCE_STREAM_BLOCKS test hook), including a
+    layered problem whose day-blocks leave gaps."""
+    import torch
+
+    for mode, kw in ((1, {}), (3, dict(nlyr=3))):
+        p = synth.make_problem(61, 47, 24 * 11, reqhgt=0.05, mode=mode, **kw)
+        if mode == 3:
+            p.lyr_st = np.array([24, 96, 192], dtype=np.int32)
+            p.lyr_ed = np.array([71, 167, 263], dtype=np.int32)
+        base = api.run_problem(p)  # pageable numpy outputs
+        n = p.ncells * p.tsteps
+        pinned_t = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(10)]
+        pinned = api.run_problem(p, out_buffers=[t.numpy() for t in pinned_t])
+        for nm in base:
+            np.testing.assert_array_equal(base[nm].view(np.uint64), pinned[nm].view(np.uint64))
+        for nb in ("1", "3"):
+            monkeypatch.setenv("MCF_FORCE_STREAM_BLOCKS", nb)
+            streamed = api.run_problem(p)
+            monkeypatch.delenv("MCF_FORCE_STREAM_BLOCKS")
+            for nm in base:
+                np.testing.assert_array_equal(base[nm].view(np.uint64), streamed[nm].view(np.uint64))
