@@ -249,6 +249,11 @@ int mcf_horizon(const double* dtm, int32_t rows, int32_t cols, double reso, int3
 int mcf_windcoef(const double* dsm, int32_t rows, int32_t cols, double reso, double hgt, int32_t ndir,
                  const double* direction_deg, double* index, double* blend8, char* err, size_t errlen);
 
+/* flowaccCpp (src/microclimfCpp.cpp:5368-5414, with flowdirCpp :5326-5366): D8 flow accumulation of a
+ * [rows, cols] elevation matrix, the input of .topidx (R/internal.R:861-874).  HOST code (one sequential
+ * sweep over the cells sorted by elevation); NaN cells receive (double)INT_MIN as in the reference. */
+int mcf_flowacc(const double* dtm, int32_t rows, int32_t cols, double* fa, char* err, size_t errlen);
+
 /* Element-wise evaluation of the kernels' own FP64 elementary functions (csrc/mcf_math.cuh) on HOST
  * buffers, for accuracy tests: fn 0 = 1/x, 1 = x/y, 2 = sqrt(x), 3 = exp(x), 4 = 2^x, 5 = log(x),
  * 6 = x^y, 7 = sin(x), 8 = cos(x).  y may be NULL for the one-operand functions. */

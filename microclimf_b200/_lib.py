@@ -51,6 +51,8 @@ def lib() -> C.CDLL:
         L.mcf_horizon.restype = C.c_int
         L.mcf_windcoef.argtypes = [pd, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, pd, pd, pd, C.c_char_p, C.c_size_t]
         L.mcf_windcoef.restype = C.c_int
+        L.mcf_flowacc.argtypes = [pd, C.c_int32, C.c_int32, pd, C.c_char_p, C.c_size_t]
+        L.mcf_flowacc.restype = C.c_int
         L.mcf_math_eval.argtypes = [C.c_int, pd, pd, C.c_int64, pd, C.c_char_p, C.c_size_t]
         L.mcf_math_eval.restype = C.c_int
         L.mcf_runmicro.argtypes = [pp, _abi.OutPtrs, C.c_char_p, C.c_size_t]

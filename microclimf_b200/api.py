@@ -283,3 +283,15 @@ def windcoef(dsm, reso: float, hgt: float, directions=None, blend8: bool = False
                               b8.ctypes.data_as(_PD) if b8 is not None else None, err, 512), err)
     out = idx.reshape((rows, cols, dr.size), order="F")
     return (out, b8.reshape((rows, cols, 8), order="F")) if blend8 else out
+
+
+def flowacc(dtm):
+    """flowaccCpp (src/microclimfCpp.cpp:5368-5414) of a [rows, cols] elevation matrix (NaN = NA)."""
+    L = _lib.lib()
+    d = np.asarray(dtm, dtype=np.float64)
+    rows, cols = d.shape
+    flat = np.ascontiguousarray(d.ravel(order="F"))
+    fa = np.empty(rows * cols)
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_flowacc(flat.ctypes.data_as(_PD), rows, cols, fa.ctypes.data_as(_PD), err, 512), err)
+    return fa.reshape((rows, cols), order="F")

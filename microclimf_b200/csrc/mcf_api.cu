@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -1029,6 +1030,72 @@ int mcf_horizon(const double* dtm, int32_t rows, int32_t cols, double reso, int3
 int mcf_windcoef(const double* dsm, int32_t rows, int32_t cols, double reso, double hgt, int32_t ndir,
                  const double* direction_deg, double* index, double* blend8, char* err, size_t errlen) {
     return report(terrain_stencil(dsm, rows, cols, reso, ndir, direction_deg, true, hgt, index, nullptr, blend8), err, errlen);
+}
+
+// flowdirCpp + flowaccCpp (src/microclimfCpp.cpp:5326-5414): D8 flow direction to the lowest of the 3x3
+// neighbourhood (first minimum in column-major scan order, the cell itself included) and accumulation by one
+// sweep over the cells in decreasing (elevation, row * cols + col) order.  A sequential sorted sweep over the
+// whole raster: HOST code, run once per model run before the solver ("TWI stays on one
+// rank/host").  NA cells receive (double)INT_MIN as in the reference (fa = NA_INTEGER stored in a double).
+// "NA" is R_IsNA, i.e. ONLY R's NA_real_ payload (low word 1954): the plain quiet NaN terra hands back for
+// missing cells is NOT NA to the reference — such cells take part in every comparison (all false), drain
+// into their lowest neighbour and are sorted by index among "equal" elevations.  Reproduced as written
+// (same std::sort, same comparator), because the accumulation next to a masked region depends on it.
+int mcf_flowacc(const double* dtm, int32_t rows, int32_t cols, double* fa, char* err, size_t errlen) {
+    auto body = [&]() -> Err {
+        if (!dtm || !fa || rows < 1 || cols < 1) return make_err(MCF_ERR_ARG, "bad argument");
+        const int64_t n = (int64_t)rows * cols;
+        const double na_int = (double)INT32_MIN;
+        std::vector<int8_t> fd((size_t)n, 0);
+        std::vector<std::pair<double, int32_t>> order;
+        order.reserve((size_t)n);
+        auto at = [&](int i, int j) { return dtm[(int64_t)j * rows + i]; };
+        auto is_na = [](double v) {
+            uint64_t b;
+            std::memcpy(&b, &v, sizeof b);
+            return std::isnan(v) && (uint32_t)(b & 0xFFFFFFFFu) == 1954u;
+        };
+        for (int i = 0; i < rows; ++i) {
+            for (int j = 0; j < cols; ++j) {
+                const double v = at(i, j);
+                if (is_na(v)) {
+                    fa[(int64_t)j * rows + i] = na_int;
+                    continue;
+                }
+                fa[(int64_t)j * rows + i] = 1.0;
+                order.push_back({v, (int32_t)(i * cols + j)});
+                double minval = 9999.99;
+                int indx = 1, best = 0;
+                for (int jj = -1; jj <= 1; ++jj) {
+                    for (int ii = -1; ii <= 1; ++ii, ++indx) {
+                        const int y = i + ii, x = j + jj;
+                        if (y < 0 || y >= rows || x < 0 || x >= cols) continue; // the NA border
+                        const double v2 = at(y, x);
+                        if (!is_na(v2) && v2 < minval) {
+                            minval = v2;
+                            best = indx;
+                        }
+                    }
+                }
+                fd[(size_t)((int64_t)j * rows + i)] = (int8_t)best;
+            }
+        }
+        if (order.empty()) return Err();
+        std::sort(order.begin(), order.end(), std::greater<std::pair<double, int32_t>>());
+        for (size_t k = 0; k + 1 < order.size(); ++k) { // the lowest cell is not propagated (ref :5392)
+            const int idx = order[k].second;
+            const int y = idx / cols, x = idx % cols;
+            const int f = fd[(size_t)((int64_t)x * rows + y)];
+            if (f < 1 || f > 9) continue;
+            const int y2 = y + (f - 1) % 3 - 1, x2 = x + (f - 1) / 3 - 1;
+            if (x2 >= 0 && x2 < cols && y2 >= 0 && y2 < rows) {
+                double& t = fa[(int64_t)x2 * rows + y2];
+                if (t != na_int) t += fa[(int64_t)x * rows + y];
+            }
+        }
+        return Err();
+    };
+    return report(body(), err, errlen);
 }
 
 void mcf_release_workspace(void) {

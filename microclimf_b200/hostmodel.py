@@ -1,0 +1,657 @@
+"""Host-side mirror of the reference's R drivers for the grid solver: `runmicro()`, `runmicro_big()`,
+`subsetpointmodel()`, `checkinputs()` and the internal packing `.runmodel1Cpp` / `.runmodel3Cpp`.
+
+These are the callers of the hot path (SURVEY.md §8f NEXT-1).  In the reference they are R functions
+(R/Cppwrappers.R:376-543, R/internal.R:1020-1170, 1345-1460, 3290-3349, R/dataprep.R:31-102, 206-397) that
+unpack terra rasters into matrices, derive the static layers and call `.Call(_microclimf_runmicroNCpp)`.
+There is no R toolchain in this build's environment, so — per the tier rules — the host side is written in
+Python with the same function names, argument names, defaults and error messages, on top of the same
+operator mirror (`api.runmicro1Cpp` / `api.runmicro3Cpp`) the Rcpp stub of INTEGRATION.md binds.
+
+What runs where:
+  * GPU (this package's CUDA kernels): the solver itself, `.horizon` x 24 + sky view, `.windcoef` x 16;
+  * host C++ (`mcf_flowacc`): the sequential flow-accumulation sweep behind `.topidx`;
+  * host numpy: everything that is O(cells) bookkeeping in R (NA cleaning, layer selection, soil lookup,
+    foliage density, slope/aspect, 16 -> 8 blend).
+
+Third-party steps (terra slope/aspect, aggregate, resample; sf reprojection) are restated from their
+published algorithms in `spatial.py` — PARITY UNPINNED there (no R, terra or sf here to compare with).
+Everything from the `.Call` boundary down is pinned against the compiled reference on identical inputs
+(tests/test_bundled_*.py).
+"""
+from __future__ import annotations
+
+import math
+import os
+import warnings
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import api
+from .spatial import Raster, aggregate_mean, as_raster, latlong_from_raster, mask, resample_bilinear, terrain
+from .tables import SOILPARAMETERS
+
+VEG_NAMES = ("pai", "hgt", "x", "gsmax", "leafr", "clump", "leafd", "leaft")
+WEATHER_COLS = ("temp", "relhum", "pres", "swdown", "difrad", "lwdown", "windspeed", "winddir", "precip")
+
+
+# ---------------------------------------------------------------------------------------------
+# micropoint
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Micropoint:
+    """The reference's S3 class `micropoint` (R/Cppwrappers.R:143-147): output of runpointmodel().
+
+    weather : dict of the climdata columns (R/data.R `climdata`) + `obs_time` (numpy datetime64[s], UTC)
+    dfo     : dict of point-model series: umu, kp, muGp, dtrp, G, soilm, Tg, Tc (+ DDp, T0p)
+    subs    : 1-based indices of the retained hours within `tmeorig` (as in R)
+    """
+    weather: Dict[str, np.ndarray]
+    dfo: Dict[str, np.ndarray]
+    Tbz: Optional[np.ndarray]
+    lat: float
+    long: float
+    zref: float
+    subs: np.ndarray
+    tmeorig: np.ndarray
+    matemp: float
+
+
+def _obstime(tme: np.ndarray) -> Dict[str, np.ndarray]:
+    """obstime data.frame of the drivers (R/internal.R:1084-1086) from datetime64 values."""
+    t = np.asarray(tme).astype("datetime64[s]")
+    Y = t.astype("datetime64[Y]")
+    M = t.astype("datetime64[M]")
+    D = t.astype("datetime64[D]")
+    year = Y.astype(int) + 1970
+    month = (M.astype(int) % 12) + 1
+    day = (D - M.astype("datetime64[D]")).astype(int) + 1
+    hour = (t - D.astype("datetime64[s]")).astype(np.float64) / 3600.0
+    return dict(year=year.astype(np.int32), month=month.astype(np.int32), day=day.astype(np.int32), hour=hour)
+
+
+def subsetpointmodel(pointmodel: Micropoint, tstep: str = "month", what: str = "tmax", days=None, Tc=None) -> Micropoint:
+    """ref subsetpointmodel (R/dataprep.R:31-102): keep the hottest / coldest / median day of each month
+    (or year), or the listed days."""
+    dfo = pointmodel.dfo
+    tme = np.asarray(pointmodel.weather["obs_time"]).astype("datetime64[s]")
+    ot = _obstime(tme)
+
+    def extractday(Tcv, sel):
+        if what == "tmax":
+            s2 = int(np.argmax(Tcv[sel]))
+        elif what == "tmin":
+            s2 = int(np.argmin(Tcv[sel]))
+        elif what == "tmedian":
+            o = np.argsort(Tcv[sel], kind="stable")
+            n = len(o) // 2
+            s2 = int(o[n - 1])
+        else:
+            raise ValueError("what must be one of tmax, tmin or tmedian")
+        k = sel[s2]
+        return np.nonzero((ot["year"] == ot["year"][k]) & (ot["month"] == ot["month"][k]) & (ot["day"] == ot["day"][k]))[0]
+
+    if days is None:
+        Tcv = np.asarray(dfo["Tc"] if Tc is None else Tc)
+        yrs = list(dict.fromkeys(ot["year"].tolist()))
+        parts: List[np.ndarray] = []
+        if tstep == "year":
+            for y in yrs:
+                parts.append(extractday(Tcv, np.nonzero(ot["year"] == y)[0]))
+        elif tstep == "month":
+            for y in yrs:
+                sely = np.nonzero(ot["year"] == y)[0]
+                for m in dict.fromkeys(ot["month"][sely].tolist()):
+                    # the reference indexes `sel` within the year's subset but applies it to the whole series
+                    # (R/dataprep.R:60-84); identical for the first year, reproduced as written for later ones
+                    sel = np.nonzero(ot["month"][sely] == m)[0]
+                    parts.append(extractday(Tcv, sel))
+        else:
+            raise ValueError("tstep must be one of year or month")
+        ai = np.concatenate(parts)
+    else:
+        d = np.asarray(days, dtype=np.int64)
+        ai = (np.repeat((d - 1) * 24, 24) + np.tile(np.arange(1, 25), d.size)) - 1
+    weather = {k: np.asarray(v)[ai] for k, v in pointmodel.weather.items()}
+    dfo2 = {k: np.asarray(v)[ai] for k, v in dfo.items()}
+    Tbz = None if pointmodel.Tbz is None else np.asarray(pointmodel.Tbz)[ai]
+    return Micropoint(weather=weather, dfo=dfo2, Tbz=Tbz, lat=pointmodel.lat, long=pointmodel.long, zref=pointmodel.zref,
+                      subs=np.asarray(pointmodel.subs)[ai], tmeorig=pointmodel.tmeorig, matemp=pointmodel.matemp)
+
+
+# ---------------------------------------------------------------------------------------------
+# small R helpers
+# ---------------------------------------------------------------------------------------------
+def _getmode(v) -> float:
+    """ref .getmode (R/internal.R:106-110)."""
+    v = np.asarray(v, dtype=np.float64).ravel()
+    v = v[~np.isnan(v)]
+    uniq, first, counts = np.unique(v, return_index=True, return_counts=True)
+    order = np.argsort(first, kind="stable")
+    return float(uniq[order][np.argmax(counts[order])])
+
+
+def _r_round(x):
+    return np.round(x)  # R's round(x, 0) and numpy both round half to even
+
+
+def _satvap(tc):
+    """ref .satvap (R/internal.R:501-507)."""
+    tc = np.asarray(tc, dtype=np.float64)
+    es = 0.61078 * np.exp(17.27 * tc / (tc + 237.3))
+    ei = 0.61078 * np.exp(21.875 * tc / (tc + 265.5))
+    return np.where(tc < 0, ei, es)
+
+
+def _dewpoint(ea, tc):
+    """ref .dewpoint (R/internal.R:509-521)."""
+    ea, tc = np.asarray(ea, dtype=np.float64), np.asarray(tc, dtype=np.float64)
+    e0 = 611.2 / 1000
+    L = (2.501 * 10 ** 6) - (2340 * tc)
+    it = 1 / 273.15 - (461.5 / L) * np.log(ea / e0)
+    Tdew = 1 / it - 273.15
+    e0 = 610.78 / 1000
+    L = 2.834 * 10 ** 6
+    it = 1 / 273.15 - (461.5 / L) * np.log(ea / e0)
+    Tfrost = 1 / it - 273.15
+    return np.where(Tdew < 0, Tfrost, Tdew)
+
+
+def _jday(year, month, day):
+    """ref .jday (R/internal.R:440-449)."""
+    year, month, day = (np.asarray(a, dtype=np.float64) for a in (year, month, day))
+    dd = day + 0.5
+    madj = month + (month < 3) * 12
+    yadj = year + (month < 3) * -1
+    j = np.trunc(365.25 * (yadj + 4716)) + np.trunc(30.6001 * (madj + 1)) + dd - 1524.5
+    b = 2 - np.trunc(yadj / 100) + np.trunc(np.trunc(yadj / 100) / 4)
+    return np.trunc(j + (j > 2299160) * b)
+
+
+def _solalt(lt, lat, lon, jd):
+    """ref .soltime / .solalt (R/internal.R:451-467)."""
+    m = 6.24004077 + 0.01720197 * (jd - 2451545)
+    eot = -7.659 * np.sin(m) + 9.863 * np.sin(2 * m + 3.5932)
+    st = lt + (4 * lon + eot) / 60
+    tt = 0.261799 * (st - 12)
+    d = (np.pi * 23.5 / 180) * np.cos(2 * np.pi * ((jd - 159.5) / 365.25))
+    sh = np.sin(d) * np.sin(lat * np.pi / 180) + np.cos(d) * np.cos(lat * np.pi / 180) * np.cos(tt)
+    return (180 * np.arctan(sh / np.sqrt(1 - sh ** 2))) / np.pi
+
+
+def _clearskyrad(ot, lat, lon, tc, rh, pk):
+    """ref .clearskyrad (R/internal.R:469-484)."""
+    jd = _jday(ot["year"], ot["month"], ot["day"])
+    sa = _solalt(ot["hour"], lat, lon, jd) * np.pi / 180
+    with np.errstate(invalid="ignore", divide="ignore"):
+        m = 35 * np.sin(sa) * ((1224 * np.sin(sa) ** 2 + 1) ** (-0.5))
+        TrTpg = 1.021 - 0.084 * (m * 0.00949 * pk + 0.051) ** 0.5
+        xx = np.log(rh / 100) + ((17.27 * tc) / (237.3 + tc))
+        Td = (237.3 * xx) / (17.27 - xx)
+        u = np.exp(0.1133 - np.log(3.78) + 0.0393 * Td)
+        Tw = 1 - 0.077 * (u * m) ** 0.3
+        Ta = 0.935 * m
+        Ic = 1352.778 * np.sin(sa) * TrTpg * Tw * Ta
+    return np.where(np.isnan(Ic), 0.0, Ic)
+
+
+def _foliageden(z, hgt, pai, paia=None, shape=1.5, rate=None):
+    """ref .foliageden (R/internal.R:937-946): gamma(shape, rate) foliage profile over rescaled depth."""
+    from scipy.special import gammainc, gammaln
+
+    rate = shape / 7 if rate is None else rate
+    with np.errstate(divide="ignore", invalid="ignore"):
+        x = ((hgt - z) / hgt) * 10
+
+        def pgamma(q):
+            q = np.asarray(q, dtype=np.float64)
+            return np.where(np.isnan(q), np.nan, np.where(q > 0, gammainc(shape, np.where(q > 0, q, 0.0) * rate), 0.0))
+
+        def dgamma(q):
+            q = np.asarray(q, dtype=np.float64)
+            qq = np.where(q > 0, q, 1.0)
+            dens = np.exp(shape * math.log(rate) + (shape - 1) * np.log(qq) - rate * qq - gammaln(shape))
+            dens = np.where(np.isinf(q), 0.0, dens)
+            return np.where(np.isnan(q), np.nan, np.where(q > 0, dens, 0.0))
+
+        td = float(pgamma(10.0))
+        rfd = dgamma(x) / td
+        tdf = (pai / hgt) * rfd * 10
+        if paia is None:
+            paia = pgamma(x) * (pai / td)
+    return dict(leafden=tdf, pai_a=paia)
+
+
+def _intr(r: Raster, n: int, subs) -> np.ndarray:
+    """ref .intr (R/internal.R:186-194): pick, for each of n steps, the nearest of the raster's layers."""
+    nr = r.nlyr
+    s = _r_round(np.linspace(0.50001, nr + 0.5, n)).astype(int)
+    s = np.clip(s, 1, nr)
+    s = s[np.asarray(subs, dtype=int) - 1]
+    return r.values[:, :, s - 1]
+
+
+def _vegpdmx(vegp: Dict[str, Raster]) -> int:
+    return max(vegp[k].nlyr for k in VEG_NAMES)
+
+
+def _unpack(dtm, vegp, soilc):
+    """ref .unpack (R/internal.R:141-167): everything to rasters on the DTM's grid."""
+    dtm = as_raster(dtm)
+    vegp = {k: as_raster(vegp[k], dtm) for k in VEG_NAMES}
+    soilc = {k: as_raster(soilc[k], dtm) for k in ("soiltype", "groundr")}
+    for r in list(vegp.values()) + list(soilc.values()):
+        if (r.nrows, r.ncols) != (dtm.nrows, dtm.ncols):
+            raise ValueError("vegp / soilc layers must have the x and y dimensions of dtm")
+    return dtm, vegp, soilc
+
+
+def _cleanvars(vegp, soilc, dtm):
+    """ref .cleanvars (R/internal.R:1020-1063): propagate NAs between layers, zero incomplete vegetation."""
+    def cleanr(r, s, v=np.nan):
+        out = r.values.copy()
+        out[s, :] = v
+        return r.like(out)
+
+    s = (np.isnan(vegp["pai"].matrix()) | np.isnan(vegp["hgt"].matrix()) | np.isnan(soilc["soiltype"].matrix())
+         | np.isnan(soilc["groundr"].matrix()) | np.isnan(dtm.matrix()))
+    vegp = dict(vegp)
+    soilc = dict(soilc)
+    for k in VEG_NAMES:
+        vegp[k] = cleanr(vegp[k], s)
+    for k in ("soiltype", "groundr"):
+        soilc[k] = cleanr(soilc[k], s)
+    dtm = cleanr(dtm, s)
+    with np.errstate(invalid="ignore"):
+        z = ((vegp["pai"].matrix() == 0) | (vegp["hgt"].matrix() == 0) | np.isnan(vegp["gsmax"].matrix())
+             | np.isnan(vegp["leafr"].matrix()) | np.isnan(vegp["clump"].matrix()) | np.isnan(vegp["leafd"].matrix())
+             | np.isnan(vegp["leaft"].matrix()))
+    vegp["pai"] = cleanr(vegp["pai"], z, 0.0)
+    # `vegp$hgt <- .cleanr(vegp$hgt, 0)` passes 0 as the INDEX set (R/internal.R:1059): a no-op, kept as one
+    vegp["pai"] = mask(vegp["pai"], dtm)
+    vegp["hgt"] = mask(vegp["hgt"], dtm)
+    return vegp, dtm, soilc
+
+
+def _cleanvegp(vegp):
+    """ref .cleanvegp (R/internal.R:119-139)."""
+    vegp = dict(vegp)
+    hm = vegp["hgt"].matrix().copy()
+    pai = vegp["pai"].values.copy()
+    with np.errstate(invalid="ignore"):
+        for i in range(pai.shape[2]):
+            pm = pai[:, :, i]
+            hm[(pm == 0) & (hm > 0)] = 0
+            pm[(hm == 0) & (pm > 0)] = 0
+    vegp["pai"] = vegp["pai"].like(pai)
+    vegp["hgt"] = vegp["hgt"].like(hm)
+    return vegp
+
+
+def checkinputs(weather, vegp, soilc, dtm, windhgt: float = 2):
+    """ref checkinputs (R/dataprep.R:206-397): validates units / ranges (same messages) and applies the
+    same corrections (humidity cap, diffuse <= total shortwave, clear-sky excess, wind direction modulo)."""
+    dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
+    weather = {k: np.array(v) for k, v in weather.items()}
+    for nm in ("obs_time",) + WEATHER_COLS:
+        if nm not in weather:
+            raise ValueError(f"Cannot find {nm} in weather")
+    for nm in WEATHER_COLS:
+        if np.isnan(np.asarray(weather[nm], dtype=np.float64)).any():
+            raise ValueError("weather contains NAs")
+    if not dtm.crs:
+        raise ValueError("dtm must have a coordinate reference system specified")
+    lat, lon = latlong_from_raster(dtm)
+    ot = _obstime(weather["obs_time"])
+
+    def check_vals(x, mn, mx, char, unit):
+        x = np.asarray(x, dtype=np.float64)
+        if np.isnan(x).any():
+            raise ValueError(f"Missing values in weather${char}")
+        if (x < mn).any():
+            raise ValueError(f"{x.min()} outside range of typical {char} values. Units should be {unit}")
+        if (x > mx).any():
+            raise ValueError(f"{x.max()} outside range of typical {char} values. Units should be {unit}")
+
+    mnelev = float(np.nanmin(dtm.matrix()))
+    mxp = 108.5 * ((293 - 0.0065 * mnelev) / 293) ** 5.26
+    mnp = 87 * ((293 - 0.0065 * mnelev) / 293) ** 5.26
+    check_vals(weather["temp"], -50, 65, "temperature", "deg C")
+    rh = np.asarray(weather["relhum"], dtype=np.float64)
+    if rh.max() > 100:
+        warnings.warn("relative humidity values capped at 100")
+    weather["relhum"] = np.minimum(rh, 100.0)
+    check_vals(weather["relhum"], 0, 100, "relative humidity", "percentage (0-100)")
+    me = float(np.mean(weather["relhum"]))
+    if me < 5 or me > 100:
+        raise ValueError(f"Mean relative humidity of {me} implausible. Units should be percentage (0-100)")
+    check_vals(weather["pres"], mnp, mxp, "pressure", "kPa ~101.3")
+    check_vals(weather["swdown"], 0, 1350, "shortwave radiation", "W / m^2")
+    check_vals(weather["difrad"], 0, 1350, "diffuse radiation", "W / m^2")
+    check_vals(weather["lwdown"], 0, 600, "longwave radiation", "W / m^2")
+    check_vals(weather["windspeed"], 0, 100, "wind speed", "m/s")
+    ws = np.asarray(weather["windspeed"], dtype=np.float64)
+    if windhgt != 2:
+        ws = (ws * 4.87) / math.log(67.8 * windhgt - 5.42)
+    if ws.max() > 30:
+        warnings.warn(f"Maximum wind speed seems quite high. Check units are m/s and for {windhgt} m above ground")
+    sw = np.asarray(weather["swdown"], dtype=np.float64)
+    dif = np.asarray(weather["difrad"], dtype=np.float64).copy()
+    dirr = sw - dif
+    sel = dirr < 0
+    if sel.any():
+        dif[sel] = sw[sel]
+        warnings.warn("Diffuse radiation values higher than shortwave radiation, and so was set to shortwave radiation values")
+    csr = _clearskyrad(ot, lat, lon, np.asarray(weather["temp"], dtype=np.float64), weather["relhum"],
+                       np.asarray(weather["pres"], dtype=np.float64))
+    sel = dirr > csr  # `dirr` is not refreshed after the diffuse fix, as in the reference
+    if sel.any():
+        warnings.warn("Direct radiation values higher than expected clear-sky radiation values. Assigning excess as diffuse radiation")
+        extra = np.ceil((dirr[sel] - csr[sel]) * 100) / 100
+        dif[sel] = np.round(dif[sel] + extra, 3)
+    weather["difrad"] = dif
+    if (sw > csr + 50).any():
+        warnings.warn("Short wave radiation values significantly higher than expected clear-sky radiation values")
+    wd = np.asarray(weather["winddir"], dtype=np.float64)
+    if wd.min() < 0 or wd.max() > 360:
+        weather["winddir"] = np.mod(wd, 360)
+        warnings.warn("wind direction adjusted to range 0-360 using modulo operation")
+    for k in ("x", "gsmax", "leafr", "leafd"):
+        if vegp[k].nlyr > 1:
+            raise ValueError(f"time variant vegp${k} not supported")
+    if vegp["clump"].nlyr > 1 and vegp["clump"].nlyr != vegp["pai"].nlyr:
+        raise ValueError("clump must be a single numeric value or have the same dimensions as vegp$pai")
+    with np.errstate(invalid="ignore"):
+        if np.nanmax(vegp["leafr"].values + vegp["leaft"].values) > 1:
+            raise ValueError("leaf reflectance + transmittance cannot be greater than one")
+        st = soilc["soiltype"].values
+        if np.nanmax(st) > 11 or np.nanmin(st) < 1:
+            raise ValueError("Unrecognised soil type")
+
+    def vals(r):
+        v = r.values.ravel()
+        return v[~np.isnan(v)]
+
+    check_vals(vals(soilc["groundr"]), 0, 1, "soil reflectivity", "range 0 to 1")
+    check_vals(vals(vegp["leafr"]), 0, 1, "leaf reflectivity", "range 0 to 1")
+    check_vals(vals(vegp["clump"]), 0, 1, "vegetation clumping factor", "range 0 to 1")
+    xx = vals(vegp["leafd"])
+    check_vals(xx, 0, 5, "leaf diamater", "metres")
+    if xx.mean() > 1:
+        warnings.warn(f"Mean leaf diameter of {xx.mean()} seems large. Check units are in metres")
+    check_vals(vals(vegp["gsmax"]), 0, 2, "maximum stomatal conductance", "mol / m^2 /s")
+    xx = vals(vegp["pai"])
+    if xx.min() < 0:
+        raise ValueError("Minimum vegp$pai must be greater than or equal to zero")
+    if xx.max() > 15:
+        warnings.warn(f"Maximum vegp$pai of {xx.max()} seems high")
+    vegp = _cleanvegp(vegp)
+    return dict(weather=weather, vegp=vegp, soilc=soilc)
+
+
+def _soilinit(soilc: Dict[str, Raster]) -> Dict[str, np.ndarray]:
+    """ref .soilinit (R/internal.R:304-335): per-cell soil parameters from the soil-type lookup table (or
+    from a layer of that name supplied in soilc)."""
+    st = soilc["soiltype"].matrix()
+    u = np.unique(st[~np.isnan(st)])
+    out = {}
+    for varn, key in (("rho", "rho"), ("Vm", "Vm"), ("Vq", "Vq"), ("Mc", "Mc"), ("psi_e", "psi_e"), ("b", "soilb"),
+                      ("Smax", "Smax"), ("Smin", "Smin")):
+        if varn in soilc:
+            out[key] = as_raster(soilc[varn]).matrix().copy()
+            continue
+        m = np.full(st.shape, np.nan)
+        for ui in u:
+            row = SOILPARAMETERS["Number"].index(int(ui))
+            m[st == ui] = SOILPARAMETERS[varn][row]
+        out[key] = m
+    return out
+
+
+def _topidx(dtm: Raster) -> Raster:
+    """ref .topidx (R/internal.R:861-874): topographic wetness index a / tan(slope)."""
+    rx, ry = dtm.res
+    minslope = math.atan(0.02 / (0.5 * (rx + ry)))
+    B = terrain(dtm, "slope", unit="radians").matrix().copy()
+    with np.errstate(invalid="ignore"):
+        B[B < minslope] = minslope
+    B[np.isnan(B)] = np.nanmedian(B)
+    a = api.flowacc(dtm.matrix()) + 1
+    a = a * rx * ry
+    a[a < 1] = 1
+    return mask(dtm.like(a / np.tan(B)), dtm)
+
+
+def _windsheltera(dtm: Raster, whgt: float, s) -> np.ndarray:
+    """ref .windsheltera (R/internal.R:970-991): .windcoef in 16 directions (GPU), block-mean + bilinear
+    smoothing (terra aggregate / resample, restated), blended to 8 directions."""
+    if s is None or (isinstance(s, float) and math.isnan(s)):
+        s = min(dtm.nrows, dtm.ncols)
+        s = 10 if s > 10 else s
+    a = api.windcoef(dtm.matrix(), dtm.res[0], whgt)  # [rows, cols, 16]
+    r = dtm.like(a)
+    a = resample_bilinear(aggregate_mean(r, int(s)), dtm).values
+    a2 = np.empty(a.shape[:2] + (8,))
+    for i in range(8):
+        mid, nxt, prv = 2 * i, 2 * i + 1, (15 if i == 0 else 2 * i - 1)
+        a2[:, :, i] = 0.5 * a[:, :, mid] + 0.25 * a[:, :, nxt] + 0.25 * a[:, :, prv]
+    return a2
+
+
+# ---------------------------------------------------------------------------------------------
+# .runmodel1Cpp / .runmodel3Cpp: build the argument list of runmicro1Cpp / runmicro3Cpp
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class ModelCall:
+    """The argument list handed to the operator (what `.Call(_microclimf_runmicroNCpp, ...)` receives)."""
+    mode: int
+    args: Dict[str, object] = field(default_factory=dict)
+
+    def run(self) -> Dict[str, np.ndarray]:
+        a = self.args
+        if self.mode == 1:
+            return api.runmicro1Cpp(a["obstime"], a["climdata"], a["pointm"], a["vegp"], a["soilc"], a["reqhgt"], a["zref"],
+                                    a["lat"], a["lon"], a["Sminp"], a["Smaxp"], a["tfact"], a["complete"], a["mat"], a["out"])
+        return api.runmicro3Cpp(a["dfsel"], a["obstime"], a["climdata"], a["pointm"], a["vegp"], a["soilc"], a["reqhgt"],
+                                a["zref"], a["lat"], a["lon"], a["Sminp"], a["Smaxp"], a["tfact"], a["complete"], a["mat"],
+                                a["out"])
+
+
+def prepare_model(micropoint: Micropoint, vegp, soilc, dtm, reqhgt: float = 0.05, runchecks: bool = True, pai_a=None,
+                  tfact: float = 1.5, out: Sequence[bool] = (True,) * 10, slr=None, apr=None, hor=None, twi=None,
+                  wsa=None, svf=None) -> ModelCall:
+    """ref .runmodel1Cpp (R/internal.R:1065-1170) and .runmodel3Cpp (R/internal.R:1345-1460): everything up
+    to, but not including, the `.Call`."""
+    dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
+    layered = _vegpdmx(vegp) > 1  # dispatch of .runmicronosnow (R/internal.R:3331-3346)
+    vegp, dtm, soilc = _cleanvars(vegp, soilc, dtm)
+    weather = micropoint.weather
+    if runchecks:
+        rc = checkinputs(weather, vegp, soilc, dtm)
+        weather, vegp, soilc = rc["weather"], rc["vegp"], rc["soilc"]
+    obstime = _obstime(weather["obs_time"])
+    temp = np.asarray(weather["temp"], dtype=np.float64)
+    es = _satvap(temp)
+    ea = es * np.asarray(weather["relhum"], dtype=np.float64) / 100
+    climdata = dict(temp=temp, es=es, ea=ea, tdew=_dewpoint(ea, temp))
+    for k in ("pres", "swdown", "difrad", "lwdown", "windspeed", "winddir"):
+        climdata[k] = np.asarray(weather[k], dtype=np.float64)
+    pointm = {k: np.asarray(v, dtype=np.float64) for k, v in micropoint.dfo.items()}
+    nT = temp.size
+    pointm["Tbp"] = np.asarray(micropoint.Tbz, dtype=np.float64) if reqhgt < 0 else np.zeros(nT)
+    # ---- vegetation: .sortvegp(method = "C") (R/internal.R:249-272)
+    n = len(micropoint.tmeorig)
+    subs = np.asarray(micropoint.subs, dtype=int)
+    dmx = _vegpdmx(vegp)
+    s_all = np.clip(_r_round(np.linspace(0.50001, dmx + 0.5, n)).astype(int), 1, dmx)
+    subs2 = np.array(list(dict.fromkeys(s_all[subs - 1].tolist())), dtype=int)
+    vg = {k: _intr(vegp[k], dmx, subs2) for k in VEG_NAMES}
+    s_raw = _r_round(np.linspace(0.50001, dmx + 0.5, n)).astype(int)[subs - 1]
+    if s_raw.size % 24 != 0:
+        raise ValueError("weather needs to include data for entire days (24 hours)")
+    sdd = np.array([_getmode(row) for row in s_raw.reshape(-1, 24)])
+    lsubs = np.repeat(sdd, 24).astype(int)
+    with np.errstate(invalid="ignore"):
+        vg["hgt"] = np.where(vg["pai"] == 0, 0.0, vg["hgt"])
+        vg["pai"] = np.where(vg["hgt"] == 0, 0.0, vg["pai"])
+    # ---- foliage density
+    paia_in = None
+    if pai_a is not None:
+        paia_in = _intr(as_raster(pai_a, dtm), n, subs)
+    fd = _foliageden(reqhgt, vg["hgt"], vg["pai"], paia_in)
+    vg["paia"], vg["leafden"] = fd["pai_a"], fd["leafden"]
+    if not layered:
+        vg = {k: v[:, :, 0] for k, v in vg.items()}
+    # ---- layer spans (R/internal.R:1388-1399)
+    dfsel = None
+    if layered:
+        lyrs = list(dict.fromkeys(lsubs.tolist()))
+        st, ed = [], []
+        for ly in lyrs:
+            s = np.nonzero(lsubs == ly)[0] + 1  # 1-based, as which()
+            st.append(int(math.floor(s[0] / 24) * 24))
+            ed.append(int(math.floor(s[-1] / 24) * 24 - 1))
+        dfsel = dict(lyr=np.arange(1, len(lyrs) + 1, dtype=np.int32), st=np.array(st, dtype=np.int32),
+                     ed=np.array(ed, dtype=np.int32))
+    # ---- soil
+    soilp = _soilinit(soilc)
+    sc: Dict[str, np.ndarray] = dict(gref=soilc["groundr"].matrix().copy(), Smin=soilp["Smin"], Smax=soilp["Smax"],
+                                     soilb=soilp["soilb"], Psie=soilp["psi_e"], Vq=soilp["Vq"], Vm=soilp["Vm"],
+                                     Mc=soilp["Mc"], rho=soilp["rho"])
+    # ---- slope, aspect, wetness index
+    slope = terrain(dtm, "slope") if slr is None else as_raster(slr, dtm)
+    aspect = terrain(dtm, "aspect") if apr is None else as_raster(apr, dtm)
+    twi_r = _topidx(dtm) if twi is None else as_raster(twi, dtm)
+
+    def fill(r: Raster, v: float) -> np.ndarray:
+        m = r.matrix().copy()
+        m[np.isnan(m)] = v
+        return mask(r.like(m), dtm).matrix()
+
+    sc["slope"], sc["aspect"], sc["twi"] = fill(slope, 0.0), fill(aspect, 0.0), fill(twi_r, 1.0)
+    # ---- horizon, sky view, wind shelter
+    lat, lon = latlong_from_raster(dtm)
+    if hor is None:
+        hor_a, svf_gpu = api.horizon(dtm.matrix(), dtm.res[0], want_svf=True)
+    else:
+        hor_a, svf_gpu = np.asarray(hor, dtype=np.float64), None
+    sc["hor"] = hor_a
+    if svf is None:
+        if svf_gpu is None:
+            msl = np.tan(np.mean(np.arctan(hor_a), axis=2))
+            svf_gpu = 0.5 * np.cos(2 * msl) + 0.5
+        sc["svfa"] = svf_gpu
+    else:
+        sc["svfa"] = as_raster(svf, dtm).matrix()
+    s = 10 if dtm.res[0] <= 100 else 1
+    sc["wsa"] = _windsheltera(dtm, micropoint.zref, s) if wsa is None else np.asarray(wsa, dtype=np.float64)
+    Sminp, Smaxp = _getmode(sc["Smin"]), _getmode(sc["Smax"])
+    complete = len(subs) == len(micropoint.tmeorig)
+    out = [bool(o) for o in out]
+    if reqhgt == 0:
+        out = [o and m for o, m in zip(out, (1, 0, 0, 1, 0, 1, 1, 1, 1, 1))]
+    if reqhgt < 0:
+        out = [o and m for o, m in zip(out, (1, 0, 0, 1, 0, 0, 0, 0, 0, 0))]
+    args = dict(obstime=obstime, climdata=climdata, pointm=pointm, vegp=vg, soilc=sc, reqhgt=float(reqhgt),
+                zref=float(micropoint.zref), lat=lat, lon=lon, Sminp=Sminp, Smaxp=Smaxp, tfact=float(tfact),
+                complete=complete, mat=float(micropoint.matemp), out=[bool(o) for o in out])
+    if layered:
+        args["dfsel"] = dfsel
+    return ModelCall(mode=3 if layered else 1, args=args)
+
+
+def runmicro(micropoint, reqhgt, vegp, soilc, dtm, dtmc=None, altcorrect=0, snow=False, snowmod=None, runchecks=True,
+             pai_a=None, tfact=1.5, out=(True,) * 10, slr=None, apr=None, hor=None, twi=None, wsa=None, svf=None,
+             method="Cpp"):
+    """ref runmicro (R/Cppwrappers.R:376-396): grid microclimate model.  Returns the reference's named list
+    (dict of [rows, cols, hours] arrays) plus `tme`.  As in the reference, `svf` and `method` are accepted
+    but not forwarded (R/internal.R:3336).  Gridded-climate input (a list of micropoints, `.runmodel2Cpp` /
+    `.runmodel4Cpp`) and the snow branch are the next rows of SURVEY.md §8f and raise NotImplementedError."""
+    if snow:
+        raise NotImplementedError("snow = TRUE (.runmicrosnow1/2) is not part of this build yet (SURVEY.md NEXT-3)")
+    if not isinstance(micropoint, Micropoint):
+        if dtmc is None:
+            raise ValueError("Require dtmc. Please provide\n")
+        raise NotImplementedError("array climate input (.runmodel2Cpp/.runmodel4Cpp packing) is not built yet; "
+                                  "call api.runmicro2Cpp / api.runmicro4Cpp with packed arrays")
+    call = prepare_model(micropoint, vegp, soilc, dtm, reqhgt, runchecks, pai_a, tfact, out, slr, apr, hor, twi, wsa)
+    mout = call.run()
+    mout["tme"] = np.asarray(micropoint.tmeorig)
+    return mout
+
+
+# ---------------------------------------------------------------------------------------------
+# runmicro_big
+# ---------------------------------------------------------------------------------------------
+def _checkbiginputs(dtm, vegp, soilc):
+    """ref .checkbiginputs (R/internal.R:1644-1662)."""
+    ok = ~np.isnan(dtm.matrix())
+    bad = [k for k in VEG_NAMES if (ok & np.isnan(vegp[k].matrix())).any()]
+    if bad:
+        raise ValueError("The following layers of vegp contain NA that are not NA in dtm: " + " ".join(bad) + "\n")
+    bad = [k for k in ("soiltype", "groundr") if (ok & np.isnan(soilc[k].matrix())).any()]
+    if bad:
+        raise ValueError("The following layers of soilc contain NA that are not NA in dtm: " + " ".join(bad) + "\n")
+
+
+def runmicro_big(micropoint, reqhgt, pathout, vegp, soilc, dtm, dtmc=None, altcorrect=0, tilesize=None, toverlap=0,
+                 writeasnc=False, runchecks=True, pai_a=None, tfact=1.5, out=(True,) * 10):
+    """ref runmicro_big (R/Cppwrappers.R:444-543): whole-area terrain layers once, then the model tile by
+    tile, one file per tile in `<pathout>microut/` (`area_RR_CC.npz`, the analogue of the reference's RDS;
+    `writeasnc = TRUE` writes the x100 integer packing of writetonc through `packing.pack_outputs`).
+    Returns the list of files written."""
+    from . import packing
+
+    dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
+    _checkbiginputs(dtm, vegp, soilc)
+    if tilesize is None:
+        nt = len(micropoint.weather["temp"])
+        osize = math.sqrt(20000000 / nt) - 2 * toverlap
+        sizeo = np.array([10, 20, 50, 100, 200, 500, 1000, 2000])
+        tilesize = int(sizeo[np.argmin(np.abs(osize - sizeo))])
+    rws, cls = -(-dtm.nrows // tilesize), -(-dtm.ncols // tilesize)
+    path2 = os.path.join(pathout, "microut")
+    os.makedirs(path2, exist_ok=True)
+
+    def fill0(r):
+        m = r.matrix().copy()
+        m[np.isnan(m)] = 0.0
+        return mask(r.like(m), dtm)
+
+    slr, apr = fill0(terrain(dtm, "slope")), fill0(terrain(dtm, "aspect"))
+    twi = _topidx(dtm)
+    hor, svfa = api.horizon(dtm.matrix(), dtm.res[0], want_svf=True)
+    dsm = dtm.like(dtm.matrix() + vegp["hgt"].matrix())
+    wsa = _windsheltera(dsm, 8, None)
+    rx, ry = dtm.res
+    written = []
+    for rw in range(1, rws + 1):
+        for cl in range(1, cls + 1):
+            # .croprast (R/internal.R:1664-1677): the overlap is subtracted in map units, as written
+            xmn = max(dtm.xmin + (cl - 1) * tilesize * rx - toverlap, dtm.xmin)
+            xmx = min(dtm.xmin + cl * tilesize * rx + toverlap, dtm.xmax)
+            ymn = max(dtm.ymax - rw * tilesize * ry - toverlap, dtm.ymin)
+            ymx = min(dtm.ymax - (rw - 1) * tilesize * ry + toverlap, dtm.ymax)
+            c0, c1 = int(round((xmn - dtm.xmin) / rx)), int(round((xmx - dtm.xmin) / rx))
+            r0, r1 = int(round((dtm.ymax - ymx) / ry)), int(round((dtm.ymax - ymn) / ry))
+            dtmi = dtm.crop(r0, r1, c0, c1)
+            if np.count_nonzero(~np.isnan(dtmi.matrix())) <= 1:
+                continue
+            vegpi = {k: v.crop(r0, r1, c0, c1) for k, v in vegp.items()}
+            soilci = {k: v.crop(r0, r1, c0, c1) for k, v in soilc.items()}
+            mout = runmicro(micropoint, reqhgt, vegpi, soilci, dtmi, dtmc, altcorrect, False, None, runchecks, pai_a,
+                            tfact, out, slr.crop(r0, r1, c0, c1), apr.crop(r0, r1, c0, c1), hor[r0:r1, c0:c1, :],
+                            twi.crop(r0, r1, c0, c1), wsa[r0:r1, c0:c1, :], svf=svfa[r0:r1, c0:c1])
+            fo = os.path.join(path2, f"area_{rw:02d}_{cl:02d}")
+            if writeasnc and all(out):
+                packed = packing.pack_outputs(mout, reqhgt)
+                np.savez(fo + "_packed.npz", extent=[dtmi.xmin, dtmi.xmax, dtmi.ymin, dtmi.ymax], **packed)
+                written.append(fo + "_packed.npz")
+            else:
+                if writeasnc:
+                    warnings.warn("Can only write as nc with all variables in out set to TRUE. Writing as RDS\n")
+                np.savez(fo + ".npz", extent=[dtmi.xmin, dtmi.xmax, dtmi.ymin, dtmi.ymax], dtm=dtmi.matrix(), **mout)
+                written.append(fo + ".npz")
+    return written

@@ -272,3 +272,120 @@ extern "C" void ref_man(const double* x, int32_t m, int32_t n, double* out) {
 }
 
 extern "C" double ref_satvap(double tc) { return satvapCpp(tc); }
+
+// ---------------------------------------------------------------------------------------------
+// Point model and terrain helpers of the reference (upstream of the grid solver), exposed so that
+// tools/make_bundled_fixtures.py can build a `micropoint` for the bundled example data the way
+// runpointmodel does (R/Cppwrappers.R:59-148), and so that mcf_flowacc has a compiled-reference checker.
+// ---------------------------------------------------------------------------------------------
+DataFrame weatherhgtCpp(DataFrame obstime, DataFrame climdata, double zin, double uzin, double zout, double lat,
+                        double lon);
+std::vector<double> soilmCpp(DataFrame climdata, double rmu, double mult, double pwr, double Smax, double Smin,
+                             double Ksat, double a);
+Rcpp::List BigLeafCpp(DataFrame obstime, DataFrame climdata, std::vector<double> vegp, std::vector<double> groundp,
+                      std::vector<double> soilm, double lat, double lon, double dTmx, double zref, int maxiter,
+                      double bwgt, double tol, double gmn, bool yearG);
+DataFrame pointmprocess(DataFrame pointvars, double zref, double h, double pai, double rho, double Vm, double Vq,
+                        double Mc);
+NumericMatrix flowaccCpp(NumericMatrix dm);
+
+namespace {
+DataFrame obstime_df(int32_t n, const int32_t* year, const int32_t* month, const int32_t* day, const double* hour) {
+    DataFrame o;
+    o["year"] = ivec(year, n);
+    o["month"] = ivec(month, n);
+    o["day"] = ivec(day, n);
+    o["hour"] = vec(hour, n);
+    return o;
+}
+// weather: 9 columns of length n in the order temp, relhum, pres, swdown, difrad, lwdown, windspeed, winddir, precip
+const char* const kWeatherCols[9] = {"temp", "relhum", "pres", "swdown", "difrad", "lwdown", "windspeed", "winddir", "precip"};
+DataFrame weather_df(int32_t n, const double* w) {
+    DataFrame c;
+    for (int k = 0; k < 9; ++k) c[kWeatherCols[k]] = vec(w + (size_t)k * n, n);
+    return c;
+}
+} // namespace
+
+// weatherhgtCpp: writes the adjusted temp / relhum / windspeed columns (3 x n)
+extern "C" int ref_weatherhgt(int32_t n, const int32_t* year, const int32_t* month, const int32_t* day,
+                              const double* hour, const double* weather, double zin, double uzin, double zout,
+                              double lat, double lon, double* out3) {
+    try {
+        DataFrame r = weatherhgtCpp(obstime_df(n, year, month, day, hour), weather_df(n, weather), zin, uzin, zout, lat, lon);
+        const char* cols[3] = {"temp", "relhum", "windspeed"};
+        for (int k = 0; k < 3; ++k) {
+            std::vector<double> v = r[cols[k]];
+            std::memcpy(out3 + (size_t)k * n, v.data(), (size_t)n * sizeof(double));
+        }
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
+// soilmCpp: daily soil moisture, n / 24 values
+extern "C" int ref_soilm(int32_t n, const double* weather, double rmu, double mult, double pwr, double Smax, double Smin,
+                         double Ksat, double a, double* out, int32_t* nout) {
+    try {
+        std::vector<double> v = soilmCpp(weather_df(n, weather), rmu, mult, pwr, Smax, Smin, Ksat, a);
+        *nout = (int32_t)v.size();
+        std::memcpy(out, v.data(), v.size() * sizeof(double));
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
+// BigLeafCpp: out6 = Tc, Tg, G, uf, RabsG, psih (6 x n)
+extern "C" int ref_bigleaf(int32_t n, const int32_t* year, const int32_t* month, const int32_t* day, const double* hour,
+                           const double* weather, const double* vegp, int32_t nvegp, const double* groundp,
+                           int32_t ngroundp, const double* soilm, double lat, double lon, double dTmx, double zref,
+                           int32_t maxiter, double bwgt, double tol, double gmn, int32_t yearG, double* out6) {
+    try {
+        Rcpp::List r = BigLeafCpp(obstime_df(n, year, month, day, hour), weather_df(n, weather),
+                                  std::vector<double>(vegp, vegp + nvegp), std::vector<double>(groundp, groundp + ngroundp),
+                                  std::vector<double>(soilm, soilm + n), lat, lon, dTmx, zref, maxiter, bwgt, tol, gmn,
+                                  yearG != 0);
+        const char* cols[6] = {"Tc", "Tg", "G", "uf", "RabsG", "psih"};
+        for (int k = 0; k < 6; ++k) {
+            std::vector<double> v = Rcpp::as<std::vector<double>>(r[cols[k]]);
+            std::memcpy(out6 + (size_t)k * n, v.data(), (size_t)n * sizeof(double));
+        }
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
+// pointmprocess: in7 = windspeed, tc, rh, pk, uf, soilm, RabsG (7 x n); out6 = umu, kp, muGp, DDp, T0p, dtrp (6 x n)
+extern "C" int ref_pointmprocess(int32_t n, const double* in7, double zref, double h, double pai, double rho, double Vm,
+                                 double Vq, double Mc, double* out6) {
+    try {
+        const char* icols[7] = {"windspeed", "tc", "rh", "pk", "uf", "soilm", "RabsG"};
+        DataFrame p;
+        for (int k = 0; k < 7; ++k) p[icols[k]] = vec(in7 + (size_t)k * n, n);
+        DataFrame r = pointmprocess(p, zref, h, pai, rho, Vm, Vq, Mc);
+        const char* cols[6] = {"umu", "kp", "muGp", "DDp", "T0p", "dtrp"};
+        for (int k = 0; k < 6; ++k) {
+            std::vector<double> v = r[cols[k]];
+            std::memcpy(out6 + (size_t)k * n, v.data(), (size_t)n * sizeof(double));
+        }
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
+// flowaccCpp on a column-major [rows, cols] matrix
+extern "C" int ref_flowacc(const double* dtm, int32_t rows, int32_t cols, double* fa) {
+    try {
+        NumericMatrix m(rows, cols);
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) m[i] = dtm[i];
+        NumericMatrix r = flowaccCpp(m);
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) fa[i] = r[i];
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}

@@ -1,0 +1,218 @@
+"""BASELINE configs[0] / [1]: `runmicro` on the reference's bundled example data (dtmcaerth + climdata + vegp +
+soilc, 50 x 50 cells, 12 vegetation layers => the runmicro3Cpp path) through the host layer
+(microclimf_b200/hostmodel.py, the mirror of R/Cppwrappers.R:376 and R/internal.R:1345-1460).
+
+The inputs come from tests/golden/bundled/bundled_example.npz (made by tools/make_bundled_fixtures.py from
+/root/reference/data/*.rda and the compiled reference's point model).  Parity is checked at the `.Call`
+boundary: the very argument list `prepare_model` builds is run through the CUDA path and through the
+UNMODIFIED compiled reference (oracle/_ref), tolerance 1e-6 abs / 1e-6 rel (tests/parity.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import parity
+from microclimf_b200 import api, hostmodel
+from microclimf_b200.hostmodel import Micropoint
+from microclimf_b200.spatial import Raster
+from oracle import pyoracle, terrain_oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX = os.path.join(HERE, "golden", "bundled", "bundled_example.npz")
+
+
+def load_example(reqhgt=0.05):
+    z = np.load(FIX)
+    xmin, xmax, ymin, ymax = z["extent"]
+    crs = str(z["crs"])
+    mk = lambda v: Raster(v, xmin, xmax, ymin, ymax, crs)  # noqa: E731
+    dtm = mk(z["dtm"])
+    vegp = {k: mk(z["vegp_" + k]) for k in hostmodel.VEG_NAMES}
+    soilc = {k: mk(z["soilc_" + k]) for k in ("soiltype", "groundr")}
+    tme = z["obs_time"].astype("datetime64[s]")
+    weather = {k: z["mpw_" + k] for k in hostmodel.WEATHER_COLS}
+    weather["obs_time"] = tme
+    dfo = {k[4:]: z[k] for k in z.files if k.startswith("dfo_")}
+    mp = Micropoint(weather=weather, dfo=dfo, Tbz=z["mp_Tbz_m005"] if reqhgt < 0 else None, lat=float(z["mp_lat"]),
+                    long=float(z["mp_long"]), zref=float(z["mp_zref"]), subs=np.arange(1, tme.size + 1), tmeorig=tme,
+                    matemp=float(z["mp_matemp"]))
+    clim = {k: z["clim_" + k] for k in hostmodel.WEATHER_COLS}
+    clim["obs_time"] = tme
+    return dtm, vegp, soilc, mp, clim
+
+
+def cpu_terrain(dtm, zref):
+    """hor / wsa through the numpy restatement, so host-logic tests run without a GPU."""
+    d = dtm.matrix()
+    hor = terrain_oracle.horizon24(d, dtm.res[0])
+    w16 = terrain_oracle.windcoef16(d, zref, dtm.res[0])
+    from microclimf_b200.spatial import aggregate_mean, resample_bilinear
+    sm = resample_bilinear(aggregate_mean(dtm.like(w16), 10), dtm).values
+    return hor, terrain_oracle.blend16to8(sm)
+
+
+def to_problem(call):
+    a = call.args
+    return api._problem(call.mode, a.get("dfsel"), a["obstime"], a["climdata"], a["pointm"], a["vegp"], a["soilc"],
+                        a["reqhgt"], a["zref"], a["lat"], a["lon"], None, None, a["Sminp"], a["Smaxp"], a["tfact"],
+                        a["complete"], a["mat"])
+
+
+# --------------------------------------------------------------------------------------------- CPU
+def test_fixture_shapes_and_geolocation():
+    dtm, vegp, soilc, mp, clim = load_example()
+    assert dtm.dim == (50, 50, 1) and vegp["pai"].nlyr == 12 and vegp["clump"].nlyr == 12
+    assert clim["temp"].size == 8760
+    lat, lon = hostmodel.latlong_from_raster(dtm)
+    # Caerthillian Cove, Lizard peninsula (R/data.R: dtmcaerth): 49.97 N, 5.21 W
+    assert abs(lat - 49.9674) < 1e-3 and abs(lon + 5.2147) < 1e-3
+
+
+def test_subsetpointmodel_month_tmax():
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, tstep="month", what="tmax")
+    assert sub.weather["temp"].size == 288 and sub.subs.size == 288
+    # each retained block is one whole calendar day and holds that month's maximum of Tc
+    ot = hostmodel._obstime(mp.weather["obs_time"])
+    for m in range(12):
+        blk = sub.subs[m * 24:(m + 1) * 24] - 1
+        assert np.all(np.diff(blk) == 1) and ot["hour"][blk[0]] == 0
+        msel = ot["month"] == m + 1
+        assert mp.dfo["Tc"][blk].max() == mp.dfo["Tc"][msel].max()
+    days = hostmodel.subsetpointmodel(mp, days=[1, 200])
+    assert np.array_equal(days.subs, np.r_[np.arange(1, 25), np.arange(199 * 24 + 1, 200 * 24 + 1)])
+
+
+def test_prepare_model_layers_and_masks():
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, tstep="month", what="tmax")
+    hor, wsa = cpu_terrain(dtm, mp.zref)
+    twi = dtm.like(np.where(np.isnan(dtm.matrix()), np.nan, 5.0))  # flow accumulation needs the built library
+    call = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=0.05, hor=hor, wsa=wsa, twi=twi)
+    a = call.args
+    assert call.mode == 3
+    # 12 monthly layers, each spanning one 24-hour block (R/internal.R:1388-1399)
+    assert a["vegp"]["pai"].shape == (50, 50, 12)
+    assert np.array_equal(a["dfsel"]["st"], np.arange(12) * 24) and np.array_equal(a["dfsel"]["ed"], np.arange(12) * 24 + 23)
+    assert a["complete"] is False and a["out"] == [True] * 10
+    # NA cells of the DTM are NA in hgt (the solver's skip rule) and zero-height cells have zero pai
+    na = np.isnan(dtm.matrix())
+    assert na.sum() == 128 and np.array_equal(np.isnan(a["vegp"]["hgt"][:, :, 0]), na)
+    assert np.all(a["vegp"]["pai"][a["vegp"]["hgt"] == 0] == 0)
+    assert np.nanmax(a["vegp"]["paia"] - a["vegp"]["pai"]) <= 1e-12
+    # soil parameters come from the lookup table
+    st = soilc["soiltype"].matrix()
+    from microclimf_b200.tables import SOILPARAMETERS
+    k = int(st[10, 10])
+    assert a["soilc"]["Smax"][10, 10] == SOILPARAMETERS["Smax"][k - 1] and a["soilc"]["soilb"][10, 10] == SOILPARAMETERS["b"][k - 1]
+    # reqhgt = 0 / < 0 mask the outputs as the reference does (R/internal.R:1159-1166)
+    call0 = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=0.0, hor=hor, wsa=wsa, twi=twi)
+    assert call0.args["out"] == [True, False, False, True, False, True, True, True, True, True]
+    p = to_problem(call)
+    p.validate()
+
+
+def test_checkinputs_messages():
+    dtm, vegp, soilc, mp, clim = load_example()
+    bad = dict(clim)
+    bad["temp"] = clim["temp"] + 100
+    with pytest.raises(ValueError, match="outside range of typical temperature values"):
+        hostmodel.checkinputs(bad, vegp, soilc, dtm)
+    bad = dict(clim)
+    bad["pres"] = clim["pres"] * 10
+    with pytest.raises(ValueError, match="pressure"):
+        hostmodel.checkinputs(bad, vegp, soilc, dtm)
+    bad = {k: v for k, v in clim.items() if k != "lwdown"}
+    with pytest.raises(ValueError, match="Cannot find lwdown in weather"):
+        hostmodel.checkinputs(bad, vegp, soilc, dtm)
+    with pytest.warns(UserWarning):
+        ok = hostmodel.checkinputs(clim, vegp, soilc, dtm)
+    assert np.all(ok["weather"]["difrad"] <= clim["swdown"] + 1e-9 + (ok["weather"]["difrad"] - clim["difrad"]))
+
+
+@pytest.mark.skipif(not pyoracle.have_ref(), reason="compiled reference absent")
+def test_reference_on_bundled_example_ranges():
+    """The compiled reference on the prepared bundled inputs gives physically sensible fields (the bounds of
+    the reference's own wrapper test, tests/testthat/test-microclimatemodel_wrapper.R:82-90, loosened to a
+    heterogeneous landscape)."""
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, days=[172])  # midsummer
+    hor, wsa = cpu_terrain(dtm, mp.zref)
+    twi = dtm.like(np.where(np.isnan(dtm.matrix()), np.nan, 5.0))
+    call = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=0.05, hor=hor, wsa=wsa, twi=twi)
+    ref = pyoracle.runmicro(to_problem(call), kind="ref")
+    ok = ~np.isnan(dtm.matrix())
+    tair = sub.weather["temp"]
+    Tz = ref["Tz"][ok]
+    assert np.isfinite(Tz).all() and np.abs(Tz - tair[None, :]).max() < 25
+    rh = ref["relhum"][ok]
+    assert rh.min() > 5 and rh.max() <= 100
+    assert (ref["windspeed"][ok] <= sub.weather["windspeed"][None, :] + 1e-9).all()
+
+
+# --------------------------------------------------------------------------------------------- GPU
+def _have_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def _parity(call):
+    got = call.run()
+    want = pyoracle.runmicro(to_problem(call), out_mask=call.args["out"], kind="ref" if pyoracle.have_ref() else "oracle")
+    ok, rows = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rows)
+    return got
+
+
+@pytest.mark.gpu
+def test_flowacc_and_terrain_on_bundled_dtm():
+    dtm, vegp, soilc, mp, clim = load_example()
+    hor, svf = api.horizon(dtm.matrix(), dtm.res[0])
+    assert np.array_equal(hor, terrain_oracle.horizon24(dtm.matrix(), dtm.res[0]))
+    np.testing.assert_allclose(svf, terrain_oracle.skyview(hor), rtol=0, atol=1e-14)
+    twi = hostmodel._topidx(dtm).matrix()
+    assert np.array_equal(np.isnan(twi), np.isnan(dtm.matrix())) and np.nanmin(twi) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reqhgt", [0.05, 0.0, 2.0])
+def test_config0_month_tmax_days(reqhgt):
+    """configs[0]: the roxygen example of runmicro (R/Cppwrappers.R:353-362): 12 hottest days, 288 h."""
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, tstep="month", what="tmax")
+    call = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=reqhgt)
+    got = _parity(call)
+    assert got["Tz"].shape == (50, 50, 288)
+    mout = hostmodel.runmicro(sub, reqhgt, vegp, soilc, dtm)
+    assert "tme" in mout and np.array_equal(np.isnan(mout["Tz"][:, :, 0]), np.isnan(dtm.matrix()))
+    for k, v in got.items():
+        assert np.array_equal(mout[k], v, equal_nan=True)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reqhgt", [-0.05, 0.05])
+def test_config1_full_year(reqhgt):
+    """configs[1]: full year hourly (8760 h, complete = TRUE), below ground and within the canopy (above-canopy heights: config0 test)."""
+    dtm, vegp, soilc, mp, clim = load_example(reqhgt)
+    call = hostmodel.prepare_model(mp, vegp, soilc, dtm, reqhgt=reqhgt)
+    assert call.args["complete"] is True and call.args["vegp"]["pai"].shape[2] == 12
+    got = _parity(call)
+    assert got["Tz"].shape == (50, 50, 8760)
+
+
+@pytest.mark.gpu
+def test_runmicro_big_tiles_match_untiled_statics(tmp_path):
+    """runmicro_big (R/Cppwrappers.R:444-543): 4 tiles of 25 x 25; each tile file equals runmicro on the cropped
+    inputs with the whole-area terrain layers."""
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, days=[100, 250])
+    files = hostmodel.runmicro_big(sub, 0.05, str(tmp_path) + "/", vegp, soilc, dtm, tilesize=25)
+    assert [os.path.basename(f) for f in files] == ["area_01_01.npz", "area_01_02.npz", "area_02_01.npz", "area_02_02.npz"]
+    t = np.load(files[3])
+    assert t["Tz"].shape == (25, 25, 48) and np.array_equal(t["dtm"], dtm.matrix()[25:, 25:], equal_nan=True)
+    ok = ~np.isnan(t["dtm"])
+    assert np.isfinite(t["Tz"][ok]).all()
