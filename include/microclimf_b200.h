@@ -206,6 +206,21 @@ int mcf_runbioclim_dev(const mcf_problem* prob, const int32_t* wetq, int32_t nwe
                        const int32_t* colq, int32_t ncolq, int32_t air, double* const bio[MCF_NBIO],
                        void* stream, char* err, size_t errlen);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Packed integer sink (SURVEY.md NEXT-4).  The reference stores hourly grids on disk as integers: */
+/* writetonc (R/dataprep.R:1063-1260) writes `as.integer(round(x * rd, 0))` with rd = 100 for Tz,   */
+/* tleaf, soilm and windspeed and rd = 1 for relhum and the radiation streams (atonc :1064-1069,     */
+/* :1164-1173), missing value -9999.  These entry points run the same solve and store exactly those  */
+/* integers (round half to even, NA / NaN / Inf -> -9999) as int16 in the kernel's store, 2 bytes    */
+/* instead of 8 per value on the PCIe link and in the sink.  Layout stays [rows, cols, tsteps] (R);  */
+/* writetonc's aperm(c(2, 1, 3)) is file-format work for the writer.  |x * rd| > 32767 saturates     */
+/* (not reachable for physical values; the reference's NC_INT would hold it).                        */
+/* ------------------------------------------------------------------------------------------- */
+#define MCF_PACKED_NA (-9999)
+int mcf_runmicro_packed(const mcf_problem* prob, int16_t* const out[MCF_NOUT], char* err, size_t errlen);
+int mcf_runmicro_packed_dev(const mcf_problem* prob, int16_t* const out[MCF_NOUT], const mcf_window* win,
+                            void* stream, char* err, size_t errlen);
+
 /* sum and count of log(twi)/tfact over the non-NaN cells of a HOST twi buffer holding n cells
  * (the two numbers the bands all-reduce before calling with has_twi_mean = 1). */
 int mcf_twi_partial(const double* twi, int64_t n, double tfact, double* sum, int64_t* count,

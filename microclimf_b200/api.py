@@ -92,6 +92,50 @@ def run_problem(p: GridProblem, out: Optional[Sequence[bool]] = None, out_buffer
             if b is not None}
 
 
+def run_problem_packed(p: GridProblem, out: Optional[Sequence[bool]] = None, out_buffers=None) -> Dict[str, np.ndarray]:
+    """mcf_runmicro_packed: the solve with writetonc's integer packing (R/dataprep.R:1064-1069, 1164-1173) applied in
+    the kernel's store.  Returns int16 arrays [rows, cols, tsteps] (Fortran order), -9999 = NA."""
+    L = _lib.lib()
+    n = p.ncells * p.tsteps
+    if out_buffers is not None:
+        bufs = list(out_buffers)
+        for b in bufs:
+            if b is not None and (b.dtype != np.int16 or b.size != n or not b.flags.c_contiguous):
+                raise ValueError("each output buffer must be a contiguous int16 array of rows*cols*tsteps")
+    else:
+        out = [True] * _abi.MCF_NOUT if out is None else [bool(o) for o in out]
+        bufs = [np.empty(n, dtype=np.int16) if o else None for o in out]
+    if len(bufs) != _abi.MCF_NOUT:
+        raise ValueError("10 outputs expected")
+    P16 = C.POINTER(C.c_int16)
+    ptrs = _abi.OutPtrs16(*[b.ctypes.data_as(P16) if b is not None else None for b in bufs])
+    s, keep = p.as_struct()
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runmicro_packed(C.byref(s), ptrs, err, 512), err)
+    del keep
+    return {nm: b.reshape((p.rows, p.cols, p.tsteps), order="F") for nm, b in zip(_abi.OUT_NAMES, bufs)
+            if b is not None}
+
+
+def run_problem_packed_dev(p: GridProblem, out_tensors, window=None, stream=None) -> None:
+    """mcf_runmicro_packed_dev: device-resident problem, 10 CUDA int16 tensors (or None) as outputs; `window` and
+    `stream` as for run_problem_dev."""
+    import torch
+
+    L = _lib.lib()
+    st = torch.cuda.current_stream() if stream is None else stream
+    P16 = C.POINTER(C.c_int16)
+    ptrs = _abi.OutPtrs16(*[C.cast(C.c_void_p(t.data_ptr()), P16) if t is not None else None for t in out_tensors])
+    s, keep = p.as_struct()
+    w = None
+    if window is not None:
+        w = _abi.McfWindow(int(window[0]), int(window[1]), int(window[2]), int(window[3]))
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runmicro_packed_dev(C.byref(s), ptrs, C.byref(w) if w is not None else None,
+                                         C.c_void_p(st.cuda_stream), err, 512), err)
+    del keep
+
+
 def run_bioclim_problem(p: GridProblem, wetq, dryq, hotq, colq, air: bool = True,
                         out: Optional[Sequence[bool]] = None) -> Dict[str, np.ndarray]:
     L = _lib.lib()

@@ -183,6 +183,7 @@ struct Plan {
     double* d_mxtc_cell = nullptr;
     double* d_stash = nullptr;
     int grid = 0;
+    int pack = 0; // outputs are int16 (the packed integer sink): out[v] pointers are int16_t* in disguise
 };
 
 Err plan_prepare(Plan& pl, const mcf_problem* p, Scratch& sc, cudaStream_t st) {
@@ -258,6 +259,7 @@ void fill_common(const Plan& pl, GridArgs& a) {
     a.hor = p->hor;
     a.blocks = pl.d_blocks;
     a.stash = pl.d_stash;
+    a.pack = pl.pack;
 }
 
 Err timed_grid_launch(const GridArgs& a, bool arr, int rq, int grid, cudaStream_t st) {
@@ -323,6 +325,9 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
     CU(cudaMemsetAsync(ctr, 0, nchunks * sizeof(unsigned int), st));
     int hiy = 365 * 24;
     if (p->year[0] % 4 == 0) hiy = 366 * 24; // ref :2171-2172
+    // packed sink: the time-axis pass produces FP64; it lands in a scratch series and is packed afterwards
+    double* tz64 = nullptr;
+    if (pl.pack && out[MCF_OUT_TZ]) CU(sc.alloc(&tz64, (size_t)T * pl.ncells));
     for (int ch = 0; ch < nchunks; ++ch) {
         const int c0 = ch * W, c1 = std::min(pl.ncells, c0 + W);
         // uncovered hours keep Tg = 0, DD = 0, as the reference's zero-initialised vectors (:2192-2193)
@@ -364,10 +369,14 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
             b.Tbp = p->p_Tbp;
             b.hgt = p->hgt;
             b.daily = daily;
-            b.Tz = out[MCF_OUT_TZ];
+            b.Tz = tz64 ? tz64 : out[MCF_OUT_TZ];
             CU(launch_below(b, st));
             count_launch();
         }
+    }
+    if (tz64) {
+        CU(launch_pack16(tz64, reinterpret_cast<int16_t*>(out[MCF_OUT_TZ]), (int64_t)T * pl.ncells, 100.0, st));
+        count_launch();
     }
     return Err();
 }
@@ -385,16 +394,18 @@ Err prefill_whole(const Plan& pl, double* const out[MCF_NOUT], cudaStream_t st) 
         const bool written = kernel_writes(pl.rq, v);
         const bool all_hours = (pl.rq == RQ_BELOW && v == MCF_OUT_TZ); // the time-axis pass writes every hour
         if (!written || (gaps && !all_hours)) {
-            CU(launch_fill_na(out[v], (int64_t)T * pl.ncells, st));
+            if (pl.pack) CU(launch_fill16(reinterpret_cast<int16_t*>(out[v]), (int64_t)T * pl.ncells, (int16_t)-9999, st));
+            else CU(launch_fill_na(out[v], (int64_t)T * pl.ncells, st));
             count_launch();
         }
     }
     return Err();
 }
 
-Err run_dev(const mcf_problem* p, double* const out[MCF_NOUT], const mcf_window* win, cudaStream_t st) {
+Err run_dev(const mcf_problem* p, double* const out[MCF_NOUT], const mcf_window* win, cudaStream_t st, int pack = 0) {
     Scratch sc(st);
     Plan pl;
+    pl.pack = pack;
     TRY(plan_prepare(pl, p, sc, st));
     const int nblk = (int)pl.blocks.size();
     int b0 = 0, nb = nblk;
@@ -469,9 +480,9 @@ struct DevCopy { // device mirror of a host problem, carved out of the workspace
         *d = (const double*)q;
         return Err();
     }
-    Err dalloc(double** d, size_t n) {
+    Err dalloc(double** d, size_t n, size_t esz = sizeof(double)) { // n elements of esz bytes
         void* q = nullptr;
-        TRY(carve(&q, n * sizeof(double)));
+        TRY(carve(&q, n * esz));
         *d = (double*)q;
         return Err();
     }
@@ -554,8 +565,8 @@ struct EventGuard {
 // memcpy's the previous chunk out of the other, so the DMA engine and several cores' worth of memcpy
 // bandwidth run concurrently.  Pinned (or registered) destinations are copied directly.
 struct CopyJob {
-    double* dst;
-    const double* src;
+    char* dst;
+    const char* src;
     size_t bytes;
     cudaEvent_t ready; // the producing kernels have completed (may be null)
 };
@@ -584,7 +595,7 @@ Err copy_back(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream) {
             CU(cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDeviceToHost, direct_stream));
         } else {
             for (size_t off = 0; off < j.bytes; off += kSlotBytes)
-                chunks.push_back(Chunk{(char*)j.dst + off, (const char*)j.src + off, std::min(kSlotBytes, j.bytes - off), j.ready});
+                chunks.push_back(Chunk{j.dst + off, j.src + off, std::min(kSlotBytes, j.bytes - off), j.ready});
         }
     }
     if (!chunks.empty()) {
@@ -633,13 +644,20 @@ Err copy_back(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream) {
     return Err();
 }
 
-void host_fill_na(double* p, size_t n) {
+void host_fill_na(double* p, size_t n, int pack) {
+    if (pack) {
+        int16_t* q = reinterpret_cast<int16_t*>(p);
+        for (size_t i = 0; i < n; ++i) q[i] = (int16_t)-9999;
+        return;
+    }
     const uint64_t bits = MCF_NA_REAL_BITS;
     uint64_t* q = reinterpret_cast<uint64_t*>(p);
     for (size_t i = 0; i < n; ++i) q[i] = bits;
 }
 
-Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
+// `pack`: out[v] are int16_t* (packed integer sink), else double*; esz = bytes per output element
+Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT], int pack = 0) {
+    const size_t esz = pack ? sizeof(int16_t) : sizeof(double);
     TRY(validate(hp));
     TRY(device_info());
     std::lock_guard<std::mutex> ws_lock(g_ws_mu);
@@ -652,7 +670,7 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
     for (int v = 0; v < MCF_NOUT; ++v) nreq += out[v] != nullptr;
     if (nreq == 0) return Err();
     const int rq = rq_of(hp->reqhgt);
-    const size_t per_hour = (size_t)nreq * nc * sizeof(double);
+    const size_t per_hour = (size_t)nreq * nc * esz;
     std::vector<DayBlock> blocks;
     TRY(build_blocks(hp, blocks));
     const int nblk = (int)blocks.size();
@@ -684,18 +702,19 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
     }
     const long long chunk_hours = chunk_blocks * 24;
     const size_t out_elems = fits ? nc * (size_t)T : nc * (size_t)chunk_hours;
-    const size_t out_bytes = (size_t)nreq * (fits ? 1 : 2) * DevCopy::pad(out_elems * sizeof(double));
+    const size_t out_bytes = (size_t)nreq * (fits ? 1 : 2) * DevCopy::pad(out_elems * esz);
     TRY(dc.reserve(in_bytes + out_bytes));
     dc.sizing = false;
     TRY(upload_problem(hp, &dp, dc)); // asynchronous H2D on the compute stream
     {
         Scratch sc(cs.s);
         Plan pl;
+        pl.pack = pack;
         TRY(plan_prepare(pl, &dp, sc, cs.s));
         if (fits) {
             double* dout[MCF_NOUT] = {nullptr};
             for (int v = 0; v < MCF_NOUT; ++v)
-                if (out[v]) TRY(dc.dalloc(&dout[v], out_elems));
+                if (out[v]) TRY(dc.dalloc(&dout[v], out_elems, esz));
             TRY(prefill_whole(pl, dout, cs.s));
             // Time windows: the device->host copy of a window's hours overlaps the kernels of the next
             // window.  Window i owns the hour range from its first block to the next window's first block
@@ -714,7 +733,8 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
                 const size_t h1 = (w == nwin - 1) ? (size_t)T : (size_t)pl.blocks[b1].k0;
                 for (int v = 0; v < MCF_NOUT; ++v)
                     if (out[v])
-                        jobs.push_back(CopyJob{out[v] + h0 * nc, dout[v] + h0 * nc, (h1 - h0) * nc * sizeof(double), done_k[w].e});
+                        jobs.push_back(CopyJob{(char*)out[v] + h0 * nc * esz, (const char*)dout[v] + h0 * nc * esz,
+                                               (h1 - h0) * nc * esz, done_k[w].e});
             }
             TRY(copy_back(jobs, xs.s));
             CU(cudaStreamSynchronize(cs.s));
@@ -724,7 +744,7 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
             double* dout[2][MCF_NOUT] = {{nullptr}, {nullptr}};
             for (int s = 0; s < 2; ++s)
                 for (int v = 0; v < MCF_NOUT; ++v)
-                    if (out[v]) TRY(dc.dalloc(&dout[s][v], out_elems));
+                    if (out[v]) TRY(dc.dalloc(&dout[s][v], out_elems, esz));
             EventGuard done_k[2];
             for (int s = 0; s < 2; ++s) CU(cudaEventCreateWithFlags(&done_k[s].e, cudaEventDisableTiming));
             // hours no day-block covers, and outputs this reqhgt never writes, are NA (host side)
@@ -733,9 +753,9 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
                 for (int h = 0; h < 24; ++h) covered[b.k0 + h] = 1;
             for (int v = 0; v < MCF_NOUT; ++v) {
                 if (!out[v]) continue;
-                if (!kernel_writes(rq, v)) { host_fill_na(out[v], nc * T); continue; }
+                if (!kernel_writes(rq, v)) { host_fill_na(out[v], nc * T, pack); continue; }
                 for (int k = 0; k < T; ++k)
-                    if (!covered[k]) host_fill_na(out[v] + (size_t)k * nc, nc);
+                    if (!covered[k]) host_fill_na((double*)((char*)out[v] + (size_t)k * nc * esz), nc, pack);
             }
             std::vector<CopyJob> pending;
             int w = 0;
@@ -752,7 +772,7 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT]) {
                 pending.clear();
                 for (int v = 0; v < MCF_NOUT; ++v)
                     if (out[v] && kernel_writes(rq, v))
-                        pending.push_back(CopyJob{out[v] + (size_t)h0 * nc, dout[s][v], nc * 24 * (size_t)nb * sizeof(double),
+                        pending.push_back(CopyJob{(char*)out[v] + (size_t)h0 * nc * esz, (const char*)dout[s][v], nc * 24 * (size_t)nb * esz,
                                                   done_k[s].e});
                 b0 += nb;
             }
@@ -901,6 +921,19 @@ int mcf_runmicro_dev(const mcf_problem* prob, double* const out[MCF_NOUT], const
 int mcf_runmicro(const mcf_problem* prob, double* const out[MCF_NOUT], char* err, size_t errlen) {
     if (!out) return report(make_err(MCF_ERR_ARG, "out is NULL"), err, errlen);
     return report(run_host(prob, out), err, errlen);
+}
+
+// Packed integer sink (SURVEY.md NEXT-4): the same solve, results stored as writetonc stores them
+// (R/dataprep.R:1064-1069, 1164-1173).  The int16_t* buffers travel through the double* plumbing.
+int mcf_runmicro_packed_dev(const mcf_problem* prob, int16_t* const out[MCF_NOUT], const mcf_window* win, void* stream,
+                            char* err, size_t errlen) {
+    if (!out) return report(make_err(MCF_ERR_ARG, "out is NULL"), err, errlen);
+    return report(run_dev(prob, reinterpret_cast<double* const*>(out), win, (cudaStream_t)stream, 1), err, errlen);
+}
+
+int mcf_runmicro_packed(const mcf_problem* prob, int16_t* const out[MCF_NOUT], char* err, size_t errlen) {
+    if (!out) return report(make_err(MCF_ERR_ARG, "out is NULL"), err, errlen);
+    return report(run_host(prob, reinterpret_cast<double* const*>(out), 1), err, errlen);
 }
 
 int mcf_runbioclim_dev(const mcf_problem* prob, const int32_t* wetq, int32_t nwetq, const int32_t* dryq, int32_t ndryq,

@@ -53,6 +53,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 __device__ __forceinline__ double na_real() { return __longlong_as_double(0x7FF00000000007A2LL); }
 
+// Packed integer sink (SURVEY.md NEXT-4): writetonc's `as.integer(round(x * rd, 0))` (R/dataprep.R:1064-1069) with
+// rd = 100 for Tz, tleaf, soilm and windspeed and 1 for relhum and the radiation streams (:1164-1173), NA and NaN
+// -> -9999 (the file's missval).  round-half-even like R's round(x, 0); values beyond int16 saturate.
+__device__ __forceinline__ int16_t pack16(double v, double rd) {
+    const double s = v * rd;
+    int r = __double2int_rn(s);
+    r = (r > 32767) ? 32767 : r;
+    r = (r < -32767) ? -32767 : r;
+    return (isnan(s) || isinf(s)) ? (int16_t)-9999 : (int16_t)r; // as.integer(NaN / Inf) is NA
+}
+__device__ __forceinline__ double pack_scale(int q) { return (q == 0 || q == 1 || q == 3 || q == 4) ? 100.0 : 1.0; }
+// one output value: FP64 streaming store, or the packed int16 store when the launch asked for the packed sink
+template <int Q>
+__device__ __forceinline__ void put(const GridArgs& a, size_t o, double v) {
+    if (a.pack) reinterpret_cast<int16_t*>(a.out[Q])[o] = pack16(v, pack_scale(Q));
+    else __stcs(&a.out[Q][o], v);
+}
+
 // ---------------------------------------------------------------------------------------------
 // prep: per-hour table (modes 1/3) or per-hour calendar (modes 2/4); series maximum of tc
 // ---------------------------------------------------------------------------------------------
@@ -463,7 +481,10 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                         const size_t o = (size_t)slot * a.ncells + cell;
 #pragma unroll
                         for (int q = 0; q < kNOut; ++q)
-                            if (om & (1u << q)) __stcs(&a.out[q][o], NA);
+                            if (om & (1u << q)) {
+                                if (a.pack) reinterpret_cast<int16_t*>(a.out[q])[o] = (int16_t)-9999;
+                                else __stcs(&a.out[q][o], NA);
+                            }
                     }
                 }
             } else {
@@ -507,7 +528,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     if (ha > h.tan_sa) si = 0.0;
                     // distributed soil moisture
                     const double soild = soil_distribute(v, h.soilmp);
-                    if (om & (1u << 3)) __stcs(&a.out[3][o], soild);
+                    if (om & (1u << 3)) put<3>(a, o, soild);
                     // shortwave
                     Rad r;
                     if (h.Rsw > 0.0) {
@@ -515,16 +536,16 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     } else {
                         r.radGsw = 0.0; r.radCsw = 0.0; r.Rbdown = 0.0; r.Rddown = 0.0; r.Rdup = 0.0; r.Lhalf = 0.0;
                     }
-                    if (om & (1u << 5)) __stcs(&a.out[5][o], r.Rbdown);
-                    if (om & (1u << 6)) __stcs(&a.out[6][o], r.Rddown);
-                    if (om & (1u << 8)) __stcs(&a.out[8][o], r.Rdup);
+                    if (om & (1u << 5)) put<5>(a, o, r.Rbdown);
+                    if (om & (1u << 6)) put<6>(a, o, r.Rddown);
+                    if (om & (1u << 8)) put<8>(a, o, r.Rdup);
                     // longwave absorbed by the ground (ref :1165-1175); lwout = h.Rem
                     double radGlw;
                     if (v.pai > 0.0) radGlw = kEm * (v.trdif * v.svfa * h.Rlw + (1.0 - v.trdif) * h.Rem);
                     else radGlw = kEm * v.svfa * h.Rlw;
                     // wind
                     const Wind w = wind_hour(v, h.u2, h.umu, ws);
-                    if (om & (1u << 4)) __stcs(&a.out[4][o], w.uz);
+                    if (om & (1u << 4)) put<4>(a, o, w.uz);
                     // ground surface temperature with G = 0 (ref soiltempG0 :1262-1275)
                     const double radabs = r.radGsw + radGlw;
                     const double matric = -v.psie_abs * mexp_nc(-v.soilb * mlog(soild * v.inv_Smax));
@@ -597,12 +618,12 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     } else {
                         const double radClw = kEm * v.svfa * h.Rlw;
                         const Above tv = above_ground(v, h, dTmx, soild, Tg, G, w, radCsw, radClw, Lhalf);
-                        if (om & (1u << 0)) __stcs(&a.out[0][o], (RQ == RQ_ABOVE) ? tv.Tz : Tg);
-                        if (om & (1u << 7)) __stcs(&a.out[7][o], tv.lwdn);
-                        if (om & (1u << 9)) __stcs(&a.out[9][o], tv.lwup);
+                        if (om & (1u << 0)) put<0>(a, o, (RQ == RQ_ABOVE) ? tv.Tz : Tg);
+                        if (om & (1u << 7)) put<7>(a, o, tv.lwdn);
+                        if (om & (1u << 9)) put<9>(a, o, tv.lwup);
                         if (RQ == RQ_ABOVE) {
-                            if (om & (1u << 1)) __stcs(&a.out[1][o], tv.tleaf);
-                            if (om & (1u << 2)) __stcs(&a.out[2][o], tv.rh);
+                            if (om & (1u << 1)) put<1>(a, o, tv.tleaf);
+                            if (om & (1u << 2)) put<2>(a, o, tv.rh);
                         }
                     }
                     o += a.ncells;
@@ -870,6 +891,30 @@ cudaError_t launch_fill_na(double* p, int64_t n, cudaStream_t stream) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     k_fill_na<<<(int)blocks, 256, 0, stream>>>(p, n);
+    return cudaGetLastError();
+}
+
+__global__ void k_fill16(int16_t* __restrict__ p, int64_t n, int16_t v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+cudaError_t launch_fill16(int16_t* p, int64_t n, int16_t v, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_fill16<<<(int)blocks, 256, 0, stream>>>(p, n, v);
+    return cudaGetLastError();
+}
+// FP64 -> packed int16 (the below-ground Tz, which the time-axis pass produces in FP64)
+__global__ void k_pack16(const double* __restrict__ src, int16_t* __restrict__ dst, int64_t n, double rd) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = pack16(src[i], rd);
+}
+cudaError_t launch_pack16(const double* src, int16_t* dst, int64_t n, double rd, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_pack16<<<(int)blocks, 256, 0, stream>>>(src, dst, n, rd);
     return cudaGetLastError();
 }
 

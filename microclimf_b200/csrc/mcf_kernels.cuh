@@ -66,8 +66,9 @@ struct GridArgs {
     int32_t block0, nblocks;
     long long hour0, ring_hours;
     // outputs
-    double* out[kNOut];
+    double* out[kNOut];     // pack != 0: each is an int16_t* in disguise (the packed integer sink)
     uint32_t outmask;
+    int32_t pack;
     // scratch
     double* stash;          // [gridDim.x][24][kStashVars][kTile]
     unsigned int* tile_counter;
@@ -117,6 +118,8 @@ int grid_blocks_per_sm(bool arr, int rq);
 cudaError_t launch_below(const BelowArgs& a, cudaStream_t stream);
 cudaError_t launch_bioclim(const BioArgs& a, cudaStream_t stream);
 cudaError_t launch_fill_na(double* p, int64_t n, cudaStream_t stream);
+cudaError_t launch_fill16(int16_t* p, int64_t n, int16_t v, cudaStream_t stream);
+cudaError_t launch_pack16(const double* src, int16_t* dst, int64_t n, double rd, cudaStream_t stream);
 // terrain preparation (mcf_terrain.cu)
 cudaError_t launch_scale_dtm(const double* dtm, int64_t n, double reso, double* out, cudaStream_t st);
 cudaError_t launch_horizon(const double* d, int rows, int cols, int ndir, const double* offs, double thr, bool windcoef,

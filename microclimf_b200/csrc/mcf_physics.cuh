@@ -593,7 +593,12 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
     double gV = 0.0;
     double gs2 = 0.0;
     bool have_gs2 = false;
-    if (v.pai != 0.0) { // pai == 0: Rshade_abs is 0/0 = NaN in the reference, so gS is NaN and gV stays 0
+    if (isnan(v.omp)) {
+        // leaf reflectance / transmittance NA (bare cells of real rasters keep NA there, R/internal.R:1052-1058):
+        // canopycondCpp skips its body and returns Gs = 9999.99 (ref :463-464), whatever pai is
+        const double gS = 9999.99;
+        gV = mdiv(w.gHa * gS, w.gHa + gS);
+    } else if (v.pai != 0.0) { // pai == 0: Rshade_abs is 0/0 = NaN in the reference, so gS is NaN and gV stays 0
         double kq = msqrt(v.x * v.x + h.kq_tan * h.kq_tan) * v.inv_kden;
         kq = (v.xflag == 1) ? h.kq1 : kq;
         kq = (v.xflag == 3) ? 1.0 : kq;

