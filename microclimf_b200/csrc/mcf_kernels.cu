@@ -65,9 +65,11 @@ __device__ __forceinline__ int16_t pack16(double v, double rd) {
 }
 __device__ __forceinline__ double pack_scale(int q) { return (q == 0 || q == 1 || q == 3 || q == 4) ? 100.0 : 1.0; }
 // one output value: FP64 streaming store, or the packed int16 store when the launch asked for the packed sink
-template <int Q>
+// (PACK is a compile-time parameter of the grid kernel: a run-time test in front of every store splits the hour
+// loops into many small basic blocks and cost 16 % of the FP64 build's throughput)
+template <int Q, bool PACK>
 __device__ __forceinline__ void put(const GridArgs& a, size_t o, double v) {
-    if (a.pack) reinterpret_cast<int16_t*>(a.out[Q])[o] = pack16(v, pack_scale(Q));
+    if (PACK) reinterpret_cast<int16_t*>(a.out[Q])[o] = pack16(v, pack_scale(Q));
     else __stcs(&a.out[Q][o], v);
 }
 
@@ -375,7 +377,7 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
     h.windex = c.windex;
 }
 
-template <bool ARR, int RQ>
+template <bool ARR, int RQ, bool PACK>
 #ifdef MCF_MAXNREG
 #define MCF_KGRID_BOUNDS __maxnreg__(MCF_MAXNREG)
 #else
@@ -482,7 +484,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
 #pragma unroll
                         for (int q = 0; q < kNOut; ++q)
                             if (om & (1u << q)) {
-                                if (a.pack) reinterpret_cast<int16_t*>(a.out[q])[o] = (int16_t)-9999;
+                                if (PACK) reinterpret_cast<int16_t*>(a.out[q])[o] = (int16_t)-9999;
                                 else __stcs(&a.out[q][o], NA);
                             }
                     }
@@ -528,7 +530,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     if (ha > h.tan_sa) si = 0.0;
                     // distributed soil moisture
                     const double soild = soil_distribute(v, h.soilmp);
-                    if (om & (1u << 3)) put<3>(a, o, soild);
+                    if (om & (1u << 3)) put<3, PACK>(a, o, soild);
                     // shortwave
                     Rad r;
                     if (h.Rsw > 0.0) {
@@ -536,16 +538,16 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     } else {
                         r.radGsw = 0.0; r.radCsw = 0.0; r.Rbdown = 0.0; r.Rddown = 0.0; r.Rdup = 0.0; r.Lhalf = 0.0;
                     }
-                    if (om & (1u << 5)) put<5>(a, o, r.Rbdown);
-                    if (om & (1u << 6)) put<6>(a, o, r.Rddown);
-                    if (om & (1u << 8)) put<8>(a, o, r.Rdup);
+                    if (om & (1u << 5)) put<5, PACK>(a, o, r.Rbdown);
+                    if (om & (1u << 6)) put<6, PACK>(a, o, r.Rddown);
+                    if (om & (1u << 8)) put<8, PACK>(a, o, r.Rdup);
                     // longwave absorbed by the ground (ref :1165-1175); lwout = h.Rem
                     double radGlw;
                     if (v.pai > 0.0) radGlw = kEm * (v.trdif * v.svfa * h.Rlw + (1.0 - v.trdif) * h.Rem);
                     else radGlw = kEm * v.svfa * h.Rlw;
                     // wind
                     const Wind w = wind_hour(v, h.u2, h.umu, ws);
-                    if (om & (1u << 4)) put<4>(a, o, w.uz);
+                    if (om & (1u << 4)) put<4, PACK>(a, o, w.uz);
                     // ground surface temperature with G = 0 (ref soiltempG0 :1262-1275)
                     const double radabs = r.radGsw + radGlw;
                     const double matric = -v.psie_abs * mexp_nc(-v.soilb * mlog(soild * v.inv_Smax));
@@ -618,12 +620,12 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     } else {
                         const double radClw = kEm * v.svfa * h.Rlw;
                         const Above tv = above_ground(v, h, dTmx, soild, Tg, G, w, radCsw, radClw, Lhalf);
-                        if (om & (1u << 0)) put<0>(a, o, (RQ == RQ_ABOVE) ? tv.Tz : Tg);
-                        if (om & (1u << 7)) put<7>(a, o, tv.lwdn);
-                        if (om & (1u << 9)) put<9>(a, o, tv.lwup);
+                        if (om & (1u << 0)) put<0, PACK>(a, o, (RQ == RQ_ABOVE) ? tv.Tz : Tg);
+                        if (om & (1u << 7)) put<7, PACK>(a, o, tv.lwdn);
+                        if (om & (1u << 9)) put<9, PACK>(a, o, tv.lwup);
                         if (RQ == RQ_ABOVE) {
-                            if (om & (1u << 1)) put<1>(a, o, tv.tleaf);
-                            if (om & (1u << 2)) put<2>(a, o, tv.rh);
+                            if (om & (1u << 1)) put<1, PACK>(a, o, tv.tleaf);
+                            if (om & (1u << 2)) put<2, PACK>(a, o, tv.rh);
                         }
                     }
                     o += a.ncells;
@@ -645,7 +647,11 @@ int grid_blocks_per_sm(bool arr, int rq) {
 }
 
 cudaError_t launch_grid(const GridArgs& a, bool arr, int rq, int grid, cudaStream_t stream) {
-#define MCF_LAUNCH(ARR, RQ) k_grid<ARR, RQ><<<grid, kTile, 0, stream>>>(a)
+#define MCF_LAUNCH(ARR, RQ)                                                      \
+    do {                                                                         \
+        if (a.pack) k_grid<ARR, RQ, true><<<grid, kTile, 0, stream>>>(a);        \
+        else k_grid<ARR, RQ, false><<<grid, kTile, 0, stream>>>(a);              \
+    } while (0)
     if (!arr) {
         if (rq == RQ_ABOVE) MCF_LAUNCH(false, RQ_ABOVE);
         else if (rq == RQ_SURFACE) MCF_LAUNCH(false, RQ_SURFACE);

@@ -593,12 +593,11 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
     double gV = 0.0;
     double gs2 = 0.0;
     bool have_gs2 = false;
-    if (isnan(v.omp)) {
-        // leaf reflectance / transmittance NA (bare cells of real rasters keep NA there, R/internal.R:1052-1058):
-        // canopycondCpp skips its body and returns Gs = 9999.99 (ref :463-464), whatever pai is
-        const double gS = 9999.99;
-        gV = mdiv(w.gHa * gS, w.gHa + gS);
-    } else if (v.pai != 0.0) { // pai == 0: Rshade_abs is 0/0 = NaN in the reference, so gS is NaN and gV stays 0
+    // leaf reflectance / transmittance NA (bare cells of real rasters keep NA there, R/internal.R:1052-1058):
+    // canopycondCpp skips its body and returns Gs = 9999.99 (ref :463-464), whatever pai is
+    const bool om_na = isnan(v.omp);
+    double gS = om_na ? 9999.99 : 0.0;
+    if (v.pai != 0.0 && !om_na) { // pai == 0: Rshade_abs is 0/0 = NaN in the reference, so gS is NaN and gV stays 0
         double kq = msqrt(v.x * v.x + h.kq_tan * h.kq_tan) * v.inv_kden;
         kq = (v.xflag == 1) ? h.kq1 : kq;
         kq = (v.xflag == 3) ? 1.0 : kq;
@@ -606,7 +605,6 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         if (kq > 6000.0) kq = 6000.0;
         double Rshade_abs = h.Rdif * v.shade_fac; // NaN for pai == 0 (0/0), as in the reference
         double Rsun_abs = (h.Rsw - h.Rdif) * kq * (1 - v.omp) + Rshade_abs;
-        double gS;
         if (Rshade_abs <= 0.0 && Rsun_abs <= 0.0) {
             gS = 0.0; // both stomcondCpp calls return 0
         } else {
@@ -626,8 +624,8 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             else gs_shade = stomcond(v, Rshade_abs, gs2);
             gS = gs_sun * P_sun + gs_shade * P_shade;
         }
-        if (gS > 0.0) gV = mdiv(w.gHa * gS, w.gHa + gS); // 1 / (1/gHa + 1/gS)
     }
+    if (gS > 0.0) gV = mdiv(w.gHa * gS, w.gHa + gS); // 1 / (1/gHa + 1/gS)
     // canopy temperature
     double Rabs = radCsw + radClw;
     double m;
@@ -656,7 +654,11 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         out.lwup = v.e_paig * lwgro + (1 - v.e_paig) * lwcan;
         out.lwdn = v.e_paia * Rlw + (1 - v.e_paia) * lwcan;
         double lwabs = kEm * 0.5 * (out.lwup + out.lwdn);
-        double leafabs = (1.0 - v.om) * Lhalf + lwabs;
+        // radLsw / radLpar are set to 0, not computed, at night and for pai == 0 (ref twostreamCpp :1147-1163): with NA
+        // leaf reflectance the product (1 - om) * 0 would be NaN where the reference has 0
+        const bool lit = (h.Rsw > 0.0) && (v.pai > 0.0);
+        const double radLsw = lit ? (1.0 - v.om) * Lhalf : 0.0;
+        double leafabs = radLsw + lwabs;
         double gh = 0.135 * msqrt(w.uz * v.inv_leafd) * 1.4;
         double Rnetl = leafabs - lwcan;
         double gmin = 0.0463 * mpow(fabs(v.Hf0 * Rnetl) * v.inv_leafd, 0.2);
@@ -665,7 +667,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         double gVl = gh;
         if (v.gsmax < 999.99) {
             gVl = 0.0;
-            double radLpar = (1.0 - v.omp) * Lhalf;
+            double radLpar = lit ? (1.0 - v.omp) * Lhalf : 0.0;
             double gs = 0.0;
             if (radLpar > 0.0) {
                 if (!have_gs2) gs2 = stom_gs2(v, soilm);

@@ -168,6 +168,15 @@ def _parity(call):
     return got
 
 
+def _fill_reflectance(vegp, dtm):
+    vegp = dict(vegp)
+    for k, v in (("leafr", 0.3), ("leaft", 0.15)):
+        m = vegp[k].values.copy()
+        m[np.isnan(m) & ~np.isnan(dtm.values)] = v
+        vegp[k] = vegp[k].like(m)
+    return vegp
+
+
 @pytest.mark.gpu
 def test_flowacc_and_terrain_on_bundled_dtm():
     dtm, vegp, soilc, mp, clim = load_example()
@@ -210,6 +219,10 @@ def test_runmicro_big_tiles_match_untiled_statics(tmp_path):
     inputs with the whole-area terrain layers."""
     dtm, vegp, soilc, mp, clim = load_example()
     sub = hostmodel.subsetpointmodel(mp, days=[100, 250])
+    # the bundled leafr / leaft are NA on bare ground: .checkbiginputs refuses that (R/internal.R:1644-1662) ...
+    with pytest.raises(ValueError, match="contain NA that are not NA in dtm: leafr leaft"):
+        hostmodel.runmicro_big(sub, 0.05, str(tmp_path) + "/", vegp, soilc, dtm, tilesize=25)
+    vegp = _fill_reflectance(vegp, dtm)  # ... so a user fills them first
     files = hostmodel.runmicro_big(sub, 0.05, str(tmp_path) + "/", vegp, soilc, dtm, tilesize=25)
     assert [os.path.basename(f) for f in files] == ["area_01_01.npz", "area_01_02.npz", "area_02_01.npz", "area_02_02.npz"]
     t = np.load(files[3])
@@ -226,6 +239,7 @@ def test_runmicro_big_writeasnc_packs_like_writetonc(tmp_path):
 
     dtm, vegp, soilc, mp, clim = load_example()
     sub = hostmodel.subsetpointmodel(mp, days=[180])
+    vegp = _fill_reflectance(vegp, dtm)
     files = hostmodel.runmicro_big(sub, 0.05, str(tmp_path) + "/", vegp, soilc, dtm, tilesize=50, writeasnc=True)
     assert [os.path.basename(f) for f in files] == ["area_01_01_packed.npz"]
     t = np.load(files[0])
