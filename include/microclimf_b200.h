@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MCF_ABI_VERSION 1
+#define MCF_ABI_VERSION 2
 
 /* status codes (the Rcpp stub maps non-zero to Rcpp::stop(err), cf. BEGIN_RCPP/END_RCPP
  * src/RcppExports.cpp:251-271) */
@@ -155,6 +155,29 @@ typedef struct mcf_problem {
      * must be supplied by the caller (all-reduce of mcf_twi_partial over the bands). */
     int32_t has_twi_mean;
     double twi_mean;
+
+    /* Coarse-grid climate (modes 2/4, clim_rows > 0).  In the reference `.runmodel2Cpp` / `.runmodel4Cpp`
+     * expand every climate and point-model variable of runpointmodela's coarse grid to the fine raster on the
+     * host (`.cca` -> terra::resample, R/internal.R:523-542, 1219-1277) and hand [rows, cols, tsteps] arrays to
+     * runmicro2Cpp: 15 arrays x 8 B per cell-hour that cannot exist for a large raster.  With
+     * clim_rows > 0 the series below are [clim_rows, clim_cols, tsteps] arrays on the COARSE grid and the
+     * kernels interpolate them bilinearly per cell-hour, deriving es / ea / tdew (R/internal.R:1222-1224), the
+     * altitude correction (:1226-1245) and the wind speed from its interpolated components (:1250-1259) on the
+     * fly.  Fields read in this layout: temp, relhum, pres, swdown, difrad, lwdown, wu, wv, winddir[tsteps],
+     * p_soilm, p_G, p_umu, p_kp, p_muGp, p_dtrp (+ p_Tg, p_Tbp when reqhgt < 0); es, ea, tdew and windspeed are
+     * ignored.  Fine row i / column j sits at fractional coarse row clim_row0 + clim_drow * i / column
+     * clim_col0 + clim_dcol * j (clamped to the hull of the coarse cell centres).
+     * altcorrect = 0: pres is the coarse pressure.  altcorrect = 1 / 2: pres is the coarse SEA-LEVEL pressure
+     * pk / ((293 - 0.0065 dtmc) / 293)^5.26, pfac[rows, cols] = ((293 - 0.0065 dtm) / 293)^5.26 and
+     * elevd[rows, cols] = resample(dtmc) - dtm; 1 = fixed lapse rate 5 K / km, 2 = humidity-dependent. */
+    int32_t clim_rows, clim_cols;
+    double clim_row0, clim_drow, clim_col0, clim_dcol;
+    int32_t altcorrect;
+    const double* relhum;
+    const double* wu;
+    const double* wv;
+    const double* elevd;
+    const double* pfac;
 } mcf_problem;
 
 /* ------------------------------------------------------------------------------------------- */

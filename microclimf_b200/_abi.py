@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-MCF_ABI_VERSION = 1
+MCF_ABI_VERSION = 2
 MCF_OK, MCF_ERR_ARG, MCF_ERR_CUDA, MCF_ERR_NOMEM = 0, 1, 2, 3
 MCF_NOUT = 10
 MCF_NBIO = 19
@@ -37,6 +37,13 @@ SOIL_FIELDS = ("Smin", "Smax", "gref", "soilb", "Psie", "Vq", "Vm", "Mc", "rho",
 for _n in CLIM_FIELDS + POINTM_FIELDS + VEG_FIELDS + SOIL_FIELDS + ("lats", "lons"):
     _PROBLEM_FIELDS.append((_n, _pd))
 _PROBLEM_FIELDS += [("has_twi_mean", C.c_int32), ("twi_mean", C.c_double)]
+# coarse-grid climate (ABI 2)
+COARSE_FIELDS = ("relhum", "wu", "wv", "elevd", "pfac")
+_PROBLEM_FIELDS += [("clim_rows", C.c_int32), ("clim_cols", C.c_int32), ("clim_row0", C.c_double),
+                    ("clim_drow", C.c_double), ("clim_col0", C.c_double), ("clim_dcol", C.c_double),
+                    ("altcorrect", C.c_int32)]
+for _n in COARSE_FIELDS:
+    _PROBLEM_FIELDS.append((_n, _pd))
 
 
 class McfProblem(C.Structure):

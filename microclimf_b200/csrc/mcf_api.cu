@@ -100,8 +100,21 @@ Err validate(const mcf_problem* p) {
     if ((int64_t)p->rows * p->cols > INT32_MAX - 256) return make_err(MCF_ERR_ARG, "rows*cols exceeds 2^31");
     const bool layered = p->mode >= 3;
     const bool arr = (p->mode == 2 || p->mode == 4);
-    const void* req[] = {p->year, p->month, p->day, p->hour, p->temp, p->es, p->ea, p->tdew, p->pres, p->swdown,
-                         p->difrad, p->lwdown, p->windspeed, p->winddir, p->p_soilm, p->p_G, p->p_umu, p->p_kp,
+    const bool coarse = arr && p->clim_rows > 0;
+    if (p->clim_rows != 0 && !arr) return make_err(MCF_ERR_ARG, "coarse-grid climate (clim_rows > 0) needs mode 2 or 4");
+    if (coarse) {
+        if (p->clim_cols <= 0) return make_err(MCF_ERR_ARG, "clim_cols must be > 0");
+        if (!p->relhum || !p->wu || !p->wv) return make_err(MCF_ERR_ARG, "coarse-grid climate needs relhum, wu and wv");
+        if (p->altcorrect < 0 || p->altcorrect > 2) return make_err(MCF_ERR_ARG, "altcorrect must be 0, 1 or 2");
+        if (p->altcorrect && (!p->elevd || !p->pfac)) return make_err(MCF_ERR_ARG, "altcorrect needs elevd and pfac");
+    }
+    // es / ea / tdew / windspeed are derived in the kernel for coarse-grid climate
+    const double* const need_es = coarse ? p->temp : p->es;
+    const double* const need_ea = coarse ? p->temp : p->ea;
+    const double* const need_td = coarse ? p->temp : p->tdew;
+    const double* const need_ws = coarse ? p->temp : p->windspeed;
+    const void* req[] = {p->year, p->month, p->day, p->hour, p->temp, need_es, need_ea, need_td, p->pres, p->swdown,
+                         p->difrad, p->lwdown, need_ws, p->winddir, p->p_soilm, p->p_G, p->p_umu, p->p_kp,
                          p->p_muGp, p->p_dtrp, p->hgt, p->pai, p->x, p->gsmax, p->leafr, p->leaft, p->clump,
                          p->leafd, p->paia, p->leafden, p->Smin, p->Smax, p->gref, p->soilb, p->Psie, p->Vq, p->Vm,
                          p->Mc, p->rho, p->slope, p->aspect, p->twi, p->svfa, p->wsa, p->hor};
@@ -172,7 +185,7 @@ void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed
 // A prepared problem on the device: everything a window launch needs.
 struct Plan {
     const mcf_problem* p = nullptr;
-    bool arr = false;
+    int arr = 0; // 0: per-hour table (modes 1/3), 1: fine [rows, cols, T] arrays, 2: coarse arrays (modes 2/4)
     int rq = RQ_ABOVE;
     int ncells = 0;
     std::vector<DayBlock> blocks;
@@ -186,11 +199,13 @@ struct Plan {
     int pack = 0; // outputs are int16 (the packed integer sink): out[v] pointers are int16_t* in disguise
 };
 
+void fill_common(const Plan& pl, GridArgs& a);
+
 Err plan_prepare(Plan& pl, const mcf_problem* p, Scratch& sc, cudaStream_t st) {
     TRY(validate(p));
     TRY(device_info());
     pl.p = p;
-    pl.arr = (p->mode == 2 || p->mode == 4);
+    pl.arr = (p->mode == 2 || p->mode == 4) ? (p->clim_rows > 0 ? 2 : 1) : 0;
     pl.rq = rq_of(p->reqhgt);
     pl.ncells = p->rows * p->cols;
     TRY(build_blocks(p, pl.blocks));
@@ -210,19 +225,25 @@ Err plan_prepare(Plan& pl, const mcf_problem* p, Scratch& sc, cudaStream_t st) {
     const double* clim[10];
     clim_ptrs(p, clim);
     const double* pnt[6] = {p->p_soilm, p->p_G, p->p_umu, p->p_kp, p->p_muGp, p->p_dtrp};
-    CU(launch_prep_hours(d_cal3, d_cal3 + T, d_cal3 + 2 * T, p->hour, clim, pnt, p->lat, p->lon, T, pl.arr, pl.d_hours,
+    CU(launch_prep_hours(d_cal3, d_cal3 + T, d_cal3 + 2 * T, p->hour, clim, pnt, p->lat, p->lon, T, pl.arr != 0, pl.d_hours,
                          pl.d_cal, pl.d_scal, st));
     count_launch();
     if (pl.arr) {
         CU(sc.alloc(&pl.d_mxtc_cell, pl.ncells));
-        CU(launch_mxtc_cell(p->temp, pl.ncells, T, pl.d_mxtc_cell, st));
+        if (pl.arr == 2) {
+            GridArgs ga;
+            fill_common(pl, ga);
+            CU(launch_mxtc_cell_coarse(ga, pl.d_mxtc_cell, st));
+        } else {
+            CU(launch_mxtc_cell(p->temp, pl.ncells, T, pl.d_mxtc_cell, st));
+        }
         count_launch();
     }
     if (!p->has_twi_mean) {
         CU(launch_twi_sum(p->twi, pl.ncells, p->tfact, pl.d_scal + 1, st));
         count_launch(2);
     }
-    pl.grid = g_sm_count * grid_blocks_per_sm(pl.arr, pl.rq);
+    pl.grid = g_sm_count * grid_blocks_per_sm(pl.arr != 0, pl.rq);
     CU(sc.alloc(&pl.d_stash, (size_t)pl.grid * 24 * kStashVars * kTile));
     return Err();
 }
@@ -260,9 +281,24 @@ void fill_common(const Plan& pl, GridArgs& a) {
     a.blocks = pl.d_blocks;
     a.stash = pl.d_stash;
     a.pack = pl.pack;
+    a.rows = p->rows;
+    if (pl.arr == 2) {
+        a.clim_rows = p->clim_rows;
+        a.clim_cols = p->clim_cols;
+        a.altcorrect = p->altcorrect;
+        a.clim_row0 = p->clim_row0;
+        a.clim_drow = p->clim_drow;
+        a.clim_col0 = p->clim_col0;
+        a.clim_dcol = p->clim_dcol;
+        a.relhum = p->relhum;
+        a.wu = p->wu;
+        a.wv = p->wv;
+        a.elevd = p->elevd;
+        a.pfac = p->pfac;
+    }
 }
 
-Err timed_grid_launch(const GridArgs& a, bool arr, int rq, int grid, cudaStream_t st) {
+Err timed_grid_launch(const GridArgs& a, int arr, int rq, int grid, cudaStream_t st) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_timing) {
         CU(cudaEventCreate(&e0));
@@ -328,6 +364,20 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
     // packed sink: the time-axis pass produces FP64; it lands in a scratch series and is packed afterwards
     double* tz64 = nullptr;
     if (pl.pack && out[MCF_OUT_TZ]) CU(sc.alloc(&tz64, (size_t)T * pl.ncells));
+    // coarse-grid climate: the time-axis pass reads the point model's Tg / Tbz per cell-hour; expand them once
+    const double *tgp = p->p_Tg, *tbp = p->p_Tbp;
+    if (pl.arr == 2 && out[MCF_OUT_TZ] && tgp && tbp) {
+        GridArgs ga;
+        fill_common(pl, ga);
+        double *f1 = nullptr, *f2 = nullptr;
+        CU(sc.alloc(&f1, (size_t)T * pl.ncells));
+        CU(sc.alloc(&f2, (size_t)T * pl.ncells));
+        CU(launch_interp_coarse(ga, tgp, f1, st));
+        CU(launch_interp_coarse(ga, tbp, f2, st));
+        count_launch(2);
+        tgp = f1;
+        tbp = f2;
+    }
     for (int ch = 0; ch < nchunks; ++ch) {
         const int c0 = ch * W, c1 = std::min(pl.ncells, c0 + W);
         // uncovered hours keep Tg = 0, DD = 0, as the reference's zero-initialised vectors (:2192-2193)
@@ -365,8 +415,8 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
             b.mat = p->mat;
             b.tg = tg;
             b.dd_sum = dds;
-            b.Tgp = p->p_Tg;
-            b.Tbp = p->p_Tbp;
+            b.Tgp = tgp;
+            b.Tbp = tbp;
             b.hgt = p->hgt;
             b.daily = daily;
             b.Tz = tz64 ? tz64 : out[MCF_OUT_TZ];
@@ -492,18 +542,24 @@ Err upload_problem(const mcf_problem* h, mcf_problem* d, DevCopy& dc) {
     *d = *h;
     const bool arr = (h->mode == 2 || h->mode == 4);
     const size_t nc = (size_t)h->rows * h->cols, T = h->tsteps;
-    const size_t ns = arr ? nc * T : T;
+    const bool coarse = arr && h->clim_rows > 0;
+    const size_t ns = coarse ? (size_t)h->clim_rows * h->clim_cols * T : (arr ? nc * T : T);
     const size_t nv = nc * (h->mode >= 3 ? h->nlyr : 1);
     TRY(dc.up(h->hour, T, &d->hour));
     TRY(dc.up(h->temp, ns, &d->temp));
-    TRY(dc.up(h->es, ns, &d->es));
-    TRY(dc.up(h->ea, ns, &d->ea));
-    TRY(dc.up(h->tdew, ns, &d->tdew));
+    TRY(dc.up(coarse ? nullptr : h->es, ns, &d->es));
+    TRY(dc.up(coarse ? nullptr : h->ea, ns, &d->ea));
+    TRY(dc.up(coarse ? nullptr : h->tdew, ns, &d->tdew));
     TRY(dc.up(h->pres, ns, &d->pres));
     TRY(dc.up(h->swdown, ns, &d->swdown));
     TRY(dc.up(h->difrad, ns, &d->difrad));
     TRY(dc.up(h->lwdown, ns, &d->lwdown));
-    TRY(dc.up(h->windspeed, ns, &d->windspeed));
+    TRY(dc.up(coarse ? nullptr : h->windspeed, ns, &d->windspeed));
+    TRY(dc.up(coarse ? h->relhum : nullptr, ns, &d->relhum));
+    TRY(dc.up(coarse ? h->wu : nullptr, ns, &d->wu));
+    TRY(dc.up(coarse ? h->wv : nullptr, ns, &d->wv));
+    TRY(dc.up(coarse && h->altcorrect ? h->elevd : nullptr, nc, &d->elevd));
+    TRY(dc.up(coarse && h->altcorrect ? h->pfac : nullptr, nc, &d->pfac));
     TRY(dc.up(h->winddir, T, &d->winddir));
     TRY(dc.up(h->p_soilm, ns, &d->p_soilm));
     TRY(dc.up(h->reqhgt < 0 ? h->p_Tg : nullptr, ns, &d->p_Tg));

@@ -302,24 +302,103 @@ __device__ __forceinline__ int azimuth_sector(double sinazi, double cosazi) { //
     return (sinazi >= 0.0) ? 12 - q : 12 + q;
 }
 
+// ---- coarse-grid climate (ARR == 2): what .cca -> terra::resample(bilinear) does on the host in the reference
+// (R/internal.R:523-542), per cell-hour.  Cell geometry once per tile, four L2-resident loads per variable.
+struct CoarseCell {
+    int32_t o00, o01, o10, o11; // offsets of the four surrounding coarse cells within one time slice
+    double wx, wy;              // weights towards the next coarse column / row
+    double elevd, pfac;         // altitude correction terms (R/internal.R:1228-1245)
+};
+__device__ __forceinline__ void coarse_setup(const GridArgs& a, int cell, CoarseCell& c) {
+    const int i = cell % a.rows, j = cell / a.rows;
+    double fy = a.clim_row0 + a.clim_drow * (double)i;
+    double fx = a.clim_col0 + a.clim_dcol * (double)j;
+    const double ymax = (double)(a.clim_rows - 1), xmax = (double)(a.clim_cols - 1);
+    fy = (fy < 0.0) ? 0.0 : ((fy > ymax) ? ymax : fy); // constant beyond the hull of the coarse cell centres
+    fx = (fx < 0.0) ? 0.0 : ((fx > xmax) ? xmax : fx);
+    int y0 = (int)floor(fy), x0 = (int)floor(fx);
+    const int y0max = (a.clim_rows - 2 > 0) ? a.clim_rows - 2 : 0, x0max = (a.clim_cols - 2 > 0) ? a.clim_cols - 2 : 0;
+    y0 = (y0 > y0max) ? y0max : y0;
+    x0 = (x0 > x0max) ? x0max : x0;
+    const int y1 = (y0 + 1 < a.clim_rows) ? y0 + 1 : a.clim_rows - 1;
+    const int x1 = (x0 + 1 < a.clim_cols) ? x0 + 1 : a.clim_cols - 1;
+    c.wy = fy - (double)y0;
+    c.wx = fx - (double)x0;
+    c.o00 = y0 + a.clim_rows * x0;
+    c.o01 = y0 + a.clim_rows * x1;
+    c.o10 = y1 + a.clim_rows * x0;
+    c.o11 = y1 + a.clim_rows * x1;
+    c.elevd = a.altcorrect ? __ldg(&a.elevd[cell]) : 0.0;
+    c.pfac = a.altcorrect ? __ldg(&a.pfac[cell]) : 1.0;
+}
+__device__ __forceinline__ double cinterp(const double* __restrict__ A, size_t koff, const CoarseCell& c) {
+    const double* p = A + koff;
+    const double top = __ldg(p + c.o00) * (1.0 - c.wx) + __ldg(p + c.o01) * c.wx;
+    const double bot = __ldg(p + c.o10) * (1.0 - c.wx) + __ldg(p + c.o11) * c.wx;
+    return top * (1.0 - c.wy) + bot * c.wy;
+}
+// air temperature, vapour pressures and pressure of one cell-hour as .runmodel2Cpp derives them
+// (R/internal.R:1219-1245; .satvap :501, .dewpoint :509, .lapserate :546): es / ea / tdew from the UNCORRECTED
+// temperature, then the altitude correction of pressure and temperature
+__device__ __forceinline__ void coarse_air(const GridArgs& a, size_t koff, const CoarseCell& c, double& tc, double& es,
+                                           double& ea, double& tdew, double& pk) {
+    const double tc0 = cinterp(a.clim[0], koff, c);
+    const double rh = cinterp(a.relhum, koff, c);
+    es = satvap_m(tc0);
+    ea = es * rh / 100;
+    const double lg = (ea > 0.0) ? mlog(ea) : log(ea); // rh == 0: -inf, as R's log(0)
+    // log(ea / e0) = log(ea) - log(e0), e0 = 0.6112 (dew) / 0.61078 (frost)
+    double Td = mrcp(1 / 273.15 - (461.5 * mrcp((2.501 * 1000000) - (2340 * tc0))) * (lg - (-0.4923310411298262))) - 273.15;
+    const double Tf = mrcp(1 / 273.15 - (461.5 / (2.834 * 1000000)) * (lg - (-0.49301845011612494))) - 273.15;
+    tdew = (Td < 0) ? Tf : Td;
+    pk = cinterp(a.clim[4], koff, c) * c.pfac;
+    tc = tc0;
+    if (a.altcorrect == 1) {
+        tc = c.elevd * (5.0 / 1000) + tc0;
+    } else if (a.altcorrect == 2) {
+        const double tk = tc0 + 273.15;
+        const double rv = 0.622 * ea * mrcp(pk - ea);
+        const double lr = 9.8076 * (1 + (2501000 * rv) * mrcp(287 * tk)) *
+                          mrcp(1003.5 + (0.622 * 2501000.0 * 2501000.0 * rv) * mrcp(287 * tk * tk));
+        tc = lr * c.elevd + tc0;
+    }
+}
+
+template <int ARR>
 __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int cell, double sl, double cl, double lon,
-                                                 bool full, HourRec& h) {
-    const size_t i = (size_t)k * a.ncells + cell;
-    h.tc = __ldg(&a.clim[0][i]);
-    h.es = __ldg(&a.clim[1][i]);
-    h.ea = __ldg(&a.clim[2][i]);
-    h.tdew = __ldg(&a.clim[3][i]);
-    h.pk = __ldg(&a.clim[4][i]);
-    h.Rsw = __ldg(&a.clim[5][i]);
-    h.Rdif = __ldg(&a.clim[6][i]);
-    h.Rlw = __ldg(&a.clim[7][i]);
-    h.u2 = __ldg(&a.clim[8][i]);
-    h.soilmp = __ldg(&a.pnt[0][i]);
-    h.Gp = __ldg(&a.pnt[1][i]);
-    h.umu = __ldg(&a.pnt[2][i]);
-    h.kp = __ldg(&a.pnt[3][i]);
-    h.muGp = __ldg(&a.pnt[4][i]);
-    h.dtrp = __ldg(&a.pnt[5][i]);
+                                                 bool full, const CoarseCell& cc, HourRec& h) {
+    if (ARR == 2) {
+        const size_t ko = (size_t)k * (size_t)(a.clim_rows * a.clim_cols);
+        coarse_air(a, ko, cc, h.tc, h.es, h.ea, h.tdew, h.pk);
+        h.Rsw = cinterp(a.clim[5], ko, cc);
+        h.Rdif = cinterp(a.clim[6], ko, cc);
+        h.Rlw = cinterp(a.clim[7], ko, cc);
+        const double wu = cinterp(a.wu, ko, cc), wv = cinterp(a.wv, ko, cc);
+        h.u2 = msqrt(wu * wu + wv * wv); // R/internal.R:1259
+        h.soilmp = cinterp(a.pnt[0], ko, cc);
+        h.Gp = cinterp(a.pnt[1], ko, cc);
+        h.umu = cinterp(a.pnt[2], ko, cc);
+        h.kp = cinterp(a.pnt[3], ko, cc);
+        h.muGp = cinterp(a.pnt[4], ko, cc);
+        h.dtrp = cinterp(a.pnt[5], ko, cc);
+    } else {
+        const size_t i = (size_t)k * a.ncells + cell;
+        h.tc = __ldg(&a.clim[0][i]);
+        h.es = __ldg(&a.clim[1][i]);
+        h.ea = __ldg(&a.clim[2][i]);
+        h.tdew = __ldg(&a.clim[3][i]);
+        h.pk = __ldg(&a.clim[4][i]);
+        h.Rsw = __ldg(&a.clim[5][i]);
+        h.Rdif = __ldg(&a.clim[6][i]);
+        h.Rlw = __ldg(&a.clim[7][i]);
+        h.u2 = __ldg(&a.clim[8][i]);
+        h.soilmp = __ldg(&a.pnt[0][i]);
+        h.Gp = __ldg(&a.pnt[1][i]);
+        h.umu = __ldg(&a.pnt[2][i]);
+        h.kp = __ldg(&a.pnt[3][i]);
+        h.muGp = __ldg(&a.pnt[4][i]);
+        h.dtrp = __ldg(&a.pnt[5][i]);
+    }
     const HourCal c = a.cal[k];
     const double st = c.lt + (4.0 * lon + c.eot) / 60.0; // ref soltimeCpp :44
     const double tt = 0.261799 * (st - 12);
@@ -377,7 +456,7 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
     h.windex = c.windex;
 }
 
-template <bool ARR, int RQ, bool PACK>
+template <int ARR, int RQ, bool PACK>
 #ifdef MCF_MAXNREG
 #define MCF_KGRID_BOUNDS __maxnreg__(MCF_MAXNREG)
 #else
@@ -441,6 +520,8 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
         const double tadd = log(__ldg(&a.soil[11][cc])) / a.tfact - tmean;
         double lat = a.lat, lon = 0.0, dTmx = -0.6273 * a.dscal[0] + 49.79;
         double sl = 0.0, cl = 1.0; // sin / cos of the cell's latitude (modes 2/4)
+        CoarseCell ccell;
+        if (ARR == 2) coarse_setup(a, cc, ccell);
         if (ARR) {
             lat = __ldg(&a.lats[cc]);
             lon = __ldg(&a.lons[cc]);
@@ -508,7 +589,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 for (int hr = 0; hr < 24; ++hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
-                    if (ARR) hour_from_arrays(a, k, cell, sl, cl, lon, true, hloc);
+                    if (ARR) hour_from_arrays<ARR>(a, k, cell, sl, cl, lon, true, ccell, hloc);
                     const HourRec& h = ARR ? hloc : slab_day[hr];
                     if (hr == wrap_at) o = cell;
                     double ws, ha;
@@ -579,7 +660,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 for (int hr = 0; hr < 24; ++hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
-                    if (ARR) hour_from_arrays(a, k, cell, sl, cl, lon, false, hloc);
+                    if (ARR) hour_from_arrays<ARR>(a, k, cell, sl, cl, lon, false, ccell, hloc);
                     const HourRec& h = ARR ? hloc : slab_day[hr];
                     if (hr == wrap_at) o = cell;
                     const double radabs = radabs_n, surfwet = surfwet_n, radCsw = radCsw_n, Lhalf = Lhalf_n;
@@ -646,22 +727,56 @@ int grid_blocks_per_sm(bool arr, int rq) {
     return arr ? (kMinBlocks > 1 ? kMinBlocks - 1 : 1) : kMinBlocks;
 }
 
-cudaError_t launch_grid(const GridArgs& a, bool arr, int rq, int grid, cudaStream_t stream) {
+cudaError_t launch_grid(const GridArgs& a, int arr, int rq, int grid, cudaStream_t stream) {
 #define MCF_LAUNCH(ARR, RQ)                                                      \
     do {                                                                         \
         if (a.pack) k_grid<ARR, RQ, true><<<grid, kTile, 0, stream>>>(a);        \
         else k_grid<ARR, RQ, false><<<grid, kTile, 0, stream>>>(a);              \
     } while (0)
-    if (!arr) {
-        if (rq == RQ_ABOVE) MCF_LAUNCH(false, RQ_ABOVE);
-        else if (rq == RQ_SURFACE) MCF_LAUNCH(false, RQ_SURFACE);
-        else MCF_LAUNCH(false, RQ_BELOW);
-    } else {
-        if (rq == RQ_ABOVE) MCF_LAUNCH(true, RQ_ABOVE);
-        else if (rq == RQ_SURFACE) MCF_LAUNCH(true, RQ_SURFACE);
-        else MCF_LAUNCH(true, RQ_BELOW);
-    }
+#define MCF_LAUNCH_RQ(ARR)                                 \
+    do {                                                   \
+        if (rq == RQ_ABOVE) MCF_LAUNCH(ARR, RQ_ABOVE);     \
+        else if (rq == RQ_SURFACE) MCF_LAUNCH(ARR, RQ_SURFACE); \
+        else MCF_LAUNCH(ARR, RQ_BELOW);                    \
+    } while (0)
+    if (arr == 0) MCF_LAUNCH_RQ(0);
+    else if (arr == 1) MCF_LAUNCH_RQ(1);
+    else MCF_LAUNCH_RQ(2);
+#undef MCF_LAUNCH_RQ
 #undef MCF_LAUNCH
+    return cudaGetLastError();
+}
+
+// per-cell maximum over time of the interpolated, altitude-corrected air temperature (coarse-grid climate)
+__global__ void k_mxtc_cell_coarse(const __grid_constant__ GridArgs a, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.ncells) return;
+    CoarseCell cc;
+    coarse_setup(a, c, cc);
+    const size_t slice = (size_t)(a.clim_rows * a.clim_cols);
+    double mx = -273.15;
+    for (int k = 0; k < a.tsteps; ++k) {
+        double tc, es, ea, tdew, pk;
+        coarse_air(a, (size_t)k * slice, cc, tc, es, ea, tdew, pk);
+        if (tc > mx) mx = tc;
+    }
+    out[c] = mx;
+}
+cudaError_t launch_mxtc_cell_coarse(const GridArgs& a, double* mxtc_cell, cudaStream_t stream) {
+    k_mxtc_cell_coarse<<<(a.ncells + 127) / 128, 128, 0, stream>>>(a, mxtc_cell);
+    return cudaGetLastError();
+}
+__global__ void k_interp_coarse(const __grid_constant__ GridArgs a, const double* __restrict__ coarse,
+                                double* __restrict__ fine) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.ncells) return;
+    CoarseCell cc;
+    coarse_setup(a, c, cc);
+    const size_t slice = (size_t)(a.clim_rows * a.clim_cols);
+    for (int k = 0; k < a.tsteps; ++k) fine[(size_t)k * a.ncells + c] = cinterp(coarse, (size_t)k * slice, cc);
+}
+cudaError_t launch_interp_coarse(const GridArgs& a, const double* coarse, double* fine, cudaStream_t stream) {
+    k_interp_coarse<<<(a.ncells + 127) / 128, 128, 0, stream>>>(a, coarse, fine);
     return cudaGetLastError();
 }
 

@@ -56,6 +56,16 @@ struct GridArgs {
     const double* lons;
     const double* mxtc_cell; // per-cell max of tc over time (ref :2467-2471)
     const HourCal* cal;
+    // coarse-grid climate (ARR == 2): clim[] / pnt[] are [clim_rows, clim_cols, tsteps] and are interpolated
+    // bilinearly per cell-hour; clim[1..3] (es, ea, tdew) and clim[8] (windspeed) are unused
+    int32_t rows;            // fine rows: cell = i + rows * j
+    int32_t clim_rows, clim_cols, altcorrect;
+    double clim_row0, clim_drow, clim_col0, clim_dcol;
+    const double* relhum;
+    const double* wu;
+    const double* wv;
+    const double* elevd;     // [ncells] (altcorrect != 0)
+    const double* pfac;      // [ncells] (altcorrect != 0)
     // statics
     const double* veg[10];  // hgt pai x gsmax leafr leaft clump leafd paia leafden   [nlyr * ncells]
     const double* soil[13]; // Smin Smax gref soilb Psie Vq Vm Mc rho slope aspect twi svfa
@@ -111,9 +121,13 @@ cudaError_t launch_prep_hours(const int32_t* year, const int32_t* month, const i
                               int tsteps, bool arr, HourRec* hours, HourCal* cal, double* mxtc_out,
                               cudaStream_t stream);
 cudaError_t launch_mxtc_cell(const double* tc, int ncells, int tsteps, double* mxtc_cell, cudaStream_t stream);
+cudaError_t launch_mxtc_cell_coarse(const GridArgs& a, double* mxtc_cell, cudaStream_t stream);
+// coarse [clim_rows, clim_cols, tsteps] -> fine [ncells, tsteps] with the grid kernel's own interpolation
+cudaError_t launch_interp_coarse(const GridArgs& a, const double* coarse, double* fine, cudaStream_t stream);
 cudaError_t launch_twi_sum(const double* twi, int64_t n, double tfact, double* sum_count /* [2] */,
                            cudaStream_t stream);
-cudaError_t launch_grid(const GridArgs& a, bool arr, int rq, int grid, cudaStream_t stream);
+cudaError_t launch_grid(const GridArgs& a, int arr /* 0 table, 1 fine arrays, 2 coarse arrays */, int rq, int grid,
+                        cudaStream_t stream);
 int grid_blocks_per_sm(bool arr, int rq);
 cudaError_t launch_below(const BelowArgs& a, cudaStream_t stream);
 cudaError_t launch_bioclim(const BioArgs& a, cudaStream_t stream);

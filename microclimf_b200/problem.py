@@ -53,6 +53,14 @@ class GridProblem:
     lyr_st: Optional[np.ndarray] = None
     lyr_ed: Optional[np.ndarray] = None
     twi_mean: Optional[float] = None
+    # coarse-grid climate (modes 2/4): series are [clim_rows, clim_cols, tsteps]; see include/microclimf_b200.h
+    clim_rows: int = 0
+    clim_cols: int = 0
+    clim_row0: float = 0.0
+    clim_drow: float = 0.0
+    clim_col0: float = 0.0
+    clim_dcol: float = 0.0
+    altcorrect: int = 0
     arrays: Dict[str, object] = field(default_factory=dict)  # flat numpy arrays or CUDA torch tensors
 
     # ------------------------------------------------------------------ construction helpers
@@ -68,6 +76,10 @@ class GridProblem:
     def layered(self) -> bool:
         return self.mode in (3, 4)
 
+    @property
+    def coarse(self) -> bool:
+        return self.array_climate and self.clim_rows > 0
+
     def set(self, name: str, value) -> None:
         if name in ("year", "month", "day"):
             self.arrays[name] = _flat_i32(value)
@@ -78,8 +90,12 @@ class GridProblem:
         nc, T = self.ncells, self.tsteps
         if name in OBSTIME_FIELDS or name == "winddir":
             return T
-        if name in SERIES_FIELDS:
+        if name in SERIES_FIELDS or name in ("relhum", "wu", "wv"):
+            if self.coarse:
+                return self.clim_rows * self.clim_cols * T
             return nc * T if self.array_climate else T
+        if name in ("elevd", "pfac"):
+            return nc
         if name in _abi.VEG_FIELDS:
             return nc * (self.nlyr if self.layered else 1)
         if name == "wsa":
@@ -93,7 +109,14 @@ class GridProblem:
     def validate(self) -> None:
         if self.mode not in (1, 2, 3, 4):
             raise ValueError("mode must be 1..4")
-        required = list(OBSTIME_FIELDS) + list(_abi.CLIM_FIELDS) + list(_abi.VEG_FIELDS) + list(_abi.SOIL_FIELDS)
+        clim = list(_abi.CLIM_FIELDS)
+        if self.coarse:
+            clim = ["temp", "relhum", "pres", "swdown", "difrad", "lwdown", "wu", "wv", "winddir"]
+            if self.altcorrect not in (0, 1, 2):
+                raise ValueError("altcorrect must be 0, 1 or 2")
+            if self.altcorrect:
+                clim += ["elevd", "pfac"]
+        required = list(OBSTIME_FIELDS) + clim + list(_abi.VEG_FIELDS) + list(_abi.SOIL_FIELDS)
         required += ["p_soilm", "p_G", "p_umu", "p_kp", "p_muGp", "p_dtrp"]
         if self.reqhgt < 0:
             required += ["p_Tg", "p_Tbp"]
@@ -139,6 +162,11 @@ class GridProblem:
             setattr(s, name, a.ctypes.data_as(_I32 if is_int else _F64))
         if self.twi_mean is not None:
             s.has_twi_mean, s.twi_mean = 1, float(self.twi_mean)
+        if self.coarse:
+            s.clim_rows, s.clim_cols = int(self.clim_rows), int(self.clim_cols)
+            s.clim_row0, s.clim_drow = float(self.clim_row0), float(self.clim_drow)
+            s.clim_col0, s.clim_dcol = float(self.clim_col0), float(self.clim_dcol)
+            s.altcorrect = int(self.altcorrect)
         return s, keep
 
     # ------------------------------------------------------------------ transforms
@@ -162,17 +190,23 @@ class GridProblem:
                            tfact=self.tfact, mat=self.mat, complete=self.complete, nlyr=self.nlyr,
                            lyr_st=None if self.lyr_st is None else np.array(self.lyr_st, dtype=np.int32),
                            lyr_ed=None if self.lyr_ed is None else np.array(self.lyr_ed, dtype=np.int32),
-                           twi_mean=self.twi_mean)
+                           twi_mean=self.twi_mean, clim_rows=self.clim_rows, clim_cols=self.clim_cols,
+                           clim_row0=self.clim_row0, clim_drow=self.clim_drow, clim_col0=self.clim_col0,
+                           clim_dcol=self.clim_dcol, altcorrect=self.altcorrect)
 
     def band(self, c0: int, c1: int) -> "GridProblem":
         """Column band [c0, c1) of a host problem: the unit of multi-GPU sharding.  In R layout a
         column band is a contiguous slab of every [rows, cols, ...] slice."""
         out = self._clone_meta()
         out.cols = c1 - c0
+        out.clim_col0 = self.clim_col0 + self.clim_dcol * c0  # the coarse grid is replicated, the mapping shifts
         R, Cc, T = self.rows, self.cols, self.tsteps
         for n, a in self.arrays.items():
             ln = self.expected_len(n)
             if ln in (T,) and (n in OBSTIME_FIELDS or n == "winddir" or (n in SERIES_FIELDS and not self.array_climate)):
+                out.arrays[n] = a
+                continue
+            if self.coarse and (n in SERIES_FIELDS or n in ("relhum", "wu", "wv")):
                 out.arrays[n] = a
                 continue
             nsl = ln // (R * Cc)

@@ -291,3 +291,60 @@ def bioclim_days(year: int = 2023):
         return np.concatenate([m * 24 + np.arange(24) for m in ms]).astype(np.int32)
 
     return days, dict(wetq=q(10), dryq=q(4), hotq=q(5), colq=q(11))
+
+
+def make_coarse_problem(rows: int, cols: int, tsteps: int, reqhgt: float = 0.05, mode: int = 2, crows: int = 5,
+                        ccols: int = 4, altcorrect: int = 0, seed: int = 20240321, nlyr: int = 1, zref: float = 30.0,
+                        lat: float = 50.0, lon: float = -5.0, complete: bool = True) -> GridProblem:
+    """Modes 2/4 with the climate and point-model series on a COARSE [crows, ccols] grid covering the same extent
+    as the fine raster (what runpointmodela produces, one series per coarse cell), to be interpolated by the kernels
+    (mcf_problem.clim_rows > 0).  oracle/prep_oracle.materialise_coarse expands it the way .runmodel2Cpp does."""
+    assert mode in (2, 4)
+    base = make_problem(rows, cols, tsteps, reqhgt=reqhgt, mode=mode - 1, seed=seed, nlyr=nlyr, zref=zref, lat=lat,
+                        lon=lon, complete=complete)
+    f = {n: base.arrays[n] for n in ("temp", "pres", "swdown", "difrad", "lwdown", "windspeed", "winddir", "ea", "es",
+                                     "p_soilm", "p_Tg", "p_Tbp", "p_G", "p_umu", "p_kp", "p_muGp", "p_dtrp")}
+    T = base.tsteps
+    rng = np.random.default_rng(seed + 7)
+    p = base.replace(mode=mode, clim_rows=crows, clim_cols=ccols, altcorrect=altcorrect)
+    p.arrays = {n: a for n, a in base.arrays.items() if n not in f and n not in ("tdew",)}
+    p.clim_drow, p.clim_dcol = crows / rows, ccols / cols
+    p.clim_row0, p.clim_col0 = 0.5 * p.clim_drow - 0.5, 0.5 * p.clim_dcol - 0.5
+    ncc = crows * ccols
+
+    def field(series, amp, lo=None):
+        a = series[:, None] + amp * rng.uniform(-1, 1, ncc)[None, :] * (1 + 0.2 * np.sin(np.arange(T) / 5.0))[:, None]
+        if lo is not None:
+            a = np.maximum(a, lo)
+        return np.ascontiguousarray(a).ravel()  # [T, ccols * crows] C-order == R's [crows, ccols, T]
+
+    p.arrays["temp"] = field(f["temp"], 1.5)
+    rh = np.clip(100 * f["ea"] / f["es"], 20, 100)
+    p.arrays["relhum"] = np.clip(field(rh, 6.0), 5.0, 100.0)
+    p.arrays["pres"] = field(f["pres"], 0.4)
+    sw = field(f["swdown"], 0.0) * np.repeat(1 + 0.1 * rng.uniform(-1, 1, ncc)[None, :], T, axis=0).ravel()
+    p.arrays["swdown"] = sw
+    p.arrays["difrad"] = np.minimum(field(f["difrad"], 0.0), sw)
+    p.arrays["lwdown"] = field(f["lwdown"], 6.0)
+    u2 = field(f["windspeed"], 0.4, lo=0.5)
+    wd = field(f["winddir"], 15.0)
+    p.arrays["wu"], p.arrays["wv"] = u2 * np.cos(wd * np.pi / 180), u2 * np.sin(wd * np.pi / 180)
+    # R/internal.R:1256-1261: the wind direction handed to the solver is that of the mean coarse wind vector
+    wuv = p.arrays["wu"].reshape(T, ncc).mean(axis=1)
+    wvv = p.arrays["wv"].reshape(T, ncc).mean(axis=1)
+    p.arrays["winddir"] = np.mod(np.arctan2(wvv, wuv) * 180 / np.pi, 360.0)
+    for n, amp in (("p_soilm", 0.02), ("p_Tg", 1.0), ("p_Tbp", 0.5), ("p_G", 5.0), ("p_umu", 0.05), ("p_kp", 0.05),
+                   ("p_muGp", 0.005)):
+        p.arrays[n] = field(f[n], amp)
+    p.arrays["p_dtrp"] = field(f["p_dtrp"], 1.0, lo=0.5)
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    u = (ii / max(rows - 1, 1)).ravel(order="F")
+    v = (jj / max(cols - 1, 1)).ravel(order="F")
+    p.arrays["lats"] = np.ascontiguousarray(lat + 0.05 * (u - 0.5))
+    p.arrays["lons"] = np.ascontiguousarray(lon + 0.08 * (v - 0.5))
+    if altcorrect:
+        dtm = 150 + 120 * np.sin(3 * u) * np.cos(2 * v)                      # fine elevations
+        p.arrays["elevd"] = np.ascontiguousarray(40 * np.sin(5 * u + 2 * v))  # resample(dtmc) - dtm
+        p.arrays["pfac"] = np.ascontiguousarray(((293 - 0.0065 * dtm) / 293) ** 5.26)
+    p.validate()
+    return p
