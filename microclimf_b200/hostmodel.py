@@ -30,7 +30,9 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import api
-from .spatial import Raster, aggregate_mean, as_raster, latlong_from_raster, mask, resample_bilinear, terrain
+from .problem import GridProblem
+from .spatial import (Raster, aggregate_mean, as_raster, latlong_from_raster, latslons_from_raster, mask,
+                      resample_bilinear, terrain)
 from .tables import SOILPARAMETERS
 
 VEG_NAMES = ("pai", "hgt", "x", "gsmax", "leafr", "clump", "leafd", "leaft")
@@ -448,8 +450,11 @@ class ModelCall:
     """The argument list handed to the operator (what `.Call(_microclimf_runmicroNCpp, ...)` receives)."""
     mode: int
     args: Dict[str, object] = field(default_factory=dict)
+    prob: Optional[GridProblem] = None  # modes 2/4: the coarse-grid problem handed to the kernels
 
     def problem(self):
+        if self.prob is not None:
+            return self.prob
         a = self.args
         return api._problem(self.mode, a.get("dfsel"), a["obstime"], a["climdata"], a["pointm"], a["vegp"], a["soilc"],
                             a["reqhgt"], a["zref"], a["lat"], a["lon"], None, None, a["Sminp"], a["Smaxp"], a["tfact"],
@@ -461,6 +466,8 @@ class ModelCall:
         a = self.args
         if packed:
             return api.run_problem_packed(self.problem(), out=a["out"])
+        if self.prob is not None:
+            return api.run_problem(self.prob, out=a["out"])
         if self.mode == 1:
             return api.runmicro1Cpp(a["obstime"], a["climdata"], a["pointm"], a["vegp"], a["soilc"], a["reqhgt"], a["zref"],
                                     a["lat"], a["lon"], a["Sminp"], a["Smaxp"], a["tfact"], a["complete"], a["mat"], a["out"])
@@ -491,72 +498,12 @@ def prepare_model(micropoint: Micropoint, vegp, soilc, dtm, reqhgt: float = 0.05
     pointm = {k: np.asarray(v, dtype=np.float64) for k, v in micropoint.dfo.items()}
     nT = temp.size
     pointm["Tbp"] = np.asarray(micropoint.Tbz, dtype=np.float64) if reqhgt < 0 else np.zeros(nT)
-    # ---- vegetation: .sortvegp(method = "C") (R/internal.R:249-272)
-    n = len(micropoint.tmeorig)
+    # ---- vegetation, soil, terrain layers
     subs = np.asarray(micropoint.subs, dtype=int)
-    dmx = _vegpdmx(vegp)
-    s_all = np.clip(_r_round(np.linspace(0.50001, dmx + 0.5, n)).astype(int), 1, dmx)
-    subs2 = np.array(list(dict.fromkeys(s_all[subs - 1].tolist())), dtype=int)
-    vg = {k: _intr(vegp[k], dmx, subs2) for k in VEG_NAMES}
-    s_raw = _r_round(np.linspace(0.50001, dmx + 0.5, n)).astype(int)[subs - 1]
-    if s_raw.size % 24 != 0:
-        raise ValueError("weather needs to include data for entire days (24 hours)")
-    sdd = np.array([_getmode(row) for row in s_raw.reshape(-1, 24)])
-    lsubs = np.repeat(sdd, 24).astype(int)
-    with np.errstate(invalid="ignore"):
-        vg["hgt"] = np.where(vg["pai"] == 0, 0.0, vg["hgt"])
-        vg["pai"] = np.where(vg["hgt"] == 0, 0.0, vg["pai"])
-    # ---- foliage density
-    paia_in = None
-    if pai_a is not None:
-        paia_in = _intr(as_raster(pai_a, dtm), n, subs)
-    fd = _foliageden(reqhgt, vg["hgt"], vg["pai"], paia_in)
-    vg["paia"], vg["leafden"] = fd["pai_a"], fd["leafden"]
-    if not layered:
-        vg = {k: v[:, :, 0] for k, v in vg.items()}
-    # ---- layer spans (R/internal.R:1388-1399)
-    dfsel = None
-    if layered:
-        lyrs = list(dict.fromkeys(lsubs.tolist()))
-        st, ed = [], []
-        for ly in lyrs:
-            s = np.nonzero(lsubs == ly)[0] + 1  # 1-based, as which()
-            st.append(int(math.floor(s[0] / 24) * 24))
-            ed.append(int(math.floor(s[-1] / 24) * 24 - 1))
-        dfsel = dict(lyr=np.arange(1, len(lyrs) + 1, dtype=np.int32), st=np.array(st, dtype=np.int32),
-                     ed=np.array(ed, dtype=np.int32))
-    # ---- soil
-    soilp = _soilinit(soilc)
-    sc: Dict[str, np.ndarray] = dict(gref=soilc["groundr"].matrix().copy(), Smin=soilp["Smin"], Smax=soilp["Smax"],
-                                     soilb=soilp["soilb"], Psie=soilp["psi_e"], Vq=soilp["Vq"], Vm=soilp["Vm"],
-                                     Mc=soilp["Mc"], rho=soilp["rho"])
-    # ---- slope, aspect, wetness index
-    slope = terrain(dtm, "slope") if slr is None else as_raster(slr, dtm)
-    aspect = terrain(dtm, "aspect") if apr is None else as_raster(apr, dtm)
-    twi_r = _topidx(dtm) if twi is None else as_raster(twi, dtm)
-
-    def fill(r: Raster, v: float) -> np.ndarray:
-        m = r.matrix().copy()
-        m[np.isnan(m)] = v
-        return mask(r.like(m), dtm).matrix()
-
-    sc["slope"], sc["aspect"], sc["twi"] = fill(slope, 0.0), fill(aspect, 0.0), fill(twi_r, 1.0)
-    # ---- horizon, sky view, wind shelter
     lat, lon = latlong_from_raster(dtm)
-    if hor is None:
-        hor_a, svf_gpu = api.horizon(dtm.matrix(), dtm.res[0], want_svf=True)
-    else:
-        hor_a, svf_gpu = np.asarray(hor, dtype=np.float64), None
-    sc["hor"] = hor_a
-    if svf is None:
-        if svf_gpu is None:
-            msl = np.tan(np.mean(np.arctan(hor_a), axis=2))
-            svf_gpu = 0.5 * np.cos(2 * msl) + 0.5
-        sc["svfa"] = svf_gpu
-    else:
-        sc["svfa"] = as_raster(svf, dtm).matrix()
-    s = 10 if dtm.res[0] <= 100 else 1
-    sc["wsa"] = _windsheltera(dtm, micropoint.zref, s) if wsa is None else np.asarray(wsa, dtype=np.float64)
+    vg, sc, dfsel, layered2 = _static_layers(vegp, soilc, dtm, micropoint, reqhgt, pai_a, slr, apr, hor, twi, wsa, svf,
+                                             micropoint.zref, zero_pairs=True)
+    assert layered2 == layered
     Sminp, Smaxp = _getmode(sc["Smin"]), _getmode(sc["Smax"])
     complete = len(subs) == len(micropoint.tmeorig)
     out = [bool(o) for o in out]
@@ -572,24 +519,198 @@ def prepare_model(micropoint: Micropoint, vegp, soilc, dtm, reqhgt: float = 0.05
     return ModelCall(mode=3 if layered else 1, args=args)
 
 
+def _static_layers(vegp, soilc, dtm, micropoint, reqhgt, pai_a, slr, apr, hor, twi, wsa, svf, zref, zero_pairs):
+    """The vegetation / soil / terrain part shared by .runmodel1Cpp ... .runmodel4Cpp (R/internal.R:1098-1156,
+    1278-1330): returns (vegp dict, soilc dict, dfsel | None, layered)."""
+    n = len(micropoint.tmeorig)
+    subs = np.asarray(micropoint.subs, dtype=int)
+    dmx = _vegpdmx(vegp)
+    layered = dmx > 1
+    s_all = np.clip(_r_round(np.linspace(0.50001, dmx + 0.5, n)).astype(int), 1, dmx)
+    subs2 = np.array(list(dict.fromkeys(s_all[subs - 1].tolist())), dtype=int)
+    vg = {k: _intr(vegp[k], dmx, subs2) for k in VEG_NAMES}
+    s_raw = _r_round(np.linspace(0.50001, dmx + 0.5, n)).astype(int)[subs - 1]
+    if s_raw.size % 24 != 0:
+        raise ValueError("weather needs to include data for entire days (24 hours)")
+    lsubs = np.repeat(np.array([_getmode(row) for row in s_raw.reshape(-1, 24)]), 24).astype(int)
+    if zero_pairs:  # only .runmodel1Cpp / .runmodel3Cpp do this (R/internal.R:1101-1104, 1382-1385)
+        with np.errstate(invalid="ignore"):
+            vg["hgt"] = np.where(vg["pai"] == 0, 0.0, vg["hgt"])
+            vg["pai"] = np.where(vg["hgt"] == 0, 0.0, vg["pai"])
+    paia_in = None if pai_a is None else _intr(as_raster(pai_a, dtm), n, subs)
+    fd = _foliageden(reqhgt, vg["hgt"], vg["pai"], paia_in)
+    vg["paia"], vg["leafden"] = fd["pai_a"], fd["leafden"]
+    if not layered:
+        vg = {k: v[:, :, 0] for k, v in vg.items()}
+    dfsel = None
+    if layered:
+        lyrs = list(dict.fromkeys(lsubs.tolist()))
+        st, ed = [], []
+        for ly in lyrs:
+            s = np.nonzero(lsubs == ly)[0] + 1
+            st.append(int(math.floor(s[0] / 24) * 24))
+            ed.append(int(math.floor(s[-1] / 24) * 24 - 1))
+        dfsel = dict(lyr=np.arange(1, len(lyrs) + 1, dtype=np.int32), st=np.array(st, dtype=np.int32),
+                     ed=np.array(ed, dtype=np.int32))
+    soilp = _soilinit(soilc)
+    sc: Dict[str, np.ndarray] = dict(gref=soilc["groundr"].matrix().copy(), Smin=soilp["Smin"], Smax=soilp["Smax"],
+                                     soilb=soilp["soilb"], Psie=soilp["psi_e"], Vq=soilp["Vq"], Vm=soilp["Vm"],
+                                     Mc=soilp["Mc"], rho=soilp["rho"])
+    slope = terrain(dtm, "slope") if slr is None else as_raster(slr, dtm)
+    aspect = terrain(dtm, "aspect") if apr is None else as_raster(apr, dtm)
+    twi_r = _topidx(dtm) if twi is None else as_raster(twi, dtm)
+
+    def fill(r: Raster, v: float) -> np.ndarray:
+        m = r.matrix().copy()
+        m[np.isnan(m)] = v
+        return mask(r.like(m), dtm).matrix()
+
+    sc["slope"], sc["aspect"], sc["twi"] = fill(slope, 0.0), fill(aspect, 0.0), fill(twi_r, 1.0)
+    if hor is None:
+        hor_a, svf_gpu = api.horizon(dtm.matrix(), dtm.res[0], want_svf=True)
+    else:
+        hor_a, svf_gpu = np.asarray(hor, dtype=np.float64), None
+    sc["hor"] = hor_a
+    if svf is None:
+        if svf_gpu is None:
+            msl = np.tan(np.mean(np.arctan(hor_a), axis=2))
+            svf_gpu = 0.5 * np.cos(2 * msl) + 0.5
+        sc["svfa"] = svf_gpu
+    else:
+        sc["svfa"] = as_raster(svf, dtm).matrix()
+    s = 10 if dtm.res[0] <= 100 else 1
+    sc["wsa"] = _windsheltera(dtm, zref, s) if wsa is None else np.asarray(wsa, dtype=np.float64)
+    return vg, sc, dfsel, layered
+
+
+def prepare_model_a(micropointa, vegp, soilc, dtm, dtmc, reqhgt: float = 0.05, runchecks: bool = True, altcorrect: int = 0,
+                    pai_a=None, tfact: float = 1.5, out: Sequence[bool] = (True,) * 10, slr=None, apr=None, hor=None,
+                    twi=None, wsa=None, svf=None) -> ModelCall:
+    """ref .runmodel2Cpp (R/internal.R:1172-1344) and .runmodel4Cpp (:1461-1642): gridded climate.  `micropointa` is
+    the list runpointmodela returns — one Micropoint (or None for a sea / NA cell) per cell of the coarse raster
+    `dtmc`, in terra's cell order (row by row).
+
+    The reference expands every series to the fine raster here, on the host (`.cca` -> terra::resample).  This build
+    hands the COARSE [rows_c, cols_c, hours] arrays to the kernels, which interpolate per cell-hour and derive
+    es / ea / tdew, the altitude correction and the wind speed themselves (include/microclimf_b200.h, clim_rows > 0);
+    only O(cells) layers (elevation difference, pressure factor) and O(coarse) arithmetic are prepared here."""
+    dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
+    vegp, dtm, soilc = _cleanvars(vegp, soilc, dtm)
+    dtmc = as_raster(dtmc)
+    cr, cc = dtmc.nrows, dtmc.ncols
+    if len(micropointa) != cr * cc:
+        raise ValueError("micropointa must hold one entry per cell of dtmc")
+    last = None
+    mats = []
+    weathers: List[Optional[Dict[str, np.ndarray]]] = []
+    for mp in micropointa:
+        if mp is None:
+            weathers.append(None)
+            continue
+        w = mp.weather
+        if runchecks:
+            rc = checkinputs(w, vegp, soilc, dtm, mp.zref)
+            w, vegp, soilc = rc["weather"], rc["vegp"], rc["soilc"]
+        weathers.append(w)
+        mats.append(mp.matemp)
+        last = mp
+    if last is None:
+        raise ValueError("micropointa holds no point-model output")
+    T = len(last.weather["temp"])
+    obstime = _obstime(last.weather["obs_time"])
+
+    def cca(getter):
+        """ref .cca (R/internal.R:523-542) without the resample: [rows_c, cols_c, T], NA where there is no point model."""
+        a = np.full((cr, cc, T), np.nan)
+        k = 0
+        for i in range(cr):
+            for j in range(cc):
+                if micropointa[k] is not None:
+                    a[i, j, :] = getter(k)
+                k += 1
+        return a
+
+    wv_ = lambda name: cca(lambda k: np.asarray(weathers[k][name], dtype=np.float64))  # noqa: E731
+    dv_ = lambda name: cca(lambda k: np.asarray(micropointa[k].dfo[name], dtype=np.float64))  # noqa: E731
+    p = GridProblem(mode=2, rows=dtm.nrows, cols=dtm.ncols, tsteps=T, reqhgt=float(reqhgt), zref=float(last.zref),
+                    tfact=float(tfact), mat=float(np.mean(mats)), complete=len(last.subs) == len(last.tmeorig))
+    for k in ("year", "month", "day", "hour"):
+        p.set(k, obstime[k])
+    p.clim_rows, p.clim_cols, p.altcorrect = cr, cc, int(altcorrect)
+    rxf, ryf = dtm.res
+    rxc, ryc = dtmc.res
+    p.clim_drow, p.clim_dcol = ryf / ryc, rxf / rxc
+    p.clim_row0 = (dtmc.ymax - (dtm.ymax - 0.5 * ryf)) / ryc - 0.5
+    p.clim_col0 = ((dtm.xmin + 0.5 * rxf) - dtmc.xmin) / rxc - 0.5
+    p.set("temp", wv_("temp"))
+    p.set("relhum", wv_("relhum"))
+    pk = wv_("pres")
+    if altcorrect:
+        zc = dtmc.matrix().copy()
+        zc[np.isnan(zc)] = 0.0  # R/internal.R:1229
+        pk = pk / (((293 - 0.0065 * zc[:, :, None]) / 293) ** 5.26)
+        zf = dtm.matrix()
+        p.set("pfac", ((293 - 0.0065 * zf) / 293) ** 5.26)
+        p.set("elevd", resample_bilinear(dtmc.like(zc), dtm).matrix() - zf)
+    p.set("pres", pk)
+    for k in ("swdown", "difrad", "lwdown"):
+        p.set(k, wv_(k))
+    u2, wd = wv_("windspeed"), wv_("winddir")
+    wu, wvv = u2 * np.cos(wd * np.pi / 180), u2 * np.sin(wd * np.pi / 180)
+    p.set("wu", wu)
+    p.set("wv", wvv)
+    p.set("winddir", np.mod(np.arctan2(np.nanmean(wvv, axis=(0, 1)), np.nanmean(wu, axis=(0, 1))) * 180 / np.pi, 360))
+    for src, dst in (("umu", "p_umu"), ("kp", "p_kp"), ("muGp", "p_muGp"), ("dtrp", "p_dtrp"), ("G", "p_G"),
+                     ("soilm", "p_soilm"), ("Tg", "p_Tg")):
+        p.set(dst, dv_(src))
+    if reqhgt < 0:
+        p.set("p_Tbp", cca(lambda k: np.asarray(micropointa[k].Tbz, dtype=np.float64)))
+    else:
+        p.set("p_Tbp", np.zeros((cr, cc, T)))
+    vg, sc, dfsel, layered = _static_layers(vegp, soilc, dtm, last, reqhgt, pai_a, slr, apr, hor, twi, wsa, svf,
+                                            last.zref, zero_pairs=False)
+    if layered:
+        p.mode, p.nlyr = 4, vg["pai"].shape[2]
+        p.lyr_st, p.lyr_ed = dfsel["st"], dfsel["ed"]
+    for k, v in vg.items():
+        p.set(k, v)
+    for k, v in sc.items():
+        p.set("Psie" if k == "Psie" else k, v)
+    lats, lons = latslons_from_raster(dtm)
+    p.set("lats", lats)
+    p.set("lons", lons)
+    p.Sminp, p.Smaxp = _getmode(sc["Smin"]), _getmode(sc["Smax"])
+    out = [bool(o) for o in out]
+    if reqhgt == 0:
+        out = [o and bool(m) for o, m in zip(out, (1, 0, 0, 1, 0, 1, 1, 1, 1, 1))]
+    if reqhgt < 0:
+        out = [o and bool(m) for o, m in zip(out, (1, 0, 0, 1, 0, 0, 0, 0, 0, 0))]
+    p.validate()
+    return ModelCall(mode=p.mode, args=dict(out=out), prob=p)
+
+
 def runmicro(micropoint, reqhgt, vegp, soilc, dtm, dtmc=None, altcorrect=0, snow=False, snowmod=None, runchecks=True,
              pai_a=None, tfact=1.5, out=(True,) * 10, slr=None, apr=None, hor=None, twi=None, wsa=None, svf=None,
              method="Cpp", packed=False):
     """ref runmicro (R/Cppwrappers.R:376-396): grid microclimate model.  Returns the reference's named list
     (dict of [rows, cols, hours] arrays) plus `tme`.  As in the reference, `svf` and `method` are accepted
-    but not forwarded (R/internal.R:3336).  Gridded-climate input (a list of micropoints, `.runmodel2Cpp` /
-    `.runmodel4Cpp`) and the snow branch are the next rows of SURVEY.md §8f and raise NotImplementedError.
+    but not forwarded (R/internal.R:3336).  A list of micropoints (runpointmodela) with `dtmc` takes the gridded-climate path
+    (`.runmodel2Cpp` / `.runmodel4Cpp` -> prepare_model_a).  The snow branch is SURVEY.md §8f NEXT-3 and raises
+    NotImplementedError.
     `packed = True` (an addition) returns writetonc's integer packing straight from the kernels."""
     if snow:
         raise NotImplementedError("snow = TRUE (.runmicrosnow1/2) is not part of this build yet (SURVEY.md NEXT-3)")
     if not isinstance(micropoint, Micropoint):
         if dtmc is None:
             raise ValueError("Require dtmc. Please provide\n")
-        raise NotImplementedError("array climate input (.runmodel2Cpp/.runmodel4Cpp packing) is not built yet; "
-                                  "call api.runmicro2Cpp / api.runmicro4Cpp with packed arrays")
-    call = prepare_model(micropoint, vegp, soilc, dtm, reqhgt, runchecks, pai_a, tfact, out, slr, apr, hor, twi, wsa)
+        call = prepare_model_a(micropoint, vegp, soilc, dtm, dtmc, reqhgt, runchecks, altcorrect, pai_a, tfact, out, slr,
+                               apr, hor, twi, wsa)
+        tme = next(m for m in micropoint if m is not None).tmeorig
+    else:
+        call = prepare_model(micropoint, vegp, soilc, dtm, reqhgt, runchecks, pai_a, tfact, out, slr, apr, hor, twi, wsa)
+        tme = micropoint.tmeorig
     mout = call.run(packed=packed)
-    mout["tme"] = np.asarray(micropoint.tmeorig)
+    mout["tme"] = np.asarray(tme)
     return mout
 
 

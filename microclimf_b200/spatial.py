@@ -191,6 +191,7 @@ def _wkt_param(crs: str, name: str) -> Optional[float]:
 def _inverse_tmerc(E, N, a, invf, lat0, lon0, k0, FE, FN):
     """Inverse transverse Mercator (Ordnance Survey 'A guide to coordinate systems in Great Britain',
     annexe C): easting / northing -> geodetic latitude / longitude on the projection's own ellipsoid."""
+    E, N = np.asarray(E, dtype=np.float64), np.asarray(N, dtype=np.float64)
     f = 1.0 / invf
     b = a * (1.0 - f)
     e2 = (a * a - b * b) / (a * a)
@@ -200,22 +201,22 @@ def _inverse_tmerc(E, N, a, invf, lat0, lon0, k0, FE, FN):
     def M(phi):
         dp, sp = phi - phi0, phi + phi0
         return b * k0 * ((1 + n + 1.25 * n * n + 1.25 * n ** 3) * dp
-                         - (3 * n + 3 * n * n + 2.625 * n ** 3) * math.sin(dp) * math.cos(sp)
-                         + (1.875 * n * n + 1.875 * n ** 3) * math.sin(2 * dp) * math.cos(2 * sp)
-                         - (35.0 / 24.0) * n ** 3 * math.sin(3 * dp) * math.cos(3 * sp))
+                         - (3 * n + 3 * n * n + 2.625 * n ** 3) * np.sin(dp) * np.cos(sp)
+                         + (1.875 * n * n + 1.875 * n ** 3) * np.sin(2 * dp) * np.cos(2 * sp)
+                         - (35.0 / 24.0) * n ** 3 * np.sin(3 * dp) * np.cos(3 * sp))
 
     phi = (N - FN) / (a * k0) + phi0
     for _ in range(100):
         m = M(phi)
-        if abs(N - FN - m) < 1e-6:
+        if np.all(np.abs(N - FN - m) < 1e-6):
             break
         phi = (N - FN - m) / (a * k0) + phi
-    s2 = math.sin(phi) ** 2
-    nu = a * k0 / math.sqrt(1 - e2 * s2)
+    s2 = np.sin(phi) ** 2
+    nu = a * k0 / np.sqrt(1 - e2 * s2)
     rho = a * k0 * (1 - e2) * (1 - e2 * s2) ** -1.5
     eta2 = nu / rho - 1.0
-    t = math.tan(phi)
-    sec = 1.0 / math.cos(phi)
+    t = np.tan(phi)
+    sec = 1.0 / np.cos(phi)
     VII = t / (2 * rho * nu)
     VIII = t / (24 * rho * nu ** 3) * (5 + 3 * t * t + eta2 - 9 * t * t * eta2)
     IX = t / (720 * rho * nu ** 5) * (61 + 90 * t * t + 45 * t ** 4)
@@ -226,7 +227,7 @@ def _inverse_tmerc(E, N, a, invf, lat0, lon0, k0, FE, FN):
     dE = E - FE
     lat = phi - VII * dE ** 2 + VIII * dE ** 4 - IX * dE ** 6
     lon = lam0 + X * dE - XI * dE ** 3 + XII * dE ** 5 - XIIA * dE ** 7
-    return math.degrees(lat), math.degrees(lon)
+    return np.degrees(lat), np.degrees(lon)
 
 
 def latlong_from_xy(crs: str, x: float, y: float) -> Tuple[float, float]:
@@ -235,7 +236,7 @@ def latlong_from_xy(crs: str, x: float, y: float) -> Tuple[float, float]:
     inverted on their own ellipsoid.  No datum shift is applied (the bundled CRS has an unknown datum,
     for which PROJ applies none either)."""
     if not crs or re.search(r"^\s*(GEOGCRS|GEOGCS)\[", crs) or "+proj=longlat" in crs:
-        return float(y), float(x)
+        return y, x
     if "Transverse Mercator" in crs or "Transverse_Mercator" in crs or "+proj=tmerc" in crs:
         m = re.search(r'ELLIPSOID\["[^"]*",\s*([-0-9.eE+]+),\s*([-0-9.eE+]+)', crs)
         if not m:
@@ -257,4 +258,15 @@ def latlong_from_xy(crs: str, x: float, y: float) -> Tuple[float, float]:
 
 def latlong_from_raster(r: Raster) -> Tuple[float, float]:
     """ref .latlongfromraster (R/internal.R:59-68): centre of the extent, transformed to EPSG:4326."""
-    return latlong_from_xy(r.crs, 0.5 * (r.xmin + r.xmax), 0.5 * (r.ymin + r.ymax))
+    lat, lon = latlong_from_xy(r.crs, 0.5 * (r.xmin + r.xmax), 0.5 * (r.ymin + r.ymax))
+    return float(lat), float(lon)
+
+
+def latslons_from_raster(r: Raster) -> Tuple[np.ndarray, np.ndarray]:
+    """ref .latslonsfromr (R/internal.R:86-99): latitude / longitude of every cell centre, [nrows, ncols]."""
+    rx, ry = r.res
+    xc = r.xmin + (np.arange(r.ncols) + 0.5) * rx
+    yc = r.ymax - (np.arange(r.nrows) + 0.5) * ry
+    X, Y = np.meshgrid(xc, yc)
+    lat, lon = latlong_from_xy(r.crs, X, Y)
+    return np.asarray(lat, dtype=np.float64), np.asarray(lon, dtype=np.float64)

@@ -48,7 +48,8 @@ def test_struct_mirror_matches_header():
             names.append(extra.strip().lstrip("*"))
     assert names == [f[0] for f in _abi.McfProblem._fields_]
     nptr = 2 + 4 + len(_abi.CLIM_FIELDS) + len(_abi.POINTM_FIELDS) + len(_abi.VEG_FIELDS) + len(_abi.SOIL_FIELDS) + 2
-    assert C.sizeof(_abi.McfProblem) == 24 + 64 + 8 * nptr + 16
+    coarse = 8 + 32 + 8 + 8 * len(_abi.COARSE_FIELDS)  # clim_rows/cols, 4 mapping doubles, altcorrect (+ pad), 5 pointers
+    assert C.sizeof(_abi.McfProblem) == 24 + 64 + 8 * nptr + 16 + coarse
 
 
 def test_no_device_fails_loudly():

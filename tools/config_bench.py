@@ -28,6 +28,20 @@ def case_runmicro(name, rows, cols, T, mode, reqhgt, nlyr=1, ring=None):
                       "ms": ms, "cell_hours_per_s": nc * (T // 24) * 24 / (ms * 1e-3)}), flush=True)
     del dp, outs; torch.cuda.empty_cache()
 
+def case_coarse(name, rows, cols, T, crows, ccols, altcorrect=2, ring=24, packed=False):
+    """config 5 as this build runs it: mode 2 with the climate on the coarse grid, interpolated in the kernels."""
+    p = synth.make_coarse_problem(rows, cols, T, reqhgt=0.05, mode=2, crows=crows, ccols=ccols, altcorrect=altcorrect)
+    dp = p.to_device()
+    nc = p.ncells
+    dt = torch.int16 if packed else torch.float64
+    outs = [torch.empty(ring * nc, dtype=dt, device="cuda") for _ in range(10)]
+    win = (0, T // 24, 0, ring)
+    run = api.run_problem_packed_dev if packed else api.run_problem_dev
+    ms = timed(lambda: run(dp, outs, window=win))
+    print(json.dumps({"case": name, "rows": rows, "cols": cols, "hours": T, "coarse": [crows, ccols], "altcorrect": altcorrect,
+                      "packed": packed, "ms": ms, "cell_hours_per_s": nc * (T // 24) * 24 / (ms * 1e-3)}), flush=True)
+    del dp, outs; torch.cuda.empty_cache()
+
 def case_bioclim(name, rows, cols, mode):
     days, q = synth.bioclim_days()
     p = synth.make_problem(rows, cols, 336, reqhgt=0.05, mode=mode, nlyr=14, day_list=days)
@@ -39,7 +53,10 @@ def case_bioclim(name, rows, cols, mode):
     del dp, bio; torch.cuda.empty_cache()
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["bio", "heights", "layers", "array"]
+    which = sys.argv[1:] or ["bio", "heights", "layers", "array", "coarse"]
+    if "coarse" in which:
+        case_coarse("config5: mode 2, 4096x4096 x 240 h, climate on a 41x41 grid interpolated in-kernel", 4096, 4096, 240, 41, 41)
+        case_coarse("same, packed int16 sink", 4096, 4096, 240, 41, 41, packed=True)
     if "bio" in which:
         case_bioclim("config3 runbioclim 2048x2048 (mode 1)", 2048, 2048, 1)
     if "heights" in which:
