@@ -331,6 +331,25 @@ def gpu_arm(args):
            "d2h_bytes_per_step": d2h, "steps": esteps, "ms_per_step": 1e3 * e_s / esteps,
            "sample": f"{er}x{ec} cells x {et} h per GPU through mcf_runmicro (pinned host buffers, all 10 outputs "
                      f"copied back; timed with the host clock around the blocking call)"}
+    # the same call with the packed integer sink (writetonc's x100 / x1 int16 packing done by the kernels, SURVEY.md
+    # NEXT-4): 20 instead of 80 bytes per cell-hour cross PCIe.  Reported beside, not instead of, the FP64 e2e.
+    pouts_t = [torch.empty(er * ec * et, dtype=torch.int16).pin_memory() for _ in range(10)]
+    pouts = [t_.numpy() for t_ in pouts_t]
+    for _ in range(2):
+        api.run_problem_packed(ep, out_buffers=pouts)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        api.run_problem_packed(ep, out_buffers=pouts)
+    torch.cuda.synchronize()
+    p_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([p_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        p_s = float(t.item())
+    e2e_packed = {"value": float(er) * ec * et * esteps * world / p_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                  "d2h_bytes_per_step": sum(o.nbytes for o in pouts), "steps": esteps, "ms_per_step": 1e3 * p_s / esteps,
+                  "sample": "same tile through mcf_runmicro_packed: int16 outputs as the reference's writetonc stores them"}
     del pin_keep
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
@@ -347,7 +366,8 @@ def gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "gpu_launches": launches,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "e2e_packed": e2e_packed,
+            "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "setup_seconds": t_gen,
         }
         print(json.dumps(line), flush=True)

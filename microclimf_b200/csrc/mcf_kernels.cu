@@ -686,10 +686,13 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     const double c2 = 1.06 * v.rho * soild;
                     const double kcon = v.c1 + c2 * soild - (v.c1 - v.c4) * mexp_lo(-pow4(v.c3 * soild));
                     const double kap = mdiv(kcon, cs * ph);
-                    const double DD = msqrt(kap * (2.0 / kOmdy));
+                    // damping depth DD = sqrt(2 kap / omega): only its reciprocal enters the heat flux, the depth
+                    // itself is needed for the below-ground pass alone
+                    const double iDD = mrsqrt(kap * (2.0 / kOmdy));
+                    const double DD = (RQ == RQ_BELOW) ? msqrt(kap * (2.0 / kOmdy)) : 0.0;
                     // ground heat flux scaled from the point model (ref soiltemp_hrCpp :1277-1296)
                     const double dtR = dtr * h.inv_dtrp;
-                    const double Gmu = dtR * (kcon * h.muGp_kp) * mrcp(DD);
+                    const double Gmu = dtR * (kcon * h.muGp_kp) * iDD;
                     double G = h.Gp * Gmu;
                     if (G > 0.6 * Rmx) G = 0.6 * Rmx;
                     if (G < -0.6 * Rmx) G = -0.6 * Rmx;

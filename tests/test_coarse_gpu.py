@@ -74,8 +74,10 @@ def test_coarse_climate_degenerate_grids_and_bands():
         b = p.band(c0, c1)
         b.twi_mean = lib_sum[0] / lib_sum[1]
         got = api.run_problem(b)
-        for k, v in got.items():
-            assert np.array_equal(v, whole[k][:, c0:c1, :], equal_nan=True), k
+        # not bit-identical: the band gets the whole-raster twi mean from the host reduction and its coarse column
+        # origin is clim_col0 + dcol * c0 (one more rounding) — equal to rounding level
+        ok, rows = parity.compare(got, {k: v[:, c0:c1, :] for k, v in whole.items()}, atol=1e-9, rtol=1e-9)
+        assert ok, "\n" + parity.fmt(rows)
 
 
 @pytest.mark.gpu
