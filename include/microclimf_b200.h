@@ -292,6 +292,55 @@ int mcf_windcoef(const double* dsm, int32_t rows, int32_t cols, double reso, dou
  * sweep over the cells sorted by elevation); NaN cells receive (double)INT_MIN as in the reference. */
 int mcf_flowacc(const double* dtm, int32_t rows, int32_t cols, double* fa, char* err, size_t errlen);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Snow (SURVEY.md NEXT-3), data.frame climate.                                                    */
+/*   mcf_gridmodelsnow  <- _microclimf_gridmodelsnow1  (src/microclimfCpp.cpp:4172-4424): the hourly   */
+/*                         snow-pack recurrence per cell (snowoneB :3835, radoneB :3773)             */
+/*   mcf_gridmicrosnow  <- _microclimf_gridmicrosnow1  (src/microclimfCpp.cpp:4894-5057): microclimate  */
+/*                         above / below the snow surface where SWE > 0, overwriting runmicro's outputs */
+/* HOST buffers, R layout.  The R drivers around them (.snowmodel1, .runmicrosnow1: 5-day chunks with  */
+/* terrain recomputed from DTM + snow depth, R/internal.R:2389-2779, 3367-3660) are host R code.       */
+/* ------------------------------------------------------------------------------------------- */
+typedef struct mcf_snow_climate { /* obstime + climdata, each of length tsteps */
+    int32_t tsteps;
+    const int32_t* year;
+    const int32_t* month;
+    const int32_t* day;
+    const double* hour;
+    const double *temp, *relhum, *pres, *swdown, *difrad, *lwdown, *windspeed, *winddir, *precip;
+} mcf_snow_climate;
+
+typedef struct mcf_snow_point { /* pointm of gridmodelsnow1 (:4181-4186), each of length tsteps */
+    const double *Gp, *Tc, *RswabsG, *RlwabsG, *umu;
+} mcf_snow_point;
+
+typedef struct mcf_snow_static { /* vegp + other ([rows, cols] unless noted) */
+    int32_t rows, cols;
+    const double *pai, *hgt, *leaft, *clump;
+    const double *paia, *leafd, *leafden, *Smax; /* gridmicrosnow only */
+    const double *slope, *aspect, *skyview;
+    const double* wsa;                          /* [rows, cols, 8]  */
+    const double* hor;                          /* [rows, cols, 24] */
+    double lat, lon, zref;
+    const double *isnowdc, *isnowdg;            /* gridmodelsnow only: initial snow depth (canopy + ground, ground) */
+    const int32_t *isnowac, *isnowag;           /* gridmodelsnow only: initial snow age, hours */
+} mcf_snow_static;
+
+typedef struct mcf_snow_state { /* snowm of gridmicrosnow1 (:4935-4940), each [rows, cols, tsteps] */
+    const double *Tc, *Tg, *totalSWE, *groundsnowdepth, *snowden;
+} mcf_snow_state;
+
+/* snowenv: 0 Alpine (default), 1 Maritime, 2 Prairie, 3 Tundra, 4 Taiga (snowdenp :3741-3750).
+ * out3d = {Tc, Tg, sdepc, sdepg, sden}, each [rows, cols, tsteps]; out2d = {agec, ageg, meltc, meltg}, each
+ * [rows, cols]; NULL entries are skipped. */
+int mcf_gridmodelsnow(const mcf_snow_climate* clim, const mcf_snow_point* pt, const mcf_snow_static* st, int32_t snowenv,
+                      double* const out3d[5], double* const out2d[4], char* err, size_t errlen);
+
+/* `umu` is the climdata$umu column (:4914).  micro[v] (NULL = out[v] FALSE) are runmicro's [rows, cols, tsteps]
+ * outputs, updated IN PLACE where totalSWE > 0. */
+int mcf_gridmicrosnow(double reqhgt, const mcf_snow_climate* clim, const double* umu, const mcf_snow_state* sm,
+                      const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err, size_t errlen);
+
 /* Element-wise evaluation of the kernels' own FP64 elementary functions (csrc/mcf_math.cuh) on HOST
  * buffers, for accuracy tests: fn 0 = 1/x, 1 = x/y, 2 = sqrt(x), 3 = exp(x), 4 = 2^x, 5 = log(x),
  * 6 = x^y, 7 = sin(x), 8 = cos(x).  y may be NULL for the one-operand functions. */

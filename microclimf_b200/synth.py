@@ -348,3 +348,34 @@ def make_coarse_problem(rows: int, cols: int, tsteps: int, reqhgt: float = 0.05,
         p.arrays["pfac"] = np.ascontiguousarray(((293 - 0.0065 * dtm) / 293) ** 5.26)
     p.validate()
     return p
+
+
+def make_snow_inputs(rows: int, cols: int, tsteps: int, seed: int = 20240321, reqhgt: float = 0.05, lat: float = 61.0,
+                     lon: float = 10.0, zref: float = 30.0):
+    """Synthetic winter scenario for the snow operators (gridmodelsnow1 / gridmicrosnow1, src/microclimfCpp.cpp:4172,
+    4894): sub-zero to just-above-zero air, precipitation events, a mix of snow-free, thinly and deeply covered cells,
+    vegetation shorter and taller than the pack.  Returns dict(obstime, climdata, pointm, vegp, other)."""
+    rng = np.random.default_rng(seed + 11)
+    f = forcing(tsteps, lat, lon, seed, start_doy=20)
+    T = len(f["hour"])
+    temp = f["temp"] - 9.0 + 3.0 * np.sin(np.arange(T) / 37.0)
+    es = _satvap_r(temp)
+    relhum = np.clip(100 * f["ea"] / _satvap_r(f["temp"]), 35, 100)
+    precip = np.where(rng.random(T) < 0.18, rng.gamma(1.5, 0.8, T), 0.0)
+    climdata = dict(temp=temp, relhum=relhum, pres=f["pres"], swdown=f["swdown"], difrad=f["difrad"], lwdown=f["lwdown"] - 40,
+                    windspeed=f["windspeed"], winddir=f["winddir"], precip=precip, umu=f["p_umu"])
+    obstime = dict(year=f["year"], month=f["month"], day=f["day"], hour=f["hour"])
+    Tcp = temp + 2.0 * np.sin(2 * np.pi * (f["hour"] - 9) / 24) - 1.0
+    rsw = 0.35 * f["swdown"]
+    rlw = 0.97 * (f["lwdown"] - 40)
+    pointm = dict(Gp=f["p_G"] * 0.5, Tc=Tcp, RswabsG=rsw, RlwabsG=rlw, umu=f["p_umu"], tr=np.full(T, 0.4))
+    s = static_layers(rows, cols, reqhgt, seed, 1, zref)
+    R = lambda n: s[n].reshape(cols, rows).T  # noqa: E731  (flat R order -> [rows, cols])
+    vegp = {n: R(n) for n in ("pai", "hgt", "leaft", "clump", "paia", "leafd", "leafden")}
+    dc = np.where(rng.random((rows, cols)) < 0.25, 0.0, rng.uniform(0.02, 0.9, (rows, cols)))
+    dg = dc * rng.uniform(0.4, 1.0, (rows, cols))
+    other = dict(slope=R("slope"), aspect=R("aspect"), skyview=R("svfa"), wsa=s["wsa"].reshape(8, cols, rows).transpose(2, 1, 0),
+                 hor=s["hor"].reshape(24, cols, rows).transpose(2, 1, 0), lat=lat, lon=lon, zref=zref, Smax=R("Smax"),
+                 isnowdc=dc, isnowdg=dg, isnowac=rng.integers(0, 400, (rows, cols)).astype(np.int32),
+                 isnowag=rng.integers(0, 400, (rows, cols)).astype(np.int32))
+    return dict(obstime=obstime, climdata=climdata, pointm=pointm, vegp=vegp, other=other)

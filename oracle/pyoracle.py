@@ -83,3 +83,18 @@ def runbioclim(prob: GridProblem, quarters: dict, air: bool = True, out_mask=Non
         raise RuntimeError(f"{kind} runbioclim failed ({rc}): {err.value.decode()}")
     del keep
     return {nm: b.reshape((prob.rows, prob.cols), order="F") for nm, b in zip(_abi.BIO_NAMES, bufs) if b is not None}
+
+
+def gridmodelsnow1(obstime, climdata, pointm, vegp, other, snowenv="Alpine"):
+    """The compiled reference's gridmodelsnow1 (src/microclimfCpp.cpp:4172) behind the product's snow structs."""
+    from microclimf_b200 import snow
+    fn = _lib("ref").ref_gridmodelsnow
+    fn.restype = C.c_int
+    return snow.call_gridmodelsnow(fn, obstime, climdata, pointm, vegp, other, snowenv)
+
+
+def gridmicrosnow1(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out):
+    from microclimf_b200 import snow
+    fn = _lib("ref").ref_gridmicrosnow
+    fn.restype = C.c_int
+    return snow.call_gridmicrosnow(fn, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)

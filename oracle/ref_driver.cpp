@@ -389,3 +389,103 @@ extern "C" int ref_flowacc(const double* dtm, int32_t rows, int32_t cols, double
         return 1;
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Snow (SURVEY.md NEXT-3): the reference's gridmodelsnow1 / gridmicrosnow1 behind the product's structs
+// ---------------------------------------------------------------------------------------------
+List gridmodelsnow1(DataFrame obstime, DataFrame climdata, DataFrame pointm, List vegp, List other, std::string snowenv);
+List gridmicrosnow1(double reqhgt, DataFrame obstime, DataFrame climdata, List snowm, List micro, List vegp, List other,
+                    double mat, std::vector<bool> out);
+
+namespace {
+IntegerMatrix imat2(const int32_t* p, int rows, int cols) {
+    IntegerMatrix m(rows, cols);
+    for (size_t i = 0; i < (size_t)rows * cols; ++i) m[i] = p[i];
+    return m;
+}
+DataFrame snow_clim_df(const mcf_snow_climate* c) {
+    const int n = c->tsteps;
+    DataFrame d;
+    d["temp"] = vec(c->temp, n); d["relhum"] = vec(c->relhum, n); d["pres"] = vec(c->pres, n);
+    d["swdown"] = vec(c->swdown, n); d["difrad"] = vec(c->difrad, n); d["lwdown"] = vec(c->lwdown, n);
+    d["windspeed"] = vec(c->windspeed, n); d["winddir"] = vec(c->winddir, n); d["precip"] = vec(c->precip, n);
+    return d;
+}
+const char* const kSnowEnv[5] = {"Alpine", "Maritime", "Prairie", "Tundra", "Taiga"};
+} // namespace
+
+extern "C" int ref_gridmodelsnow(const mcf_snow_climate* c, const mcf_snow_point* pt, const mcf_snow_static* st,
+                                 int32_t snowenv, double* const out3d[5], double* const out2d[4], char* err, size_t errlen) {
+    try {
+        const int n = c->tsteps, R = st->rows, C = st->cols;
+        DataFrame pm;
+        pm["Gp"] = vec(pt->Gp, n); pm["Tc"] = vec(pt->Tc, n); pm["RswabsG"] = vec(pt->RswabsG, n);
+        pm["RlwabsG"] = vec(pt->RlwabsG, n); pm["umu"] = vec(pt->umu, n); pm["tr"] = vec(pt->umu, n);
+        List vegp;
+        vegp["pai"] = mat2(st->pai, R, C); vegp["hgt"] = mat2(st->hgt, R, C); vegp["leaft"] = mat2(st->leaft, R, C);
+        vegp["clump"] = mat2(st->clump, R, C);
+        List other;
+        other["slope"] = mat2(st->slope, R, C); other["aspect"] = mat2(st->aspect, R, C);
+        other["skyview"] = mat2(st->skyview, R, C); other["wsa"] = arr3(st->wsa, R, C, 8); other["hor"] = arr3(st->hor, R, C, 24);
+        other["lat"] = st->lat; other["lon"] = st->lon; other["zref"] = st->zref;
+        other["isnowdc"] = mat2(st->isnowdc, R, C); other["isnowdg"] = mat2(st->isnowdg, R, C);
+        other["isnowac"] = imat2(st->isnowac, R, C); other["isnowag"] = imat2(st->isnowag, R, C);
+        List r = gridmodelsnow1(obstime_df(n, c->year, c->month, c->day, c->hour), snow_clim_df(c), pm, vegp, other,
+                                kSnowEnv[snowenv]);
+        const char* n3[5] = {"Tc", "Tg", "sdepc", "sdepg", "sden"};
+        for (int v = 0; v < 5; ++v)
+            if (out3d[v]) {
+                NumericVector a = r[n3[v]];
+                std::memcpy(out3d[v], a.raw(), (size_t)R * C * n * sizeof(double));
+            }
+        const char* n2[4] = {"agec", "ageg", "meltc", "meltg"};
+        for (int v = 0; v < 4; ++v)
+            if (out2d[v]) {
+                NumericMatrix a = r[n2[v]];
+                for (size_t i = 0; i < (size_t)R * C; ++i) out2d[v][i] = a[i];
+            }
+        return MCF_OK;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return MCF_ERR_ARG;
+    }
+}
+
+extern "C" int ref_gridmicrosnow(double reqhgt, const mcf_snow_climate* c, const double* umu, const mcf_snow_state* sm,
+                                 const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err,
+                                 size_t errlen) {
+    try {
+        const int n = c->tsteps, R = st->rows, C = st->cols;
+        DataFrame clim = snow_clim_df(c);
+        clim["umu"] = vec(umu, n);
+        List snowm;
+        snowm["Tc"] = arr3(sm->Tc, R, C, n); snowm["Tg"] = arr3(sm->Tg, R, C, n); snowm["totalSWE"] = arr3(sm->totalSWE, R, C, n);
+        snowm["groundsnowdepth"] = arr3(sm->groundsnowdepth, R, C, n); snowm["snowden"] = arr3(sm->snowden, R, C, n);
+        static const char* nm[MCF_NOUT] = {"Tz", "tleaf", "relhum", "soilm", "windspeed", "Rdirdown", "Rdifdown", "Rlwdown",
+                                           "Rswup", "Rlwup"};
+        List mic;
+        std::vector<bool> o(MCF_NOUT);
+        for (int v = 0; v < MCF_NOUT; ++v) {
+            o[v] = micro[v] != nullptr;
+            if (micro[v]) mic[nm[v]] = arr3(micro[v], R, C, n);
+        }
+        List vegp;
+        vegp["pai"] = mat2(st->pai, R, C); vegp["paia"] = mat2(st->paia, R, C); vegp["hgt"] = mat2(st->hgt, R, C);
+        vegp["leaft"] = mat2(st->leaft, R, C); vegp["clump"] = mat2(st->clump, R, C); vegp["leafd"] = mat2(st->leafd, R, C);
+        vegp["leafden"] = mat2(st->leafden, R, C);
+        List other;
+        other["slope"] = mat2(st->slope, R, C); other["aspect"] = mat2(st->aspect, R, C);
+        other["skyview"] = mat2(st->skyview, R, C); other["wsa"] = arr3(st->wsa, R, C, 8); other["hor"] = arr3(st->hor, R, C, 24);
+        other["lat"] = st->lat; other["lon"] = st->lon; other["zref"] = st->zref; other["Smax"] = mat2(st->Smax, R, C);
+        List r = gridmicrosnow1(reqhgt, obstime_df(n, c->year, c->month, c->day, c->hour), clim, snowm, mic, vegp, other, mat, o);
+        for (int v = 0; v < MCF_NOUT; ++v)
+            if (micro[v]) {
+                NumericVector a = r[nm[v]];
+                std::memcpy(micro[v], a.raw(), (size_t)R * C * n * sizeof(double));
+            }
+        return MCF_OK;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return MCF_ERR_ARG;
+    }
+}

@@ -1,0 +1,61 @@
+"""Snow operators (SURVEY.md NEXT-3): gridmodelsnow1 (hourly snow-pack recurrence) and gridmicrosnow1 (microclimate on
+snow-covered cell-hours), CUDA kernels of csrc/mcf_snow.cu against the UNMODIFIED compiled reference
+(src/microclimfCpp.cpp:4172-4424, 4894-5057 in oracle/_ref).  Tolerance 1e-6 abs / 1e-6 rel, identical NA masks."""
+import numpy as np
+import pytest
+
+import parity
+from microclimf_b200 import _abi, api, snow, synth
+from oracle import pyoracle
+
+needs_ref = pytest.mark.skipif(not pyoracle.have_ref(), reason="compiled reference absent (snow has no C restatement)")
+
+
+@needs_ref
+def test_reference_snow_scenario_cpu():
+    """The scenario exercises accumulation, melt-out, snow-free hours and vegetation above / below the pack."""
+    s = synth.make_snow_inputs(9, 7, 24 * 6)
+    r = pyoracle.gridmodelsnow1(s["obstime"], s["climdata"], s["pointm"], s["vegp"], s["other"])
+    ok = ~np.isnan(s["vegp"]["hgt"])
+    d = r["sdepc"][ok]
+    assert np.isfinite(d).all() and d.max() > 0.3 and (d == 0).any() and (np.diff(d, axis=1) > 0).any()
+    assert np.isnan(r["meltg"]).all()  # never initialised by the reference (bioclimfill + accumulate)
+    assert (r["Tg"][ok] <= 1e-12).mean() > 0.5
+
+
+def _snowm(r):
+    return dict(Tc=r["Tc"], Tg=r["Tg"], totalSWE=r["sdepc"] * r["sden"], groundsnowdepth=r["sdepg"], snowden=r["sden"])
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("snowenv", ["Alpine", "Tundra", "Taiga"])
+def test_gridmodelsnow1_parity(snowenv):
+    s = synth.make_snow_inputs(23, 17, 24 * 8, seed=5)
+    want = pyoracle.gridmodelsnow1(s["obstime"], s["climdata"], s["pointm"], s["vegp"], s["other"], snowenv)
+    got = snow.gridmodelsnow1(s["obstime"], s["climdata"], s["pointm"], s["vegp"], s["other"], snowenv)
+    ok, rows = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rows)
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("reqhgt", [0.05, 0.0, 1.0, 0.3])
+def test_gridmicrosnow1_parity(reqhgt):
+    """reqhgt 0.05 / 0.0 fall below the pack for deep snow (belowpointsnow) and above it elsewhere; 1.0 and 0.3 cut through
+    the canopy-above-snow and above-canopy branches of snowabovepoint."""
+    s = synth.make_snow_inputs(19, 13, 24 * 5, seed=9, reqhgt=max(reqhgt, 0.0))
+    model = pyoracle.gridmodelsnow1(s["obstime"], s["climdata"], s["pointm"], s["vegp"], s["other"])
+    snowm = _snowm(model)
+    rng = np.random.default_rng(3)
+    shape = model["Tc"].shape
+    micro = {n: rng.uniform(-5, 5, shape) for n in _abi.OUT_NAMES}
+    out = [True] * 10 if reqhgt > 0 else [True, False, False, True, False, True, True, True, True, True]
+    want = pyoracle.gridmicrosnow1(reqhgt, s["obstime"], s["climdata"], snowm, micro, s["vegp"], s["other"], 4.0, out)
+    got = snow.gridmicrosnow1(reqhgt, s["obstime"], s["climdata"], snowm, micro, s["vegp"], s["other"], 4.0, out)
+    assert set(got) == set(want)
+    ok, rows = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rows)
+    # cell-hours without snow keep runmicro's values
+    nosnow = ~(snowm["totalSWE"] > 0)
+    assert nosnow.any() and np.array_equal(got["Tz"][nosnow], micro["Tz"][nosnow])

@@ -5,6 +5,6 @@ TAG=${TAG:-}
 mkdir -p variants
 cd microclimf_b200/csrc
 nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -I../../include \
-  -DMCF_TILE=$T -DMCF_MINB=$B "$@" -shared -o ../../variants/lib_${T}_${B}${TAG}.so mcf_kernels.cu mcf_terrain.cu mcf_api.cu -Xptxas -v 2>&1 \
+  -DMCF_TILE=$T -DMCF_MINB=$B "$@" -shared -o ../../variants/lib_${T}_${B}${TAG}.so mcf_kernels.cu mcf_terrain.cu mcf_snow.cu mcf_api.cu -Xptxas -v 2>&1 \
   | grep -A2 "k_gridILi0ELi0ELb0" | grep "Used\|spill" | tr '\n' ' '
 echo " <= $T x $B $TAG"
