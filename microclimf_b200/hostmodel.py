@@ -788,3 +788,107 @@ def runmicro_big(micropoint, reqhgt, pathout, vegp, soilc, dtm, dtmc=None, altco
                 np.savez(fo + ".npz", extent=ext, dtm=dtmi.matrix(), **mout)
                 written.append(fo + ".npz")
     return written
+
+
+# ---------------------------------------------------------------------------------------------
+# snow: .snowmodel1 (the 5-day chunk driver around gridmodelsnow1)
+# ---------------------------------------------------------------------------------------------
+def _sortl(vegp: Dict[str, Raster], sdep: np.ndarray) -> Dict[str, np.ndarray]:
+    """ref .sortl (R/internal.R:2389-2420): vegetation averaged over the layers of the hours with snow."""
+    out = {}
+    for k in ("pai", "hgt", "leaft", "clump"):
+        a = vegp[k].values
+        dmx = a.shape[2]
+        if dmx > 1:
+            n = len(sdep)
+            s = np.clip(_r_round(np.linspace(0.50001, dmx + 0.5, n)).astype(int), 1, dmx)
+            sel = np.nonzero(np.asarray(sdep) > 0)[0]
+            s = s[sel] if sel.size else s[:1]
+            num, fre = np.unique(s, return_counts=True)
+            m = a[:, :, 0] * 0
+            for j in range(len(num)):
+                m = m + a[:, :, j] * fre[j]  # the reference indexes layer j, not num[j] (R/internal.R:2413): as written
+            out[k] = m / fre.sum()
+        else:
+            out[k] = a[:, :, 0].copy()
+    return out
+
+
+def _tpicalc(af: int, me: int, dtm: Raster, tfact: float) -> np.ndarray:
+    """ref .tpicalc (R/internal.R:2479-2493): topographic positioning index for snow redistribution."""
+    z = dtm.matrix()
+    if af < me / 2 and af >= 1:
+        dtmc = resample_bilinear(aggregate_mean(dtm, af, na_rm=True), dtm).matrix()
+    else:
+        dtmc = z * 0 + np.nanmean(z)
+    tpic = np.exp((dtmc - z) * tfact)
+    with np.errstate(invalid="ignore"):
+        tpic[tpic < 0.05] = 0.1
+        tpic[tpic > 10] = 10
+    return tpic / np.nanmean(tpic)
+
+
+def snowmodel1(weather, pointm, dtm, vegp, soilc, snowenv: str = "Taiga", snowinitd: float = 0, snowinita: float = 0,
+               zref: float = 2, tfact: float = 0.02, chunk_days: int = 5, operator=None):
+    """ref .snowmodel1 (R/internal.R:2498-2616) from the point where the point snow model has run: `pointm` is the
+    data.frame built from pointmodelsnow's output (Gp, Tc, RswabsG, RlwabsG, umu, tr, and sdepc for .sortl) — the
+    point model is upstream of this build.  The grid model runs in 5-day chunks; between chunks slope,
+    aspect, the 24 horizons, sky view and wind shelter are recomputed from DTM + ground snow depth (GPU stencils) and
+    fresh snow is redistributed by the topographic positioning index.  `operator` defaults to the CUDA
+    `snow.gridmodelsnow1`; the tests pass the compiled reference's to check the driver end to end."""
+    from . import snow as snowops
+
+    op = operator or snowops.gridmodelsnow1
+    dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
+    tme = np.asarray(weather["obs_time"]).astype("datetime64[s]")
+    ot = _obstime(tme)
+    ot["hour"] = np.floor(ot["hour"])  # obstime$hour = tme$hour here (R/internal.R:2531), no minutes
+    z = dtm.matrix()
+    sdep = z * 0 + snowinitd
+    sage = z * 0 + snowinita
+    lat, lon = latlong_from_raster(dtm)
+    vg = _sortl(vegp, np.asarray(pointm["sdepc"])[:tme.size])
+    other = dict(zref=float(zref), lat=lat, lon=lon, isnowdc=sdep, isnowac=np.nan_to_num(sage).astype(np.int32),
+                 isnowdg=sdep * 0.5, isnowag=np.nan_to_num(sage).astype(np.int32))
+    h = tme.size
+    span = 24 * chunk_days
+    nchunks = h // span
+    shape = z.shape + (h,)
+    Tc, Tg, snowdepg, swe, sden = (np.full(shape, np.nan) for _ in range(5))
+    dtms = dtm.like(z + sdep * 0.5)
+    climcols = ("temp", "relhum", "pres", "swdown", "difrad", "lwdown", "windspeed", "winddir", "precip")
+    for ch in range(nchunks):
+        sl = terrain(dtms, "slope").matrix()
+        sl[np.isnan(sl)] = 0
+        other["slope"] = mask(dtm.like(sl), dtm).matrix()
+        ap = terrain(dtms, "aspect").matrix()
+        ap[np.isnan(ap)] = 180
+        other["aspect"] = mask(dtm.like(ap), dtm).matrix()
+        other["hor"], other["skyview"] = api.horizon(dtms.matrix(), dtm.res[0], want_svf=True)
+        other["wsa"] = _windsheltera(dtms, zref, 10 if dtm.res[0] <= 100 else 1)
+        s = slice(ch * span, min((ch + 1) * span, h))
+        ns = s.stop - s.start
+        smod = op({k: v[s] for k, v in ot.items()}, {k: np.asarray(weather[k], dtype=np.float64)[s] for k in climcols},
+                  {k: np.asarray(pointm[k], dtype=np.float64)[s] for k in ("Gp", "Tc", "RswabsG", "RlwabsG", "umu", "tr")},
+                  vg, other, snowenv)
+        # topographic snow redistribution (R/internal.R:2584-2599)
+        tpr = 10 * np.mean(np.asarray(weather["windspeed"], dtype=np.float64)[s]) ** 0.5
+        af = int(round(tpr / dtm.res[0]))
+        tpi = _tpicalc(af, min(dtm.nrows, dtm.ncols), dtms, tfact)
+        asd = np.repeat(other["isnowdg"][:, :, None], ns, axis=2)
+        dsnow = smod["sdepg"] - asd
+        dsnow2 = dsnow * tpi[:, :, None]
+        with np.errstate(invalid="ignore"):
+            dsnow2 = np.where(dsnow < 0, dsnow, dsnow2)
+        asc = np.repeat(other["isnowdc"][:, :, None], ns, axis=2)
+        cdsnow = smod["sdepc"] - asc - dsnow
+        Tc[:, :, s], Tg[:, :, s], sden[:, :, s] = smod["Tc"], smod["Tg"], smod["sden"]
+        swe[:, :, s] = (asc + cdsnow + dsnow2) * smod["sden"]
+        snowdepg[:, :, s] = asd + dsnow2
+        other["isnowdc"] = (asc + cdsnow + dsnow2)[:, :, -1]
+        # `other$isnowac <- (asd + dsnow2)[,,n]` is immediately overwritten by the ages and isnowdg is never advanced
+        # (R/internal.R:2606-2609): reproduced
+        other["isnowac"] = np.nan_to_num(smod["agec"]).astype(np.int32)
+        other["isnowag"] = np.nan_to_num(smod["ageg"]).astype(np.int32)
+        dtms = dtm.like(z + snowdepg[:, :, s.stop - 1])
+    return dict(Tc=Tc, Tg=Tg, groundsnowdepth=snowdepg, totalSWE=swe, snowden=sden, umu=np.asarray(pointm["umu"]))

@@ -59,3 +59,34 @@ def test_gridmicrosnow1_parity(reqhgt):
     # cell-hours without snow keep runmicro's values
     nosnow = ~(snowm["totalSWE"] > 0)
     assert nosnow.any() and np.array_equal(got["Tz"][nosnow], micro["Tz"][nosnow])
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_snowmodel1_chunk_driver_matches_reference_operator():
+    """hostmodel.snowmodel1 (the 5-day chunk loop of .snowmodel1, R/internal.R:2498-2616) driven by the CUDA operator and
+    by the compiled reference's gridmodelsnow1: same terrain updates, same redistribution, same result."""
+    from microclimf_b200 import hostmodel
+    from microclimf_b200.spatial import Raster
+    rows, cols, days = 30, 26, 10
+    s = synth.make_snow_inputs(rows, cols, 24 * days, seed=21)
+    rng = np.random.default_rng(2)
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    z = 300 + 40 * np.sin(ii / 5.0) * np.cos(jj / 4.0) + rng.normal(0, 0.5, (rows, cols))
+    mk = lambda v: Raster(v, 0, cols * 10.0, 0, rows * 10.0, "")  # noqa: E731
+    hgt = np.nan_to_num(s["vegp"]["hgt"], nan=0.5)
+    vegp = {k: mk(np.nan_to_num(s["vegp"].get(k, hgt), nan=0.3)) for k in hostmodel.VEG_NAMES if k in s["vegp"] or k == "hgt"}
+    for k in hostmodel.VEG_NAMES:
+        vegp.setdefault(k, mk(np.full((rows, cols), 0.3)))
+    soilc = dict(soiltype=mk(np.full((rows, cols), 4.0)), groundr=mk(np.full((rows, cols), 0.15)))
+    T = 24 * days
+    tme = (np.datetime64("2023-01-20T00:00:00") + np.arange(T) * np.timedelta64(3600, "s")).astype("datetime64[s]")
+    weather = dict(s["climdata"], obs_time=tme)
+    pointm = dict(s["pointm"], sdepc=np.full(T, 0.2))
+    a = hostmodel.snowmodel1(weather, pointm, mk(z), vegp, soilc, snowenv="Alpine", snowinitd=0.1, zref=30.0)
+    b = hostmodel.snowmodel1(weather, pointm, mk(z), vegp, soilc, snowenv="Alpine", snowinitd=0.1, zref=30.0,
+                             operator=pyoracle.gridmodelsnow1)
+    ok, rows_ = parity.compare({k: a[k] for k in ("Tc", "Tg", "groundsnowdepth", "totalSWE", "snowden")},
+                               {k: b[k] for k in ("Tc", "Tg", "groundsnowdepth", "totalSWE", "snowden")})
+    assert ok, "\n" + parity.fmt(rows_)
+    assert np.isfinite(a["totalSWE"]).all() and a["totalSWE"].max() > 0
