@@ -45,6 +45,12 @@ def _problem(mode, dfsel, obstime, climdata, pointm, vegp, soilc, reqhgt, zref, 
     tsteps = int(np.asarray(obstime["hour"]).size)
     layered = mode in (3, 4)
     nlyr = hgt.shape[2] if (layered and hgt.ndim == 3) else 1
+    if layered and dfsel is not None and nlyr > len(np.asarray(dfsel["st"])):
+        # .sortvegp can hand over more layers than dfsel has rows (short series: several layers share a day and the
+        # day-mode keeps one of them, R/internal.R:262-270); the drivers index layers 0 .. nrow(dfsel) - 1 only
+        # (src/microclimfCpp.cpp:2770-2778), so the surplus layers are never read
+        nlyr = len(np.asarray(dfsel["st"]))
+        vegp = {k: (np.asarray(v)[:, :, :nlyr] if np.asarray(v).ndim == 3 else v) for k, v in vegp.items()}
     p = GridProblem(mode=mode, rows=rows, cols=cols, tsteps=tsteps, reqhgt=float(reqhgt), zref=float(zref),
                     lat=float(lat), lon=float(lon), Sminp=float(Sminp), Smaxp=float(Smaxp), tfact=float(tfact),
                     mat=float(mat), complete=bool(complete), nlyr=nlyr)

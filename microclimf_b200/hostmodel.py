@@ -695,11 +695,16 @@ def runmicro(micropoint, reqhgt, vegp, soilc, dtm, dtmc=None, altcorrect=0, snow
     """ref runmicro (R/Cppwrappers.R:376-396): grid microclimate model.  Returns the reference's named list
     (dict of [rows, cols, hours] arrays) plus `tme`.  As in the reference, `svf` and `method` are accepted
     but not forwarded (R/internal.R:3336).  A list of micropoints (runpointmodela) with `dtmc` takes the gridded-climate path
-    (`.runmodel2Cpp` / `.runmodel4Cpp` -> prepare_model_a).  The snow branch is SURVEY.md §8f NEXT-3 and raises
-    NotImplementedError.
+    (`.runmodel2Cpp` / `.runmodel4Cpp` -> prepare_model_a); `snow = TRUE` with a data.frame micropoint and `snowmod` (snowmodel1's output)
+    takes `.runmicrosnow1` (runmicrosnow1); gridded-climate snow is not built yet.
     `packed = True` (an addition) returns writetonc's integer packing straight from the kernels."""
     if snow:
-        raise NotImplementedError("snow = TRUE (.runmicrosnow1/2) is not part of this build yet (SURVEY.md NEXT-3)")
+        if not isinstance(micropoint, Micropoint):
+            raise NotImplementedError("snow = TRUE with gridded climate (.runmicrosnow2 / gridmicrosnow2) is not built yet")
+        mout = runmicrosnow1(micropoint, reqhgt, vegp, soilc, dtm, snowmod, runchecks, pai_a, tfact, out, slr, apr, hor, twi,
+                             wsa, svf)
+        mout["tme"] = np.asarray(micropoint.tmeorig)
+        return mout
     if not isinstance(micropoint, Micropoint):
         if dtmc is None:
             raise ValueError("Require dtmc. Please provide\n")
@@ -892,3 +897,141 @@ def snowmodel1(weather, pointm, dtm, vegp, soilc, snowenv: str = "Taiga", snowin
         other["isnowag"] = np.nan_to_num(smod["ageg"]).astype(np.int32)
         dtms = dtm.like(z + snowdepg[:, :, s.stop - 1])
     return dict(Tc=Tc, Tg=Tg, groundsnowdepth=snowdepg, totalSWE=swe, snowden=sden, umu=np.asarray(pointm["umu"]))
+
+
+# ---------------------------------------------------------------------------------------------
+# runmicro(snow = TRUE), data.frame climate: .runmicrosnow1
+# ---------------------------------------------------------------------------------------------
+def subsetsnowmodel(snowmod, subs):
+    """ref subsetsnowmodel (R/dataprep.R:148-159); `subs` 1-based hours."""
+    ix = np.asarray(subs, dtype=int) - 1
+    out = {k: np.asarray(snowmod[k])[:, :, ix] for k in ("Tc", "Tg", "groundsnowdepth", "totalSWE", "snowden")}
+    u = np.asarray(snowmod["umu"])
+    out["umu"] = u[:, :, ix] if u.ndim == 3 else u[ix]
+    return out
+
+
+def _sortl2(vegp, sdep, reqhgt, pai_a):
+    """ref .sortl2 (R/internal.R:2422-2477): snow-hour vegetation averages + foliage density."""
+    out = {}
+    for k in ("pai", "hgt", "leaft", "clump", "leafd"):
+        a = vegp[k].values
+        dmx = a.shape[2]
+        if dmx > 1:
+            n = len(sdep)
+            s = np.clip(_r_round(np.linspace(0.50001, dmx + 0.5, n)).astype(int), 1, dmx)
+            sel = np.nonzero(np.asarray(sdep) > 0)[0]
+            s = s[sel] if sel.size else s[:1]
+            num, fre = np.unique(s, return_counts=True)
+            m = a[:, :, 0] * 0
+            for j in range(len(num)):
+                m = m + a[:, :, j] * fre[j]  # layer j, not num[j], as written (R/internal.R:2446)
+            out[k] = m / fre.sum()
+        else:
+            out[k] = a[:, :, 0].copy()
+    paia = None if pai_a is None else as_raster(pai_a, vegp["hgt"]).values.mean(axis=2)
+    fd = _foliageden(reqhgt, out["hgt"], out["pai"], paia)
+    out["paia"], out["leafden"] = fd["pai_a"], fd["leafden"]
+    return out
+
+
+def _hours_of_days(days):
+    d = np.asarray(days, dtype=int)
+    return np.repeat((d - 1) * 24, 24) + np.tile(np.arange(1, 25), d.size)
+
+
+def runmicrosnow1(micropoint: Micropoint, reqhgt, vegp, soilc, dtm, smod, runchecks=True, pai_a=None, tfact=1.5,
+                  out=(True,) * 10, slr=None, apr=None, hor=None, twi=None, wsa=None, svf=None, snow_operator=None):
+    """ref .runmicrosnow1 (R/internal.R:3580-3660): days without snow anywhere go through the ordinary grid model, days
+    with snow somewhere through gridmicrosnow1 (seeded with the ordinary model's values where a day is in both sets),
+    and the two are merged by day.  `smod` is the snow model's output (snowmodel1)."""
+    from . import snow as snowops
+
+    op = snow_operator or snowops.gridmicrosnow1
+    dtm_r = as_raster(dtm)
+    smod = dict(smod)
+    swe = np.array(smod["totalSWE"], dtype=np.float64)
+    swe[np.isnan(swe)] = 0
+    swe[np.isnan(dtm_r.matrix()), :] = np.nan  # mask(totalSWE, dtm)
+    smod["totalSWE"] = swe
+    # applycpp3 min / max over space per hour (src/microclimfCpp.cpp:5553) and snowdaysfun (:5531)
+    with np.errstate(all="ignore"):
+        minsnow = np.nanmin(swe, axis=(0, 1))
+        maxsnow = np.nanmax(swe, axis=(0, 1))
+    ndays = swe.shape[2] // 24
+    snowflag = (maxsnow[:ndays * 24].reshape(ndays, 24) > 0.0).any(axis=1)
+    nosnowflag = (minsnow[:ndays * 24].reshape(ndays, 24) == 0.0).any(axis=1)
+    v = np.arange(1, ndays + 1)
+    snowdays, nosnowdays = v[snowflag], v[nosnowflag]
+    micropoints = subsetpointmodel(micropoint, days=snowdays) if snowdays.size else None
+    if nosnowdays.size:
+        micropointn = subsetpointmodel(micropoint, days=nosnowdays)
+        moutn = prepare_model(micropointn, vegp, soilc, dtm, reqhgt, runchecks, pai_a, tfact, out, slr, apr, hor, twi,
+                              wsa).run()
+    else:  # .createblanktemplate1
+        micropointn = subsetpointmodel(micropoint, days=[1])
+        moutn = prepare_model(micropointn, vegp, soilc, dtm, reqhgt, False, None, 1.5, out).run()
+        moutn = {k: a * np.nan for k, a in moutn.items()}
+    if not snowdays.size:
+        return moutn
+    # ---- .prepsnowinputs1
+    dtm_u, vegp_u, soilc_u = _unpack(dtm, vegp, soilc)
+    vegp_u, dtm_u, soilc_u = _cleanvars(vegp_u, soilc_u, dtm_u)
+    weather = micropoints.weather
+    if runchecks:
+        rc = checkinputs(weather, vegp_u, soilc_u, dtm_u)
+        weather, vegp_u, soilc_u = rc["weather"], rc["vegp"], rc["soilc"]
+    ai = _hours_of_days(snowdays)
+    obstime = _obstime(weather["obs_time"])
+    climdata = {k: np.asarray(weather[k], dtype=np.float64) for k in WEATHER_COLS}
+    climdata["umu"] = np.asarray(smod["umu"], dtype=np.float64)[ai - 1]
+    sdept = np.zeros(len(micropoint.tmeorig))
+    sdept[np.asarray(micropoints.subs, dtype=int) - 1] = 1
+    vg = _sortl2(vegp_u, sdept, reqhgt, pai_a)
+    other: Dict[str, object] = {}
+    other["slope"] = (terrain(dtm_u, "slope") if slr is None else as_raster(slr, dtm_u)).matrix()
+    other["aspect"] = (terrain(dtm_u, "aspect") if apr is None else as_raster(apr, dtm_u)).matrix()
+    lat, lon = latlong_from_raster(dtm_u)
+    if hor is None:
+        other["hor"], sv = api.horizon(dtm_u.matrix(), dtm_u.res[0], want_svf=True)
+    else:
+        other["hor"] = np.asarray(hor, dtype=np.float64)
+        sv = 0.5 * np.cos(2 * np.tan(np.mean(np.arctan(other["hor"]), axis=2))) + 0.5
+    other["skyview"] = sv if svf is None else as_raster(svf, dtm_u).matrix()
+    other["wsa"] = (_windsheltera(dtm_u, micropoint.zref, 10 if dtm_u.res[0] <= 100 else 1) if wsa is None
+                    else np.asarray(wsa, dtype=np.float64))
+    other["lat"], other["lon"], other["zref"] = lat, lon, micropoints.zref  # `ll$lon` is NULL in R (the column is `long`)
+    other["Smax"] = _soilinit(soilc_u)["Smax"]
+    # blank micro seeded with the no-snow model on days present in both sets
+    t1 = snowdays.size * 24
+    s1 = np.arange(t1)[np.repeat(np.isin(snowdays, nosnowdays), 24)]
+    s2 = np.arange(nosnowdays.size * 24)[np.repeat(np.isin(nosnowdays, snowdays), 24)]
+    micros = {}
+    for k, a in moutn.items():
+        vv = np.full(a.shape[:2] + (t1,), np.nan)
+        vv[:, :, s1] = a[:, :, s2]
+        micros[k] = vv
+    smods = subsetsnowmodel(smod, ai)
+    outm = [bool(o) for o in out]
+    if reqhgt == 0:
+        outm = [i in (0, 3, 5, 6, 7, 8, 9) for i in range(10)]
+    elif reqhgt < 0:
+        outm = [i in (0, 3) for i in range(10)]
+    names = ("Tz", "tleaf", "relhum", "soilm", "windspeed", "Rdirdown", "Rdifdown", "Rlwdown", "Rswup", "Rlwup")
+    outm = [o and (n in micros) for o, n in zip(outm, names)]
+    mouts = op(reqhgt, obstime, climdata, smods, micros, vg, other, micropoint.matemp, outm)
+    if not nosnowdays.size:
+        return mouts
+    # ---- merge by day (R/internal.R:3634-3656)
+    nosnow = np.setdiff1d(np.union1d(snowdays, nosnowdays), snowdays)
+    s1 = np.arange(next(iter(moutn.values())).shape[2])[np.repeat(np.isin(nosnowdays, nosnow), 24)]
+    nosnowh, snowh = _hours_of_days(nosnow) - 1, _hours_of_days(snowdays) - 1
+    n = nosnowh.size + snowh.size
+    mout = {}
+    for k, a in moutn.items():
+        m = np.full(a.shape[:2] + (n,), np.nan)
+        m[:, :, nosnowh] = a[:, :, s1]
+        if k in mouts:
+            m[:, :, snowh] = mouts[k]
+        mout[k] = m
+    return mout

@@ -90,3 +90,37 @@ def test_snowmodel1_chunk_driver_matches_reference_operator():
                                {k: b[k] for k in ("Tc", "Tg", "groundsnowdepth", "totalSWE", "snowden")})
     assert ok, "\n" + parity.fmt(rows_)
     assert np.isfinite(a["totalSWE"]).all() and a["totalSWE"].max() > 0
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_runmicro_snow_true_merges_snow_and_snowfree_days():
+    """runmicro(snow = TRUE) on the bundled raster (R/Cppwrappers.R:380-383 -> .runmicrosnow1): a synthetic snow-model
+    output with snow on days 2-3 of 4; snow days come from gridmicrosnow1, snow-free days from the ordinary model, and
+    the whole thing agrees with the same driver run on the compiled reference's snow operator."""
+    from microclimf_b200 import hostmodel
+    from test_bundled_example import load_example
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, days=[10, 11, 12, 13])
+    sub.tmeorig = sub.weather["obs_time"]          # a 4-day model in its own right
+    sub.subs = np.arange(1, 97)
+    sub.weather["temp"] = sub.weather["temp"] - 8.0
+    rng = np.random.default_rng(4)
+    shp = (50, 50, 96)
+    swe = np.zeros(shp)
+    swe[:, :, 24:72] = rng.uniform(5, 60, shp[:2])[:, :, None] * (rng.random(shp[:2]) < 0.8)[:, :, None]
+    den = np.full(shp, 250.0)
+    smod = dict(Tc=np.minimum(sub.weather["temp"][None, None, :] + rng.normal(0, 0.5, shp), 0.0),
+                Tg=np.minimum(sub.weather["temp"][None, None, :] * 0.5 + rng.normal(0, 0.3, shp), 0.0),
+                totalSWE=swe, groundsnowdepth=swe / den * 0.8, snowden=den, umu=sub.dfo["umu"])
+    a = hostmodel.runmicro(sub, 0.05, vegp, soilc, dtm, snow=True, snowmod=smod)
+    b = hostmodel.runmicrosnow1(sub, 0.05, vegp, soilc, dtm, smod, snow_operator=pyoracle.gridmicrosnow1)
+    assert a["Tz"].shape == shp
+    ok, rows = parity.compare({k: v for k, v in a.items() if k != "tme"}, b)
+    assert ok, "\n" + parity.fmt(rows)
+    plain = hostmodel.runmicro(sub, 0.05, vegp, soilc, dtm)
+    land = ~np.isnan(dtm.matrix())
+    assert np.array_equal(a["Tz"][:, :, :24][land], plain["Tz"][:, :, :24][land])        # snow-free day: ordinary model
+    snowy = (swe[:, :, 30] > 0) & land
+    assert snowy.any() and not np.allclose(a["Tz"][:, :, 30][snowy], plain["Tz"][:, :, 30][snowy])
+    assert np.all(a["soilm"][:, :, 30][snowy] == 0.419)                                     # Smax under snow (:5029)
