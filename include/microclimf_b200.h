@@ -324,6 +324,7 @@ typedef struct mcf_snow_static { /* vegp + other ([rows, cols] unless noted) */
     double lat, lon, zref;
     const double *isnowdc, *isnowdg;            /* gridmodelsnow only: initial snow depth (canopy + ground, ground) */
     const int32_t *isnowac, *isnowag;           /* gridmodelsnow only: initial snow age, hours */
+    const double *lats, *lons;                  /* array-climate variants only: per-cell latitude / longitude */
 } mcf_snow_static;
 
 typedef struct mcf_snow_state { /* snowm of gridmicrosnow1 (:4935-4940), each [rows, cols, tsteps] */
@@ -340,6 +341,14 @@ int mcf_gridmodelsnow(const mcf_snow_climate* clim, const mcf_snow_point* pt, co
  * outputs, updated IN PLACE where totalSWE > 0. */
 int mcf_gridmicrosnow(double reqhgt, const mcf_snow_climate* clim, const double* umu, const mcf_snow_state* sm,
                       const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err, size_t errlen);
+
+/* Array climate: _microclimf_gridmodelsnow2 (src/microclimfCpp.cpp:4426-4673) and _microclimf_gridmicrosnow2
+ * (:5059-5214).  Every series of `clim` (except winddir, length tsteps), of `pt` and `umu` is a
+ * [rows, cols, tsteps] array; st->lats / st->lons are required, st->lat / st->lon ignored. */
+int mcf_gridmodelsnow2(const mcf_snow_climate* clim, const mcf_snow_point* pt, const mcf_snow_static* st, int32_t snowenv,
+                       double* const out3d[5], double* const out2d[4], char* err, size_t errlen);
+int mcf_gridmicrosnow2(double reqhgt, const mcf_snow_climate* clim, const double* umu, const mcf_snow_state* sm,
+                       const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err, size_t errlen);
 
 /* Element-wise evaluation of the kernels' own FP64 elementary functions (csrc/mcf_math.cuh) on HOST
  * buffers, for accuracy tests: fn 0 = 1/x, 1 = x/y, 2 = sqrt(x), 3 = exp(x), 4 = 2^x, 5 = log(x),

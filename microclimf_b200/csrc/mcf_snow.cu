@@ -331,6 +331,117 @@ __device__ SnowRad radone(const SnowHour& h, double Rsw, double Rdif, double Rlw
     return out;
 }
 
+struct SnowStep { double Tc, Tg, sdepc, sdepg, sdenc, sdeng, agec, ageg, melc, melg; };
+// one hour of one cell: snowoneB (ref :3835-3972) with umu = 1, psim = psih = 0
+__device__ SnowStep snow_step(const SnowHour& h, double Rswp, double Rdifp, double Rlwp, double u2p, double G, double hgt0,
+                              double pai0, double ltra0, double clump, double slope, double aspect, double zref,
+                              const double* sdp, double sdepcp, double sdepgp, double sdencp, double sdengp, int snowagec,
+                              int snowageg) {
+    // ---- snowoneB (ref :3835-3972), umu = 1
+    double pai = 0.0;
+    if (hgt0 > sdepgp) pai = pai0 * (hgt0 - sdepgp) / hgt0;
+    double hgt = hgt0 - sdepgp;
+    if (hgt < 0.0) hgt = 0.0;
+    double zi = 0.0;
+    if (sdepgp > 0.0 && hgt > 0.0) zi = ((sdepcp - sdepgp) * sdencp) / (hgt * 1000.0);
+    const double ltra = ltra0 * exp(-10.1 * zi);
+    const SnowRad rad = radone(h, Rswp, Rdifp, Rlwp, pai, hgt, ltra, clump, h.salb, slope, aspect);
+    const double RabsG = rad.RswabsG + rad.RlwabsG;
+    double d = 0.0, zm = 0.005;
+    if (hgt > 0.0) {
+        d = zeroplanedisS(hgt, pai);
+        zm = roughlengthS(hgt, pai, d, 0.0);
+    }
+    if (zm < 0.0009) zm = 0.0009;
+    const double uf = (kKaS * u2p) / (log((zref - d) / zm) + 0.0);
+    const double ph = 44.6 * (h.pk / 101.3) * (273.15 / (h.tc + 273.15)); // phairCpp :280
+    const double gHa = gturbS(uf, d, zm, zref, ph, 0.0, 0.03);
+    double Tc = penmanmonteith(rad.RabsC, gHa, gHa, h.tc, h.te, h.pk, h.ea, 0.97, G, 1.0);
+    double Tg = penmanmonteith(RabsG, gHa, gHa, h.tc, h.te, h.pk, h.ea, 0.97, G, 1.0);
+    const double tdew = dewpointC(h.ea);
+    if (Tc < tdew) Tc = tdew;
+    if (Tg < tdew) Tg = tdew;
+    // canopy + ground pack
+    double la;
+    if (Tc < 0.0) la = 51078.69 - 4.338 * Tc - 0.06367 * Tc * Tc;
+    else la = 45068.7 - 42.8428 * Tc;
+    double L = la * (gHa / h.pk) * (satvapS(Tc) - h.ea);
+    la = la / 0.018015;
+    const double mSc = (L / la) * 3.6;
+    double mMc = 0.0;
+    if (Tc > 0.0) {
+        const double S = sdepcp * (sdencp / 1000);
+        const double Fm = 583.3 * Tc * S;
+        mMc = (Fm / 334000.0) * 3.6;
+        if (sdepcp > 0.0) Tc = 0.0;
+    }
+    double mRc = 0.0;
+    if (h.tc > 0.0) mRc = 0.0125 * h.tc * h.prec / 1000;
+    // ground-only pack
+    if (Tg < 0.0) la = 51078.69 - 4.338 * Tg - 0.06367 * Tg * Tg;
+    else la = 45068.7 - 42.8428 * Tg;
+    double mu = exp(-pai);
+    if (mu > 1.0) mu = 1.0;
+    L = la * (gHa / h.pk) * (satvapS(Tg) - h.ea) * mu;
+    la = la / 0.018015;
+    const double mSg = (L / la) * 3.6;
+    double mMg = 0.0;
+    if (Tg > 0.0) {
+        const double S = sdepgp * (sdengp / 1000.0);
+        const double Fm = 583.3 * Tg * S;
+        mMg = (Fm / 334000.0) * 3.6;
+        if (sdepgp > 0.0) Tg = 0.0;
+    }
+    double Li = 0.0;
+    if (sdepcp > 0.0) {
+        double wgtg = sdepgp / sdepcp;
+        if (wgtg < 0.0) wgtg = 0.0;
+        if (wgtg > 1.0) wgtg = 1.0;
+        const double sdencc = wgtg * sdengp + (1.0 - wgtg) * sdencp;
+        Li = (sdepcp - sdepgp) * sdencc;
+    }
+    if (Li < 0.0) Li = 0.0;
+    double cis = canopysnowint(hgt, pai, uf, h.prec, h.tc, Li);
+    if (cis > h.prec) cis = h.prec;
+    double mRg = 0.0;
+    if (h.tc > 0.0) mRg = 0.0125 * h.tc * (h.prec - cis) / 1000.0;
+    double snowc = h.prec, snowg = h.prec - cis;
+    if (h.tc > 2.0) { snowc = 0.0; snowg = 0.0; }
+    const double swec = snowc / 1000.0 - mSc - mMc - mRc;
+    const double sweg = snowg / 1000.0 - mSg - mMg - mRg;
+    double agec_n = (double)snowagec + 1.0, ageg_n = (double)snowageg + 1.0;
+    const double sdenc_n = ((sdp[0] - sdp[1]) * (1.0 - exp(-sdp[2] * sdepcp / 100.0 - sdp[3] * agec_n / 24.0)) + sdp[1]) * 1000.0;
+    const double sdeng_n = ((sdp[0] - sdp[1]) * (1.0 - exp(-sdp[2] * sdepgp / 100.0 - sdp[3] * ageg_n / 24.0)) + sdp[1]) * 1000.0;
+    double sdepc_n = sdepcp + (swec * 1000.0) / sdenc_n;
+    double sdepg_n = sdepgp + (sweg * 1000.0) / sdeng_n;
+    if (sdepc_n < 0.0) { sdepc_n = 0.0; agec_n = 0.0; }
+    if (sdepg_n < 0.0) { sdepg_n = 0.0; ageg_n = 0.0; }
+    SnowStep o;
+    o.Tc = Tc; o.Tg = Tg; o.sdepc = sdepc_n; o.sdepg = sdepg_n; o.sdenc = sdenc_n; o.sdeng = sdeng_n;
+    o.agec = agec_n; o.ageg = ageg_n;
+    o.melc = mSc + mMc + mRc;
+    o.melg = mSg + mMg + mRg;
+    return o;
+}
+
+// ref belowpointsnow :4868-4892
+__device__ double below_snow(double reqhgts, double meanD, double stg, double Tzd, double mat, int hiy) {
+    const double nb = -118.35 * reqhgts / meanD;
+    double Tz = stg;
+    if (nb > 1.0) {
+        if (nb <= 24.0) {
+            const double w1 = 1.0 / nb, w2 = nb / 24.0, wgt = w1 / (w1 + w2);
+            Tz = wgt * stg + (1 - wgt) * Tzd;
+        } else if (nb <= (double)hiy) {
+            const double w1 = 24.0 / nb, w2 = nb / (double)hiy, wgt = w1 / (w1 + w2);
+            Tz = wgt * Tzd + (1 - wgt) * mat;
+        } else {
+            Tz = mat;
+        }
+    }
+    return Tz;
+}
+
 __global__ void __launch_bounds__(128) k_snowmodel(const __grid_constant__ SnowModelArgs a) {
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     const int nc = a.rows * a.cols;
@@ -384,85 +495,10 @@ __global__ void __launch_bounds__(128) k_snowmodel(const __grid_constant__ SnowM
             const double Rdirp = (h.Rsw - h.Rdif) * smu;
             const double Rswp = Rdirp + Rdifp;
             const double Rlwp = h.Rlw * svf;
-            // ---- snowoneB (ref :3835-3972), umu = 1
-            double pai = 0.0;
-            if (hgt0 > sdepgp) pai = pai0 * (hgt0 - sdepgp) / hgt0;
-            double hgt = hgt0 - sdepgp;
-            if (hgt < 0.0) hgt = 0.0;
-            double zi = 0.0;
-            if (sdepgp > 0.0 && hgt > 0.0) zi = ((sdepcp - sdepgp) * sdencp) / (hgt * 1000.0);
-            const double ltra = ltra0 * exp(-10.1 * zi);
-            const SnowRad rad = radone(h, Rswp, Rdifp, Rlwp, pai, hgt, ltra, clump, h.salb, slope, aspect);
-            const double RabsG = rad.RswabsG + rad.RlwabsG;
-            double d = 0.0, zm = 0.005;
-            if (hgt > 0.0) {
-                d = zeroplanedisS(hgt, pai);
-                zm = roughlengthS(hgt, pai, d, 0.0);
-            }
-            if (zm < 0.0009) zm = 0.0009;
-            const double uf = (kKaS * u2p) / (log((a.zref - d) / zm) + 0.0);
-            const double ph = 44.6 * (h.pk / 101.3) * (273.15 / (h.tc + 273.15)); // phairCpp :280
-            const double gHa = gturbS(uf, d, zm, a.zref, ph, 0.0, 0.03);
-            double Tc = penmanmonteith(rad.RabsC, gHa, gHa, h.tc, h.te, h.pk, h.ea, 0.97, G, 1.0);
-            double Tg = penmanmonteith(RabsG, gHa, gHa, h.tc, h.te, h.pk, h.ea, 0.97, G, 1.0);
-            const double tdew = dewpointC(h.ea);
-            if (Tc < tdew) Tc = tdew;
-            if (Tg < tdew) Tg = tdew;
-            // canopy + ground pack
-            double la;
-            if (Tc < 0.0) la = 51078.69 - 4.338 * Tc - 0.06367 * Tc * Tc;
-            else la = 45068.7 - 42.8428 * Tc;
-            double L = la * (gHa / h.pk) * (satvapS(Tc) - h.ea);
-            la = la / 0.018015;
-            const double mSc = (L / la) * 3.6;
-            double mMc = 0.0;
-            if (Tc > 0.0) {
-                const double S = sdepcp * (sdencp / 1000);
-                const double Fm = 583.3 * Tc * S;
-                mMc = (Fm / 334000.0) * 3.6;
-                if (sdepcp > 0.0) Tc = 0.0;
-            }
-            double mRc = 0.0;
-            if (h.tc > 0.0) mRc = 0.0125 * h.tc * h.prec / 1000;
-            // ground-only pack
-            if (Tg < 0.0) la = 51078.69 - 4.338 * Tg - 0.06367 * Tg * Tg;
-            else la = 45068.7 - 42.8428 * Tg;
-            double mu = exp(-pai);
-            if (mu > 1.0) mu = 1.0;
-            L = la * (gHa / h.pk) * (satvapS(Tg) - h.ea) * mu;
-            la = la / 0.018015;
-            const double mSg = (L / la) * 3.6;
-            double mMg = 0.0;
-            if (Tg > 0.0) {
-                const double S = sdepgp * (sdengp / 1000.0);
-                const double Fm = 583.3 * Tg * S;
-                mMg = (Fm / 334000.0) * 3.6;
-                if (sdepgp > 0.0) Tg = 0.0;
-            }
-            double Li = 0.0;
-            if (sdepcp > 0.0) {
-                double wgtg = sdepgp / sdepcp;
-                if (wgtg < 0.0) wgtg = 0.0;
-                if (wgtg > 1.0) wgtg = 1.0;
-                const double sdencc = wgtg * sdengp + (1.0 - wgtg) * sdencp;
-                Li = (sdepcp - sdepgp) * sdencc;
-            }
-            if (Li < 0.0) Li = 0.0;
-            double cis = canopysnowint(hgt, pai, uf, h.prec, h.tc, Li);
-            if (cis > h.prec) cis = h.prec;
-            double mRg = 0.0;
-            if (h.tc > 0.0) mRg = 0.0125 * h.tc * (h.prec - cis) / 1000.0;
-            double snowc = h.prec, snowg = h.prec - cis;
-            if (h.tc > 2.0) { snowc = 0.0; snowg = 0.0; }
-            const double swec = snowc / 1000.0 - mSc - mMc - mRc;
-            const double sweg = snowg / 1000.0 - mSg - mMg - mRg;
-            double agec_n = (double)snowagec + 1.0, ageg_n = (double)snowageg + 1.0;
-            const double sdenc_n = ((sdp[0] - sdp[1]) * (1.0 - exp(-sdp[2] * sdepcp / 100.0 - sdp[3] * agec_n / 24.0)) + sdp[1]) * 1000.0;
-            const double sdeng_n = ((sdp[0] - sdp[1]) * (1.0 - exp(-sdp[2] * sdepgp / 100.0 - sdp[3] * ageg_n / 24.0)) + sdp[1]) * 1000.0;
-            double sdepc_n = sdepcp + (swec * 1000.0) / sdenc_n;
-            double sdepg_n = sdepgp + (sweg * 1000.0) / sdeng_n;
-            if (sdepc_n < 0.0) { sdepc_n = 0.0; agec_n = 0.0; }
-            if (sdepg_n < 0.0) { sdepg_n = 0.0; ageg_n = 0.0; }
+            const SnowStep st = snow_step(h, Rswp, Rdifp, Rlwp, u2p, G, hgt0, pai0, ltra0, clump, slope, aspect, a.zref, sdp,
+                                          sdepcp, sdepgp, sdencp, sdengp, snowagec, snowageg);
+            const double Tc = st.Tc, Tg = st.Tg, sdepc_n = st.sdepc, sdepg_n = st.sdepg, sdenc_n = st.sdenc, sdeng_n = st.sdeng;
+            const double agec_n = st.agec, ageg_n = st.ageg;
             // ---- outputs and state update (ref :4382-4402)
             a.Tc[idx] = Tc;
             a.Tg[idx] = Tg;
@@ -475,8 +511,7 @@ __global__ void __launch_bounds__(128) k_snowmodel(const __grid_constant__ SnowM
             sdepgp = sdepg_n;
             snowagec = (int)agec_n; // double -> int, as the reference's assignment (:4393-4394)
             snowageg = (int)ageg_n;
-            const double melc = mSc + mMc + mRc;
-            const double melg = mSg + mMg + mRg;
+            const double melc = st.melc, melg = st.melg;
             meltc = meltc + melc;
             meltc = meltc + (melc * 1000.0) / sdenc_n;
             meltg = meltg + (melg * 1000.0) / sdeng_n;
@@ -865,21 +900,228 @@ __global__ void __launch_bounds__(128) k_snowmicro(const __grid_constant__ SnowM
             if (a.out[8]) a.out[8][idx] = o.Rdup;
             if (a.out[9]) a.out[9][idx] = o.Rlwup;
         } else {
-            // belowpointsnow (ref :4868-4892)
-            const double nb = -118.35 * reqhgts / meanD;
-            const double stg = a.snowtempg[idx];
-            double Tz = stg;
-            if (nb > 1.0) {
-                if (nb <= 24.0) {
-                    const double w1 = 1.0 / nb, w2 = nb / 24.0, wgt = w1 / (w1 + w2);
-                    Tz = wgt * stg + (1 - wgt) * Tzd;
-                } else if (nb <= (double)a.hiy) {
-                    const double w1 = 24.0 / nb, w2 = nb / (double)a.hiy, wgt = w1 / (w1 + w2);
-                    Tz = wgt * Tzd + (1 - wgt) * a.mat;
-                } else {
-                    Tz = a.mat;
+            const double Tz = below_snow(reqhgts, meanD, a.snowtempg[idx], Tzd, a.mat, a.hiy);
+            if (a.out[0]) a.out[0][idx] = Tz;
+            if (a.out[1]) a.out[1][idx] = Tz;
+            if (a.out[2]) a.out[2][idx] = 100.0;
+            if (a.out[4]) a.out[4][idx] = 0.0;
+            if (a.out[5]) a.out[5][idx] = 0.0;
+            if (a.out[6]) a.out[6][idx] = 0.0;
+            if (a.out[7]) a.out[7][idx] = 0.0;
+            if (a.out[8]) a.out[8][idx] = 0.0;
+            if (a.out[9]) a.out[9][idx] = 0.0;
+        }
+        if (a.out[3]) a.out[3][idx] = Smax;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// array climate: gridmodelsnow2 (ref :4426-4673) and gridmicrosnow2 (ref :5059-5214)
+// ---------------------------------------------------------------------------------------------
+// Climate and point-model series are [rows, cols, tsteps] arrays (coalesced per hour); winddir stays a per-hour
+// vector.  What the data.frame kernels take from the hour table is formed per cell here: the snow-albedo age scan
+// runs along the cell's own precipitation series, the daily radiation extremes are gathered at each day start, the
+// solar position comes from the cell's latitude / longitude.
+struct SnowArr {
+    const int32_t *year, *month, *day;
+    const double* hour;
+    const double *temp, *relhum, *pres, *swdown, *difrad, *lwdown, *windspeed, *precip; // [nc * T]
+    const double* winddir;                                                              // [T]
+    const double *Gp, *Tcp, *RswabsG, *RlwabsG, *umu;                                  // [nc * T]
+    const double *lats, *lons;                                                          // [nc]
+};
+
+__device__ __forceinline__ double snow_albedo(int hs) { // ref snowalbCpp :3765-3769 (integer hs / 24)
+    double alb = (-9.8740 * log((double)(hs / 24)) + 78.3434) / 100.0;
+    if (alb > 0.95) alb = 0.95;
+    if (alb < 0.1) alb = 0.1;
+    return alb;
+}
+
+__global__ void __launch_bounds__(128) k_snowmodel_arr(const __grid_constant__ SnowModelArgs a, const __grid_constant__ SnowArr c) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nc = a.rows * a.cols;
+    if (cell >= nc) return;
+    const double hgt0 = a.hgt[cell];
+    const double NA = na_realS();
+    if (isnan(hgt0)) {
+        for (int k = 0; k < a.tsteps; ++k) {
+            const size_t idx = (size_t)k * nc + cell;
+            a.Tc[idx] = NA; a.Tg[idx] = NA; a.sdepc[idx] = NA; a.sdepg[idx] = NA; a.sden[idx] = NA;
+        }
+        a.agec[cell] = NA; a.ageg[cell] = NA; a.meltc[cell] = NA; a.meltg[cell] = NA;
+        return;
+    }
+    const double pai0 = a.pai[cell], clump = a.clump[cell], ltra0 = a.ltra[cell];
+    const double slope = a.slope[cell], aspect = a.aspect[cell], svf = a.skyview[cell];
+    const double lat = c.lats[cell], lon = c.lons[cell];
+    const double* sdp = a.sdp;
+    int snowagec = a.isnowac[cell], snowageg = a.isnowag[cell];
+    double sdepcp = a.isnowdc[cell], sdepgp = a.isnowdg[cell];
+    double sdencp = ((sdp[0] - sdp[1]) * (1 - exp(-sdp[2] * sdepcp / 100.0 - sdp[3] * snowagec / 24.0)) + sdp[1]) * 1000.0;
+    double sdengp = ((sdp[0] - sdp[1]) * (1 - exp(-sdp[2] * sdepgp * 0.5 / 100.0 - sdp[3] * snowageg / 24.0)) + sdp[1]) * 1000.0;
+    double meltc = NA, meltg = NA; // neither is initialised in the array-climate driver (:4487-4488)
+    const int ndays = a.tsteps / 24;
+    int hs = 0;
+    double Rmx = 0, Rmn = 0, Rswmx = 0, Rlwmx = 0, Rswmn = 0, Rlwmn = 0, Gmx = 0;
+#pragma unroll 1
+    for (int k = 0; k < a.tsteps; ++k) {
+        const size_t idx = (size_t)k * nc + cell;
+        const double tc = c.temp[idx], prec = c.precip[idx];
+        if (k > 0) hs = (prec > 0) ? 0 : hs + 1;
+        if ((k % 24) == 0) { // daily extremes of the cell's net radiation (:4503-4566); zero beyond the whole days
+            Rmx = Rmn = Rswmx = Rlwmx = Rswmn = Rlwmn = Gmx = 0.0;
+            if (k / 24 < ndays) {
+                double mx = -1352.0, mn = 1352.0;
+                for (int hh = 0; hh < 24; ++hh) {
+                    const size_t i2 = (size_t)(k + hh) * nc + cell;
+                    const double Rnet = c.RswabsG[i2] + c.RlwabsG[i2] - 0.97 * kSbS * radem(c.temp[i2]);
+                    if (mx < Rnet) { mx = Rnet; Rswmx = c.swdown[i2]; Rlwmx = c.lwdown[i2]; }
+                    if (mn > Rnet) { mn = Rnet; Rswmn = c.swdown[i2]; Rlwmn = c.lwdown[i2]; }
+                    if (fabs(Rnet) > Gmx) Gmx = fabs(Rnet);
                 }
+                Rmx = mx;
+                Rmn = mn;
             }
+        }
+        int snowtest = 0;
+        if (sdepcp > 0.0) snowtest = 1;
+        if (tc < 2.0 && prec > 0.0) snowtest = 1;
+        if (snowtest > 0) {
+            SnowHour h;
+            h.tc = tc;
+            h.rh = c.relhum[idx];
+            h.ea = satvapS(tc) * h.rh / 100.0;
+            h.pk = c.pres[idx];
+            h.u2 = c.windspeed[idx];
+            h.Rsw = c.swdown[idx];
+            h.Rdif = c.difrad[idx];
+            h.Rlw = c.lwdown[idx];
+            h.prec = prec;
+            h.Tcp = c.Tcp[idx];
+            h.te = (h.Tcp + tc) / 2.0;
+            h.Gp = c.Gp[idx];
+            h.umu = c.umu[idx];
+            h.salb = snow_albedo(hs);
+            const SolPos sp = solposition(lat, lon, c.year[k], c.month[k], c.day[k], c.hour[k]);
+            h.zend = sp.zend; h.zenr = sp.zenr; h.azid = sp.azid; h.cosz = cos(sp.zenr);
+            h.sindex = ((int)round(sp.azid / 15.0)) % 24;
+            h.windex = ((int)round(c.winddir[k] / 45)) % 8;
+            double paip = pai0;
+            if (hgt0 > sdepgp) paip = paip * (hgt0 - sdepgp) / hgt0;
+            const double dtR = Rmx - Rmn;
+            const double trS = svf * exp(-paip);
+            const double Rem = 0.97 * kSbS * radem(tc);
+            const double dmxS = trS * Rswmx + trS * Rlwmx + (1 - trS) * Rem - Rem;
+            const double dmnS = trS * Rswmn + trS * Rlwmn + (1 - trS) * Rem - Rem;
+            const double Gmu = (dmxS - dmnS) / dtR;
+            double G = h.Gp * Gmu;
+            if (G > Gmx) G = Gmx;
+            if (G < -Gmx) G = -Gmx;
+            const double ha = a.hor[(size_t)h.sindex * nc + cell];
+            const double sa = kPiS / 2.0 - h.zenr; // radians here, degrees in the data.frame driver
+            double smu = 1.0;
+            if (ha > tan(sa)) smu = 0.0;
+            const double ws = a.wsa[(size_t)h.windex * nc + cell];
+            const double u2p = h.umu * ws * h.u2;
+            const double Rdifp = h.Rdif * svf;
+            const double Rdirp = (h.Rsw - h.Rdif) * smu;
+            const double Rswp = Rdirp + Rdifp;
+            const double Rlwp = h.Rlw * svf;
+            const SnowStep st = snow_step(h, Rswp, Rdifp, Rlwp, u2p, G, hgt0, pai0, ltra0, clump, slope, aspect, a.zref, sdp,
+                                          sdepcp, sdepgp, sdencp, sdengp, snowagec, snowageg);
+            a.Tc[idx] = st.Tc; a.Tg[idx] = st.Tg; a.sdepc[idx] = st.sdepc; a.sdepg[idx] = st.sdepg; a.sden[idx] = st.sdenc;
+            sdencp = st.sdenc; sdengp = st.sdeng; sdepcp = st.sdepc; sdepgp = st.sdepg;
+            snowagec = (int)st.agec; snowageg = (int)st.ageg;
+            meltc = meltc + st.melc;
+            meltc = meltc + (st.melc * 1000.0) / st.sdenc;
+            meltg = meltg + (st.melg * 1000.0) / st.sdeng;
+        } else {
+            a.Tc[idx] = 0.0; a.Tg[idx] = 0.0; a.sdepc[idx] = 0.0; a.sdepg[idx] = 0.0; a.sden[idx] = sdp[1] * 1000.0;
+        }
+    }
+    a.agec[cell] = (double)snowagec;
+    a.ageg[cell] = (double)snowageg;
+    a.meltc[cell] = meltc;
+    a.meltg[cell] = meltg;
+}
+
+__global__ void __launch_bounds__(128) k_snowmicro_arr(const __grid_constant__ SnowMicroArgs a, const __grid_constant__ SnowArr c) {
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nc = a.rows * a.cols;
+    if (cell >= nc) return;
+    const double hgt = a.hgt[cell];
+    if (isnan(hgt)) return;
+    const int T = a.tsteps;
+    double meanD = na_realS();
+    if (!isnan(a.sden[cell])) {
+        double sumD = 0.0;
+        for (int k = 0; k < T; ++k) {
+            const double sd = a.sden[(size_t)k * nc + cell];
+            const double co = 0.0442 * exp(5.181 * sd / 1000.0);
+            sumD += sqrt(2.0 * (co / (sd * 2090.0)) / kOmdyS);
+        }
+        meanD = sumD / (double)T;
+    }
+    double mxtc = -273.15; // per cell here (:5138-5143)
+    for (int k = 0; k < T; ++k) {
+        const double t = c.temp[(size_t)k * nc + cell];
+        if (t > mxtc) mxtc = t;
+    }
+    const bool tzd_ok = !isnan(a.snowtempg[cell]);
+    const double pai = a.pai[cell], paia = a.paia[cell], ltra = a.ltra[cell], clump = a.clump[cell];
+    const double leafd = a.leafd[cell], leafden = a.leafden[cell];
+    const double slope = a.slope[cell], aspect = a.aspect[cell], svf = a.skyview[cell], Smax = a.Smax[cell];
+    const double lat = c.lats[cell], lon = c.lons[cell];
+    const int ndays = T / 24;
+    double Tzd = na_realS();
+    int hs = 0;
+#pragma unroll 1
+    for (int k = 0; k < T; ++k) {
+        const size_t idx = (size_t)k * nc + cell;
+        if (k > 0) hs = (c.precip[idx] > 0) ? 0 : hs + 1;
+        if ((k % 24) == 0) {
+            Tzd = na_realS();
+            if (tzd_ok && k / 24 < ndays) {
+                double s = 0.0;
+                for (int hh = 0; hh < 24; ++hh) s += a.snowtempg[(size_t)(k + hh) * nc + cell];
+                Tzd = s / 24.0;
+            }
+        }
+        const double swe = a.swe[idx];
+        if (!(swe > 0.0)) continue;
+        const double sdepg = a.sdepg[idx];
+        const double reqhgts = a.reqhgt - sdepg;
+        if (reqhgts >= 0.0) {
+            SnowHour h;
+            h.tc = c.temp[idx]; h.rh = c.relhum[idx]; h.pk = c.pres[idx]; h.u2 = c.windspeed[idx];
+            h.Rsw = c.swdown[idx]; h.Rdif = c.difrad[idx]; h.Rlw = c.lwdown[idx]; h.umu = c.umu[idx];
+            const SolPos sp = solposition(lat, lon, c.year[k], c.month[k], c.day[k], c.hour[k]);
+            h.zend = sp.zend; h.zenr = sp.zenr; h.azid = sp.azid;
+            const int sindex = ((int)round(sp.azid / 15)) % 24;
+            const int windex = ((int)round(c.winddir[k] / 45)) % 8;
+            int shadowmask = 1;
+            const double ha = a.hor[(size_t)sindex * nc + cell];
+            const double sa = (kPiS / 2.0) - sp.zenr;
+            double si = solarindex(slope, aspect, sp.zend, sp.azid, true);
+            if (isnan(si)) si = cos(sp.zenr);
+            if (ha > tan(sa)) shadowmask = 0;
+            const double ws = a.wsa[(size_t)windex * nc + cell];
+            const double sden = a.sden[idx];
+            const double alb = snow_albedo(hs);
+            const SnowMicroOut o = snowabove(reqhgts, a.zref, h, hgt, pai, paia, leafd, clump, ltra, leafden, si, svf, shadowmask,
+                                             ws, mxtc, a.snowtempg[idx], a.snowtempc[idx], swe / sden, sdepg, sden, alb, alb);
+            if (a.out[0]) a.out[0][idx] = o.Tz;
+            if (a.out[1]) a.out[1][idx] = o.tleaf;
+            if (a.out[2]) a.out[2][idx] = o.rh;
+            if (a.out[4]) a.out[4][idx] = o.uz;
+            if (a.out[5]) a.out[5][idx] = o.Rbdown;
+            if (a.out[6]) a.out[6][idx] = o.Rddown;
+            if (a.out[7]) a.out[7][idx] = o.Rlwdn;
+            if (a.out[8]) a.out[8][idx] = o.Rdup;
+            if (a.out[9]) a.out[9][idx] = o.Rlwup;
+        } else {
+            const double Tz = below_snow(reqhgts, meanD, a.snowtempg[idx], Tzd, a.mat, a.hiy);
             if (a.out[0]) a.out[0][idx] = Tz;
             if (a.out[1]) a.out[1][idx] = Tz;
             if (a.out[2]) a.out[2][idx] = 100.0;
@@ -979,10 +1221,36 @@ int prep_hours(DevBuf& db, const mcf_snow_climate* c, const double* Gp, const do
     SCU(cudaGetLastError());
     return MCF_OK;
 }
+
+int upload_arr(DevBuf& db, const mcf_snow_climate* c, const double* Gp, const double* Tcp, const double* RswabsG,
+               const double* RlwabsG, const double* umu, const mcf_snow_static* st, SnowArr* ca, char* err, size_t errlen) {
+    const size_t T = (size_t)c->tsteps, nc = (size_t)st->rows * st->cols, n = nc * T;
+    SCU(db.up(c->year, T, &ca->year));
+    SCU(db.up(c->month, T, &ca->month));
+    SCU(db.up(c->day, T, &ca->day));
+    SCU(db.up(c->hour, T, &ca->hour));
+    SCU(db.up(c->temp, n, &ca->temp));
+    SCU(db.up(c->relhum, n, &ca->relhum));
+    SCU(db.up(c->pres, n, &ca->pres));
+    SCU(db.up(c->swdown, n, &ca->swdown));
+    SCU(db.up(c->difrad, n, &ca->difrad));
+    SCU(db.up(c->lwdown, n, &ca->lwdown));
+    SCU(db.up(c->windspeed, n, &ca->windspeed));
+    SCU(db.up(c->precip, n, &ca->precip));
+    SCU(db.up(c->winddir, T, &ca->winddir));
+    SCU(db.up(Gp, n, &ca->Gp));
+    SCU(db.up(Tcp, n, &ca->Tcp));
+    SCU(db.up(RswabsG, n, &ca->RswabsG));
+    SCU(db.up(RlwabsG, n, &ca->RlwabsG));
+    SCU(db.up(umu, n, &ca->umu));
+    SCU(db.up(st->lats, nc, &ca->lats));
+    SCU(db.up(st->lons, nc, &ca->lons));
+    return MCF_OK;
+}
 } // namespace
 
-extern "C" int mcf_gridmodelsnow(const mcf_snow_climate* clim, const mcf_snow_point* pt, const mcf_snow_static* st,
-                                 int32_t snowenv, double* const out3d[5], double* const out2d[4], char* err, size_t errlen) {
+static int gridmodelsnow_impl(bool arr, const mcf_snow_climate* clim, const mcf_snow_point* pt, const mcf_snow_static* st,
+                              int32_t snowenv, double* const out3d[5], double* const out2d[4], char* err, size_t errlen) {
     if (!clim || !pt || !st || !out3d || !out2d) return fail(MCF_ERR_ARG, "NULL argument", err, errlen);
     if (st->rows <= 0 || st->cols <= 0 || clim->tsteps <= 0) return fail(MCF_ERR_ARG, "rows, cols, tsteps must be > 0", err, errlen);
     int ndev = 0;
@@ -990,9 +1258,17 @@ extern "C" int mcf_gridmodelsnow(const mcf_snow_climate* clim, const mcf_snow_po
     DevBuf db;
     SnowHour* hours = nullptr;
     double* scal = nullptr;
-    int rc = prep_hours(db, clim, pt->Gp, pt->Tc, pt->RswabsG, pt->RlwabsG, pt->umu, st->lat, st->lon, &hours, &scal, err, errlen);
-    if (rc != MCF_OK) return rc;
     const size_t nc = (size_t)st->rows * st->cols, T = (size_t)clim->tsteps;
+    SnowArr ca;
+    std::memset(&ca, 0, sizeof ca);
+    if (arr) {
+        if (!st->lats || !st->lons) return fail(MCF_ERR_ARG, "array-climate snow needs lats and lons", err, errlen);
+        int rc2 = upload_arr(db, clim, pt->Gp, pt->Tc, pt->RswabsG, pt->RlwabsG, pt->umu, st, &ca, err, errlen);
+        if (rc2 != MCF_OK) return rc2;
+    } else {
+        int rc = prep_hours(db, clim, pt->Gp, pt->Tc, pt->RswabsG, pt->RlwabsG, pt->umu, st->lat, st->lon, &hours, &scal, err, errlen);
+        if (rc != MCF_OK) return rc;
+    }
     SnowModelArgs a;
     std::memset(&a, 0, sizeof a);
     a.rows = st->rows; a.cols = st->cols; a.tsteps = clim->tsteps; a.hours = hours; a.zref = st->zref;
@@ -1021,7 +1297,8 @@ extern "C" int mcf_gridmodelsnow(const mcf_snow_climate* clim, const mcf_snow_po
     for (int v = 0; v < 4; ++v) SCU(db.alloc(&d2[v], nc));
     a.Tc = d3[0]; a.Tg = d3[1]; a.sdepc = d3[2]; a.sdepg = d3[3]; a.sden = d3[4];
     a.agec = d2[0]; a.ageg = d2[1]; a.meltc = d2[2]; a.meltg = d2[3];
-    k_snowmodel<<<(unsigned)((nc + 127) / 128), 128>>>(a);
+    if (arr) k_snowmodel_arr<<<(unsigned)((nc + 127) / 128), 128>>>(a, ca);
+    else k_snowmodel<<<(unsigned)((nc + 127) / 128), 128>>>(a);
     SCU(cudaGetLastError());
     for (int v = 0; v < 5; ++v)
         if (out3d[v]) SCU(cudaMemcpy(out3d[v], d3[v], nc * T * sizeof(double), cudaMemcpyDeviceToHost));
@@ -1031,9 +1308,18 @@ extern "C" int mcf_gridmodelsnow(const mcf_snow_climate* clim, const mcf_snow_po
     return MCF_OK;
 }
 
-extern "C" int mcf_gridmicrosnow(double reqhgt, const mcf_snow_climate* clim, const double* umu, const mcf_snow_state* sm,
-                                 const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err,
-                                 size_t errlen) {
+extern "C" int mcf_gridmodelsnow(const mcf_snow_climate* clim, const mcf_snow_point* pt, const mcf_snow_static* st,
+                                 int32_t snowenv, double* const out3d[5], double* const out2d[4], char* err, size_t errlen) {
+    return gridmodelsnow_impl(false, clim, pt, st, snowenv, out3d, out2d, err, errlen);
+}
+extern "C" int mcf_gridmodelsnow2(const mcf_snow_climate* clim, const mcf_snow_point* pt, const mcf_snow_static* st,
+                                  int32_t snowenv, double* const out3d[5], double* const out2d[4], char* err, size_t errlen) {
+    return gridmodelsnow_impl(true, clim, pt, st, snowenv, out3d, out2d, err, errlen);
+}
+
+static int gridmicrosnow_impl(bool arr, double reqhgt, const mcf_snow_climate* clim, const double* umu, const mcf_snow_state* sm,
+                              const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err,
+                              size_t errlen) {
     if (!clim || !sm || !st || !micro) return fail(MCF_ERR_ARG, "NULL argument", err, errlen);
     if (st->rows <= 0 || st->cols <= 0 || clim->tsteps <= 0) return fail(MCF_ERR_ARG, "rows, cols, tsteps must be > 0", err, errlen);
     int ndev = 0;
@@ -1041,9 +1327,17 @@ extern "C" int mcf_gridmicrosnow(double reqhgt, const mcf_snow_climate* clim, co
     DevBuf db;
     SnowHour* hours = nullptr;
     double* scal = nullptr;
-    int rc = prep_hours(db, clim, nullptr, nullptr, nullptr, nullptr, umu, st->lat, st->lon, &hours, &scal, err, errlen);
-    if (rc != MCF_OK) return rc;
     const size_t nc = (size_t)st->rows * st->cols, T = (size_t)clim->tsteps;
+    SnowArr ca;
+    std::memset(&ca, 0, sizeof ca);
+    if (arr) {
+        if (!st->lats || !st->lons) return fail(MCF_ERR_ARG, "array-climate snow needs lats and lons", err, errlen);
+        int rc2 = upload_arr(db, clim, nullptr, nullptr, nullptr, nullptr, umu, st, &ca, err, errlen);
+        if (rc2 != MCF_OK) return rc2;
+    } else {
+        int rc = prep_hours(db, clim, nullptr, nullptr, nullptr, nullptr, umu, st->lat, st->lon, &hours, &scal, err, errlen);
+        if (rc != MCF_OK) return rc;
+    }
     SnowMicroArgs a;
     std::memset(&a, 0, sizeof a);
     a.rows = st->rows; a.cols = st->cols; a.tsteps = clim->tsteps; a.hours = hours; a.scal = scal;
@@ -1076,10 +1370,22 @@ extern "C" int mcf_gridmicrosnow(double reqhgt, const mcf_snow_climate* clim, co
             a.out[v] = const_cast<double*>(d);
         }
     }
-    k_snowmicro<<<(unsigned)((nc + 127) / 128), 128>>>(a);
+    if (arr) k_snowmicro_arr<<<(unsigned)((nc + 127) / 128), 128>>>(a, ca);
+    else k_snowmicro<<<(unsigned)((nc + 127) / 128), 128>>>(a);
     SCU(cudaGetLastError());
     for (int v = 0; v < MCF_NOUT; ++v)
         if (micro[v]) SCU(cudaMemcpy(micro[v], a.out[v], nc * T * sizeof(double), cudaMemcpyDeviceToHost));
     SCU(cudaDeviceSynchronize());
     return MCF_OK;
+}
+
+extern "C" int mcf_gridmicrosnow(double reqhgt, const mcf_snow_climate* clim, const double* umu, const mcf_snow_state* sm,
+                                 const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err,
+                                 size_t errlen) {
+    return gridmicrosnow_impl(false, reqhgt, clim, umu, sm, st, mat, micro, err, errlen);
+}
+extern "C" int mcf_gridmicrosnow2(double reqhgt, const mcf_snow_climate* clim, const double* umu, const mcf_snow_state* sm,
+                                  const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err,
+                                  size_t errlen) {
+    return gridmicrosnow_impl(true, reqhgt, clim, umu, sm, st, mat, micro, err, errlen);
 }

@@ -30,7 +30,7 @@ class SnowStatic(C.Structure):
                 + [(n, _PD) for n in ("pai", "hgt", "leaft", "clump", "paia", "leafd", "leafden", "Smax", "slope", "aspect",
                                       "skyview", "wsa", "hor")]
                 + [("lat", C.c_double), ("lon", C.c_double), ("zref", C.c_double), ("isnowdc", _PD), ("isnowdg", _PD),
-                   ("isnowac", _PI), ("isnowag", _PI)])
+                   ("isnowac", _PI), ("isnowag", _PI), ("lats", _PD), ("lons", _PD)])
 
 
 class SnowState(C.Structure):
@@ -71,13 +71,15 @@ def pack_static(vegp, other, keep):
     for n in ("pai", "hgt", "leaft", "clump", "paia", "leafd", "leafden"):
         if n in vegp:
             a = _f(vegp[n]); keep.append(a); setattr(s, n, a.ctypes.data_as(_PD))
-    for n in ("slope", "aspect", "skyview", "wsa", "hor", "Smax", "isnowdc", "isnowdg"):
+    for n in ("slope", "aspect", "skyview", "wsa", "hor", "Smax", "isnowdc", "isnowdg", "lats", "lons"):
         if n in other:
             a = _f(other[n]); keep.append(a); setattr(s, n, a.ctypes.data_as(_PD))
     for n in ("isnowac", "isnowag"):
         if n in other:
             a = _i(other[n]); keep.append(a); setattr(s, n, a.ctypes.data_as(_PI))
-    s.lat, s.lon, s.zref = float(other["lat"]), float(other["lon"]), float(other["zref"])
+    if np.ndim(other.get("lat", 0.0)) == 0:
+        s.lat, s.lon = float(other.get("lat", 0.0)), float(other.get("lon", 0.0))
+    s.zref = float(other["zref"])
     return s
 
 
@@ -104,6 +106,10 @@ def _bind(L):
     L.mcf_gridmicrosnow.argtypes = [C.c_double, C.POINTER(SnowClimate), _PD, C.POINTER(SnowState), C.POINTER(SnowStatic),
                                     C.c_double, _abi.OutPtrs, C.c_char_p, C.c_size_t]
     L.mcf_gridmicrosnow.restype = C.c_int
+    L.mcf_gridmodelsnow2.argtypes = L.mcf_gridmodelsnow.argtypes
+    L.mcf_gridmodelsnow2.restype = C.c_int
+    L.mcf_gridmicrosnow2.argtypes = L.mcf_gridmicrosnow.argtypes
+    L.mcf_gridmicrosnow2.restype = C.c_int
     L._snow_bound = True
 
 
@@ -150,3 +156,18 @@ def gridmicrosnow1(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, ou
     L = _lib.lib()
     _bind(L)
     return call_gridmicrosnow(L.mcf_gridmicrosnow, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)
+
+
+def gridmodelsnow2(obstime, climdata, pointm, vegp, other, snowenv: str = "Alpine") -> Dict[str, np.ndarray]:
+    """src/microclimfCpp.cpp:4426 — snow-pack model, array climate ([rows, cols, hours] series; other$lats / lons)."""
+    L = _lib.lib()
+    _bind(L)
+    return call_gridmodelsnow(L.mcf_gridmodelsnow2, obstime, climdata, pointm, vegp, other, snowenv)
+
+
+def gridmicrosnow2(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out: Sequence[bool]) -> Dict[str, np.ndarray]:
+    """src/microclimfCpp.cpp:5059 — snow microclimate, array climate (climdata$prec, climdata$umu arrays; other$lat / lon
+    matrices, passed here as other["lats"] / other["lons"])."""
+    L = _lib.lib()
+    _bind(L)
+    return call_gridmicrosnow(L.mcf_gridmicrosnow2, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)

@@ -98,3 +98,17 @@ def gridmicrosnow1(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, ou
     fn = _lib("ref").ref_gridmicrosnow
     fn.restype = C.c_int
     return snow.call_gridmicrosnow(fn, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)
+
+
+def gridmodelsnow2(obstime, climdata, pointm, vegp, other, snowenv="Alpine"):
+    from microclimf_b200 import snow
+    fn = _lib("ref").ref_gridmodelsnow2
+    fn.restype = C.c_int
+    return snow.call_gridmodelsnow(fn, obstime, climdata, pointm, vegp, other, snowenv)
+
+
+def gridmicrosnow2(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out):
+    from microclimf_b200 import snow
+    fn = _lib("ref").ref_gridmicrosnow2
+    fn.restype = C.c_int
+    return snow.call_gridmicrosnow(fn, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)

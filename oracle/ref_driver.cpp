@@ -489,3 +489,91 @@ extern "C" int ref_gridmicrosnow(double reqhgt, const mcf_snow_climate* c, const
         return MCF_ERR_ARG;
     }
 }
+
+// array-climate snow drivers
+List gridmodelsnow2(DataFrame obstime, List climdata, List pointm, List vegp, List other, std::string snowenv);
+List gridmicrosnow2(double reqhgt, DataFrame obstime, List climdata, List snowm, List micro, List vegp, List other, double mat,
+                    std::vector<bool> out);
+
+extern "C" int ref_gridmodelsnow2(const mcf_snow_climate* c, const mcf_snow_point* pt, const mcf_snow_static* st,
+                                  int32_t snowenv, double* const out3d[5], double* const out2d[4], char* err, size_t errlen) {
+    try {
+        const int n = c->tsteps, R = st->rows, C = st->cols;
+        List clim;
+        clim["temp"] = arr3(c->temp, R, C, n); clim["relhum"] = arr3(c->relhum, R, C, n); clim["pres"] = arr3(c->pres, R, C, n);
+        clim["swdown"] = arr3(c->swdown, R, C, n); clim["difrad"] = arr3(c->difrad, R, C, n); clim["lwdown"] = arr3(c->lwdown, R, C, n);
+        clim["windspeed"] = arr3(c->windspeed, R, C, n); clim["winddir"] = vec(c->winddir, n); clim["precip"] = arr3(c->precip, R, C, n);
+        List pm;
+        pm["Gp"] = arr3(pt->Gp, R, C, n); pm["Tc"] = arr3(pt->Tc, R, C, n); pm["RswabsG"] = arr3(pt->RswabsG, R, C, n);
+        pm["RlwabsG"] = arr3(pt->RlwabsG, R, C, n); pm["umu"] = arr3(pt->umu, R, C, n); pm["tr"] = arr3(pt->umu, R, C, n);
+        List vegp;
+        vegp["pai"] = mat2(st->pai, R, C); vegp["hgt"] = mat2(st->hgt, R, C); vegp["leaft"] = mat2(st->leaft, R, C);
+        vegp["clump"] = mat2(st->clump, R, C);
+        List other;
+        other["slope"] = mat2(st->slope, R, C); other["aspect"] = mat2(st->aspect, R, C);
+        other["skyview"] = mat2(st->skyview, R, C); other["wsa"] = arr3(st->wsa, R, C, 8); other["hor"] = arr3(st->hor, R, C, 24);
+        other["lats"] = mat2(st->lats, R, C); other["lons"] = mat2(st->lons, R, C); other["zref"] = st->zref;
+        other["isnowdc"] = mat2(st->isnowdc, R, C); other["isnowdg"] = mat2(st->isnowdg, R, C);
+        other["isnowac"] = imat2(st->isnowac, R, C); other["isnowag"] = imat2(st->isnowag, R, C);
+        List r = gridmodelsnow2(obstime_df(n, c->year, c->month, c->day, c->hour), clim, pm, vegp, other, kSnowEnv[snowenv]);
+        const char* n3[5] = {"Tc", "Tg", "sdepc", "sdepg", "sden"};
+        for (int v = 0; v < 5; ++v)
+            if (out3d[v]) {
+                NumericVector a = r[n3[v]];
+                std::memcpy(out3d[v], a.raw(), (size_t)R * C * n * sizeof(double));
+            }
+        const char* n2[4] = {"agec", "ageg", "meltc", "meltg"};
+        for (int v = 0; v < 4; ++v)
+            if (out2d[v]) {
+                NumericMatrix a = r[n2[v]];
+                for (size_t i = 0; i < (size_t)R * C; ++i) out2d[v][i] = a[i];
+            }
+        return MCF_OK;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return MCF_ERR_ARG;
+    }
+}
+
+extern "C" int ref_gridmicrosnow2(double reqhgt, const mcf_snow_climate* c, const double* umu, const mcf_snow_state* sm,
+                                  const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err,
+                                  size_t errlen) {
+    try {
+        const int n = c->tsteps, R = st->rows, C = st->cols;
+        List clim;
+        clim["temp"] = arr3(c->temp, R, C, n); clim["relhum"] = arr3(c->relhum, R, C, n); clim["pres"] = arr3(c->pres, R, C, n);
+        clim["swdown"] = arr3(c->swdown, R, C, n); clim["difrad"] = arr3(c->difrad, R, C, n); clim["lwdown"] = arr3(c->lwdown, R, C, n);
+        clim["windspeed"] = arr3(c->windspeed, R, C, n); clim["winddir"] = vec(c->winddir, n); clim["prec"] = arr3(c->precip, R, C, n);
+        clim["umu"] = arr3(umu, R, C, n);
+        List snowm;
+        snowm["Tc"] = arr3(sm->Tc, R, C, n); snowm["Tg"] = arr3(sm->Tg, R, C, n); snowm["totalSWE"] = arr3(sm->totalSWE, R, C, n);
+        snowm["groundsnowdepth"] = arr3(sm->groundsnowdepth, R, C, n); snowm["snowden"] = arr3(sm->snowden, R, C, n);
+        static const char* nm[MCF_NOUT] = {"Tz", "tleaf", "relhum", "soilm", "windspeed", "Rdirdown", "Rdifdown", "Rlwdown",
+                                           "Rswup", "Rlwup"};
+        List mic;
+        std::vector<bool> o(MCF_NOUT);
+        for (int v = 0; v < MCF_NOUT; ++v) {
+            o[v] = micro[v] != nullptr;
+            if (micro[v]) mic[nm[v]] = arr3(micro[v], R, C, n);
+        }
+        List vegp;
+        vegp["pai"] = mat2(st->pai, R, C); vegp["paia"] = mat2(st->paia, R, C); vegp["hgt"] = mat2(st->hgt, R, C);
+        vegp["leaft"] = mat2(st->leaft, R, C); vegp["clump"] = mat2(st->clump, R, C); vegp["leafd"] = mat2(st->leafd, R, C);
+        vegp["leafden"] = mat2(st->leafden, R, C);
+        List other;
+        other["slope"] = mat2(st->slope, R, C); other["aspect"] = mat2(st->aspect, R, C);
+        other["skyview"] = mat2(st->skyview, R, C); other["wsa"] = arr3(st->wsa, R, C, 8); other["hor"] = arr3(st->hor, R, C, 24);
+        other["lat"] = mat2(st->lats, R, C); other["lon"] = mat2(st->lons, R, C); other["zref"] = st->zref;
+        other["Smax"] = mat2(st->Smax, R, C);
+        List r = gridmicrosnow2(reqhgt, obstime_df(n, c->year, c->month, c->day, c->hour), clim, snowm, mic, vegp, other, mat, o);
+        for (int v = 0; v < MCF_NOUT; ++v)
+            if (micro[v]) {
+                NumericVector a = r[nm[v]];
+                std::memcpy(micro[v], a.raw(), (size_t)R * C * n * sizeof(double));
+            }
+        return MCF_OK;
+    } catch (const std::exception& e) {
+        std::snprintf(err, errlen, "%s", e.what());
+        return MCF_ERR_ARG;
+    }
+}

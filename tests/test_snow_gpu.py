@@ -124,3 +124,48 @@ def test_runmicro_snow_true_merges_snow_and_snowfree_days():
     snowy = (swe[:, :, 30] > 0) & land
     assert snowy.any() and not np.allclose(a["Tz"][:, :, 30][snowy], plain["Tz"][:, :, 30][snowy])
     assert np.all(a["soilm"][:, :, 30][snowy] == 0.419)                                     # Smax under snow (:5029)
+
+
+def _array_inputs(s, rows, cols):
+    """Expand the data.frame scenario to [rows, cols, hours] arrays with a smooth spatial modulation."""
+    rng = np.random.default_rng(8)
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    u, v = ii / max(rows - 1, 1) - 0.5, jj / max(cols - 1, 1) - 0.5
+    ex = lambda a, amp: np.asarray(a)[None, None, :] + amp * (u + 0.5 * v)[:, :, None]  # noqa: E731
+    c = s["climdata"]
+    clim = dict(temp=ex(c["temp"], 2.0), relhum=np.clip(ex(c["relhum"], 6.0), 20, 100), pres=ex(c["pres"], 0.4),
+                swdown=ex(c["swdown"], 0.0) * (1 + 0.1 * v)[:, :, None], lwdown=ex(c["lwdown"], 5.0),
+                windspeed=np.maximum(ex(c["windspeed"], 0.5), 0.3), winddir=c["winddir"],
+                precip=np.asarray(c["precip"])[None, None, :] * (rng.random((rows, cols)) < 0.85)[:, :, None],
+                umu=ex(c["umu"], 0.05))
+    clim["difrad"] = np.minimum(ex(c["difrad"], 0.0), clim["swdown"])
+    p = s["pointm"]
+    pointm = dict(Gp=ex(p["Gp"], 3.0), Tc=ex(p["Tc"], 1.0), RswabsG=np.maximum(ex(p["RswabsG"], 0.0), 0), RlwabsG=ex(p["RlwabsG"], 4.0),
+                  umu=clim["umu"], tr=clim["umu"])
+    other = dict(s["other"])
+    other["lats"] = s["other"]["lat"] + 0.4 * u
+    other["lons"] = s["other"]["lon"] + 0.6 * v
+    return clim, pointm, other
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_array_climate_snow_parity():
+    """gridmodelsnow2 / gridmicrosnow2 (src/microclimfCpp.cpp:4426, 5059): per-cell albedo scan, daily extremes and solar
+    position."""
+    rows, cols = 17, 13
+    s = synth.make_snow_inputs(rows, cols, 24 * 5 + 7, seed=31)   # ragged tail: the last 7 hours have no daily extremes
+    clim, pointm, other = _array_inputs(s, rows, cols)
+    want = pyoracle.gridmodelsnow2(s["obstime"], clim, pointm, s["vegp"], other, "Maritime")
+    got = snow.gridmodelsnow2(s["obstime"], clim, pointm, s["vegp"], other, "Maritime")
+    ok, rws = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rws)
+    assert np.isnan(want["meltc"]).all()  # not initialised in the array-climate driver
+    snowm = _snowm(want)
+    rng = np.random.default_rng(3)
+    micro = {n: rng.uniform(-5, 5, want["Tc"].shape) for n in _abi.OUT_NAMES}
+    for reqhgt in (0.05, 0.6):
+        w = pyoracle.gridmicrosnow2(reqhgt, s["obstime"], clim, snowm, micro, s["vegp"], other, 3.0, [True] * 10)
+        g = snow.gridmicrosnow2(reqhgt, s["obstime"], clim, snowm, micro, s["vegp"], other, 3.0, [True] * 10)
+        ok, rws = parity.compare(g, w)
+        assert ok, "\n" + parity.fmt(rws)
