@@ -42,6 +42,25 @@ def case_coarse(name, rows, cols, T, crows, ccols, altcorrect=2, ring=24, packed
                       "packed": packed, "ms": ms, "cell_hours_per_s": nc * (T // 24) * 24 / (ms * 1e-3)}), flush=True)
     del dp, outs; torch.cuda.empty_cache()
 
+def case_snow(rows, cols, T):
+    """Snow operators through the host-buffer C ABI (uploads and copies back included; host clock)."""
+    from microclimf_b200 import snow
+    s = synth.make_snow_inputs(rows, cols, T)
+    for rep in range(2):
+        t0 = time.perf_counter()
+        r = snow.gridmodelsnow1(s["obstime"], s["climdata"], s["pointm"], s["vegp"], s["other"], "Alpine")
+        t1 = time.perf_counter()
+    snowm = dict(Tc=r["Tc"], Tg=r["Tg"], totalSWE=np.nan_to_num(r["sdepc"] * r["sden"]), groundsnowdepth=r["sdepg"], snowden=r["sden"])
+    micro = {n: np.zeros(r["Tc"].shape) for n in ("Tz", "tleaf", "relhum", "soilm", "windspeed", "Rdirdown", "Rdifdown", "Rlwdown", "Rswup", "Rlwup")}
+    for rep in range(2):
+        t2 = time.perf_counter()
+        snow.gridmicrosnow1(0.05, s["obstime"], s["climdata"], snowm, micro, s["vegp"], s["other"], 3.0, [True] * 10)
+        t3 = time.perf_counter()
+    ch = rows * cols * T
+    print(json.dumps({"case": "snow: gridmodelsnow1 / gridmicrosnow1 through the host C ABI", "rows": rows, "cols": cols, "hours": T,
+                      "gridmodelsnow1_cell_hours_per_s": ch / (t1 - t0), "gridmicrosnow1_cell_hours_per_s": ch / (t3 - t2),
+                      "snow_covered_fraction": float((snowm["totalSWE"] > 0).mean())}), flush=True)
+
 def case_bioclim(name, rows, cols, mode):
     days, q = synth.bioclim_days()
     p = synth.make_problem(rows, cols, 336, reqhgt=0.05, mode=mode, nlyr=14, day_list=days)
@@ -54,6 +73,8 @@ def case_bioclim(name, rows, cols, mode):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["bio", "heights", "layers", "array", "coarse"]
+    if "snow" in which:
+        case_snow(int(os.environ.get("SNOW_N", "1024")), int(os.environ.get("SNOW_N", "1024")), 240)
     if "coarse" in which:
         case_coarse("config5: mode 2, 4096x4096 x 240 h, climate on a 41x41 grid interpolated in-kernel", 4096, 4096, 240, 41, 41)
         case_coarse("same, packed int16 sink", 4096, 4096, 240, 41, 41, packed=True)
