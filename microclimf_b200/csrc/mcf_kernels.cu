@@ -53,6 +53,30 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 __device__ __forceinline__ double na_real() { return __longlong_as_double(0x7FF00000000007A2LL); }
 
+// The day stash (4 doubles per cell-hour, written in pass 1 and read once in pass 2 of the same day) is private to
+// the thread and small enough for L2 (44 MB for 148 CTAs), but the write-once outputs stream through the same L2 and
+// push it out to DRAM (170 B instead of 105 B per cell-hour measured, profiles/r01_kgrid_v6_tablemath.txt).  The
+// stash therefore carries an L2 evict_last policy (createpolicy + L2::cache_hint), loads bypass L1; the outputs keep
+// their evict-first streaming stores.  -DMCF_STASH_PLAIN restores plain .cg accesses.
+#ifndef MCF_STASH_PLAIN
+__device__ __forceinline__ uint64_t stash_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_stash(double* p, double v) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(stash_policy()) : "memory");
+}
+__device__ __forceinline__ double ld_stash(const double* p) {
+    double v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(stash_policy()));
+    return v;
+}
+#else
+__device__ __forceinline__ void st_stash(double* p, double v) { __stcg(p, v); }
+__device__ __forceinline__ double ld_stash(const double* p) { return __ldcg(p); }
+#endif
+
 // Packed integer sink (SURVEY.md NEXT-4): writetonc's `as.integer(round(x * rd, 0))` (R/dataprep.R:1064-1069) with
 // rd = 100 for Tz, tleaf, soilm and windspeed and 1 for relhum and the radiation streams (:1164-1173), NA and NaN
 // -> -9999 (the file's missval).  round-half-even like R's round(x, 0); values beyond int16 saturate.
@@ -643,18 +667,18 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     if (tmn > Tg0) tmn = Tg0;
                     // the day stash is private to the thread and re-read once: keep it out of L1 (.cg)
                     double* st = stash + (size_t)hr * (kStashVars * kTile);
-                    __stcg(&st[0 * kTile], radabs);
-                    __stcg(&st[1 * kTile], surfwet);
-                    __stcg(&st[2 * kTile], r.radCsw);
-                    __stcg(&st[3 * kTile], r.Lhalf);
+                    st_stash(&st[0 * kTile], radabs);
+                    st_stash(&st[1 * kTile], surfwet);
+                    st_stash(&st[2 * kTile], r.radCsw);
+                    st_stash(&st[3 * kTile], r.Lhalf);
                     o += a.ncells;
                 }
                 // ------------------------------------------------------------------ pass 2
                 const double dtr = tmx - tmn;
                 o = o_first;
                 // stash and wind-sector values of the coming hour are fetched one hour ahead
-                double radabs_n = __ldcg(&stash[0 * kTile]), surfwet_n = __ldcg(&stash[1 * kTile]);
-                double radCsw_n = __ldcg(&stash[2 * kTile]), Lhalf_n = __ldcg(&stash[3 * kTile]);
+                double radabs_n = ld_stash(&stash[0 * kTile]), surfwet_n = ld_stash(&stash[1 * kTile]);
+                double radCsw_n = ld_stash(&stash[2 * kTile]), Lhalf_n = ld_stash(&stash[3 * kTile]);
                 if (!ARR) ws_n = __ldg(&a.wsa[(size_t)slab_day[0].windex * a.ncells + cell]);
 #pragma unroll 1
                 for (int hr = 0; hr < 24; ++hr) {
@@ -666,10 +690,10 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     const double radabs = radabs_n, surfwet = surfwet_n, radCsw = radCsw_n, Lhalf = Lhalf_n;
                     {
                         const double* st = stash + (size_t)(hr < 23 ? hr + 1 : 23) * (kStashVars * kTile);
-                        radabs_n = __ldcg(&st[0 * kTile]);
-                        surfwet_n = __ldcg(&st[1 * kTile]);
-                        radCsw_n = __ldcg(&st[2 * kTile]);
-                        Lhalf_n = __ldcg(&st[3 * kTile]);
+                        radabs_n = ld_stash(&st[0 * kTile]);
+                        surfwet_n = ld_stash(&st[1 * kTile]);
+                        radCsw_n = ld_stash(&st[2 * kTile]);
+                        Lhalf_n = ld_stash(&st[3 * kTile]);
                     }
                     double ws;
                     if (ARR) {
