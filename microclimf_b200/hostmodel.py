@@ -782,13 +782,14 @@ def runmicro_big(micropoint, reqhgt, pathout, vegp, soilc, dtm, dtmc=None, altco
             mout = runmicro(micropoint, reqhgt, vegpi, soilci, dtmi, dtmc, altcorrect, False, None, runchecks, pai_a,
                             tfact, out, slr.crop(r0, r1, c0, c1), apr.crop(r0, r1, c0, c1), hor[r0:r1, c0:c1, :],
                             twi.crop(r0, r1, c0, c1), wsa[r0:r1, c0:c1, :], svf=svfa[r0:r1, c0:c1], packed=want_packed)
+            mp1 = micropoint if isinstance(micropoint, Micropoint) else next(m for m in micropoint if m is not None)
+            mout["tme"] = np.asarray(mp1.weather["obs_time"])  # `mout$tme <- tme`: the hours actually modelled (wrap:517)
             fo = os.path.join(path2, f"area_{rw:02d}_{cl:02d}")
             ext = [dtmi.xmin, dtmi.xmax, dtmi.ymin, dtmi.ymax]
             if want_packed:
-                # writetonc's variable layout: [east, north, time] = aperm(a, c(2, 1, 3)) (R/dataprep.R:1065)
-                tme = mout.pop("tme")
-                np.savez(fo + "_packed.npz", extent=ext, tme=tme, **{k: np.transpose(v, (1, 0, 2)) for k, v in mout.items()})
-                written.append(fo + "_packed.npz")
+                from .ncwriter import writetonc
+                writetonc(mout, fo + ".nc", dtmi, reqhgt)  # the integers come from the kernels' packed sink
+                written.append(fo + ".nc")
             else:
                 np.savez(fo + ".npz", extent=ext, dtm=dtmi.matrix(), **mout)
                 written.append(fo + ".npz")

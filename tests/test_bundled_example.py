@@ -233,82 +233,27 @@ def test_runmicro_big_tiles_match_untiled_statics(tmp_path):
 
 @pytest.mark.gpu
 def test_runmicro_big_writeasnc_packs_like_writetonc(tmp_path):
-    """writeasnc = TRUE: each tile holds the integers writetonc stores (R/dataprep.R:1064-1069, 1164-1173), produced by
-    the kernels' packed sink, in the file's [east, north, time] order."""
+    """writeasnc = TRUE: each tile is a netCDF file holding the integers writetonc stores (R/dataprep.R:1064-1069,
+    1164-1173), produced by the kernels' packed sink, with writetonc's dimensions, names, units and missing value."""
     from oracle import packing_oracle
 
     dtm, vegp, soilc, mp, clim = load_example()
     sub = hostmodel.subsetpointmodel(mp, days=[180])
     vegp = _fill_reflectance(vegp, dtm)
     files = hostmodel.runmicro_big(sub, 0.05, str(tmp_path) + "/", vegp, soilc, dtm, tilesize=50, writeasnc=True)
-    assert [os.path.basename(f) for f in files] == ["area_01_01_packed.npz"]
-    t = np.load(files[0])
+    assert [os.path.basename(f) for f in files] == ["area_01_01.nc"]
+    from scipy.io import netcdf_file
+    nc = netcdf_file(files[0], "r", mmap=False)
+    t = {k: nc.variables[k][:] for k in ("Tz", "Rdirdown", "Rdifdown", "Rswup", "windspeed")}   # [time, north, east]
+    assert nc.variables["Tz"].units == b"deg C x 100" and nc.variables["Tz"].missing_value == -9999
+    assert np.allclose(nc.variables["east"][:], dtm.xmin + 0.5 + np.arange(50)) and nc.variables["time"].units.startswith(b"hours since 1970")
+    assert "soilm" not in nc.variables  # not among writetonc's default variables above ground (R/dataprep.R:1112)
     fp = hostmodel.runmicro(sub, 0.05, vegp, soilc, dtm)  # tile == whole raster here, so the statics coincide...
-    dsm_wsa = t["Tz"].shape
-    assert dsm_wsa == (50, 50, 24) and t["Tz"].dtype == np.int16
+    assert t["Tz"].shape == (24, 50, 50) and t["Tz"].dtype.kind == "i"
     # ...except the wind shelter, which runmicro_big derives from dtm + vegetation height at 8 m (R/Cppwrappers.R:493-494):
-    # compare the wind-independent radiation streams exactly and the temperatures within the packing step
-    for name in ("Rdirdown", "Rdifdown", "Rswup", "soilm"):
-        assert np.array_equal(t[name], packing_oracle.file_layout(packing_oracle.pack(name, fp[name]))), name
-    na = np.isnan(dtm.matrix()).T
-    assert np.all(t["Tz"][na] == packing_oracle.NA) and np.all(t["Tz"][~na] != packing_oracle.NA)
-
-
-# --------------------------------------------------------------------------------------------- gridded climate
-def _micropointa(mp, dtm, cr=2, cc=2):
-    """A runpointmodela-like list: the bundled point model perturbed per coarse cell (row by row, terra order)."""
-    from microclimf_b200.spatial import aggregate_mean
-    dtmc = aggregate_mean(dtm.like(np.where(np.isnan(dtm.values), 0.0, dtm.values)), dtm.nrows // cr)
-    out = []
-    for k in range(cr * cc):
-        w = {n: np.array(v) for n, v in mp.weather.items()}
-        w["temp"] = w["temp"] + 0.4 * k
-        w["relhum"] = np.clip(w["relhum"] - 2.0 * k, 10, 100)
-        w["windspeed"] = w["windspeed"] * (1 + 0.05 * k)
-        w["winddir"] = np.mod(w["winddir"] + 10.0 * k, 360)
-        dfo = {n: np.array(v) for n, v in mp.dfo.items()}
-        dfo["G"] = dfo["G"] * (1 + 0.03 * k)
-        dfo["Tg"] = dfo["Tg"] + 0.3 * k
-        out.append(Micropoint(weather=w, dfo=dfo, Tbz=mp.Tbz, lat=mp.lat, long=mp.long, zref=mp.zref, subs=mp.subs,
-                              tmeorig=mp.tmeorig, matemp=mp.matemp + 0.4 * k))
-    return out, dtmc
-
-
-def test_gridded_climate_mapping_cpu():
-    """prepare_model_a places fine cell centres on the coarse grid as terra::resample does."""
-    from microclimf_b200.spatial import resample_bilinear
-    from oracle import prep_oracle
-    dtm, vegp, soilc, mp, clim = load_example()
-    sub = hostmodel.subsetpointmodel(mp, days=[172])
-    mpa, dtmc = _micropointa(sub, dtm)
-    hor, wsa = cpu_terrain(dtm, mp.zref)
-    twi = dtm.like(np.where(np.isnan(dtm.matrix()), np.nan, 5.0))
-    call = hostmodel.prepare_model_a(mpa, vegp, soilc, dtm, dtmc, reqhgt=0.05, altcorrect=2, hor=hor, wsa=wsa, twi=twi)
-    p = call.prob
-    assert (p.mode, p.clim_rows, p.clim_cols, p.nlyr) == (4, 2, 2, 1) or p.mode == 4
-    tc = p.arrays["temp"].reshape(p.tsteps, 2, 2)  # [k, cj, ci]
-    want = resample_bilinear(dtmc.like(tc[5].T), dtm).matrix()
-    got = prep_oracle.resample(p, p.arrays["temp"])[5].reshape(dtm.ncols, dtm.nrows).T
-    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
-    assert np.isclose(p.mat, mp.matemp + 0.4 * 1.5)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("altcorrect", [0, 2])
-def test_gridded_climate_runmicro(altcorrect):
-    """runmicro with a list of micropoints and dtmc (R/Cppwrappers.R:389-391 -> .runmodel4Cpp): the kernels' fused
-    expansion against the compiled reference on the arrays .runmodel4Cpp would have built."""
-    from oracle import prep_oracle
-    dtm, vegp, soilc, mp, clim = load_example()
-    sub = hostmodel.subsetpointmodel(mp, days=[30, 172])
-    mpa, dtmc = _micropointa(sub, dtm)
-    call = hostmodel.prepare_model_a(mpa, vegp, soilc, dtm, dtmc, reqhgt=0.05, altcorrect=altcorrect)
-    got = call.run()
-    want = pyoracle.runmicro(prep_oracle.materialise_coarse(call.prob), out_mask=call.args["out"],
-                             kind="ref" if pyoracle.have_ref() else "oracle")
-    ok, rows = parity.compare(got, want)
-    assert ok, "\n" + parity.fmt(rows)
-    mout = hostmodel.runmicro(mpa, 0.05, vegp, soilc, dtm, dtmc=dtmc, altcorrect=altcorrect)
-    assert np.array_equal(mout["Tz"], got["Tz"], equal_nan=True)
-    with pytest.raises(ValueError, match="Require dtmc"):
-        hostmodel.runmicro(mpa, 0.05, vegp, soilc, dtm)
+    # compare the wind-independent radiation streams exactly
+    for name in ("Rdirdown", "Rdifdown", "Rswup"):
+        want = np.transpose(packing_oracle.pack(name, fp[name]), (2, 0, 1))
+        assert np.array_equal(t[name], want), name
+    na = np.isnan(dtm.matrix())
+    assert np.all(t["Tz"][:, na] == packing_oracle.NA) and np.all(t["Tz"][:, ~na] != packing_oracle.NA)
