@@ -352,6 +352,41 @@ def gpu_arm(args):
                   "sample": "same tile through mcf_runmicro_packed: int16 outputs as the reference's writetonc stores them"}
     del pin_keep
 
+    # ------------------------------------------------------------------ the optional FP32 build, same workload
+    # (north_star: within 0.05 degC / 0.5 % radiation; tests/test_f32_gpu.py).  Reported beside the FP64 headline.
+    fp32 = None
+    try:
+        outs32 = [torch.empty(ring_hours * ncells, dtype=torch.float32, device="cuda") for _ in range(10)]
+
+        def step32(i):
+            b0 = (i % nwin) * args.win_days
+            api.run_problem_f32_dev(dp, outs32, window=(b0, args.win_days, b0 * 24, ring_hours))
+
+        for i in range(2):
+            step32(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nf = max(1, min(args.steps, 4))
+        f0.record()
+        for i in range(nf):
+            step32(2 + i)
+        f1.record()
+        barrier()
+        fms = f0.elapsed_time(f1)
+        if dist is not None:
+            t = torch.tensor([fms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            fms = float(t.item())
+        v32 = cell_hours_step * nf * world / (fms * 1e-3)
+        b32 = (cell_hours_step * 40.0 + ncells * BYTES_PER_CELL_STATIC) / (fms / nf * 1e-3) / 1e9
+        fp32 = {"value": v32, "unit": UNIT, "dtype": "f32", "ms_per_step": fms / nf, "steps": nf,
+                "roofline": {"bound": "hbm", "achieved": b32, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": b32 / peaks["hbm_gbs"],
+                             "algorithmic_bytes_per_cell_hour": 40.0},
+                "note": "k_grid_f32: FP32 hour loops (SFU transcendentals), FP64 per-cell invariants, FP32 outputs"}
+        del outs32
+    except Exception as ex:  # the FP32 build is optional: never let it break the headline line
+        fp32 = {"unavailable": str(ex)[:200]}
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -366,7 +401,7 @@ def gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "e2e_packed": e2e_packed,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "e2e_packed": e2e_packed, "fp32": fp32,
             "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "setup_seconds": t_gen,
         }

@@ -244,6 +244,15 @@ int mcf_runmicro_packed(const mcf_problem* prob, int16_t* const out[MCF_NOUT], c
 int mcf_runmicro_packed_dev(const mcf_problem* prob, int16_t* const out[MCF_NOUT], const mcf_window* win,
                             void* stream, char* err, size_t errlen);
 
+/* ------------------------------------------------------------------------------------------- */
+/* FP32 build (BASELINE north_star: "an optional FP32 build must stay within 0.05 degC and 0.5 %      */
+/* radiation").  Device buffers, modes 1/3 (per-hour forcing), reqhgt >= 0.  `prob` is the FP64 problem  */
+/* of mcf_runmicro_dev; the hour loops run in FP32 (SFU transcendentals), per-cell invariants in FP64;   */
+/* outputs are float arrays (quiet NaN in skipped cells), window / ring as for mcf_runmicro_dev.          */
+/* ------------------------------------------------------------------------------------------- */
+int mcf_runmicro_f32_dev(const mcf_problem* prob, float* const out[MCF_NOUT], const mcf_window* win, void* stream,
+                         char* err, size_t errlen);
+
 /* sum and count of log(twi)/tfact over the non-NaN cells of a HOST twi buffer holding n cells
  * (the two numbers the bands all-reduce before calling with has_twi_mean = 1). */
 int mcf_twi_partial(const double* twi, int64_t n, double tfact, double* sum, int64_t* count,

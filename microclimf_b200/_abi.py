@@ -56,6 +56,7 @@ class McfWindow(C.Structure):
 
 OutPtrs = _pd * MCF_NOUT
 OutPtrs16 = C.POINTER(C.c_int16) * MCF_NOUT
+OutPtrsF = C.POINTER(C.c_float) * MCF_NOUT
 PACKED_NA = -9999
 PACK_SCALE = (100.0, 100.0, 1.0, 100.0, 100.0, 1.0, 1.0, 1.0, 1.0, 1.0)  # writetonc, R/dataprep.R:1164-1173
 BioPtrs = _pd * MCF_NBIO
@@ -64,5 +65,5 @@ BioPtrs = _pd * MCF_NBIO
 EXPORTED_SYMBOLS = (
     "mcf_runmicro", "mcf_runbioclim", "mcf_runmicro_dev", "mcf_runbioclim_dev", "mcf_twi_partial",
     "mcf_abi_version", "mcf_device_count", "mcf_set_device", "mcf_launch_count", "mcf_launch_count_reset",
-    "mcf_kernel_time", "mcf_kernel_time_reset", "mcf_kernel_timing_enable", "mcf_fp64_peak", "mcf_math_eval", "mcf_release_workspace", "mcf_horizon", "mcf_windcoef", "mcf_flowacc", "mcf_runmicro_packed", "mcf_runmicro_packed_dev", "mcf_gridmodelsnow", "mcf_gridmicrosnow", "mcf_gridmodelsnow2", "mcf_gridmicrosnow2",
+    "mcf_kernel_time", "mcf_kernel_time_reset", "mcf_kernel_timing_enable", "mcf_fp64_peak", "mcf_math_eval", "mcf_release_workspace", "mcf_horizon", "mcf_windcoef", "mcf_flowacc", "mcf_runmicro_packed", "mcf_runmicro_packed_dev", "mcf_gridmodelsnow", "mcf_gridmicrosnow", "mcf_gridmodelsnow2", "mcf_gridmicrosnow2", "mcf_runmicro_f32_dev",
 )

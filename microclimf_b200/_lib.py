@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
         L.mcf_runmicro_packed.restype = C.c_int
         L.mcf_runmicro_packed_dev.argtypes = [pp, _abi.OutPtrs16, pw, C.c_void_p, C.c_char_p, C.c_size_t]
         L.mcf_runmicro_packed_dev.restype = C.c_int
+        L.mcf_runmicro_f32_dev.argtypes = [pp, _abi.OutPtrsF, pw, C.c_void_p, C.c_char_p, C.c_size_t]
+        L.mcf_runmicro_f32_dev.restype = C.c_int
         q = [pi, C.c_int32] * 4
         L.mcf_runbioclim.argtypes = [pp] + q + [C.c_int32, _abi.BioPtrs, C.c_char_p, C.c_size_t]
         L.mcf_runbioclim.restype = C.c_int

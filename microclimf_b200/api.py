@@ -142,6 +142,25 @@ def run_problem_packed_dev(p: GridProblem, out_tensors, window=None, stream=None
     del keep
 
 
+def run_problem_f32_dev(p: GridProblem, out_tensors, window=None, stream=None) -> None:
+    """mcf_runmicro_f32_dev: the FP32 build (modes 1/3, reqhgt >= 0).  `p` holds CUDA float64 tensors
+    (GridProblem.to_device); `out_tensors`: 10 CUDA float32 tensors or None; window / stream as run_problem_dev."""
+    import torch
+
+    L = _lib.lib()
+    st = torch.cuda.current_stream() if stream is None else stream
+    PF = C.POINTER(C.c_float)
+    ptrs = _abi.OutPtrsF(*[C.cast(C.c_void_p(t.data_ptr()), PF) if t is not None else None for t in out_tensors])
+    s, keep = p.as_struct()
+    w = None
+    if window is not None:
+        w = _abi.McfWindow(int(window[0]), int(window[1]), int(window[2]), int(window[3]))
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runmicro_f32_dev(C.byref(s), ptrs, C.byref(w) if w is not None else None,
+                                      C.c_void_p(st.cuda_stream), err, 512), err)
+    del keep
+
+
 def run_bioclim_problem(p: GridProblem, wetq, dryq, hotq, colq, air: bool = True,
                         out: Optional[Sequence[bool]] = None) -> Dict[str, np.ndarray]:
     L = _lib.lib()

@@ -979,6 +979,71 @@ int mcf_runmicro(const mcf_problem* prob, double* const out[MCF_NOUT], char* err
     return report(run_host(prob, out), err, errlen);
 }
 
+// FP32 build (north_star: optional, within 0.05 degC / 0.5 % radiation): modes 1/3, reqhgt >= 0, device buffers.
+// Inputs are the FP64 problem; the hour loops, the day stash and the outputs are FP32.
+static Err run_dev_f32(const mcf_problem* p, float* const out[MCF_NOUT], const mcf_window* win, cudaStream_t st) {
+    if (p && (p->mode == 2 || p->mode == 4)) return make_err(MCF_ERR_ARG, "the FP32 build covers modes 1 and 3 (per-hour forcing table)");
+    if (p && p->reqhgt < 0) return make_err(MCF_ERR_ARG, "the FP32 build covers reqhgt >= 0");
+    Scratch sc(st);
+    Plan pl;
+    TRY(plan_prepare(pl, p, sc, st));
+    const int nblk = (int)pl.blocks.size();
+    int b0 = 0, nb = nblk;
+    long long hour0 = 0, ring = p->tsteps;
+    if (win) {
+        b0 = win->block0;
+        nb = win->nblocks < 0 ? nblk - b0 : win->nblocks;
+        hour0 = win->hour0;
+        ring = win->ring_hours;
+        if (b0 < 0 || nb < 0 || b0 + nb > nblk) return make_err(MCF_ERR_ARG, "window outside the %d day-blocks", nblk);
+        if (ring < 24) return make_err(MCF_ERR_ARG, "ring_hours must be >= 24");
+    }
+    if (nb <= 0) return Err();
+    char* hoursf = nullptr;
+    CU(sc.alloc(&hoursf, (size_t)p->tsteps * hourrec_f32_bytes()));
+    CU(launch_narrow_hours(pl.d_hours, p->tsteps, hoursf, st));
+    count_launch();
+    const int grid_max = g_sm_count * f32_blocks_per_sm();
+    float* stashf = nullptr;
+    CU(sc.alloc(&stashf, (size_t)grid_max * 24 * kStashVars * kTile));
+    GridArgs a;
+    fill_common(pl, a);
+    a.cell_begin = 0;
+    a.cell_end = pl.ncells;
+    a.block0 = b0;
+    a.nblocks = nb;
+    a.hour0 = hour0;
+    a.ring_hours = ring;
+    a.outmask = 0;
+    for (int v = 0; v < MCF_NOUT; ++v)
+        if (out[v] && kernel_writes(pl.rq, v)) a.outmask |= 1u << v;
+    unsigned int* ctr = nullptr;
+    CU(sc.alloc(&ctr, 1));
+    CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+    a.tile_counter = ctr;
+    const int ntiles = (pl.ncells + kTile - 1) / kTile;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (g_timing) {
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, st));
+    }
+    CU(launch_grid_f32(a, hoursf, out, stashf, pl.rq, std::min(grid_max, ntiles), st));
+    count_launch();
+    if (g_timing) {
+        CU(cudaEventRecord(e1, st));
+        std::lock_guard<std::mutex> lk(g_time_mu);
+        g_events.emplace_back(e0, e1);
+    }
+    return Err();
+}
+
+int mcf_runmicro_f32_dev(const mcf_problem* prob, float* const out[MCF_NOUT], const mcf_window* win, void* stream, char* err,
+                         size_t errlen) {
+    if (!out) return report(make_err(MCF_ERR_ARG, "out is NULL"), err, errlen);
+    return report(run_dev_f32(prob, out, win, (cudaStream_t)stream), err, errlen);
+}
+
 // Packed integer sink (SURVEY.md NEXT-4): the same solve, results stored as writetonc stores them
 // (R/dataprep.R:1064-1069, 1164-1173).  The int16_t* buffers travel through the double* plumbing.
 int mcf_runmicro_packed_dev(const mcf_problem* prob, int16_t* const out[MCF_NOUT], const mcf_window* win, void* stream,

@@ -12,6 +12,7 @@
 //     pass 1 reduces Rmx / tmx / tmn over the 24 hours in registers, pass 2 re-reads 4 stashed doubles
 //     per hour from a CTA-private, L2-resident scratch laid out [hour][var][thread] (coalesced).
 #include "mcf_kernels.cuh"
+#include "mcf_physics_f32.cuh"
 
 #include <cooperative_groups.h>
 
@@ -1117,5 +1118,7 @@ cudaError_t launch_fp64_peak(double* sink, int grid, int iters, cudaStream_t str
     k_fp64_peak<<<grid, 256, 0, stream>>>(sink, iters);
     return cudaGetLastError();
 }
+
+#include "mcf_kernels_f32.inl"
 
 } // namespace mcf

@@ -129,6 +129,12 @@ cudaError_t launch_twi_sum(const double* twi, int64_t n, double tfact, double* s
 cudaError_t launch_grid(const GridArgs& a, int arr /* 0 table, 1 fine arrays, 2 coarse arrays */, int rq, int grid,
                         cudaStream_t stream);
 int grid_blocks_per_sm(bool arr, int rq);
+// FP32 build (modes 1/3, reqhgt >= 0): narrowed hour table, FP32 stash and outputs
+cudaError_t launch_narrow_hours(const HourRec* in, int n, void* out, cudaStream_t stream);
+size_t hourrec_f32_bytes();
+int f32_blocks_per_sm();
+cudaError_t launch_grid_f32(const GridArgs& a, const void* hoursf, float* const outf[kNOut], float* stashf, int rq, int grid,
+                            cudaStream_t stream);
 cudaError_t launch_below(const BelowArgs& a, cudaStream_t stream);
 cudaError_t launch_bioclim(const BioArgs& a, cudaStream_t stream);
 cudaError_t launch_fill_na(double* p, int64_t n, cudaStream_t stream);

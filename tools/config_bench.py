@@ -61,6 +61,22 @@ def case_snow(rows, cols, T):
                       "gridmodelsnow1_cell_hours_per_s": ch / (t1 - t0), "gridmicrosnow1_cell_hours_per_s": ch / (t3 - t2),
                       "snow_covered_fraction": float((snowm["totalSWE"] > 0).mean())}), flush=True)
 
+def case_f32(rows, cols, T, ring=24):
+    """The optional FP32 build on the headline workload shape (mode 1, reqhgt 0.05, 10 outputs, 24-h ring)."""
+    p = synth.make_problem(rows, cols, T, reqhgt=0.05, mode=1)
+    dp = p.to_device()
+    nc = p.ncells
+    win = (0, T // 24, 0, ring)
+    o32 = [torch.empty(ring * nc, dtype=torch.float32, device="cuda") for _ in range(10)]
+    o64 = [torch.empty(ring * nc, dtype=torch.float64, device="cuda") for _ in range(10)]
+    ms32 = timed(lambda: api.run_problem_f32_dev(dp, o32, window=win))
+    ms64 = timed(lambda: api.run_problem_dev(dp, o64, window=win))
+    err = {n: float((a.double() - b).abs().nan_to_num().max()) for n, a, b in zip(("Tz", "tleaf", "relhum", "soilm", "windspeed", "Rdirdown", "Rdifdown", "Rlwdown", "Rswup", "Rlwup"), o32, o64)}
+    ch = nc * (T // 24) * 24
+    print(json.dumps({"case": "FP32 build vs FP64 build, mode 1, reqhgt 0.05, 10 outputs, 24-h ring", "rows": rows, "cols": cols, "hours": T,
+                      "fp32_ms": ms32, "fp64_ms": ms64, "fp32_cell_hours_per_s": ch / (ms32 * 1e-3), "fp64_cell_hours_per_s": ch / (ms64 * 1e-3),
+                      "fp32_algorithmic_GBps": ch * 40 / (ms32 * 1e-3) / 1e9, "max_abs_diff_last_day": err}), flush=True)
+
 def case_bioclim(name, rows, cols, mode):
     days, q = synth.bioclim_days()
     p = synth.make_problem(rows, cols, 336, reqhgt=0.05, mode=mode, nlyr=14, day_list=days)
@@ -73,6 +89,8 @@ def case_bioclim(name, rows, cols, mode):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["bio", "heights", "layers", "array", "coarse"]
+    if "f32" in which:
+        case_f32(4096, 1024, 240)
     if "snow" in which:
         case_snow(int(os.environ.get("SNOW_N", "1024")), int(os.environ.get("SNOW_N", "1024")), 240)
     if "coarse" in which:
