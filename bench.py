@@ -295,6 +295,11 @@ def gpu_arm(args):
                 roofline["fp64"] = {"achieved": ach, "peak": fpk, "unit": "TFLOP/s", "frac": ach / fpk,
                                     "peak_source": "mcf_fp64_peak DFMA micro-benchmark, this run",
                                     "flop_per_cell_hour": pm["fp64_flop_per_cell_hour"],
+                                    # from the committed ncu capture (not live): share of cycles the FP64 pipe is busy
+                                    # and the FP64 instructions behind it; fewer instructions for the same physics lower
+                                    # `achieved` flop/s while raising cell-hours/s, so read `frac` together with these
+                                    "pipe_active_pct_ncu": pm.get("fp64_pipe_active_pct"),
+                                    "fp64_instr_per_cell_hour_ncu": pm.get("fp64_instr_per_cell_hour"),
                                     "flop_source": pm.get("source", "profiles/")}
 
     # ------------------------------------------------------------------ e2e through the host-buffer C ABI
