@@ -38,6 +38,12 @@ __device__ __forceinline__ double satvapS(double tc) { // ref :480-490
 __device__ __forceinline__ double dewpointC(double ea) { // ref dewpointCpp :493-496
     return 243.5 * log(ea / 0.6112) / (17.67 - log(ea / 0.6112));
 }
+// round(x) % n as the reference forms its horizon / wind-shelter sector; a negative angle (outside what checkinputs
+// admits; the reference would index out of bounds) is folded into range instead
+__device__ __forceinline__ int sector(double x, int n) {
+    const int s = ((int)round(x)) % n;
+    return s < 0 ? s + n : s;
+}
 __device__ __forceinline__ double na_realS() { return __longlong_as_double(0x7FF00000000007A2LL); }
 
 // ref solarindexCpp :85-102
@@ -224,8 +230,8 @@ __global__ void __launch_bounds__(256) k_snow_prep(const __grid_constant__ SnowP
         h.zenr = s.zenr;
         h.azid = s.azid;
         h.cosz = cos(s.zenr);
-        h.sindex = ((int)round(s.azid / 15)) % 24;
-        h.windex = ((int)round(a.winddir[k] / 45)) % 8;
+        h.sindex = sector(s.azid / 15, 24);
+        h.windex = sector(a.winddir[k] / 45, 8);
         h.salb = 0.0;
         h.Rmx = h.Rmn = h.Rswmx = h.Rlwmx = h.Rswmn = h.Rlwmn = h.Gmx = 0.0;
         a.hours[k] = h;
@@ -1005,8 +1011,8 @@ __global__ void __launch_bounds__(128) k_snowmodel_arr(const __grid_constant__ S
             h.salb = snow_albedo(hs);
             const SolPos sp = solposition(lat, lon, c.year[k], c.month[k], c.day[k], c.hour[k]);
             h.zend = sp.zend; h.zenr = sp.zenr; h.azid = sp.azid; h.cosz = cos(sp.zenr);
-            h.sindex = ((int)round(sp.azid / 15.0)) % 24;
-            h.windex = ((int)round(c.winddir[k] / 45)) % 8;
+            h.sindex = sector(sp.azid / 15, 24);
+            h.windex = sector(c.winddir[k] / 45, 8);
             double paip = pai0;
             if (hgt0 > sdepgp) paip = paip * (hgt0 - sdepgp) / hgt0;
             const double dtR = Rmx - Rmn;
@@ -1098,8 +1104,8 @@ __global__ void __launch_bounds__(128) k_snowmicro_arr(const __grid_constant__ S
             h.Rsw = c.swdown[idx]; h.Rdif = c.difrad[idx]; h.Rlw = c.lwdown[idx]; h.umu = c.umu[idx];
             const SolPos sp = solposition(lat, lon, c.year[k], c.month[k], c.day[k], c.hour[k]);
             h.zend = sp.zend; h.zenr = sp.zenr; h.azid = sp.azid;
-            const int sindex = ((int)round(sp.azid / 15)) % 24;
-            const int windex = ((int)round(c.winddir[k] / 45)) % 8;
+            const int sindex = sector(sp.azid / 15, 24);
+            const int windex = sector(c.winddir[k] / 45, 8);
             int shadowmask = 1;
             const double ha = a.hor[(size_t)sindex * nc + cell];
             const double sa = (kPiS / 2.0) - sp.zenr;

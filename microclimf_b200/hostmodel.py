@@ -1036,3 +1036,137 @@ def runmicrosnow1(micropoint: Micropoint, reqhgt, vegp, soilc, dtm, smod, runche
             m[:, :, snowh] = mouts[k]
         mout[k] = m
     return mout
+
+
+# ---------------------------------------------------------------------------------------------
+# runbioclim (data.frame climate): .runbioclim1 / .runbioclim3
+# ---------------------------------------------------------------------------------------------
+def _biosel(tme, tc):
+    """ref .biosel (R/internal.R:1690-1727): the 14 days of the bioclim run — each month's median-temperature day, then
+    the (median over years of the) hottest and coldest day.  Returns (selh, seld), 1-based."""
+    tc = np.asarray(tc, dtype=np.float64)
+    nd = tc.size // 24
+    tcd = tc[:nd * 24].reshape(nd, 24).mean(axis=1)
+    t = np.asarray(tme).astype("datetime64[s]").astype(np.int64)[:nd * 24].reshape(nd, 24).mean(axis=1)
+    tmd = _obstime(t.astype("int64").astype("datetime64[s]"))
+    sel_med = []
+    for mth in range(1, 13):
+        s = np.nonzero(tmd["month"] == mth)[0] + 1
+        o = np.argsort(tcd[s - 1], kind="stable") + 1
+        n = len(o) // 2
+        sel_med.append(int(s[0] - 1 + o[n - 1]))
+    yrs = list(dict.fromkeys(tmd["year"].tolist()))
+    sel_max, sel_min = [], []
+    for y in yrs:
+        s = np.nonzero(tmd["year"] == y)[0] + 1
+        sel_max.append(int(np.argmax(tcd[s - 1]) + s[0]))
+        sel_min.append(int(np.argmin(tcd[s - 1]) + s[0]))
+    sel_max = np.array(sel_max)[np.argsort(tcd[np.array(sel_max) - 1], kind="stable")]
+    sel_min = np.array(sel_min)[np.argsort(tcd[np.array(sel_min) - 1], kind="stable")]
+    n = len(sel_max) // 2
+    seld = np.array(sel_med + [int(sel_max[n]), int(sel_min[n])])
+    return _hours_of_days(seld), seld
+
+
+def _quarter(agg, fun):
+    """which.max / which.min of stats::filter(agg, rep(1/3, 3), sides = 2, circular = TRUE): 1-based centre month."""
+    a = np.asarray(agg, dtype=np.float64)
+    f = (np.roll(a, 1) + a + np.roll(a, -1)) / 3.0
+    return int(fun(f)) + 1
+
+
+def _getselq(iq, month):
+    """ref .getselq (R/internal.R:1764-1774): 1-based hours of the three months around month iq."""
+    imn, imx = (12 if iq - 1 == 0 else iq - 1), (1 if iq + 1 == 13 else iq + 1)
+    return np.sort(np.nonzero((month == imn) | (month == iq) | (month == imx))[0] + 1)
+
+
+def _sortvegp2(vegp, seld, vegpisannual, n):
+    """ref .sortvegp2 (R/internal.R:276-302): the vegetation layer in force on each of the 14 selected days."""
+    if vegpisannual:
+        sd, nd = np.asarray(seld) % 365, 365
+    else:
+        sd, nd = np.asarray(seld), int(round(n / 24))
+    out = {}
+    for k in VEG_NAMES:
+        a = vegp[k].values
+        dmx = a.shape[2]
+        if dmx == 1:
+            out[k] = np.repeat(a, 14, axis=2)
+        else:
+            s = np.clip(_r_round(np.linspace(0.50001, dmx + 0.5, nd)).astype(int), 1, dmx)
+            s = np.append(s, s[-1])
+            # R subscripts: element 0 of `seld %% 365` selects nothing in R; the bundled data never produce it
+            out[k] = a[:, :, s[np.maximum(sd, 1) - 1] - 1]
+    return out
+
+
+def runbioclim(climdata, reqhgt, vegp, soilc, dtm, pointmodel, temp="air", zref=2, windhgt=None, soilm=None, runchecks=True,
+               pai_a=None, tfact=1.5, out=(True,) * 19, vegpisannual=True, operator=None):
+    """ref runbioclim (R/Cppwrappers.R:628-651) for data.frame climate -> .runbioclim1 (static vegetation,
+    R/internal.R:1776-1894) / .runbioclim3 (layered vegetation, :2082-2181): quarters from the monthly weather, the 14
+    bioclim days, the point model on those 336 hours, the usual static layers, then the fused CUDA operator
+    (`api.runbioclim1Cpp` / `runbioclim3Cpp`: grid solve + 19 reductions on the device).
+
+    The point model is upstream of this build: `pointmodel(weather336, reqhgt, dtm, vegp, soilc, zref,
+    windhgt, soilm)` must return a `Micropoint` for the 336 selected hours, as `runpointmodel(..., yearG = FALSE)` does
+    (R/internal.R:1747).  Returns {"bio1": [rows, cols], ...} masked by the DTM."""
+    dtm_u, vegp_u, soilc_u = _unpack(dtm, vegp, soilc)
+    layered = _vegpdmx(vegp_u) > 1
+    vegp_u, dtm_u, soilc_u = _cleanvars(vegp_u, soilc_u, dtm_u)
+    weather = climdata
+    if runchecks:
+        rc = checkinputs(weather, vegp_u, soilc_u, dtm_u)
+        weather, vegp_u, soilc_u = rc["weather"], rc["vegp"], rc["soilc"]
+    tme = np.asarray(weather["obs_time"]).astype("datetime64[s]")
+    ot = _obstime(tme)
+    n = tme.size
+    months = sorted(set(ot["month"].tolist()))
+    pmean = [np.nanmean(np.asarray(weather["precip"], dtype=np.float64)[ot["month"] == m]) for m in months]
+    tsum = [np.nansum(np.asarray(weather["temp"], dtype=np.float64)[ot["month"] == m]) for m in months]
+    wq, dq = _quarter(pmean, np.argmax), _quarter(pmean, np.argmin)
+    hq, cq = _quarter(tsum, np.argmax), _quarter(tsum, np.argmin)
+    selh, seld = _biosel(tme, weather["temp"])
+    w336 = {k: np.asarray(v)[selh - 1] for k, v in weather.items()}
+    micropoint = pointmodel(w336, reqhgt, dtm_u, vegp_u, soilc_u, zref, zref if windhgt is None else windhgt, soilm)
+    weather = micropoint.weather
+    obstime = _obstime(weather["obs_time"])
+    tempv = np.asarray(weather["temp"], dtype=np.float64)
+    es = _satvap(tempv)
+    ea = es * np.asarray(weather["relhum"], dtype=np.float64) / 100
+    clim = dict(temp=tempv, es=es, ea=ea, tdew=_dewpoint(ea, tempv))
+    for k in ("pres", "swdown", "difrad", "lwdown", "windspeed", "winddir"):
+        clim[k] = np.asarray(weather[k], dtype=np.float64)
+    pointm = {k: np.asarray(v, dtype=np.float64) for k, v in micropoint.dfo.items()}
+    pointm["Tbp"] = np.asarray(micropoint.Tbz, dtype=np.float64) if reqhgt < 0 else np.zeros(tempv.size)
+    if layered:
+        vg = _sortvegp2(vegp_u, seld, vegpisannual, n)
+    else:
+        vg = {k: vegp_u[k].values[:, :, 0].copy() for k in VEG_NAMES}
+        with np.errstate(invalid="ignore"):
+            vg["hgt"] = np.where(vg["pai"] == 0, 0.0, vg["hgt"])
+            vg["pai"] = np.where(vg["hgt"] == 0, 0.0, vg["pai"])
+    fd = _foliageden(reqhgt, vg["hgt"], vg["pai"], None if pai_a is None else as_raster(pai_a, dtm_u).values.squeeze())
+    vg["paia"], vg["leafden"] = fd["pai_a"], fd["leafden"]
+    soilp = _soilinit(soilc_u)
+    sc = dict(gref=soilc_u["groundr"].matrix().copy(), Smin=soilp["Smin"], Smax=soilp["Smax"], soilb=soilp["soilb"],
+              Psie=soilp["psi_e"], Vq=soilp["Vq"], Vm=soilp["Vm"], Mc=soilp["Mc"], rho=soilp["rho"])
+
+    def fill(r, v):
+        m = r.matrix().copy()
+        m[np.isnan(m)] = v
+        return mask(r.like(m), dtm_u).matrix()
+
+    sc["slope"], sc["aspect"] = fill(terrain(dtm_u, "slope"), 0.0), fill(terrain(dtm_u, "aspect"), 0.0)
+    sc["twi"] = fill(_topidx(dtm_u), 1.0)
+    lat, lon = latlong_from_raster(dtm_u)
+    sc["hor"], sc["svfa"] = api.horizon(dtm_u.matrix(), dtm_u.res[0], want_svf=True)
+    sc["wsa"] = _windsheltera(dtm_u, micropoint.zref, 10 if dtm_u.res[0] <= 100 else 1)
+    month = obstime["month"]
+    q = [(_getselq(x, month) - 1).astype(np.int32) for x in (wq, dq, hq, cq)]
+    fn = operator or (api.runbioclim3Cpp if layered else api.runbioclim1Cpp)  # tests inject the reference's
+    bio = fn(obstime, clim, pointm, vg, sc, float(reqhgt), float(micropoint.zref), lat, lon, _getmode(sc["Smin"]),
+             _getmode(sc["Smax"]), float(tfact), float(micropoint.matemp), [bool(o) for o in out], q[0], q[1], q[2], q[3],
+             temp == "air")
+    na = np.isnan(dtm_u.matrix())
+    return {k: np.where(na, np.nan, v) for k, v in bio.items()}

@@ -257,3 +257,65 @@ def test_runmicro_big_writeasnc_packs_like_writetonc(tmp_path):
         assert np.array_equal(t[name], want), name
     na = np.isnan(dtm.matrix())
     assert np.all(t["Tz"][:, na] == packing_oracle.NA) and np.all(t["Tz"][:, ~na] != packing_oracle.NA)
+
+
+# --------------------------------------------------------------------------------------------- runbioclim
+def _pointmodel336(w336, reqhgt, dtm, vegp, soilc, zref, windhgt, soilm):
+    """runpointmodel(weather2, ..., yearG = FALSE) on the 14 bioclim days (R/internal.R:1747) through the compiled
+    reference's point model (oracle/pointmodel.py, test infrastructure)."""
+    from microclimf_b200.tables import SOILPARAMSP
+    from oracle import pointmodel
+    vm = lambda k: float(np.nanmean(vegp[k].values))  # noqa: E731
+    vegp_p = [vm("hgt"), vm("pai"), vm("x"), vm("clump"), vm("leafr"), vm("leaft"), vm("leafd"), 0.97, vm("gsmax"), 100.0]
+    sl = hostmodel._soilinit(soilc)
+    sn = int(pointmodel.getmode(soilc["soiltype"].values))
+    gm = pointmodel.getmode
+    groundp_p = [gm(soilc["groundr"].values), 0.0, 180.0, 0.97, gm(sl["rho"]), gm(sl["Vm"]), gm(sl["Vq"]), gm(sl["Mc"]), gm(sl["soilb"]),
+                 gm(sl["psi_e"]), gm(sl["Smax"]), gm(sl["Smin"]), SOILPARAMSP["alpha"][sn - 1], SOILPARAMSP["n"][sn - 1],
+                 SOILPARAMSP["Ksat"][sn - 1]]
+    sprow = {k: SOILPARAMSP[k][sn - 1] for k in ("rmu", "mult", "pwr", "Smax", "Smin", "Ksat", "a")}
+    lat, lon = hostmodel.latlong_from_raster(dtm)
+    tme = w336["obs_time"]
+    mp = pointmodel.runpointmodel(w336, hostmodel._obstime(tme), reqhgt, vegp_p, groundp_p, sprow, lat, lon,
+                                  float(np.nanmax(vegp["hgt"].values)), zref=zref, yearG=False)
+    w = dict(mp["weather"], obs_time=tme)
+    return Micropoint(weather=w, dfo=mp["dfo"], Tbz=mp["Tbz"], lat=lat, long=lon, zref=mp["zref"], subs=np.arange(1, tme.size + 1),
+                      tmeorig=tme, matemp=mp["matemp"])
+
+
+def test_bioclim_day_selection_cpu():
+    """.biosel / quarters (R/internal.R:1690-1727, 1796-1801) on the bundled weather: 14 whole days, one per month in
+    calendar order, then the year's hottest and coldest day."""
+    dtm, vegp, soilc, mp, clim = load_example()
+    selh, seld = hostmodel._biosel(clim["obs_time"], clim["temp"])
+    assert selh.size == 336 and seld.size == 14
+    ot = hostmodel._obstime(clim["obs_time"])
+    assert [int(ot["month"][(d - 1) * 24]) for d in seld[:12]] == list(range(1, 13))
+    tcd = clim["temp"].reshape(365, 24).mean(axis=1)
+    assert seld[12] == np.argmax(tcd) + 1 and seld[13] == np.argmin(tcd) + 1
+    # the quarter around January: the 14 selected days whose month is 12, 1 or 2 (the coldest day, in February, included)
+    m14 = np.array([int(ot["month"][(d - 1) * 24]) for d in seld])
+    want = np.concatenate([np.arange(i * 24 + 1, i * 24 + 25) for i in np.nonzero(np.isin(m14, (12, 1, 2)))[0]])
+    assert np.array_equal(hostmodel._getselq(1, ot["month"][selh - 1]), want) and want.size == 96
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not pyoracle.have_ref(), reason="compiled reference (its point model) absent")
+def test_runbioclim_bundled():
+    """BASELINE configs[2] in miniature: runbioclim on the bundled raster (12 vegetation layers => .runbioclim3 /
+    runbioclim3Cpp), CUDA operator against the compiled reference's on the same prepared arguments."""
+    dtm, vegp, soilc, mp, clim = load_example()
+
+    def ref_op(obstime, climdata, pointm, vg, sc, reqhgt, zref, lat, lon, Sminp, Smaxp, tfact, mat, out, wetq, dryq, hotq, colq, air):
+        p = api._problem(3, dict(st=np.arange(14) * 24, ed=np.arange(14) * 24 + 23), obstime, climdata, pointm, vg, sc, reqhgt, zref,
+                         lat, lon, None, None, Sminp, Smaxp, tfact, True, mat)
+        return pyoracle.runbioclim(p, dict(wetq=wetq, dryq=dryq, hotq=hotq, colq=colq), air=air, out_mask=out, kind="ref")
+
+    got = hostmodel.runbioclim(clim, 0.05, vegp, soilc, dtm, _pointmodel336)
+    want = hostmodel.runbioclim(clim, 0.05, vegp, soilc, dtm, _pointmodel336, operator=ref_op)
+    assert set(got) == {f"bio{i}" for i in range(1, 20)}
+    ok, rows = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rows)
+    land = ~np.isnan(dtm.matrix())
+    assert np.isfinite(got["bio1"][land]).all() and 5 < np.nanmean(got["bio1"]) < 20   # annual mean temperature, Cornwall
+    assert np.all(got["bio5"][land] >= got["bio6"][land])
