@@ -1005,7 +1005,7 @@ static Err run_dev_f32(const mcf_problem* p, float* const out[MCF_NOUT], const m
     count_launch();
     const int grid_max = g_sm_count * f32_blocks_per_sm();
     float* stashf = nullptr;
-    CU(sc.alloc(&stashf, (size_t)grid_max * 24 * kStashVars * kTile));
+    CU(sc.alloc(&stashf, (size_t)grid_max * 24 * kStashVars * f32_tile()));
     GridArgs a;
     fill_common(pl, a);
     a.cell_begin = 0;
@@ -1021,7 +1021,7 @@ static Err run_dev_f32(const mcf_problem* p, float* const out[MCF_NOUT], const m
     CU(sc.alloc(&ctr, 1));
     CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
     a.tile_counter = ctr;
-    const int ntiles = (pl.ncells + kTile - 1) / kTile;
+    const int ntiles = (pl.ncells + f32_tile() - 1) / f32_tile();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_timing) {
         CU(cudaEventCreate(&e0));

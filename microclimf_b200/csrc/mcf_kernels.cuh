@@ -133,6 +133,7 @@ int grid_blocks_per_sm(bool arr, int rq);
 cudaError_t launch_narrow_hours(const HourRec* in, int n, void* out, cudaStream_t stream);
 size_t hourrec_f32_bytes();
 int f32_blocks_per_sm();
+int f32_tile();
 cudaError_t launch_grid_f32(const GridArgs& a, const void* hoursf, float* const outf[kNOut], float* stashf, int rq, int grid,
                             cudaStream_t stream);
 cudaError_t launch_below(const BelowArgs& a, cudaStream_t stream);

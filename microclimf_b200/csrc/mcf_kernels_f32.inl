@@ -9,6 +9,10 @@
 //     the day stash and the outputs are FP32: 40 algorithmic bytes per cell-hour instead of 80.
 // (mcf_physics_f32.cuh is included at the top of mcf_kernels.cu)
 
+#ifndef MCF_F32_TILE
+#define MCF_F32_TILE 512
+#endif
+constexpr int kTileF = MCF_F32_TILE; // cells per CTA tile of the FP32 kernel (16 warps at 128 registers)
 #ifndef MCF_F32_MINB
 #define MCF_F32_MINB 1
 #endif
@@ -16,7 +20,7 @@ struct GridArgsF {
     GridArgs g;                 // everything of the FP64 launch (outputs unused)
     const f32::HourRecF* hoursf; // [tsteps]
     float* outf[kNOut];
-    float* stashf;              // [gridDim.x][24][kStashVars][kTile]
+    float* stashf;              // [gridDim.x][24][kStashVars][kTileF]
 };
 
 __global__ void k_narrow_hours(const HourRec* __restrict__ in, int n, f32::HourRecF* __restrict__ out) {
@@ -28,7 +32,7 @@ __global__ void k_narrow_hours(const HourRec* __restrict__ in, int n, f32::HourR
 }
 
 template <int RQ>
-__global__ void __launch_bounds__(kTile, MCF_F32_MINB) k_grid_f32(const __grid_constant__ GridArgsF af) {
+__global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_constant__ GridArgsF af) {
     using f32::HourRecF;
     const GridArgs& a = af.g;
     constexpr int kStages = 4, kAhead = 2;
@@ -37,13 +41,13 @@ __global__ void __launch_bounds__(kTile, MCF_F32_MINB) k_grid_f32(const __grid_c
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     __shared__ int s_tile;
     const int tid = threadIdx.x;
-    const int ntiles = (a.cell_end - a.cell_begin + kTile - 1) / kTile;
-    float* const stash = af.stashf + (size_t)blockIdx.x * (24 * kStashVars * kTile) + tid;
+    const int ntiles = (a.cell_end - a.cell_begin + kTileF - 1) / kTileF;
+    float* const stash = af.stashf + (size_t)blockIdx.x * (24 * kStashVars * kTileF) + tid;
     unsigned int q0 = 0;
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kTile / 32);
+            mbar_init(&empty_bar[s], kTileF / 32);
         }
         mbar_fence_init();
     }
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(kTile, MCF_F32_MINB) k_grid_f32(const __grid_c
         __syncthreads();
         const int tile = s_tile;
         if (tile >= ntiles) break;
-        const int cell = a.cell_begin + tile * kTile + tid;
+        const int cell = a.cell_begin + tile * kTileF + tid;
         const bool valid = cell < a.cell_end;
         const int cc = valid ? cell : a.cell_end - 1;
         const bool active = valid && !isnan(__ldg(&a.veg[0][cc]));
@@ -146,11 +150,11 @@ __global__ void __launch_bounds__(kTile, MCF_F32_MINB) k_grid_f32(const __grid_c
                     if (Rmx < Rval) Rmx = Rval;
                     if (tmx < Tg0) tmx = Tg0;
                     if (tmn > Tg0) tmn = Tg0;
-                    float* st = stash + (size_t)hr * (kStashVars * kTile);
-                    __stcg(&st[0 * kTile], radabs);
-                    __stcg(&st[1 * kTile], surfwet);
-                    __stcg(&st[2 * kTile], r.radCsw);
-                    __stcg(&st[3 * kTile], r.Lhalf);
+                    float* st = stash + (size_t)hr * (kStashVars * kTileF);
+                    __stcg(&st[0 * kTileF], radabs);
+                    __stcg(&st[1 * kTileF], surfwet);
+                    __stcg(&st[2 * kTileF], r.radCsw);
+                    __stcg(&st[3 * kTileF], r.Lhalf);
                     o += a.ncells;
                 }
                 const float dtr = tmx - tmn;
@@ -160,9 +164,9 @@ __global__ void __launch_bounds__(kTile, MCF_F32_MINB) k_grid_f32(const __grid_c
                 for (int hr = 0; hr < 24; ++hr) {
                     const HourRecF& h = slab_day[hr];
                     if (hr == wrap_at) o = cell;
-                    const float* st = stash + (size_t)hr * (kStashVars * kTile);
-                    const float radabs = __ldcg(&st[0 * kTile]), surfwet = __ldcg(&st[1 * kTile]);
-                    const float radCsw = __ldcg(&st[2 * kTile]), Lhalf = __ldcg(&st[3 * kTile]);
+                    const float* st = stash + (size_t)hr * (kStashVars * kTileF);
+                    const float radabs = __ldcg(&st[0 * kTileF]), surfwet = __ldcg(&st[1 * kTileF]);
+                    const float radCsw = __ldcg(&st[2 * kTileF]), Lhalf = __ldcg(&st[3 * kTileF]);
                     const float ws = ws_n;
                     ws_n = (float)__ldg(&a.wsa[(size_t)slab_day[hr < 23 ? hr + 1 : 23].windex * a.ncells + cell]);
                     const float soild = f32::soil_distribute(v, h.soilmp);
@@ -206,6 +210,7 @@ cudaError_t launch_narrow_hours(const HourRec* in, int n, void* out, cudaStream_
 }
 size_t hourrec_f32_bytes() { return sizeof(f32::HourRecF); }
 int f32_blocks_per_sm() { return MCF_F32_MINB; }
+int f32_tile() { return kTileF; }
 
 cudaError_t launch_grid_f32(const GridArgs& a, const void* hoursf, float* const outf[kNOut], float* stashf, int rq, int grid,
                             cudaStream_t stream) {
@@ -214,7 +219,7 @@ cudaError_t launch_grid_f32(const GridArgs& a, const void* hoursf, float* const 
     af.hoursf = (const f32::HourRecF*)hoursf;
     for (int i = 0; i < kNOut; ++i) af.outf[i] = outf[i];
     af.stashf = stashf;
-    if (rq == RQ_ABOVE) k_grid_f32<RQ_ABOVE><<<grid, kTile, 0, stream>>>(af);
-    else k_grid_f32<RQ_SURFACE><<<grid, kTile, 0, stream>>>(af);
+    if (rq == RQ_ABOVE) k_grid_f32<RQ_ABOVE><<<grid, kTileF, 0, stream>>>(af);
+    else k_grid_f32<RQ_SURFACE><<<grid, kTileF, 0, stream>>>(af);
     return cudaGetLastError();
 }
