@@ -177,6 +177,15 @@ Err device_info() {
         return make_err(MCF_ERR_CUDA, "device %s is sm_%d%d; this library is built for sm_100a only", prop.name,
                         prop.major, prop.minor);
     g_sm_count = prop.multiProcessorCount;
+    // Scratch is stream-ordered (cudaMallocAsync): keep freed blocks in the pool instead of returning them to the
+    // driver at every synchronisation — the bioclim path alone re-allocates 2 x rows*cols*336 doubles per call
+    // (22.6 GB for config 3), the windowed drivers a stash and a few tables per launch.
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    (void)cudaGetLastError();
     return Err();
 }
 
@@ -1259,6 +1268,14 @@ void mcf_release_workspace(void) {
     g_ws.cap = 0;
     if (g_stage) cudaFreeHost(g_stage);
     g_stage = nullptr;
+    // scratch blocks retained by the stream-ordered pool (see device_info) go back to the driver too
+    int dev = 0;
+    cudaMemPool_t pool = nullptr;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        (void)cudaDeviceSynchronize();
+        (void)cudaMemPoolTrimTo(pool, 0);
+    }
+    (void)cudaGetLastError();
 }
 
 int mcf_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, char* err, size_t errlen) {
