@@ -204,6 +204,7 @@ struct CellInv {
     double leafd, leafden, nearcoef; // nearcoef = 3.047519 + 0.128642*log(pai)
     double a2h, inth_h, inth_z, zq, hmz; // rhcanopy pieces; zq = reqhgt, hmz = hgt - reqhgt
     double Hf0;           // mincondCpp's Hf for gs = 999.99 (first call in leaftemp :1348)
+    double Hf500;         // mincondCpp's Hf for rs = 500 (gs = 0: every night hour)
     // reciprocals of cell invariants (IEEE division, once per cell)
     double inv_rge, inv_Smax, inv_kden, inv_leafd, inv_hgt, inv_a2h;
 };
@@ -381,6 +382,7 @@ static __device__ __noinline__ void cell_setup(const CellIn& c, double reqhgt2, 
     v.hmz = c.hgt - reqhgt2;
     double Hlf0 = 1.09767 * pow(1 / 999.99, 0.2672778);
     v.Hf0 = -1.0 / (1.0 + exp(2.0 - Hlf0));
+    v.Hf500 = -1.0 / (1.0 + exp(2.0 - 1.09767 * pow(500.0, 0.2672778)));
     v.inv_rge = 1.0 / v.rge;
     v.inv_Smax = 1.0 / c.Smax;
     v.inv_kden = 1.0 / v.kden;
@@ -558,20 +560,6 @@ __device__ __forceinline__ double stomcond(const CellInv& v, double Rswabs, doub
     return gs;
 }
 
-// ref mincondCpp :1316-1331 (second call in leaftemp, rs from gs)
-__device__ __forceinline__ double mincond(double Rnet, double gs, double inv_leafd) {
-    double rs = 500.0;
-    if (gs > 0.0) rs = mrcp(gs);
-    if (rs > 500.0) rs = 500.0;
-    double Hlf = 1.09767 * mpow(rs, 0.2672778);
-    double Hf = -mrcp(1.0 + mexp_nc(2.0 - Hlf));
-    double H = Hf * Rnet;
-    // H == 0: mlog(0) ~ -709, so the power is ~1e-62 instead of 0; either way gmin takes its floor
-    double gmin = 0.0463 * mpow(fabs(H) * inv_leafd, 0.2);
-    if (gmin < 0.05) gmin = 0.05;
-    return gmin;
-}
-
 struct Above {
     double Tz, tleaf, rh, lwdn, lwup;
 };
@@ -661,20 +649,35 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         double leafabs = radLsw + lwabs;
         double gh = 0.135 * msqrt(w.uz * v.inv_leafd) * 1.4;
         double Rnetl = leafabs - lwcan;
-        double gmin = 0.0463 * mpow(fabs(v.Hf0 * Rnetl) * v.inv_leafd, 0.2);
-        if (gmin < 0.05) gmin = 0.05;
-        if (gh < gmin) gh = gmin;
-        double gVl = gh;
-        if (v.gsmax < 999.99) {
-            gVl = 0.0;
+        // leaftemp calls mincondCpp twice (gs = 999.99, then the stomatal gs; ref :1348, :1354) and keeps the larger
+        // gmin.  gmin = 0.0463 (|Hf| |Rnet| / leafd)^0.2 is monotone in |Hf|, so one power of the larger |Hf| gives
+        // max(gmin1, gmin2) exactly; at night (gs = 0, rs = 500) the second |Hf| is a constant.
+        double Hfmag = fabs(v.Hf0);
+        const bool stom = v.gsmax < 999.99;
+        double gs = 0.0;
+        if (stom) {
             double radLpar = lit ? (1.0 - v.omp) * Lhalf : 0.0;
-            double gs = 0.0;
             if (radLpar > 0.0) {
                 if (!have_gs2) gs2 = stom_gs2(v, soilm);
                 gs = stomcond(v, radLpar, gs2);
             }
-            gmin = mincond(Rnetl, gs, v.inv_leafd);
-            if (gh < gmin) gh = gmin;
+            double Hf2 = v.Hf500;
+            if (gs > 0.0) {
+                double rs = mrcp(gs);
+                if (rs > 500.0) rs = 500.0;
+                const double Hlf = 1.09767 * mpow(rs, 0.2672778);
+                Hf2 = -mrcp(1.0 + mexp_nc(2.0 - Hlf));
+            }
+            const double m2 = fabs(Hf2);
+            if (Hfmag < m2) Hfmag = m2;
+        }
+        // H == 0: mlog(0) ~ -709, so the power is ~1e-62 instead of 0; either way gmin takes its floor
+        double gmin = 0.0463 * mpow((Hfmag * fabs(Rnetl)) * v.inv_leafd, 0.2);
+        if (gmin < 0.05) gmin = 0.05;
+        if (gh < gmin) gh = gmin;
+        double gVl = gh;
+        if (stom) {
+            gVl = 0.0;
             if (gs > 0.0) gVl = mdiv(gh * gs, gh + gs); // 1 / (1/gh + 1/gs)
         }
         double ml;
