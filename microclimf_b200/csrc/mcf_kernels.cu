@@ -672,6 +672,10 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     st_stash(&st[1 * kTile], surfwet);
                     st_stash(&st[2 * kTile], r.radCsw);
                     st_stash(&st[3 * kTile], r.Lhalf);
+#ifdef MCF_STASH6
+                    st_stash(&st[4 * kTile], soild);
+                    st_stash(&st[5 * kTile], w.uf);
+#endif
                     o += a.ncells;
                 }
                 // ------------------------------------------------------------------ pass 2
@@ -680,7 +684,11 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 // stash and wind-sector values of the coming hour are fetched one hour ahead
                 double radabs_n = ld_stash(&stash[0 * kTile]), surfwet_n = ld_stash(&stash[1 * kTile]);
                 double radCsw_n = ld_stash(&stash[2 * kTile]), Lhalf_n = ld_stash(&stash[3 * kTile]);
+#ifdef MCF_STASH6
+                double soild_n = ld_stash(&stash[4 * kTile]), uf_n = ld_stash(&stash[5 * kTile]);
+#else
                 if (!ARR) ws_n = __ldg(&a.wsa[(size_t)slab_day[0].windex * a.ncells + cell]);
+#endif
 #pragma unroll 1
                 for (int hr = 0; hr < 24; ++hr) {
                     const int k = blk.k0 + hr;
@@ -689,13 +697,31 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     const HourRec& h = ARR ? hloc : slab_day[hr];
                     if (hr == wrap_at) o = cell;
                     const double radabs = radabs_n, surfwet = surfwet_n, radCsw = radCsw_n, Lhalf = Lhalf_n;
+#ifdef MCF_STASH6
+                    double soild_n2, uf_n2;
+#endif
                     {
                         const double* st = stash + (size_t)(hr < 23 ? hr + 1 : 23) * (kStashVars * kTile);
                         radabs_n = ld_stash(&st[0 * kTile]);
                         surfwet_n = ld_stash(&st[1 * kTile]);
                         radCsw_n = ld_stash(&st[2 * kTile]);
                         Lhalf_n = ld_stash(&st[3 * kTile]);
+#ifdef MCF_STASH6
+                        soild_n2 = ld_stash(&st[4 * kTile]);
+                        uf_n2 = ld_stash(&st[5 * kTile]);
+#endif
                     }
+#ifdef MCF_STASH6
+                    const double soild = soild_n;
+                    Wind w; // windCpp's uz / gHa from the stashed friction velocity (ref :1199-1217)
+                    w.uf = uf_n;
+                    w.uz = w.uf * v.uz_coef;
+                    if (w.uz > h.u2) w.uz = h.u2;
+                    w.gHa = w.uf * v.gHa_coef;
+                    if (w.gHa < 0.0001) w.gHa = 0.0001;
+                    soild_n = soild_n2;
+                    uf_n = uf_n2;
+#else
                     double ws;
                     if (ARR) {
                         ws = __ldg(&a.wsa[(size_t)h.windex * a.ncells + cell]);
@@ -705,6 +731,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     }
                     const double soild = soil_distribute(v, h.soilmp);
                     const Wind w = wind_hour(v, h.u2, h.umu, ws);
+#endif
                     // soil conductivity and damping depth (ref soilcondCpp :1249-1260)
                     const double cs = (2400 * v.rho / 2.64 + 4180.0 * soild);
                     const double ph = (v.rho * (1.0 - soild) + soild) * 1000.0;

@@ -155,11 +155,12 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                     __stcg(&st[1 * kTileF], surfwet);
                     __stcg(&st[2 * kTileF], r.radCsw);
                     __stcg(&st[3 * kTileF], r.Lhalf);
+                    __stcg(&st[4 * kTileF], soild);
+                    __stcg(&st[5 * kTileF], w.uf);
                     o += a.ncells;
                 }
                 const float dtr = tmx - tmn;
                 o = o_first;
-                ws_n = (float)__ldg(&a.wsa[(size_t)slab_day[0].windex * a.ncells + cell]);
 #pragma unroll 1
                 for (int hr = 0; hr < 24; ++hr) {
                     const HourRecF& h = slab_day[hr];
@@ -167,10 +168,13 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                     const float* st = stash + (size_t)hr * (kStashVars * kTileF);
                     const float radabs = __ldcg(&st[0 * kTileF]), surfwet = __ldcg(&st[1 * kTileF]);
                     const float radCsw = __ldcg(&st[2 * kTileF]), Lhalf = __ldcg(&st[3 * kTileF]);
-                    const float ws = ws_n;
-                    ws_n = (float)__ldg(&a.wsa[(size_t)slab_day[hr < 23 ? hr + 1 : 23].windex * a.ncells + cell]);
-                    const float soild = f32::soil_distribute(v, h.soilmp);
-                    const f32::Wind w = f32::wind_hour(v, h.u2, h.umu, ws);
+                    const float soild = __ldcg(&st[4 * kTileF]);
+                    f32::Wind w; // uz / gHa from the stashed friction velocity (ref windCpp :1199-1217)
+                    w.uf = __ldcg(&st[5 * kTileF]);
+                    w.uz = w.uf * v.uz_coef;
+                    if (w.uz > h.u2) w.uz = h.u2;
+                    w.gHa = w.uf * v.gHa_coef;
+                    if (w.gHa < 0.0001f) w.gHa = 0.0001f;
                     const float cs = (2400.0f * v.rho / 2.64f + 4180.0f * soild);
                     const float ph = (v.rho * (1.0f - soild) + soild) * 1000.0f;
                     const float c2 = 1.06f * v.rho * soild;

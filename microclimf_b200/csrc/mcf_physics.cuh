@@ -395,14 +395,24 @@ static __device__ __noinline__ void cell_setup(const CellIn& c, double reqhgt2, 
 // Per-cell-hour physics
 // ---------------------------------------------------------------------------------------------
 
-// Pass-1 products that pass 2 needs again (the day stash): 4 doubles per hour.  Everything else pass 2
-// uses (soil moisture, wind, longwave) is cheap to recompute from cell/hour invariants.
+// Pass-1 products that pass 2 needs again (the day stash): 6 doubles per hour.  Everything else pass 2
+// uses (longwave, conductances) is cheap to recompute from cell/hour invariants.
 //   radabs  : ground absorbed SW + LW                        (ref soilmodelG0.radabs)
 //   surfwet : soil surface wetness                           (ref soilmodelG0.surfwet)
 //   radCsw  : canopy absorbed SW                             (ref radmodel2.radCsw)
 //   Lhalf   : 0.5*(Rddown + Rdup + k cosz Rbdown), so that radLsw = (1-om)*Lhalf and
 //             radLpar = (1-omp)*Lhalf                        (ref :1142-1143)
+//   soild   : redistributed soil moisture                    (ref soildCpp :1021-1032)
+//   uf      : friction velocity; uz and gHa follow from it   (ref windCpp :1196-1217) — 2.4 % faster than
+//             recomputing both in pass 2, and pass 2 no longer reads the wind-shelter sector layer
+#ifndef MCF_STASH4
+#define MCF_STASH6 1 // default; -DMCF_STASH4 restores the four-variable stash (pass 2 recomputes soil moisture and wind)
+#endif
+#ifdef MCF_STASH6
+constexpr int kStashVars = 6; // + soild, uf: pass 2 rebuilds soil moisture and wind from two loads instead of recomputing them
+#else
 constexpr int kStashVars = 4;
+#endif
 
 // ref soildCpp :1021-1032, closed form of logistic(logit(theta) + tadd)
 __device__ __forceinline__ double soil_distribute(const CellInv& v, double soilmp) {
