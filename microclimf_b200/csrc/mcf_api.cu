@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "mcf_kernels.cuh"
+#include "mcf_host.h"
 #include "microclimf_b200.h"
 
 using namespace mcf;
@@ -649,15 +650,19 @@ bool is_pinned(const void* p) {
     return at.type == cudaMemoryTypeHost;
 }
 
-Err copy_back(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream) {
-    // split into pinned destinations (direct) and pageable ones (staged, chunked)
+// `to_device` reverses the roles: the copy threads memcpy a chunk of the pageable source into a pinned slot and DMA it
+// to the device while they fill the other slot (used by the snow operators, whose inputs are [rows, cols, hours]
+// arrays as large as their outputs).
+Err stage_copies(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream, bool to_device) {
+    const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    // split into pinned host buffers (direct) and pageable ones (staged, chunked)
     struct Chunk { char* dst; const char* src; size_t bytes; cudaEvent_t ready; };
     std::vector<Chunk> chunks;
     for (const CopyJob& j : jobs) {
         if (!j.bytes) continue;
-        if (is_pinned(j.dst)) {
+        if (is_pinned(to_device ? (const void*)j.src : (const void*)j.dst)) {
             if (j.ready) CU(cudaStreamWaitEvent(direct_stream, j.ready, 0));
-            CU(cudaMemcpyAsync(j.dst, j.src, j.bytes, cudaMemcpyDeviceToHost, direct_stream));
+            CU(cudaMemcpyAsync(j.dst, j.src, j.bytes, kind, direct_stream));
         } else {
             for (size_t off = 0; off < j.bytes; off += kSlotBytes)
                 chunks.push_back(Chunk{j.dst + off, j.src + off, std::min(kSlotBytes, j.bytes - off), j.ready});
@@ -679,22 +684,38 @@ Err copy_back(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream) {
                 if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
                 for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming);
                 char* slot[2] = {(char*)g_stage + kSlotBytes * (2 * t), (char*)g_stage + kSlotBytes * (2 * t + 1)};
-                // chunks t, t + nthreads, ...; DMA of chunk i+1 overlaps the memcpy of chunk i
+                // chunks t, t + nthreads, ...
                 std::vector<size_t> mine;
                 for (size_t c = t; c < chunks.size(); c += nthreads) mine.push_back(c);
-                auto issue = [&](size_t i) {
-                    const Chunk& c = chunks[mine[i]];
-                    if (c.ready) e = cudaStreamWaitEvent(st, c.ready, 0);
-                    if (e == cudaSuccess) e = cudaMemcpyAsync(slot[i & 1], c.src, c.bytes, cudaMemcpyDeviceToHost, st);
-                    if (e == cudaSuccess) e = cudaEventRecord(ev[i & 1], st);
-                };
-                if (e == cudaSuccess && !mine.empty()) issue(0);
-                for (size_t i = 0; i < mine.size() && e == cudaSuccess; ++i) {
-                    if (i + 1 < mine.size()) issue(i + 1);
-                    if (e == cudaSuccess) e = cudaEventSynchronize(ev[i & 1]);
-                    if (e == cudaSuccess) std::memcpy(chunks[mine[i]].dst, slot[i & 1], chunks[mine[i]].bytes);
+                if (to_device) {
+                    // fill slot i&1 on the CPU while the DMA of the other slot is in flight
+                    for (size_t i = 0; i < mine.size() && e == cudaSuccess; ++i) {
+                        const Chunk& c = chunks[mine[i]];
+                        if (i >= 2) e = cudaEventSynchronize(ev[i & 1]); // the slot's previous DMA has drained
+                        if (e != cudaSuccess) break;
+                        std::memcpy(slot[i & 1], c.src, c.bytes);
+                        e = cudaMemcpyAsync(c.dst, slot[i & 1], c.bytes, kind, st);
+                        if (e == cudaSuccess) e = cudaEventRecord(ev[i & 1], st);
+                    }
+                } else {
+                    // DMA of chunk i+1 overlaps the memcpy of chunk i
+                    auto issue = [&](size_t i) {
+                        const Chunk& c = chunks[mine[i]];
+                        if (c.ready) e = cudaStreamWaitEvent(st, c.ready, 0);
+                        if (e == cudaSuccess) e = cudaMemcpyAsync(slot[i & 1], c.src, c.bytes, kind, st);
+                        if (e == cudaSuccess) e = cudaEventRecord(ev[i & 1], st);
+                    };
+                    if (e == cudaSuccess && !mine.empty()) issue(0);
+                    for (size_t i = 0; i < mine.size() && e == cudaSuccess; ++i) {
+                        if (i + 1 < mine.size()) issue(i + 1);
+                        if (e == cudaSuccess) e = cudaEventSynchronize(ev[i & 1]);
+                        if (e == cudaSuccess) std::memcpy(chunks[mine[i]].dst, slot[i & 1], chunks[mine[i]].bytes);
+                    }
                 }
-                if (st) cudaStreamSynchronize(st);
+                if (st) {
+                    const cudaError_t e2 = cudaStreamSynchronize(st);
+                    if (e == cudaSuccess) e = e2;
+                }
                 for (int k = 0; k < 2; ++k)
                     if (ev[k]) cudaEventDestroy(ev[k]);
                 if (st) cudaStreamDestroy(st);
@@ -703,11 +724,14 @@ Err copy_back(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream) {
         }
         for (auto& th : pool) th.join();
         for (cudaError_t e : status)
-            if (e != cudaSuccess) return make_err(MCF_ERR_CUDA, "staged device->host copy failed: %s", cudaGetErrorString(e));
+            if (e != cudaSuccess)
+                return make_err(MCF_ERR_CUDA, "staged %s copy failed: %s", to_device ? "host->device" : "device->host",
+                                cudaGetErrorString(e));
     }
     CU(cudaStreamSynchronize(direct_stream));
     return Err();
 }
+Err copy_back(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream) { return stage_copies(jobs, direct_stream, false); }
 
 void host_fill_na(double* p, size_t n, int pack) {
     if (pack) {
@@ -924,6 +948,18 @@ Err run_bioclim_dev(const mcf_problem* p, const int32_t* const q[4], const int32
 }
 
 } // namespace
+
+// Internal services for the other translation units (mcf_snow.cu): device check + memory-pool retention, and the
+// staged host<->device copy pool above.  Declared in mcf_kernels.cuh.
+namespace mcf {
+int host_prepare_device(char* err, size_t errlen) { return report(device_info(), err, errlen); }
+int host_transfer(const HostXfer* jobs, int n, bool to_device, char* err, size_t errlen) {
+    std::lock_guard<std::mutex> ws_lock(g_ws_mu); // the pinned slots are shared with the grid solver's copy-back
+    std::vector<CopyJob> cj;
+    for (int i = 0; i < n; ++i) cj.push_back(CopyJob{(char*)jobs[i].dst, (const char*)jobs[i].src, jobs[i].bytes, nullptr});
+    return report(stage_copies(cj, nullptr, to_device), err, errlen);
+}
+} // namespace mcf
 
 // ------------------------------------------------------------------------------------------------
 // exported C ABI

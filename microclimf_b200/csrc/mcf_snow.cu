@@ -1152,33 +1152,51 @@ __global__ void __launch_bounds__(128) k_snowmicro_arr(const __grid_constant__ S
 #include <cstring>
 #include <vector>
 
+#include "mcf_host.h"
 #include "microclimf_b200.h"
 
 namespace {
 using namespace mcf::snow;
 
-struct DevBuf { // RAII device allocations of one call
+struct DevBuf { // RAII device allocations of one call, and its queue of host->device uploads
+    // Allocations are stream-ordered on the default stream, out of the device's default memory pool (kept between
+    // calls: host_prepare_device sets the release threshold).  Uploads are queued and sent in one batch by flush()
+    // through the copy pool of mcf_api.cu — R hands us pageable arrays as large as the outputs.
     std::vector<void*> ptrs;
+    std::vector<mcf::HostXfer> pend;
     ~DevBuf() {
-        for (void* p : ptrs) cudaFree(p);
+        for (void* p : ptrs) cudaFreeAsync(p, 0);
     }
     template <class T> cudaError_t up(const T* h, size_t n, const T** d) {
         *d = nullptr;
         if (!h) return cudaSuccess;
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+        cudaError_t e = cudaMallocAsync(&q, n * sizeof(T), 0);
         if (e != cudaSuccess) return e;
         ptrs.push_back(q);
         *d = (const T*)q;
-        return cudaMemcpy(q, h, n * sizeof(T), cudaMemcpyHostToDevice);
+        pend.push_back(mcf::HostXfer{q, h, n * sizeof(T)});
+        return cudaSuccess;
     }
     template <class T> cudaError_t alloc(T** d, size_t n) {
         void* q = nullptr;
-        cudaError_t e = cudaMalloc(&q, n * sizeof(T));
+        cudaError_t e = cudaMallocAsync(&q, n * sizeof(T), 0);
         if (e != cudaSuccess) return e;
         ptrs.push_back(q);
         *d = (T*)q;
         return cudaSuccess;
+    }
+    // sends the queued uploads; on return they have landed (the copy pool synchronises its streams)
+    int flush(char* err, size_t errlen) {
+        if (pend.empty()) return MCF_OK;
+        cudaError_t e = cudaStreamSynchronize(0); // the allocations are ordered on the default stream
+        if (e != cudaSuccess) {
+            if (err && errlen) snprintf(err, errlen, "%s", cudaGetErrorString(e));
+            return MCF_ERR_CUDA;
+        }
+        const int rc = mcf::host_transfer(pend.data(), (int)pend.size(), true, err, errlen);
+        pend.clear();
+        return rc;
     }
 };
 
@@ -1223,6 +1241,10 @@ int prep_hours(DevBuf& db, const mcf_snow_climate* c, const double* Gp, const do
     SCU(db.alloc(scal, 4));
     pa.hours = *hours;
     pa.scal = *scal;
+    {
+        const int rc = db.flush(err, errlen);
+        if (rc != MCF_OK) return rc;
+    }
     k_snow_prep<<<1, 256>>>(pa);
     SCU(cudaGetLastError());
     return MCF_OK;
@@ -1261,6 +1283,10 @@ static int gridmodelsnow_impl(bool arr, const mcf_snow_climate* clim, const mcf_
     if (st->rows <= 0 || st->cols <= 0 || clim->tsteps <= 0) return fail(MCF_ERR_ARG, "rows, cols, tsteps must be > 0", err, errlen);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(MCF_ERR_CUDA, "no CUDA device (there is no CPU fallback)", err, errlen);
+    {
+        const int rc0 = mcf::host_prepare_device(err, errlen);
+        if (rc0 != MCF_OK) return rc0;
+    }
     DevBuf db;
     SnowHour* hours = nullptr;
     double* scal = nullptr;
@@ -1303,15 +1329,20 @@ static int gridmodelsnow_impl(bool arr, const mcf_snow_climate* clim, const mcf_
     for (int v = 0; v < 4; ++v) SCU(db.alloc(&d2[v], nc));
     a.Tc = d3[0]; a.Tg = d3[1]; a.sdepc = d3[2]; a.sdepg = d3[3]; a.sden = d3[4];
     a.agec = d2[0]; a.ageg = d2[1]; a.meltc = d2[2]; a.meltg = d2[3];
+    {
+        const int rc = db.flush(err, errlen);
+        if (rc != MCF_OK) return rc;
+    }
     if (arr) k_snowmodel_arr<<<(unsigned)((nc + 127) / 128), 128>>>(a, ca);
     else k_snowmodel<<<(unsigned)((nc + 127) / 128), 128>>>(a);
     SCU(cudaGetLastError());
-    for (int v = 0; v < 5; ++v)
-        if (out3d[v]) SCU(cudaMemcpy(out3d[v], d3[v], nc * T * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int v = 0; v < 4; ++v)
-        if (out2d[v]) SCU(cudaMemcpy(out2d[v], d2[v], nc * sizeof(double), cudaMemcpyDeviceToHost));
     SCU(cudaDeviceSynchronize());
-    return MCF_OK;
+    std::vector<mcf::HostXfer> back;
+    for (int v = 0; v < 5; ++v)
+        if (out3d[v]) back.push_back(mcf::HostXfer{out3d[v], d3[v], nc * T * sizeof(double)});
+    for (int v = 0; v < 4; ++v)
+        if (out2d[v]) back.push_back(mcf::HostXfer{out2d[v], d2[v], nc * sizeof(double)});
+    return mcf::host_transfer(back.data(), (int)back.size(), false, err, errlen);
 }
 
 extern "C" int mcf_gridmodelsnow(const mcf_snow_climate* clim, const mcf_snow_point* pt, const mcf_snow_static* st,
@@ -1330,6 +1361,10 @@ static int gridmicrosnow_impl(bool arr, double reqhgt, const mcf_snow_climate* c
     if (st->rows <= 0 || st->cols <= 0 || clim->tsteps <= 0) return fail(MCF_ERR_ARG, "rows, cols, tsteps must be > 0", err, errlen);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(MCF_ERR_CUDA, "no CUDA device (there is no CPU fallback)", err, errlen);
+    {
+        const int rc0 = mcf::host_prepare_device(err, errlen);
+        if (rc0 != MCF_OK) return rc0;
+    }
     DevBuf db;
     SnowHour* hours = nullptr;
     double* scal = nullptr;
@@ -1376,13 +1411,18 @@ static int gridmicrosnow_impl(bool arr, double reqhgt, const mcf_snow_climate* c
             a.out[v] = const_cast<double*>(d);
         }
     }
+    {
+        const int rc = db.flush(err, errlen);
+        if (rc != MCF_OK) return rc;
+    }
     if (arr) k_snowmicro_arr<<<(unsigned)((nc + 127) / 128), 128>>>(a, ca);
     else k_snowmicro<<<(unsigned)((nc + 127) / 128), 128>>>(a);
     SCU(cudaGetLastError());
-    for (int v = 0; v < MCF_NOUT; ++v)
-        if (micro[v]) SCU(cudaMemcpy(micro[v], a.out[v], nc * T * sizeof(double), cudaMemcpyDeviceToHost));
     SCU(cudaDeviceSynchronize());
-    return MCF_OK;
+    std::vector<mcf::HostXfer> back;
+    for (int v = 0; v < MCF_NOUT; ++v)
+        if (micro[v]) back.push_back(mcf::HostXfer{micro[v], a.out[v], nc * T * sizeof(double)});
+    return mcf::host_transfer(back.data(), (int)back.size(), false, err, errlen);
 }
 
 extern "C" int mcf_gridmicrosnow(double reqhgt, const mcf_snow_climate* clim, const double* umu, const mcf_snow_state* sm,

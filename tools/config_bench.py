@@ -51,7 +51,7 @@ def case_snow(rows, cols, T):
         r = snow.gridmodelsnow1(s["obstime"], s["climdata"], s["pointm"], s["vegp"], s["other"], "Alpine")
         t1 = time.perf_counter()
     snowm = dict(Tc=r["Tc"], Tg=r["Tg"], totalSWE=np.nan_to_num(r["sdepc"] * r["sden"]), groundsnowdepth=r["sdepg"], snowden=r["sden"])
-    micro = {n: np.zeros(r["Tc"].shape) for n in ("Tz", "tleaf", "relhum", "soilm", "windspeed", "Rdirdown", "Rdifdown", "Rlwdown", "Rswup", "Rlwup")}
+    micro = {n: np.zeros(r["Tc"].shape, order="F") for n in ("Tz", "tleaf", "relhum", "soilm", "windspeed", "Rdirdown", "Rdifdown", "Rlwdown", "Rswup", "Rlwup")}
     for rep in range(2):
         t2 = time.perf_counter()
         snow.gridmicrosnow1(0.05, s["obstime"], s["climdata"], snowm, micro, s["vegp"], s["other"], 3.0, [True] * 10)
