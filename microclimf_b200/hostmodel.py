@@ -670,7 +670,11 @@ def prepare_model_a(micropointa, vegp, soilc, dtm, dtmc, reqhgt: float = 0.05, r
     vg, sc, dfsel, layered = _static_layers(vegp, soilc, dtm, last, reqhgt, pai_a, slr, apr, hor, twi, wsa, svf,
                                             last.zref, zero_pairs=False)
     if layered:
-        p.mode, p.nlyr = 4, vg["pai"].shape[2]
+        # .sortvegp can hand over more layers than dfsel has rows (short series, R/internal.R:262-270); the drivers
+        # index layers 0 .. nrow(dfsel) - 1 only
+        nl = min(vg["pai"].shape[2], len(dfsel["st"]))
+        vg = {k: (v[:, :, :nl] if np.ndim(v) == 3 else v) for k, v in vg.items()}
+        p.mode, p.nlyr = 4, nl
         p.lyr_st, p.lyr_ed = dfsel["st"], dfsel["ed"]
     for k, v in vg.items():
         p.set(k, v)
@@ -696,11 +700,16 @@ def runmicro(micropoint, reqhgt, vegp, soilc, dtm, dtmc=None, altcorrect=0, snow
     (dict of [rows, cols, hours] arrays) plus `tme`.  As in the reference, `svf` and `method` are accepted
     but not forwarded (R/internal.R:3336).  A list of micropoints (runpointmodela) with `dtmc` takes the gridded-climate path
     (`.runmodel2Cpp` / `.runmodel4Cpp` -> prepare_model_a); `snow = TRUE` with a data.frame micropoint and `snowmod` (snowmodel1's output)
-    takes `.runmicrosnow1` (runmicrosnow1); gridded-climate snow is not built yet.
+    takes `.runmicrosnow1` (runmicrosnow1), with a list of micropoints and `dtmc` `.runmicrosnow2` (runmicrosnow2).
     `packed = True` (an addition) returns writetonc's integer packing straight from the kernels."""
     if snow:
         if not isinstance(micropoint, Micropoint):
-            raise NotImplementedError("snow = TRUE with gridded climate (.runmicrosnow2 / gridmicrosnow2) is not built yet")
+            if dtmc is None:
+                raise ValueError("Require dtmc. Please provide\n")
+            mout = runmicrosnow2(micropoint, reqhgt, vegp, soilc, dtm, dtmc, snowmod, altcorrect, runchecks, pai_a, tfact, out,
+                                 slr, apr, hor, twi, wsa, svf)
+            mout["tme"] = np.asarray(next(m for m in micropoint if m is not None).tmeorig)
+            return mout
         mout = runmicrosnow1(micropoint, reqhgt, vegp, soilc, dtm, snowmod, runchecks, pai_a, tfact, out, slr, apr, hor, twi,
                              wsa, svf)
         mout["tme"] = np.asarray(micropoint.tmeorig)
@@ -834,6 +843,56 @@ def _tpicalc(af: int, me: int, dtm: Raster, tfact: float) -> np.ndarray:
     return tpic / np.nanmean(tpic)
 
 
+def _snow_chunks(op, ot, clim_of, point_of, wss_of, umu, dtm, vg, other, snowenv, snowinitd, tfact, zref, chunk_days,
+                 smooth_shelter, af_floor=None):
+    """The 5-day chunk loop shared by .snowmodel1 (R/internal.R:2553-2613) and .snowmodel2 (:2948-3006): terrain of
+    DTM + ground snow depth before each chunk (slope/aspect in numpy, horizons / sky view / wind shelter as GPU
+    stencils), the grid snow operator, then the topographic redistribution of fresh snow.  `clim_of(s)`, `point_of(s)`
+    slice the operator's climate and point-model inputs to the chunk's hours, `wss_of(s)` gives its wind speeds."""
+    z = dtm.matrix()
+    h = ot["hour"].size
+    span = 24 * chunk_days
+    nchunks = h // span
+    shape = z.shape + (h,)
+    Tc, Tg, snowdepg, swe, sden = (np.full(shape, np.nan) for _ in range(5))
+    dtms = dtm.like(z + (z * 0 + snowinitd) * 0.5)
+    for ch in range(nchunks):
+        sl = terrain(dtms, "slope").matrix()
+        sl[np.isnan(sl)] = 0
+        other["slope"] = mask(dtm.like(sl), dtm).matrix()
+        ap = terrain(dtms, "aspect").matrix()
+        ap[np.isnan(ap)] = 180
+        other["aspect"] = mask(dtm.like(ap), dtm).matrix()
+        other["hor"], other["skyview"] = api.horizon(dtms.matrix(), dtm.res[0], want_svf=True)
+        other["wsa"] = _windsheltera(dtms, zref, 10 if smooth_shelter else 1)
+        s = slice(ch * span, min((ch + 1) * span, h))
+        ns = s.stop - s.start
+        smod = op({k: v[s] for k, v in ot.items()}, clim_of(s), point_of(s), vg, other, snowenv)
+        # topographic snow redistribution (R/internal.R:2584-2599 / :2977-2992)
+        tpr = 10 * np.mean(wss_of(s)) ** 0.5
+        af = int(round(tpr / dtm.res[0]))
+        if af_floor is not None and af < af_floor:  # only .snowmodel2 floors the radius (R/internal.R:2980)
+            af = af_floor
+        tpi = _tpicalc(af, min(dtm.nrows, dtm.ncols), dtms, tfact)
+        asd = np.repeat(other["isnowdg"][:, :, None], ns, axis=2)
+        dsnow = smod["sdepg"] - asd
+        dsnow2 = dsnow * tpi[:, :, None]
+        with np.errstate(invalid="ignore"):
+            dsnow2 = np.where(dsnow < 0, dsnow, dsnow2)
+        asc = np.repeat(other["isnowdc"][:, :, None], ns, axis=2)
+        cdsnow = smod["sdepc"] - asc - dsnow
+        Tc[:, :, s], Tg[:, :, s], sden[:, :, s] = smod["Tc"], smod["Tg"], smod["sden"]
+        swe[:, :, s] = (asc + cdsnow + dsnow2) * smod["sden"]
+        snowdepg[:, :, s] = asd + dsnow2
+        other["isnowdc"] = (asc + cdsnow + dsnow2)[:, :, -1]
+        # `other$isnowac <- (asd + dsnow2)[,,n]` is immediately overwritten by the ages and isnowdg is never advanced
+        # (R/internal.R:2606-2609, :2999-3002): reproduced
+        other["isnowac"] = np.nan_to_num(smod["agec"]).astype(np.int32)
+        other["isnowag"] = np.nan_to_num(smod["ageg"]).astype(np.int32)
+        dtms = dtm.like(z + snowdepg[:, :, s.stop - 1])
+    return dict(Tc=Tc, Tg=Tg, groundsnowdepth=snowdepg, totalSWE=swe, snowden=sden, umu=umu)
+
+
 def snowmodel1(weather, pointm, dtm, vegp, soilc, snowenv: str = "Taiga", snowinitd: float = 0, snowinita: float = 0,
                zref: float = 2, tfact: float = 0.02, chunk_days: int = 5, operator=None):
     """ref .snowmodel1 (R/internal.R:2498-2616) from the point where the point snow model has run: `pointm` is the
@@ -856,48 +915,56 @@ def snowmodel1(weather, pointm, dtm, vegp, soilc, snowenv: str = "Taiga", snowin
     vg = _sortl(vegp, np.asarray(pointm["sdepc"])[:tme.size])
     other = dict(zref=float(zref), lat=lat, lon=lon, isnowdc=sdep, isnowac=np.nan_to_num(sage).astype(np.int32),
                  isnowdg=sdep * 0.5, isnowag=np.nan_to_num(sage).astype(np.int32))
-    h = tme.size
-    span = 24 * chunk_days
-    nchunks = h // span
-    shape = z.shape + (h,)
-    Tc, Tg, snowdepg, swe, sden = (np.full(shape, np.nan) for _ in range(5))
-    dtms = dtm.like(z + sdep * 0.5)
     climcols = ("temp", "relhum", "pres", "swdown", "difrad", "lwdown", "windspeed", "winddir", "precip")
-    for ch in range(nchunks):
-        sl = terrain(dtms, "slope").matrix()
-        sl[np.isnan(sl)] = 0
-        other["slope"] = mask(dtm.like(sl), dtm).matrix()
-        ap = terrain(dtms, "aspect").matrix()
-        ap[np.isnan(ap)] = 180
-        other["aspect"] = mask(dtm.like(ap), dtm).matrix()
-        other["hor"], other["skyview"] = api.horizon(dtms.matrix(), dtm.res[0], want_svf=True)
-        other["wsa"] = _windsheltera(dtms, zref, 10 if dtm.res[0] <= 100 else 1)
-        s = slice(ch * span, min((ch + 1) * span, h))
-        ns = s.stop - s.start
-        smod = op({k: v[s] for k, v in ot.items()}, {k: np.asarray(weather[k], dtype=np.float64)[s] for k in climcols},
-                  {k: np.asarray(pointm[k], dtype=np.float64)[s] for k in ("Gp", "Tc", "RswabsG", "RlwabsG", "umu", "tr")},
-                  vg, other, snowenv)
-        # topographic snow redistribution (R/internal.R:2584-2599)
-        tpr = 10 * np.mean(np.asarray(weather["windspeed"], dtype=np.float64)[s]) ** 0.5
-        af = int(round(tpr / dtm.res[0]))
-        tpi = _tpicalc(af, min(dtm.nrows, dtm.ncols), dtms, tfact)
-        asd = np.repeat(other["isnowdg"][:, :, None], ns, axis=2)
-        dsnow = smod["sdepg"] - asd
-        dsnow2 = dsnow * tpi[:, :, None]
-        with np.errstate(invalid="ignore"):
-            dsnow2 = np.where(dsnow < 0, dsnow, dsnow2)
-        asc = np.repeat(other["isnowdc"][:, :, None], ns, axis=2)
-        cdsnow = smod["sdepc"] - asc - dsnow
-        Tc[:, :, s], Tg[:, :, s], sden[:, :, s] = smod["Tc"], smod["Tg"], smod["sden"]
-        swe[:, :, s] = (asc + cdsnow + dsnow2) * smod["sden"]
-        snowdepg[:, :, s] = asd + dsnow2
-        other["isnowdc"] = (asc + cdsnow + dsnow2)[:, :, -1]
-        # `other$isnowac <- (asd + dsnow2)[,,n]` is immediately overwritten by the ages and isnowdg is never advanced
-        # (R/internal.R:2606-2609): reproduced
-        other["isnowac"] = np.nan_to_num(smod["agec"]).astype(np.int32)
-        other["isnowag"] = np.nan_to_num(smod["ageg"]).astype(np.int32)
-        dtms = dtm.like(z + snowdepg[:, :, s.stop - 1])
-    return dict(Tc=Tc, Tg=Tg, groundsnowdepth=snowdepg, totalSWE=swe, snowden=sden, umu=np.asarray(pointm["umu"]))
+    wind = np.asarray(weather["windspeed"], dtype=np.float64)
+    return _snow_chunks(op, ot,
+                        lambda s: {k: np.asarray(weather[k], dtype=np.float64)[s] for k in climcols},
+                        lambda s: {k: np.asarray(pointm[k], dtype=np.float64)[s]
+                                   for k in ("Gp", "Tc", "RswabsG", "RlwabsG", "umu", "tr")},
+                        lambda s: wind[s], np.asarray(pointm["umu"]), dtm, vg, other, snowenv, snowinitd, tfact, zref,
+                        chunk_days, dtm.res[0] <= 100)
+
+
+def snowmodel2(climdata, pointm, tme, dtm, vegp, soilc, sdept, wuv, wvv, coarse_dims=(10, 10), snowenv: str = "Taiga",
+               snowinitd: float = 0, snowinita: float = 0, zref: float = 2, tfact: float = 0.02, chunk_days: int = 5,
+               operator=None):
+    """ref .snowmodel2 (R/internal.R:2780-3015) from the point where the per-coarse-cell point snow models have run
+    and their series have been resampled to the DTM (:2866-2933; `.cca` + terra::resample — spatial.resample_bilinear
+    here — and the altitude correction are the caller's, as is pointmodelsnow itself).
+
+    `climdata`: temp, relhum, pres, swdown, difrad, lwdown, windspeed, precip as [rows, cols, hours] arrays and
+    winddir [hours]; `pointm`: Gp, Tc, RswabsG, RlwabsG, umu, tr as [rows, cols, hours]; `sdept`: the hourly maximum of
+    the point models' canopy snow depth (selects the vegetation layers, :2936-2938); `wuv`, `wvv`: the coarse grid's
+    mean wind components per hour (:2918-2919, they set the redistribution radius); `coarse_dims`: rows, cols of the
+    climate grid (wind shelter is smoothed only when both are >= 10, :2963-2964).  Returns .snowmodel2's list, masked by
+    the DTM (.cleansmod, :3811)."""
+    from . import snow as snowops
+
+    op = operator or snowops.gridmodelsnow2
+    dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
+    tme = np.asarray(tme).astype("datetime64[s]")
+    ot = _obstime(tme)
+    ot["hour"] = np.floor(ot["hour"])
+    z = dtm.matrix()
+    sdep = z * 0 + snowinitd
+    sage = z * 0 + snowinita
+    vg = _sortl(vegp, np.asarray(sdept)[:tme.size])
+    vg["leaft"] = np.where(np.isnan(vg["leaft"]), 0.001, vg["leaft"])  # :2971
+    lats, lons = latslons_from_raster(dtm)
+    other = dict(zref=float(zref), lats=lats, lons=lons, isnowdc=sdep, isnowac=np.nan_to_num(sage).astype(np.int32),
+                 isnowdg=sdep * 0.5, isnowag=np.nan_to_num(sage).astype(np.int32))
+    arr3 = ("temp", "relhum", "pres", "swdown", "difrad", "lwdown", "windspeed", "precip")
+    clim = {k: np.asarray(climdata[k], dtype=np.float64) for k in arr3}
+    wdir = np.asarray(climdata["winddir"], dtype=np.float64)
+    pnt = {k: np.asarray(pointm[k], dtype=np.float64) for k in ("Gp", "Tc", "RswabsG", "RlwabsG", "umu", "tr")}
+    wss = np.sqrt(np.asarray(wuv, dtype=np.float64) ** 2 + np.asarray(wvv, dtype=np.float64) ** 2)
+    out = _snow_chunks(op, ot,
+                       lambda s: dict({k: v[:, :, s] for k, v in clim.items()}, winddir=wdir[s]),
+                       lambda s: {k: v[:, :, s] for k, v in pnt.items()},
+                       lambda s: wss[s], pnt["umu"], dtm, vg, other, snowenv, snowinitd, tfact, zref, chunk_days,
+                       dtm.res[0] <= 100 and min(coarse_dims) >= 10, af_floor=2)
+    land = ~np.isnan(z)
+    return {k: np.where(land[:, :, None], v, np.nan) for k, v in out.items()}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -950,20 +1017,7 @@ def runmicrosnow1(micropoint: Micropoint, reqhgt, vegp, soilc, dtm, smod, runche
 
     op = snow_operator or snowops.gridmicrosnow1
     dtm_r = as_raster(dtm)
-    smod = dict(smod)
-    swe = np.array(smod["totalSWE"], dtype=np.float64)
-    swe[np.isnan(swe)] = 0
-    swe[np.isnan(dtm_r.matrix()), :] = np.nan  # mask(totalSWE, dtm)
-    smod["totalSWE"] = swe
-    # applycpp3 min / max over space per hour (src/microclimfCpp.cpp:5553) and snowdaysfun (:5531)
-    with np.errstate(all="ignore"):
-        minsnow = np.nanmin(swe, axis=(0, 1))
-        maxsnow = np.nanmax(swe, axis=(0, 1))
-    ndays = swe.shape[2] // 24
-    snowflag = (maxsnow[:ndays * 24].reshape(ndays, 24) > 0.0).any(axis=1)
-    nosnowflag = (minsnow[:ndays * 24].reshape(ndays, 24) == 0.0).any(axis=1)
-    v = np.arange(1, ndays + 1)
-    snowdays, nosnowdays = v[snowflag], v[nosnowflag]
+    smod, snowdays, nosnowdays = _snow_day_sets(smod, dtm_r)
     micropoints = subsetpointmodel(micropoint, days=snowdays) if snowdays.size else None
     if nosnowdays.size:
         micropointn = subsetpointmodel(micropoint, days=nosnowdays)
@@ -1003,7 +1057,47 @@ def runmicrosnow1(micropoint: Micropoint, reqhgt, vegp, soilc, dtm, smod, runche
                     else np.asarray(wsa, dtype=np.float64))
     other["lat"], other["lon"], other["zref"] = lat, lon, micropoints.zref  # `ll$lon` is NULL in R (the column is `long`)
     other["Smax"] = _soilinit(soilc_u)["Smax"]
-    # blank micro seeded with the no-snow model on days present in both sets
+    micros = _seed_snow_micro(moutn, snowdays, nosnowdays)
+    smods = subsetsnowmodel(smod, ai)
+    outm = _snow_out_mask(out, reqhgt, micros)
+    mouts = op(reqhgt, obstime, climdata, smods, micros, vg, other, micropoint.matemp, outm)
+    if not nosnowdays.size:
+        return mouts
+    return _merge_snow_days(moutn, mouts, snowdays, nosnowdays)
+
+
+# ---------------------------------------------------------------------------------------------
+# runmicro(snow = TRUE), gridded climate: .runmicrosnow2
+# ---------------------------------------------------------------------------------------------
+def subsetpointmodela(pointmodela, tstep: str = "month", what: str = "tmax", days=None):
+    """ref subsetpointmodela (R/dataprep.R:114-133): every point model of the coarse grid subset to the same days,
+    chosen on the grid-mean canopy temperature."""
+    live = [mp for mp in pointmodela if mp is not None]
+    Tc = sum(np.asarray(mp.dfo["Tc"], dtype=np.float64) for mp in live) / len(live)
+    return [None if mp is None else subsetpointmodel(mp, tstep, what, days, Tc=Tc) for mp in pointmodela]
+
+
+def _snow_day_sets(smod, dtm_r):
+    """Days with snow somewhere / without snow somewhere (applycpp3 min / max over space per hour,
+    src/microclimfCpp.cpp:5553, and snowdaysfun :5531) from the masked total SWE; returns the cleaned snow model too."""
+    smod = dict(smod)
+    swe = np.array(smod["totalSWE"], dtype=np.float64)
+    swe[np.isnan(swe)] = 0
+    swe[np.isnan(dtm_r.matrix()), :] = np.nan  # mask(totalSWE, dtm)
+    smod["totalSWE"] = swe
+    with np.errstate(all="ignore"):
+        minsnow = np.nanmin(swe, axis=(0, 1))
+        maxsnow = np.nanmax(swe, axis=(0, 1))
+    ndays = swe.shape[2] // 24
+    snowflag = (maxsnow[:ndays * 24].reshape(ndays, 24) > 0.0).any(axis=1)
+    nosnowflag = (minsnow[:ndays * 24].reshape(ndays, 24) == 0.0).any(axis=1)
+    v = np.arange(1, ndays + 1)
+    return smod, v[snowflag], v[nosnowflag]
+
+
+def _seed_snow_micro(moutn, snowdays, nosnowdays):
+    """Blank [rows, cols, snow hours] arrays seeded with the snow-free model on days present in both sets
+    (R/internal.R:3430-3443 / :3561-3577)."""
     t1 = snowdays.size * 24
     s1 = np.arange(t1)[np.repeat(np.isin(snowdays, nosnowdays), 24)]
     s2 = np.arange(nosnowdays.size * 24)[np.repeat(np.isin(nosnowdays, snowdays), 24)]
@@ -1012,18 +1106,11 @@ def runmicrosnow1(micropoint: Micropoint, reqhgt, vegp, soilc, dtm, smod, runche
         vv = np.full(a.shape[:2] + (t1,), np.nan)
         vv[:, :, s1] = a[:, :, s2]
         micros[k] = vv
-    smods = subsetsnowmodel(smod, ai)
-    outm = [bool(o) for o in out]
-    if reqhgt == 0:
-        outm = [i in (0, 3, 5, 6, 7, 8, 9) for i in range(10)]
-    elif reqhgt < 0:
-        outm = [i in (0, 3) for i in range(10)]
-    names = ("Tz", "tleaf", "relhum", "soilm", "windspeed", "Rdirdown", "Rdifdown", "Rlwdown", "Rswup", "Rlwup")
-    outm = [o and (n in micros) for o, n in zip(outm, names)]
-    mouts = op(reqhgt, obstime, climdata, smods, micros, vg, other, micropoint.matemp, outm)
-    if not nosnowdays.size:
-        return mouts
-    # ---- merge by day (R/internal.R:3634-3656)
+    return micros
+
+
+def _merge_snow_days(moutn, mouts, snowdays, nosnowdays):
+    """ref R/internal.R:3634-3656 / :3717-3742: snow days from the snow operator, the other days from the ordinary model."""
     nosnow = np.setdiff1d(np.union1d(snowdays, nosnowdays), snowdays)
     s1 = np.arange(next(iter(moutn.values())).shape[2])[np.repeat(np.isin(nosnowdays, nosnow), 24)]
     nosnowh, snowh = _hours_of_days(nosnow) - 1, _hours_of_days(snowdays) - 1
@@ -1036,6 +1123,135 @@ def runmicrosnow1(micropoint: Micropoint, reqhgt, vegp, soilc, dtm, smod, runche
             m[:, :, snowh] = mouts[k]
         mout[k] = m
     return mout
+
+
+def _snow_out_mask(out, reqhgt, micros):
+    outm = [bool(o) for o in out]
+    if reqhgt == 0:
+        outm = [i in (0, 3, 5, 6, 7, 8, 9) for i in range(10)]
+    elif reqhgt < 0:
+        outm = [i in (0, 3) for i in range(10)]
+    names = ("Tz", "tleaf", "relhum", "soilm", "windspeed", "Rdirdown", "Rdifdown", "Rlwdown", "Rswup", "Rlwup")
+    return [o and (n in micros) for o, n in zip(outm, names)]
+
+
+def prepsnowinputs2(reqhgt, dtm, dtmc, vegp, soilc, micropoints, altcorrect, runchecks, snowdays, nosnowdays, moutn,
+                    slr=None, apr=None, hor=None, svf=None, wsa=None, pai_a=None):
+    """ref .prepsnowinputs2 (R/internal.R:3445-3579): the fine-raster [rows, cols, hours] climate arrays gridmicrosnow2
+    takes (`.cca` + terra::resample of every series of the coarse grid, with the altitude correction of pressure and
+    temperature), the snow-hour vegetation averages, terrain layers and the seeded blank microclimate arrays."""
+    dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
+    dtmc = as_raster(dtmc)
+    cr, cc = dtmc.nrows, dtmc.ncols
+    weathers, last = [], None
+    for mp in micropoints:
+        if mp is None:
+            weathers.append(None)
+            continue
+        w = mp.weather
+        if runchecks:
+            rc = checkinputs(w, vegp, soilc, dtm, mp.zref)
+            w, vegp, soilc = rc["weather"], rc["vegp"], rc["soilc"]
+        weathers.append(w)
+        last = mp
+    if last is None:
+        raise ValueError("micropoints holds no point-model output")
+    obstime = _obstime(last.weather["obs_time"])
+    h = len(last.weather["temp"])
+
+    def cca(series):
+        a = np.full((cr, cc, h), np.nan)
+        k = 0
+        for i in range(cr):
+            for j in range(cc):
+                if micropoints[k] is not None:
+                    a[i, j, :] = np.asarray(series(k), dtype=np.float64)
+                k += 1
+        return a
+
+    fine = lambda a: resample_bilinear(dtmc.like(a), dtm).values  # noqa: E731  .cca(..., dtmc, dtm)
+    wv_ = lambda name: cca(lambda k: weathers[k][name])  # noqa: E731
+    tc, pk, rh = wv_("temp"), wv_("pres"), wv_("relhum")
+    ea = fine(_satvap(tc) * (rh / 100))
+    clim: Dict[str, np.ndarray] = {"temp": fine(tc)}
+    if altcorrect == 0:
+        clim["pres"] = fine(pk)
+    else:
+        zc = dtmc.matrix().copy()
+        zc[np.isnan(zc)] = 0.0
+        zf = dtm.matrix()
+        psl = fine(pk / (((293 - 0.0065 * zc[:, :, None]) / 293) ** 5.26))
+        clim["pres"] = psl * (((293 - 0.0065 * zf[:, :, None]) / 293) ** 5.26)
+        elevd = (resample_bilinear(dtmc.like(zc), dtm).matrix() - zf)[:, :, None]
+        if altcorrect == 1:
+            tcdif = elevd * (5 / 1000)
+        else:  # .lapserate (R/internal.R:546-553)
+            tk = clim["temp"] + 273.15
+            rv = 0.622 * ea / (clim["pres"] - ea)
+            lr = 9.8076 * (1 + (2501000 * rv) / (287 * tk)) / (1003.5 + (0.622 * 2501000 ** 2 * rv) / (287 * tk ** 2))
+            tcdif = lr * elevd
+        clim["temp"] = tcdif + clim["temp"]
+    with np.errstate(invalid="ignore"):
+        clim["relhum"] = np.clip((ea / _satvap(clim["temp"])) * 100, 20, 100)
+    for k in ("swdown", "difrad", "lwdown"):
+        clim[k] = fine(wv_(k))
+    u2, wd = wv_("windspeed"), wv_("winddir")
+    wu, wvc = u2 * np.cos(wd * np.pi / 180), u2 * np.sin(wd * np.pi / 180)
+    clim["windspeed"] = np.sqrt(fine(wu) ** 2 + fine(wvc) ** 2)
+    clim["winddir"] = np.mod(np.arctan2(np.nanmean(wvc, axis=(0, 1)), np.nanmean(wu, axis=(0, 1))) * 180 / np.pi, 360)
+    clim["precip"] = fine(wv_("precip"))  # `climdata$prec` in the reference; the operator does not read it
+    clim["umu"] = fine(cca(lambda k: micropoints[k].dfo["umu"]))
+    sdept = np.zeros(len(last.tmeorig))
+    sdept[np.asarray(last.subs, dtype=int) - 1] = 1
+    vg = _sortl2(vegp, sdept, reqhgt, pai_a)
+    other: Dict[str, object] = {}
+    other["slope"] = (terrain(dtm, "slope") if slr is None else as_raster(slr, dtm)).matrix()
+    other["aspect"] = (terrain(dtm, "aspect") if apr is None else as_raster(apr, dtm)).matrix()
+    if hor is None:
+        other["hor"], sv = api.horizon(dtm.matrix(), dtm.res[0], want_svf=True)
+    else:
+        other["hor"] = np.asarray(hor, dtype=np.float64)
+        sv = 0.5 * np.cos(2 * np.tan(np.mean(np.arctan(other["hor"]), axis=2))) + 0.5
+    other["skyview"] = sv if svf is None else as_raster(svf, dtm).matrix()
+    other["wsa"] = (_windsheltera(dtm, last.zref, 10 if dtm.res[0] <= 100 else 1) if wsa is None
+                    else np.asarray(wsa, dtype=np.float64))
+    other["lats"], other["lons"] = latslons_from_raster(dtm)
+    other["zref"] = last.zref
+    other["Smax"] = _soilinit(soilc)["Smax"]
+    return dict(obstime=obstime, weather=clim, micro=_seed_snow_micro(moutn, snowdays, nosnowdays), vegp=vg, other=other)
+
+
+def runmicrosnow2(micropoint, reqhgt, vegp, soilc, dtm, dtmc, smod, altcorrect=0, runchecks=True, pai_a=None, tfact=1.5,
+                  out=(True,) * 10, slr=None, apr=None, hor=None, twi=None, wsa=None, svf=None, snow_operator=None):
+    """ref .runmicrosnow2 (R/internal.R:3661-3745): runmicro(snow = TRUE) with gridded climate.  `micropoint` is
+    runpointmodela's list (one Micropoint or None per cell of `dtmc`), `smod` the snow model's output (snowmodel2).
+    Days without snow anywhere go through the gridded-climate grid model (prepare_model_a: coarse arrays interpolated
+    in the kernels), days with snow somewhere through gridmicrosnow2 on the fine arrays prepsnowinputs2 builds."""
+    from . import snow as snowops
+
+    op = snow_operator or snowops.gridmicrosnow2
+    dtm_r = as_raster(dtm)
+    smod, snowdays, nosnowdays = _snow_day_sets(smod, dtm_r)
+    micropoints = subsetpointmodela(micropoint, days=snowdays) if snowdays.size else None
+    matemp = float(np.mean([mp.matemp for mp in micropoint if mp is not None]))
+    if nosnowdays.size:
+        micropointn = subsetpointmodela(micropoint, days=nosnowdays)
+        moutn = prepare_model_a(micropointn, vegp, soilc, dtm, dtmc, reqhgt, runchecks, altcorrect, pai_a, tfact, out, slr,
+                                apr, hor, twi, wsa).run()
+    else:  # .createblanktemplate2
+        micropointn = subsetpointmodela(micropoint, days=[1])
+        moutn = prepare_model_a(micropointn, vegp, soilc, dtm, dtmc, reqhgt, False, 0, None, 1.5, out).run()
+        moutn = {k: a * np.nan for k, a in moutn.items()}
+    if not snowdays.size:
+        return moutn
+    sin = prepsnowinputs2(reqhgt, dtm, dtmc, vegp, soilc, micropoints, altcorrect, runchecks, snowdays, nosnowdays, moutn,
+                          slr, apr, hor, svf, wsa, pai_a)
+    smods = subsetsnowmodel(smod, _hours_of_days(snowdays))
+    outm = _snow_out_mask(out, reqhgt, sin["micro"])
+    mouts = op(reqhgt, sin["obstime"], sin["weather"], smods, sin["micro"], sin["vegp"], sin["other"], matemp, outm)
+    if not nosnowdays.size:
+        return mouts
+    return _merge_snow_days(moutn, mouts, snowdays, nosnowdays)
 
 
 # ---------------------------------------------------------------------------------------------

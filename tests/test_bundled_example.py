@@ -319,3 +319,63 @@ def test_runbioclim_bundled():
     land = ~np.isnan(dtm.matrix())
     assert np.isfinite(got["bio1"][land]).all() and 5 < np.nanmean(got["bio1"]) < 20   # annual mean temperature, Cornwall
     assert np.all(got["bio5"][land] >= got["bio6"][land])
+
+
+# --------------------------------------------------------------------------------------------- gridded climate
+def _micropointa(mp, dtm, cr=2, cc=2):
+    """A runpointmodela-like list: the bundled point model perturbed per coarse cell (row by row, terra order)."""
+    from microclimf_b200.spatial import aggregate_mean
+    dtmc = aggregate_mean(dtm.like(np.where(np.isnan(dtm.values), 0.0, dtm.values)), dtm.nrows // cr)
+    out = []
+    for k in range(cr * cc):
+        w = {n: np.array(v) for n, v in mp.weather.items()}
+        w["temp"] = w["temp"] + 0.4 * k
+        w["relhum"] = np.clip(w["relhum"] - 2.0 * k, 10, 100)
+        w["windspeed"] = w["windspeed"] * (1 + 0.05 * k)
+        w["winddir"] = np.mod(w["winddir"] + 10.0 * k, 360)
+        dfo = {n: np.array(v) for n, v in mp.dfo.items()}
+        dfo["G"] = dfo["G"] * (1 + 0.03 * k)
+        dfo["Tg"] = dfo["Tg"] + 0.3 * k
+        out.append(Micropoint(weather=w, dfo=dfo, Tbz=mp.Tbz, lat=mp.lat, long=mp.long, zref=mp.zref, subs=mp.subs,
+                              tmeorig=mp.tmeorig, matemp=mp.matemp + 0.4 * k))
+    return out, dtmc
+
+
+def test_gridded_climate_mapping_cpu():
+    """prepare_model_a places fine cell centres on the coarse grid as terra::resample does."""
+    from microclimf_b200.spatial import resample_bilinear
+    from oracle import prep_oracle
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, days=[172])
+    mpa, dtmc = _micropointa(sub, dtm)
+    hor, wsa = cpu_terrain(dtm, mp.zref)
+    twi = dtm.like(np.where(np.isnan(dtm.matrix()), np.nan, 5.0))
+    call = hostmodel.prepare_model_a(mpa, vegp, soilc, dtm, dtmc, reqhgt=0.05, altcorrect=2, hor=hor, wsa=wsa, twi=twi)
+    p = call.prob
+    assert (p.mode, p.clim_rows, p.clim_cols, p.nlyr) == (4, 2, 2, 1) or p.mode == 4
+    tc = p.arrays["temp"].reshape(p.tsteps, 2, 2)  # [k, cj, ci]
+    want = resample_bilinear(dtmc.like(tc[5].T), dtm).matrix()
+    got = prep_oracle.resample(p, p.arrays["temp"])[5].reshape(dtm.ncols, dtm.nrows).T
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12)
+    assert np.isclose(p.mat, mp.matemp + 0.4 * 1.5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("altcorrect", [0, 2])
+def test_gridded_climate_runmicro(altcorrect):
+    """runmicro with a list of micropoints and dtmc (R/Cppwrappers.R:389-391 -> .runmodel4Cpp): the kernels' fused
+    expansion against the compiled reference on the arrays .runmodel4Cpp would have built."""
+    from oracle import prep_oracle
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, days=[30, 172])
+    mpa, dtmc = _micropointa(sub, dtm)
+    call = hostmodel.prepare_model_a(mpa, vegp, soilc, dtm, dtmc, reqhgt=0.05, altcorrect=altcorrect)
+    got = call.run()
+    want = pyoracle.runmicro(prep_oracle.materialise_coarse(call.prob), out_mask=call.args["out"],
+                             kind="ref" if pyoracle.have_ref() else "oracle")
+    ok, rows = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rows)
+    mout = hostmodel.runmicro(mpa, 0.05, vegp, soilc, dtm, dtmc=dtmc, altcorrect=altcorrect)
+    assert np.array_equal(mout["Tz"], got["Tz"], equal_nan=True)
+    with pytest.raises(ValueError, match="Require dtmc"):
+        hostmodel.runmicro(mpa, 0.05, vegp, soilc, dtm)

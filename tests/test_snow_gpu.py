@@ -169,3 +169,84 @@ def test_array_climate_snow_parity():
         g = snow.gridmicrosnow2(reqhgt, s["obstime"], clim, snowm, micro, s["vegp"], other, 3.0, [True] * 10)
         ok, rws = parity.compare(g, w)
         assert ok, "\n" + parity.fmt(rws)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_snowmodel2_chunk_driver_matches_reference_operator():
+    """hostmodel.snowmodel2 (the 5-day chunk loop of .snowmodel2, R/internal.R:2948-3010, on fine-raster climate arrays)
+    driven by the CUDA gridmodelsnow2 and by the compiled reference's: same terrain updates, redistribution radius floor
+    and DTM mask."""
+    from microclimf_b200 import hostmodel
+    from microclimf_b200.spatial import Raster
+    rows, cols, days = 24, 20, 10
+    T = 24 * days
+    s = synth.make_snow_inputs(rows, cols, T, seed=23)
+    clim, pointm, _ = _array_inputs(s, rows, cols)
+    rng = np.random.default_rng(5)
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    z = 250 + 30 * np.sin(ii / 4.0) * np.cos(jj / 5.0) + rng.normal(0, 0.5, (rows, cols))
+    z[0, :3] = np.nan  # sea cells: masked in the result (.cleansmod)
+    crs = ('PROJCRS["OSGB36 / British National Grid",BASEGEOGCRS["OSGB36",DATUM["Ordnance Survey of Great Britain 1936",'
+           'ELLIPSOID["Airy 1830",6377563.396,299.3249646]]],CONVERSION["British National Grid",METHOD["Transverse Mercator"],'
+           'PARAMETER["Latitude of natural origin",49],PARAMETER["Longitude of natural origin",-2],'
+           'PARAMETER["Scale factor at natural origin",0.9996012717],PARAMETER["False easting",400000],'
+           'PARAMETER["False northing",-100000]]]')
+    mk = lambda v: Raster(v, 170000.0, 170000.0 + cols * 10.0, 12000.0, 12000.0 + rows * 10.0, crs)  # noqa: E731
+    hgt = np.nan_to_num(s["vegp"]["hgt"], nan=0.5)
+    vegp = {k: mk(np.nan_to_num(s["vegp"].get(k, hgt), nan=0.3)) for k in hostmodel.VEG_NAMES if k in s["vegp"] or k == "hgt"}
+    for k in hostmodel.VEG_NAMES:
+        vegp.setdefault(k, mk(np.full((rows, cols), 0.3)))
+    soilc = dict(soiltype=mk(np.full((rows, cols), 4.0)), groundr=mk(np.full((rows, cols), 0.15)))
+    tme = (np.datetime64("2023-01-20T00:00:00") + np.arange(T) * np.timedelta64(3600, "s")).astype("datetime64[s]")
+    wuv = np.asarray(s["climdata"]["windspeed"]) * 0.6
+    wvv = np.asarray(s["climdata"]["windspeed"]) * 0.5
+    kw = dict(sdept=np.full(T, 0.2), wuv=wuv, wvv=wvv, coarse_dims=(3, 3), snowenv="Prairie", snowinitd=0.1, zref=30.0)
+    a = hostmodel.snowmodel2(clim, pointm, tme, mk(z), vegp, soilc, **kw)
+    b = hostmodel.snowmodel2(clim, pointm, tme, mk(z), vegp, soilc, operator=pyoracle.gridmodelsnow2, **kw)
+    keys = ("Tc", "Tg", "groundsnowdepth", "totalSWE", "snowden")
+    ok, rows_ = parity.compare({k: a[k] for k in keys}, {k: b[k] for k in keys})
+    assert ok, "\n" + parity.fmt(rows_)
+    land = ~np.isnan(z)
+    assert np.isfinite(a["totalSWE"][land]).all() and np.nanmax(a["totalSWE"]) > 0
+    assert np.isnan(a["Tc"][0, 0]).all() and a["umu"].shape == (rows, cols, T)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_runmicro_snow_true_gridded_climate():
+    """runmicro(snow = TRUE) with a list of micropoints and dtmc (R/Cppwrappers.R:380-383 -> .runmicrosnow2): snow-free
+    days through the coarse-grid kernels, snow days through gridmicrosnow2 on the arrays .prepsnowinputs2 builds; the
+    driver agrees with itself run on the compiled reference's snow operator, and its snow-free days with the plain
+    gridded-climate model."""
+    from microclimf_b200 import hostmodel
+    from test_bundled_example import _micropointa, load_example
+    dtm, vegp, soilc, mp, clim = load_example()
+    sub = hostmodel.subsetpointmodel(mp, days=[10, 11, 12, 13])
+    sub.tmeorig = sub.weather["obs_time"]
+    sub.subs = np.arange(1, 97)
+    sub.weather["temp"] = sub.weather["temp"] - 8.0
+    mpa, dtmc = _micropointa(sub, dtm)
+    rng = np.random.default_rng(6)
+    shp = (50, 50, 96)
+    swe = np.zeros(shp)
+    swe[:, :, 24:72] = rng.uniform(5, 60, shp[:2])[:, :, None] * (rng.random(shp[:2]) < 0.8)[:, :, None]
+    den = np.full(shp, 250.0)
+    tair = sub.weather["temp"][None, None, :]
+    smod = dict(Tc=np.minimum(tair + rng.normal(0, 0.5, shp), 0.0), Tg=np.minimum(tair * 0.5 + rng.normal(0, 0.3, shp), 0.0),
+                totalSWE=swe, groundsnowdepth=swe / den * 0.8, snowden=den,
+                umu=np.repeat(np.asarray(sub.dfo["umu"])[None, None, :], 50, 0).repeat(50, 1))
+    for altcorrect in (0, 2):
+        a = hostmodel.runmicro(mpa, 0.05, vegp, soilc, dtm, dtmc=dtmc, altcorrect=altcorrect, snow=True, snowmod=smod)
+        b = hostmodel.runmicrosnow2(mpa, 0.05, vegp, soilc, dtm, dtmc, smod, altcorrect=altcorrect,
+                                    snow_operator=pyoracle.gridmicrosnow2)
+        assert a["Tz"].shape == shp
+        ok, rws = parity.compare({k: v for k, v in a.items() if k != "tme"}, b)
+        assert ok, "\n" + parity.fmt(rws)
+    plain = hostmodel.runmicro(mpa, 0.05, vegp, soilc, dtm, dtmc=dtmc, altcorrect=2)
+    land = ~np.isnan(dtm.matrix())
+    assert np.array_equal(a["Tz"][:, :, :24][land], plain["Tz"][:, :, :24][land])
+    snowy = (swe[:, :, 30] > 0) & land
+    assert snowy.any() and not np.allclose(a["Tz"][:, :, 30][snowy], plain["Tz"][:, :, 30][snowy])
+    with pytest.raises(ValueError, match="Require dtmc"):
+        hostmodel.runmicro(mpa, 0.05, vegp, soilc, dtm, snow=True, snowmod=smod)
