@@ -287,7 +287,14 @@ def gpu_arm(args):
     if os.path.exists(prof):
         with open(prof) as f:
             pm = json.load(f)
-        roofline["traffic"] = pm.get("dram_bytes_per_cell_hour", 0) * cell_hours_step or None
+        # DRAM bytes per launch from the committed ncu capture: of a launch of exactly this size when the workload is the
+        # default one (profiles/r01_dram_benchwindow_v9.csv), else the per-cell-hour figure of the 48-hour profile window
+        per_ch = pm.get("dram_bytes_per_cell_hour", 0)
+        if (args.rows, args.band_cols, args.win_days) == (8192, 1024, 30):
+            per_ch = pm.get("dram_bytes_per_cell_hour_bench_window", per_ch)
+        roofline["traffic"] = per_ch * cell_hours_step or None
+        if pm.get("dram_breakdown_bench_window"):
+            roofline["traffic_breakdown_bytes_per_cell_hour"] = pm["dram_breakdown_bench_window"]
         if pm.get("fp64_flop_per_cell_hour"):
             fpk = api.fp64_peak_tflops() if rank == 0 else None
             if fpk:
