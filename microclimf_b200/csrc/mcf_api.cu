@@ -186,6 +186,15 @@ Err device_info() {
         uint64_t keep = UINT64_MAX;
         (void)cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
+    // The day stash of k_grid is written and read back with the L2 evict_last ("persisting") policy, which only has
+    // somewhere to persist if part of L2 is set aside for it (the default set-aside is 0).  MCF_L2_PERSIST_MB overrides
+    // the size (0 = leave the device as it is).
+    // 48 MB holds the live stash of 148 CTAs; 64 MB and more starve the write stream of the outputs of L2 ways and
+    // cost 4-20 %.
+    size_t persist = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)48 << 20);
+    if (const char* e = std::getenv("MCF_L2_PERSIST_MB"))
+        persist = std::min((size_t)prop.persistingL2CacheMaxSize, (size_t)std::atoll(e) << 20);
+    if (persist > 0) (void)cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
     (void)cudaGetLastError();
     return Err();
 }
@@ -1311,6 +1320,7 @@ void mcf_release_workspace(void) {
         (void)cudaDeviceSynchronize();
         (void)cudaMemPoolTrimTo(pool, 0);
     }
+    (void)cudaCtxResetPersistingL2Cache(); // stash lines still marked persisting become ordinary lines
     (void)cudaGetLastError();
 }
 

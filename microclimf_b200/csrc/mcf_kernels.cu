@@ -9,8 +9,9 @@
 //   * modes 1/3: the day's 24 HourRec (6 KB) are staged into shared memory by one TMA bulk copy
 //     (cp.async.bulk + mbarrier), double-buffered across days, and read by all threads as broadcasts;
 //   * the reference's two passes per day (ref src/microclimfCpp.cpp:2214-2262 and :2264-2305) are kept:
-//     pass 1 reduces Rmx / tmx / tmn over the 24 hours in registers, pass 2 re-reads 4 stashed doubles
-//     per hour from a CTA-private, L2-resident scratch laid out [hour][var][thread] (coalesced).
+//     pass 1 reduces Rmx / tmx / tmn over the 24 hours in registers, pass 2 walks the day backwards and re-reads
+//     6 stashed doubles per hour from a CTA-private, L2-resident scratch laid out [hour][var][thread] (coalesced),
+//     discarding each line from L2 after its only read.
 #include "mcf_kernels.cuh"
 #include "mcf_physics_f32.cuh"
 
@@ -54,12 +55,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 __device__ __forceinline__ double na_real() { return __longlong_as_double(0x7FF00000000007A2LL); }
 
-// The day stash (4 doubles per cell-hour, written in pass 1 and read once in pass 2 of the same day) is private to
-// the thread and small enough for L2 (44 MB for 148 CTAs), but the write-once outputs stream through the same L2 and
-// push it out to DRAM (170 B instead of 105 B per cell-hour measured, profiles/r01_kgrid_v6_tablemath.txt).  The
-// stash therefore carries an L2 evict_last policy (createpolicy + L2::cache_hint), loads bypass L1; the outputs keep
-// their evict-first streaming stores.  -DMCF_STASH_PLAIN restores plain .cg accesses.
-#ifndef MCF_STASH_PLAIN
+// The day stash (6 doubles per cell-hour, written in pass 1 and read once in pass 2 of the same day) is private to
+// the thread and small enough for L2 (65 MB for 148 CTAs, half of it live on average because pass 2 reads it
+// last-in-first-out), but the write-once outputs stream through the same L2 and push it out to DRAM (189 B instead of
+// ~100 B per cell-hour measured, profiles/r01_dram_benchwindow_v9.csv).  The stash therefore carries the L2 evict_last
+// ("persisting") policy (createpolicy + L2::cache_hint) — which needs an L2 set-aside to persist in, see device_info()
+// in mcf_api.cu — loads bypass L1, and dead lines are discarded; the outputs keep their evict-first streaming stores.
 __device__ __forceinline__ uint64_t stash_policy() {
     uint64_t pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
@@ -73,10 +74,13 @@ __device__ __forceinline__ double ld_stash(const double* p) {
     asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(stash_policy()));
     return v;
 }
-#else
-__device__ __forceinline__ void st_stash(double* p, double v) { __stcg(p, v); }
-__device__ __forceinline__ double ld_stash(const double* p) { return __ldcg(p); }
-#endif
+// A stash line is dead once pass 2 has read it: drop it from L2 without writing it back (the 128 B hold the same
+// variable and hour of 16 consecutive lanes; the caller is the lane that owns the line's first element).
+// `loaded` is the value this lane read from the line: naming it as an operand orders the discard after the load's
+// completion (the warp's load instruction has then returned for all its lanes).
+__device__ __forceinline__ void discard_line(const double* p, double loaded) {
+    asm volatile("discard.global.L2 [%0], 128; // after %1" ::"l"(p), "d"(loaded) : "memory");
+}
 
 // Packed integer sink (SURVEY.md NEXT-4): writetonc's `as.integer(round(x * rd, 0))` (R/dataprep.R:1064-1069) with
 // rd = 100 for Tz, tleaf, soilm and windspeed and 1 for relhum and the radiation streams (:1164-1173), NA and NaN
@@ -516,6 +520,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
             mbar_fence_init();
         }
     }
+    static_assert(kStashVars == 6, "pass 2 takes six variables per cell-hour from the day stash");
     const uint32_t om = a.outmask;
     const double NA = na_real();
 
@@ -672,46 +677,50 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     st_stash(&st[1 * kTile], surfwet);
                     st_stash(&st[2 * kTile], r.radCsw);
                     st_stash(&st[3 * kTile], r.Lhalf);
-#ifdef MCF_STASH6
                     st_stash(&st[4 * kTile], soild);
                     st_stash(&st[5 * kTile], w.uf);
-#endif
                     o += a.ncells;
                 }
                 // ------------------------------------------------------------------ pass 2
                 const double dtr = tmx - tmn;
-                o = o_first;
-                // stash and wind-sector values of the coming hour are fetched one hour ahead
-                double radabs_n = ld_stash(&stash[0 * kTile]), surfwet_n = ld_stash(&stash[1 * kTile]);
-                double radCsw_n = ld_stash(&stash[2 * kTile]), Lhalf_n = ld_stash(&stash[3 * kTile]);
-#ifdef MCF_STASH6
-                double soild_n = ld_stash(&stash[4 * kTile]), uf_n = ld_stash(&stash[5 * kTile]);
-#else
-                if (!ARR) ws_n = __ldg(&a.wsa[(size_t)slab_day[0].windex * a.ncells + cell]);
-#endif
+                // The hours of pass 2 are independent of each other, so it walks the day BACKWARDS: the stash is then
+                // read last-in-first-out (the lines written most recently are still in L2), and every line is
+                // discarded from L2 after its only read instead of being written back to DRAM behind the outputs.
+                const int last_slot_wraps = (23 >= wrap_at);
+                o = last_slot_wraps ? (size_t)cell + (size_t)(23 - wrap_at) * a.ncells : o_first + (size_t)23 * a.ncells;
+                const double* st0 = stash + (size_t)23 * (kStashVars * kTile);
+                double radabs_n = ld_stash(&st0[0 * kTile]), surfwet_n = ld_stash(&st0[1 * kTile]);
+                double radCsw_n = ld_stash(&st0[2 * kTile]), Lhalf_n = ld_stash(&st0[3 * kTile]);
+                double soild_n = ld_stash(&st0[4 * kTile]), uf_n = ld_stash(&st0[5 * kTile]);
 #pragma unroll 1
-                for (int hr = 0; hr < 24; ++hr) {
+                for (int hr = 23; hr >= 0; --hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
                     if (ARR) hour_from_arrays<ARR>(a, k, cell, sl, cl, lon, false, ccell, hloc);
                     const HourRec& h = ARR ? hloc : slab_day[hr];
-                    if (hr == wrap_at) o = cell;
                     const double radabs = radabs_n, surfwet = surfwet_n, radCsw = radCsw_n, Lhalf = Lhalf_n;
-#ifdef MCF_STASH6
                     double soild_n2, uf_n2;
-#endif
                     {
-                        const double* st = stash + (size_t)(hr < 23 ? hr + 1 : 23) * (kStashVars * kTile);
+                        // the hour before, one iteration ahead (hour 0 re-reads itself, before its lines go: no branch
+                        // in the loop body, which would cost the compiler its scheduling window)
+                        const double* st = stash + (size_t)(hr > 0 ? hr - 1 : 0) * (kStashVars * kTile);
                         radabs_n = ld_stash(&st[0 * kTile]);
                         surfwet_n = ld_stash(&st[1 * kTile]);
                         radCsw_n = ld_stash(&st[2 * kTile]);
                         Lhalf_n = ld_stash(&st[3 * kTile]);
-#ifdef MCF_STASH6
                         soild_n2 = ld_stash(&st[4 * kTile]);
                         uf_n2 = ld_stash(&st[5 * kTile]);
-#endif
+                        // this hour's values are in registers: its lines are dead
+                        if ((tid & 15) == 0) {
+                            const double* sd = stash + (size_t)hr * (kStashVars * kTile);
+                            discard_line(&sd[0 * kTile], radabs);
+                            discard_line(&sd[1 * kTile], surfwet);
+                            discard_line(&sd[2 * kTile], radCsw);
+                            discard_line(&sd[3 * kTile], Lhalf);
+                            discard_line(&sd[4 * kTile], soild_n);
+                            discard_line(&sd[5 * kTile], uf_n);
+                        }
                     }
-#ifdef MCF_STASH6
                     const double soild = soild_n;
                     Wind w; // windCpp's uz / gHa from the stashed friction velocity (ref :1199-1217)
                     w.uf = uf_n;
@@ -721,17 +730,6 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     if (w.gHa < 0.0001) w.gHa = 0.0001;
                     soild_n = soild_n2;
                     uf_n = uf_n2;
-#else
-                    double ws;
-                    if (ARR) {
-                        ws = __ldg(&a.wsa[(size_t)h.windex * a.ncells + cell]);
-                    } else {
-                        ws = ws_n;
-                        ws_n = __ldg(&a.wsa[(size_t)slab_day[hr < 23 ? hr + 1 : 23].windex * a.ncells + cell]);
-                    }
-                    const double soild = soil_distribute(v, h.soilmp);
-                    const Wind w = wind_hour(v, h.u2, h.umu, ws);
-#endif
                     // soil conductivity and damping depth (ref soilcondCpp :1249-1260)
                     const double cs = (2400 * v.rho / 2.64 + 4180.0 * soild);
                     const double ph = (v.rho * (1.0 - soild) + soild) * 1000.0;
@@ -764,7 +762,8 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                             if (ALLOUT || (om & (1u << 2))) put<2, PACK>(a, o, tv.rh);
                         }
                     }
-                    o += a.ncells;
+                    if (hr == wrap_at) o = (size_t)(a.ring_hours - 1) * a.ncells + cell; // back across the ring's seam
+                    else o -= a.ncells;
                 }
             }
             if (!ARR) { // this warp is done with the stage: one arrival per warp

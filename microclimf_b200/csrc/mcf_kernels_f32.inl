@@ -31,6 +31,18 @@ __global__ void k_narrow_hours(const HourRec* __restrict__ in, int n, f32::HourR
     out[k] = h;
 }
 
+__device__ __forceinline__ void st_stash_f(float* p, float v) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(stash_policy()) : "memory");
+}
+__device__ __forceinline__ float ld_stash_f(const float* p) {
+    float v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(stash_policy()));
+    return v;
+}
+__device__ __forceinline__ void discard_line_f(const float* p, float loaded) {
+    asm volatile("discard.global.L2 [%0], 128; // after %1" ::"l"(p), "f"(loaded) : "memory");
+}
+
 template <int RQ>
 __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_constant__ GridArgsF af) {
     using f32::HourRecF;
@@ -151,26 +163,35 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                     if (tmx < Tg0) tmx = Tg0;
                     if (tmn > Tg0) tmn = Tg0;
                     float* st = stash + (size_t)hr * (kStashVars * kTileF);
-                    __stcg(&st[0 * kTileF], radabs);
-                    __stcg(&st[1 * kTileF], surfwet);
-                    __stcg(&st[2 * kTileF], r.radCsw);
-                    __stcg(&st[3 * kTileF], r.Lhalf);
-                    __stcg(&st[4 * kTileF], soild);
-                    __stcg(&st[5 * kTileF], w.uf);
+                    st_stash_f(&st[0 * kTileF], radabs);
+                    st_stash_f(&st[1 * kTileF], surfwet);
+                    st_stash_f(&st[2 * kTileF], r.radCsw);
+                    st_stash_f(&st[3 * kTileF], r.Lhalf);
+                    st_stash_f(&st[4 * kTileF], soild);
+                    st_stash_f(&st[5 * kTileF], w.uf);
                     o += a.ncells;
                 }
                 const float dtr = tmx - tmn;
-                o = o_first;
+                // pass 2 walks the day backwards (last-in-first-out on the stash) and drops each stash line from L2
+                // after its only read, as k_grid does; a 128-byte line is one warp's 32 floats
+                o = (23 >= wrap_at) ? (size_t)cell + (size_t)(23 - wrap_at) * a.ncells : o_first + (size_t)23 * a.ncells;
 #pragma unroll 1
-                for (int hr = 0; hr < 24; ++hr) {
+                for (int hr = 23; hr >= 0; --hr) {
                     const HourRecF& h = slab_day[hr];
-                    if (hr == wrap_at) o = cell;
                     const float* st = stash + (size_t)hr * (kStashVars * kTileF);
-                    const float radabs = __ldcg(&st[0 * kTileF]), surfwet = __ldcg(&st[1 * kTileF]);
-                    const float radCsw = __ldcg(&st[2 * kTileF]), Lhalf = __ldcg(&st[3 * kTileF]);
-                    const float soild = __ldcg(&st[4 * kTileF]);
+                    const float radabs = ld_stash_f(&st[0 * kTileF]), surfwet = ld_stash_f(&st[1 * kTileF]);
+                    const float radCsw = ld_stash_f(&st[2 * kTileF]), Lhalf = ld_stash_f(&st[3 * kTileF]);
+                    const float soild = ld_stash_f(&st[4 * kTileF]);
                     f32::Wind w; // uz / gHa from the stashed friction velocity (ref windCpp :1199-1217)
-                    w.uf = __ldcg(&st[5 * kTileF]);
+                    w.uf = ld_stash_f(&st[5 * kTileF]);
+                    if ((tid & 31) == 0) {
+                        discard_line_f(&st[0 * kTileF], radabs);
+                        discard_line_f(&st[1 * kTileF], surfwet);
+                        discard_line_f(&st[2 * kTileF], radCsw);
+                        discard_line_f(&st[3 * kTileF], Lhalf);
+                        discard_line_f(&st[4 * kTileF], soild);
+                        discard_line_f(&st[5 * kTileF], w.uf);
+                    }
                     w.uz = w.uf * v.uz_coef;
                     if (w.uz > h.u2) w.uz = h.u2;
                     w.gHa = w.uf * v.gHa_coef;
@@ -198,7 +219,8 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                         if (om & (1u << 1)) __stcs(&af.outf[1][o], tv.tleaf);
                         if (om & (1u << 2)) __stcs(&af.outf[2][o], tv.rh);
                     }
-                    o += a.ncells;
+                    if (hr == wrap_at) o = (size_t)(a.ring_hours - 1) * a.ncells + cell; // back across the ring's seam
+                    else o -= a.ncells;
                 }
             }
             __syncwarp();
