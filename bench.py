@@ -288,7 +288,7 @@ def gpu_arm(args):
         with open(prof) as f:
             pm = json.load(f)
         # DRAM bytes per launch from the committed ncu capture: of a launch of exactly this size when the workload is the
-        # default one (profiles/r01_dram_benchwindow_v9.csv), else the per-cell-hour figure of the 48-hour profile window
+        # default one (profiles/r01_dram_benchwindow_v10.csv), else the per-cell-hour figure of the 48-hour profile window
         per_ch = pm.get("dram_bytes_per_cell_hour", 0)
         if (args.rows, args.band_cols, args.win_days) == (8192, 1024, 30):
             per_ch = pm.get("dram_bytes_per_cell_hour_bench_window", per_ch)
