@@ -341,6 +341,9 @@ def gpu_arm(args):
         e_s = float(t.item())
     e2e = {"value": float(er) * ec * et * esteps * world / e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "steps": esteps, "ms_per_step": 1e3 * e_s / esteps,
+           # bytes over PCIe per second of the whole call: the host-buffer path is bound by the link (80 B per cell-hour
+           # of FP64 results), not by the kernels
+           "pcie_gb_per_s": (h2d + d2h) * esteps / e_s / 1e9,
            "sample": f"{er}x{ec} cells x {et} h per GPU through mcf_runmicro (pinned host buffers, all 10 outputs "
                      f"copied back; timed with the host clock around the blocking call)"}
     # the same call with the packed integer sink (writetonc's x100 / x1 int16 packing done by the kernels, SURVEY.md
@@ -361,6 +364,7 @@ def gpu_arm(args):
         p_s = float(t.item())
     e2e_packed = {"value": float(er) * ec * et * esteps * world / p_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": sum(o.nbytes for o in pouts), "steps": esteps, "ms_per_step": 1e3 * p_s / esteps,
+                  "pcie_gb_per_s": (h2d + sum(o.nbytes for o in pouts)) * esteps / p_s / 1e9,
                   "sample": "same tile through mcf_runmicro_packed: int16 outputs as the reference's writetonc stores them"}
     del pin_keep
 
