@@ -198,6 +198,43 @@ def test_device_window_ring_matches_whole():
         np.testing.assert_array_equal(ring, whole[nm][:, :, 96:120])
 
 
+@pytest.mark.parametrize("ring_hours,hour0", [(31, 48), (24, 37), (50, 0)])
+def test_device_window_ring_seam_inside_a_day(ring_hours, hour0):
+    """A ring whose seam falls inside a day block (ring_hours not a multiple of 24, or a window origin that is not a
+    day boundary): pass 1 walks the ring forwards and pass 2 backwards across the seam; every slot must hold the hour
+    (slot + hour0) mod ring of the window's last ring_hours hours — FP64, packed and FP32 sinks."""
+    import torch
+
+    from oracle import packing_oracle
+
+    p = synth.make_problem(29, 13, 24 * 6, reqhgt=0.05, mode=1)
+    whole = api.run_problem(p)
+    dp = p.to_device()
+    nc = p.ncells
+    block0, nblocks = 2, 3
+    k_last = (block0 + nblocks) * 24 - 1
+    hours = np.arange(max(block0 * 24, k_last - ring_hours + 1), k_last + 1)
+    slots = (hours - hour0) % ring_hours
+    outs = [torch.full((ring_hours * nc,), -1.0, dtype=torch.float64, device="cuda") for _ in range(10)]
+    api.run_problem_dev(dp, outs, window=(block0, nblocks, hour0, ring_hours))
+    outs16 = [torch.full((ring_hours * nc,), 7, dtype=torch.int16, device="cuda") for _ in range(10)]
+    api.run_problem_packed_dev(dp, outs16, window=(block0, nblocks, hour0, ring_hours))
+    outsf = [torch.full((ring_hours * nc,), -1.0, dtype=torch.float32, device="cuda") for _ in range(10)]
+    api.run_problem_f32_dev(dp, outsf, window=(block0, nblocks, hour0, ring_hours))
+    torch.cuda.synchronize()
+    for nm, t, t16, tf in zip(_abi.OUT_NAMES, outs, outs16, outsf):
+        ring = t.cpu().numpy().reshape(p.rows, p.cols, ring_hours, order="F")
+        np.testing.assert_array_equal(ring[:, :, slots], whole[nm][:, :, hours], err_msg=nm)
+        ring16 = t16.cpu().numpy().reshape(p.rows, p.cols, ring_hours, order="F")
+        assert np.array_equal(ring16[:, :, slots], packing_oracle.pack(nm, whole[nm][:, :, hours])), nm
+        ringf = tf.cpu().numpy().reshape(p.rows, p.cols, ring_hours, order="F")[:, :, slots].astype(np.float64)
+        want = whole[nm][:, :, hours]
+        m = np.isfinite(want)
+        assert np.array_equal(np.isfinite(ringf), m), nm
+        # FP32 build: coarse agreement is enough to tell a misplaced hour (the FP32 tests hold its tolerances)
+        assert np.all(np.abs(ringf[m] - want[m]) <= 0.5 + 0.02 * np.abs(want[m])), nm
+
+
 def test_physical_ranges_wrapper_scenario():
     """Known-range bounds in the spirit of the reference's own test (tests/testthat/
     test-microclimatemodel_wrapper.R:40-48 parameters, 82-90 bounds), re-expressed on the grid kernels:
