@@ -818,12 +818,19 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT], int pack = 0) {
             // window.  Window i owns the hour range from its first block to the next window's first block
             // (the first from hour 0, the last to T), so gaps the day-blocks do not cover travel with the NA
             // prefill.  reqhgt < 0 needs the whole series before its time-axis pass: one window.
-            const int nwin = (rq == RQ_BELOW || nblk < 8) ? 1 : 4;
+            // The first window is a single day, so that the copy engine starts as early as possible; the rest of
+            // the series is split into up to five windows.
+            const int nrest = (rq == RQ_BELOW || nblk < 2) ? 0 : std::min(nblk - 1, 5);
+            const int nwin = 1 + nrest;
+            auto first_block = [&](int w) { // first day-block of window w; first_block(nwin) = nblk
+                if (nrest == 0) return w == 0 ? 0 : nblk;
+                return w == 0 ? 0 : 1 + (int)((long long)(nblk - 1) * (w - 1) / nrest);
+            };
             std::vector<EventGuard> done_k(nwin);
             std::vector<CopyJob> jobs;
             for (int w = 0; w < nwin; ++w) {
                 CU(cudaEventCreateWithFlags(&done_k[w].e, cudaEventDisableTiming));
-                const int b0 = (int)((long long)nblk * w / nwin), b1 = (int)((long long)nblk * (w + 1) / nwin);
+                const int b0 = first_block(w), b1 = first_block(w + 1);
                 if (rq == RQ_BELOW) TRY(plan_run_below(pl, dout, sc, cs.s));
                 else TRY(plan_run_window(pl, dout, b0, b1 - b0, 0, T, sc, cs.s));
                 CU(cudaEventRecord(done_k[w].e, cs.s));
