@@ -967,6 +967,150 @@ def snowmodel2(climdata, pointm, tme, dtm, vegp, soilc, sdept, wuv, wvv, coarse_
     return {k: np.where(land[:, :, None], v, np.nan) for k, v in out.items()}
 
 
+def canintfrac(hgt, pai, uf, prec, tc, Li):
+    """ref canintfrac (src/microclimfCpp.cpp:5417-5451) around canopysnowintCpp (:3713-3739): fraction of a snowfall
+    `prec` (mm SWE) the canopy intercepts, per cell; 0.5 everywhere when prec <= 0, NA where hgt is NA."""
+    hgt = np.asarray(hgt, dtype=np.float64)
+    pai = np.asarray(pai, dtype=np.float64)
+    na = np.isnan(hgt)
+    if not prec > 0.0:
+        return np.where(na, np.nan, 0.5)
+    with np.errstate(invalid="ignore", divide="ignore", over="ignore"):
+        h = np.where(hgt < 0.001, 0.001, hgt)
+        p = np.where(pai < 0.001, 0.001, pai)
+        Be = np.sqrt(0.003 + (0.2 * p) / 2.0)
+        uh = uf / Be
+        Lc = (0.25 * (p / h)) ** -1.0
+        Lm = 2.0 * Be ** 3.0 * Lc
+        k1 = Be / Lm
+        uzm = (uh / (h * k1)) * (1 - np.exp(-k1 * h))
+        uzm = np.where(uzm < uf, uf, uzm)
+        rhos = 67.92 + 51.25 * np.exp(tc / 2.59)
+        Lstr = 6.2 * (0.26 + 46 / rhos) * p
+        kc = 1.0 / (2.0 * np.cos(np.arctan(uzm / 0.8)))
+        Cp = 1.0 - np.exp(-kc * p)
+        I1 = (Lstr - Li) * (1.0 - np.exp(-(Cp / Lstr) * prec))
+        cis = I1 * 0.678
+        cis = np.where(cis > prec, prec, cis)
+        return np.where(na, np.nan, cis / prec)
+
+
+def meltmu(skyview, stemp, tc):
+    """ref meltmu (src/microclimfCpp.cpp:5454-5492): per-cell multiplier of the point model's temperature melt — the
+    positive degree-hours of the snow surface temperature blended towards air temperature by the sky view, over those of
+    the point model; 1 everywhere when the point model has none."""
+    sv = np.asarray(skyview, dtype=np.float64)
+    st = np.asarray(stemp, dtype=np.float64)
+    t = np.asarray(tc, dtype=np.float64)
+    dhp = st[st > 0.0].sum()
+    if not dhp > 0.0:
+        return np.ones(sv.shape)
+    with np.errstate(invalid="ignore"):
+        dhm = np.zeros(sv.shape)
+        for k in range(st.size):  # sequential sum, as the reference accumulates it
+            s2 = (st[k] - t[k]) * sv + t[k]
+            dhm = dhm + np.where(s2 > 0.0, s2, 0.0)
+        return np.where(np.isnan(sv), np.nan, dhm / dhp)
+
+
+def snowmodelq1(weather, pmod, subs, dtm, vegp, soilc, snowenv: str = "Taiga", snowinitd: float = 0, snowinita: float = 0,
+                zref: float = 2, tfact: float = 0.02, operator=None):
+    """ref .snowmodelq1 (R/internal.R:2627-2778), the quick snow model, from the point where the point snow model has run:
+    the grid model runs only on the days of `subs` (1-based hours into the full series, whole days); between two modelled
+    days the snow balance comes from the point model's melt terms (`pmod`: G, Tc, RswabsG, RlwabsG, umu, tr, sdepc, sdepg,
+    sublmelt, tempmelt, rainmelt, sstemp, sdenc, sdeng over the FULL series; sdepc / sdepg one element longer, as
+    pointmodelsnow returns them), scaled per cell by meltmu and the canopy interception fraction.  `weather` is the full
+    hourly data.frame (`precip` in mm).  The terrain is that of the bare DTM throughout (:2686-2699)."""
+    from . import snow as snowops
+
+    op = operator or snowops.gridmodelsnow1
+    dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
+    subs = np.asarray(subs, dtype=int)
+    tme = np.asarray(weather["obs_time"]).astype("datetime64[s]")
+    n_full = tme.size
+    ot = _obstime(tme)
+    ot["hour"] = np.floor(ot["hour"])
+    z = dtm.matrix()
+    sage = z * 0 + snowinita
+    lat, lon = latlong_from_raster(dtm)
+    g = lambda k: np.asarray(pmod[k], dtype=np.float64)  # noqa: E731
+    w_full = {k: np.asarray(weather[k], dtype=np.float64) for k in WEATHER_COLS}
+    # `weather$prec` (R/internal.R:2675) partially matches the `precip` column
+    snow = np.where(w_full["temp"] > 2, 0.0, w_full["precip"])
+    vg = _sortl(vegp, g("sdepc")[:n_full])
+    vg["leaft"] = np.where(np.isnan(vg["leaft"]), 0.01, vg["leaft"])
+    ix = subs - 1
+    pointm = {"Gp": g("G")[ix], "Tc": g("Tc")[ix], "RswabsG": g("RswabsG")[ix], "RlwabsG": g("RlwabsG")[ix],
+              "umu": g("umu")[ix], "tr": g("tr")[ix]}
+    wsub = {k: v[ix] for k, v in w_full.items()}
+    osub = {k: v[ix] for k, v in ot.items()}
+    other: Dict[str, object] = dict(zref=float(zref), lat=lat, lon=lon, isnowdc=snowinitd * (z * 0 + 1),
+                                    isnowac=np.nan_to_num(sage).astype(np.int32),
+                                    isnowag=np.nan_to_num(sage).astype(np.int32))
+    sl = terrain(dtm, "slope").matrix()
+    sl[np.isnan(sl)] = 0
+    other["slope"] = mask(dtm.like(sl), dtm).matrix()
+    ap = terrain(dtm, "aspect").matrix()
+    ap[np.isnan(ap)] = 180
+    other["aspect"] = mask(dtm.like(ap), dtm).matrix()
+    other["hor"], other["skyview"] = api.horizon(z, dtm.res[0], want_svf=True)
+    other["wsa"] = _windsheltera(dtm, zref, 10 if dtm.res[0] <= 100 else 1)
+    n = ix.size
+    shape = z.shape + (n,)
+    Tc, Tg, sdepc, sden = (np.full(shape, np.nan) for _ in range(4))
+    sdepg = np.zeros(shape)
+    pos = snow[snow > 0]
+    msnow = pos.mean() if pos.size else np.nan
+    intfrac = canintfrac(vg["hgt"], vg["pai"], 2, msnow, wsub["temp"].mean(), 0)
+    other["isnowdg"] = (1 - intfrac) * other["isnowdc"]
+    climcols = ("temp", "relhum", "pres", "swdown", "difrad", "lwdown", "windspeed", "winddir", "precip")
+    ped = 0
+    sbtn = None
+    for day in range(n // 24):
+        s = slice(day * 24, day * 24 + 24)
+        first = int(subs[s.start])
+        if first - 1 > 1:
+            sbtn = np.arange(ped + 1, first)  # 1-based hours between the previous modelled day and this one
+            b = sbtn - 1
+            mu = meltmu(other["skyview"], g("sstemp")[b], w_full["temp"][b])
+            melt = g("sublmelt")[b].sum() + g("rainmelt")[b].sum() + mu * g("tempmelt")[b].sum()
+            balancec = (snow[b] / 1000).sum() - melt
+            balanceg = (1 - intfrac) * (snow[b] / 1000).sum() - np.exp(-vg["pai"]) * melt
+        else:
+            balancec = 0.0
+            balanceg = 0.0
+        if sbtn is None:
+            # R evaluates mean(pmod$sdenc[sbtn]) with `sbtn` undefined on a first day that starts the series: an error
+            raise ValueError("snowmodelq1: the first modelled day must not start the series (object 'sbtn' not found in R)")
+        bb = sbtn - 1
+        with np.errstate(invalid="ignore"):
+            dc = other["isnowdc"] + balancec * (1000 / g("sdenc")[bb].mean())
+            dg = other["isnowdg"] + balanceg * (1000 / g("sdeng")[bb].mean())
+            other["isnowdc"] = np.where(dc < 0, 0.0, dc)
+            other["isnowdg"] = np.where(dg < 0, 0.0, dg)
+        smod = op({k: v[s] for k, v in osub.items()}, {k: wsub[k][s] for k in climcols}, {k: v[s] for k, v in pointm.items()},
+                  vg, other, snowenv)
+        dsnow = smod["sdepc"] - other["isnowdc"][:, :, None]
+        dsnowg = smod["sdepg"] - other["isnowdg"][:, :, None]
+        dsnowc = dsnow - dsnowg
+        dtms = dtm.like(z + sdepg[:, :, s.stop - 1])  # (still zero for this day: the DTM itself, as written :2745)
+        tpr = 10 * np.mean(wsub["windspeed"][s]) ** 0.5
+        af = int(round(tpr / dtm.res[0]))
+        tpi = _tpicalc(af, min(dtm.nrows, dtm.ncols), dtms, tfact)
+        dsnowg2 = dsnowg * tpi[:, :, None]
+        dsnowc2 = dsnowc + dsnowg2
+        Tc[:, :, s], Tg[:, :, s], sden[:, :, s] = smod["Tc"], smod["Tg"], smod["sden"]
+        with np.errstate(invalid="ignore"):
+            sdc = dsnowc2 + other["isnowdc"][:, :, None]
+            sdg = dsnowg2 + other["isnowdg"][:, :, None]
+            sdc = np.where(sdc < 0, 0.0, sdc)
+            sdg = np.where(sdg < 0, 0.0, sdg)
+        sdepc[:, :, s], sdepg[:, :, s] = sdc, sdg
+        ped = int(subs[s.stop - 1])
+        other["isnowdc"], other["isnowdg"] = sdc[:, :, 23], sdg[:, :, 23]
+    return dict(Tc=Tc, Tg=Tg, groundsnowdepth=sdepg, totalSWE=sdepc * sden, snowden=sden, umu=pointm["umu"])
+
+
 # ---------------------------------------------------------------------------------------------
 # runmicro(snow = TRUE), data.frame climate: .runmicrosnow1
 # ---------------------------------------------------------------------------------------------

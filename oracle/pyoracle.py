@@ -112,3 +112,34 @@ def gridmicrosnow2(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, ou
     fn = _lib("ref").ref_gridmicrosnow2
     fn.restype = C.c_int
     return snow.call_gridmicrosnow(fn, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)
+
+
+def canintfrac(hgt, pai, uf, prec, tc, Li):
+    """The compiled reference's canintfrac (src/microclimfCpp.cpp:5417) on [rows, cols] matrices."""
+    lib = _lib("ref")
+    h = np.asfortranarray(hgt, dtype=np.float64)
+    p = np.asfortranarray(pai, dtype=np.float64)
+    out = np.empty(h.shape, dtype=np.float64, order="F")
+    PD = C.POINTER(C.c_double)
+    lib.ref_canintfrac.argtypes = [PD, PD, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, PD]
+    rc = lib.ref_canintfrac(h.ctypes.data_as(PD), p.ctypes.data_as(PD), h.shape[0], h.shape[1], float(uf), float(prec), float(tc),
+                            float(Li), out.ctypes.data_as(PD))
+    if rc != 0:
+        raise RuntimeError("ref_canintfrac failed")
+    return out
+
+
+def meltmu(skyview, stemp, tc):
+    """The compiled reference's meltmu (src/microclimfCpp.cpp:5454)."""
+    lib = _lib("ref")
+    sv = np.asfortranarray(skyview, dtype=np.float64)
+    st = np.ascontiguousarray(stemp, dtype=np.float64)
+    t = np.ascontiguousarray(tc, dtype=np.float64)
+    out = np.empty(sv.shape, dtype=np.float64, order="F")
+    PD = C.POINTER(C.c_double)
+    lib.ref_meltmu.argtypes = [PD, C.c_int32, C.c_int32, PD, PD, C.c_int32, PD]
+    rc = lib.ref_meltmu(sv.ctypes.data_as(PD), sv.shape[0], sv.shape[1], st.ctypes.data_as(PD), t.ctypes.data_as(PD), st.size,
+                        out.ctypes.data_as(PD))
+    if rc != 0:
+        raise RuntimeError("ref_meltmu failed")
+    return out

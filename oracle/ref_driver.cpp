@@ -390,6 +390,36 @@ extern "C" int ref_flowacc(const double* dtm, int32_t rows, int32_t cols, double
     }
 }
 
+// canintfrac (src/microclimfCpp.cpp:5417) and meltmu (:5454) of the quick snow model, on column-major matrices
+NumericMatrix canintfrac(NumericMatrix hgt, NumericMatrix pai, double uf, double prec, double tc, double Li);
+NumericMatrix meltmu(NumericMatrix skyview, NumericVector stemp, NumericVector tc);
+extern "C" int ref_canintfrac(const double* hgt, const double* pai, int32_t rows, int32_t cols, double uf, double prec, double tc,
+                              double Li, double* out) {
+    try {
+        NumericMatrix h(rows, cols), p(rows, cols);
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) { h[i] = hgt[i]; p[i] = pai[i]; }
+        NumericMatrix r = canintfrac(h, p, uf, prec, tc, Li);
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) out[i] = r[i];
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+extern "C" int ref_meltmu(const double* skyview, int32_t rows, int32_t cols, const double* stemp, const double* tc, int32_t n,
+                          double* out) {
+    try {
+        NumericMatrix sv(rows, cols);
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) sv[i] = skyview[i];
+        NumericVector st(n), t(n);
+        for (int i = 0; i < n; ++i) { st[i] = stemp[i]; t[i] = tc[i]; }
+        NumericMatrix r = meltmu(sv, st, t);
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) out[i] = r[i];
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Snow (SURVEY.md NEXT-3): the reference's gridmodelsnow1 / gridmicrosnow1 behind the product's structs
 // ---------------------------------------------------------------------------------------------

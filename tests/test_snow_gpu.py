@@ -250,3 +250,59 @@ def test_runmicro_snow_true_gridded_climate():
     assert snowy.any() and not np.allclose(a["Tz"][:, :, 30][snowy], plain["Tz"][:, :, 30][snowy])
     with pytest.raises(ValueError, match="Require dtmc"):
         hostmodel.runmicro(mpa, 0.05, vegp, soilc, dtm, snow=True, snowmod=smod)
+
+
+@needs_ref
+def test_quick_snow_model_helpers_match_reference_cpu():
+    """hostmodel.canintfrac / meltmu against the compiled reference's canintfrac (src/microclimfCpp.cpp:5417) and meltmu
+    (:5454), special cases included (no snowfall, NA cells, bare cells, no positive degree-hours)."""
+    from microclimf_b200 import hostmodel
+    rng = np.random.default_rng(12)
+    hgt = rng.uniform(0, 25, (9, 7)); hgt[0, 0] = np.nan; hgt[1, 1] = 0.0
+    pai = rng.uniform(0, 6, (9, 7)); pai[2, 2] = 0.0
+    for prec, tc, li in ((0.0, -3.0, 0.0), (0.4, -8.0, 0.0), (15.0, 1.5, 0.3)):
+        a, b = hostmodel.canintfrac(hgt, pai, 2, prec, tc, li), pyoracle.canintfrac(hgt, pai, 2, prec, tc, li)
+        np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-15, equal_nan=True)
+    sv = rng.uniform(0.3, 1, (9, 7)); sv[0, 0] = np.nan
+    st, tc = rng.normal(-1, 3, 60), rng.normal(0, 4, 60)
+    np.testing.assert_allclose(hostmodel.meltmu(sv, st, tc), pyoracle.meltmu(sv, st, tc), rtol=1e-13, equal_nan=True)
+    assert np.array_equal(hostmodel.meltmu(sv, -np.abs(st), tc), pyoracle.meltmu(sv, -np.abs(st), tc))  # all ones
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_snowmodelq1_quick_driver_matches_reference_operator():
+    """hostmodel.snowmodelq1 (.snowmodelq1, R/internal.R:2627-2778): the grid snow model on 3 of 12 days, the point
+    model's melt terms bridging the gaps; CUDA operator against the compiled reference's in the same driver."""
+    from microclimf_b200 import hostmodel
+    from microclimf_b200.spatial import Raster
+    rows, cols, days = 22, 18, 12
+    T = 24 * days
+    s = synth.make_snow_inputs(rows, cols, T, seed=29)
+    rng = np.random.default_rng(9)
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    z = 320 + 35 * np.sin(ii / 4.0) * np.cos(jj / 3.0) + rng.normal(0, 0.5, (rows, cols))
+    mk = lambda v: Raster(v, 0, cols * 10.0, 0, rows * 10.0, "")  # noqa: E731
+    hgt = np.nan_to_num(s["vegp"]["hgt"], nan=0.5)
+    vegp = {k: mk(np.nan_to_num(s["vegp"].get(k, hgt), nan=0.3)) for k in hostmodel.VEG_NAMES if k in s["vegp"] or k == "hgt"}
+    for k in hostmodel.VEG_NAMES:
+        vegp.setdefault(k, mk(np.full((rows, cols), 0.3)))
+    soilc = dict(soiltype=mk(np.full((rows, cols), 4.0)), groundr=mk(np.full((rows, cols), 0.15)))
+    tme = (np.datetime64("2023-01-10T00:00:00") + np.arange(T) * np.timedelta64(3600, "s")).astype("datetime64[s]")
+    weather = dict(s["climdata"], obs_time=tme)
+    p = s["pointm"]
+    pmod = dict(G=p["Gp"], Tc=p["Tc"], RswabsG=p["RswabsG"], RlwabsG=p["RlwabsG"], umu=p["umu"], tr=p["tr"],
+                sdepc=np.full(T + 1, 0.25), sdepg=np.full(T + 1, 0.2), sublmelt=np.full(T, 2e-6),
+                tempmelt=np.maximum(np.asarray(s["climdata"]["temp"]), 0) * 4e-5, rainmelt=np.full(T, 1e-6),
+                sstemp=np.minimum(np.asarray(s["climdata"]["temp"]) + 0.5, 1.0), sdenc=np.full(T, 210.0), sdeng=np.full(T, 260.0))
+    sel_days = np.array([3, 7, 11])
+    subs = (np.repeat((sel_days - 1) * 24, 24) + np.tile(np.arange(1, 25), sel_days.size))
+    kw = dict(snowenv="Tundra", snowinitd=0.15, zref=30.0)
+    a = hostmodel.snowmodelq1(weather, pmod, subs, mk(z), vegp, soilc, **kw)
+    b = hostmodel.snowmodelq1(weather, pmod, subs, mk(z), vegp, soilc, operator=pyoracle.gridmodelsnow1, **kw)
+    keys = ("Tc", "Tg", "groundsnowdepth", "totalSWE", "snowden")
+    ok, rows_ = parity.compare({k: a[k] for k in keys}, {k: b[k] for k in keys})
+    assert ok, "\n" + parity.fmt(rows_)
+    assert a["Tc"].shape == (rows, cols, 72) and np.nanmax(a["totalSWE"]) > 0
+    with pytest.raises(ValueError, match="sbtn"):
+        hostmodel.snowmodelq1(weather, pmod, np.arange(1, 25), mk(z), vegp, soilc, **kw)
