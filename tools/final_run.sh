@@ -1,9 +1,11 @@
-set -x
-python bench.py > gpurun_out/bench_v10.json 2> gpurun_out/bench_v10.err; echo "bench rc=$?"
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_v10_ref.json 2>/dev/null
-CMD="python bench.py --rows 2048 --band-cols 512 --win-days 2 --steps 2 --warmup 3 --no-cpu --e2e-rows 256 --e2e-cols 256 --e2e-hours 48"
-$CMD > gpurun_out/prof_cmd_plain.log 2>&1; echo "plain rc=$?"
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_v10.csv $CMD > gpurun_out/ncu_launch_v10.log 2>&1; echo "launchlist rc=$?"
-ncu --set full --clock-control none --import-source on -k "regex:^k_grid$" --launch-skip 4 --launch-count 1 -f -o gpurun_out/prof_kgrid10 $CMD > gpurun_out/ncu_full_v10.log 2>&1; echo "full rc=$?"
-ncu --set full --clock-control none --import-source on -k "regex:^k_grid_f32$" --launch-skip 1 --launch-count 1 -f -o gpurun_out/prof_kgrid_f32_v10 $CMD > gpurun_out/ncu_full_f32_v10.log 2>&1; echo "full f32 rc=$?"
-ls -la gpurun_out/*.ncu-rep | tail -3
+# dev aid: the round-end sequence on one box — GPU tests, smoke, both bench arms
+python -m pytest tests -q -m gpu -x > gpurun_out/pytest_final.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest_final.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python bench.py --impl reference > gpurun_out/bench_final_ref.json 2>/dev/null; echo "ref rc=$?"; wc -l gpurun_out/bench_final_ref.json
+python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err; echo "bench rc=$?"; wc -l gpurun_out/bench_final.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_final.json')); r=json.load(open('gpurun_out/bench_final_ref.json'))
+print('value %.4e  e2e %.4e (%.1f GB/s)  packed %.4e  fp32 %.4e  cpu %.3e  ref-arm %.3e' % (d['value'], d['e2e']['value'], d['e2e']['pcie_gb_per_s'], d['e2e_packed']['value'], d['fp32']['value'], d['cpu_baseline']['value'], r['value']))
+print(d['clocks'], d['roofline']['frac'], d['roofline']['fp64']['frac'], d['roofline']['traffic']/d['roofline']['algorithmic_bytes_per_launch'], d['gpu_launches'])
+PY
