@@ -1111,6 +1111,119 @@ def snowmodelq1(weather, pmod, subs, dtm, vegp, soilc, snowenv: str = "Taiga", s
     return dict(Tc=Tc, Tg=Tg, groundsnowdepth=sdepg, totalSWE=sdepc * sden, snowden=sden, umu=pointm["umu"])
 
 
+def meltmu2(mu, stemp, tc):
+    """ref meltmu2 (src/microclimfCpp.cpp:5495-5528): meltmu with the snow surface and air temperatures as
+    [rows, cols, hours] arrays; 0.5 where a cell's point series has no positive degree-hours."""
+    mu = np.asarray(mu, dtype=np.float64)
+    st = np.asarray(stemp, dtype=np.float64)
+    t = np.asarray(tc, dtype=np.float64)
+    dhp = np.zeros(mu.shape)
+    dhm = np.zeros(mu.shape)
+    with np.errstate(invalid="ignore"):
+        for k in range(st.shape[2]):  # sequential sums, as the reference accumulates them
+            dhp = dhp + np.where(st[:, :, k] > 0.0, st[:, :, k], 0.0)
+            s2 = (st[:, :, k] - t[:, :, k]) * mu + t[:, :, k]
+            dhm = dhm + np.where(s2 > 0.0, s2, 0.0)
+        out = np.where(dhp > 0.0, dhm / np.where(dhp > 0.0, dhp, 1.0), 0.5)
+    return np.where(np.isnan(mu), np.nan, out)
+
+
+def snowmodelq2(climdata, pointm, pointm2, tme, subs, dtm, dtmc, vegp, soilc, sdept, wuv, wvv, snowenv: str = "Taiga",
+                snowinitd: float = 0, snowinita: float = 0, zref: float = 2, tfact: float = 0.02, operator=None):
+    """ref .snowmodelq2 (R/internal.R:3017-3290), the quick snow model with gridded climate, from the point where the
+    per-coarse-cell point snow models have run and their series have been turned into arrays (:3117-3180).
+
+    `climdata` (temp, relhum, pres, swdown, difrad, lwdown, windspeed, precip as [rows, cols, n] on the DTM, winddir [n])
+    and `pointm` (Gp, Tc, RswabsG, RlwabsG, umu, tr as [rows, cols, n]) hold the n = len(subs) modelled hours, `tme`
+    their times; `pointm2` holds the FULL series: sstemp and tc on the DTM, sublmelt, tempmelt, rainmelt, snow, sdenc and
+    sdeng on the coarse grid `dtmc` (they are summed over each gap and then resampled, `.resamplemelt` :2620); `sdept`
+    the hourly maximum of the point models' canopy snow depth over the full series; `wuv`, `wvv` the coarse grid's mean
+    wind components of the modelled hours.  Result masked by the DTM (.cleansmod)."""
+    from . import snow as snowops
+
+    op = operator or snowops.gridmodelsnow2
+    dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
+    dtmc = as_raster(dtmc)
+    subs = np.asarray(subs, dtype=int)
+    ot = _obstime(np.asarray(tme).astype("datetime64[s]"))
+    ot["hour"] = np.floor(ot["hour"])
+    z = dtm.matrix()
+    vg = _sortl(vegp, np.asarray(sdept))
+    vg["leaft"] = np.where(np.isnan(vg["leaft"]), 0.01, vg["leaft"])
+    lats, lons = latslons_from_raster(dtm)
+    other: Dict[str, object] = dict(zref=float(zref), lats=lats, lons=lons, isnowdc=z * 0 + snowinitd,
+                                    isnowac=np.nan_to_num(z * 0 + snowinita).astype(np.int32),
+                                    isnowag=np.nan_to_num(z * 0 + snowinita).astype(np.int32))
+    sl = terrain(dtm, "slope").matrix()
+    sl[np.isnan(sl)] = 0
+    other["slope"] = mask(dtm.like(sl), dtm).matrix()
+    ap = terrain(dtm, "aspect").matrix()
+    ap[np.isnan(ap)] = 180
+    other["aspect"] = mask(dtm.like(ap), dtm).matrix()
+    other["hor"], other["skyview"] = api.horizon(z, dtm.res[0], want_svf=True)
+    other["wsa"] = _windsheltera(dtm, zref, 10 if dtm.res[0] <= 100 else 1)
+    arr3 = ("temp", "relhum", "pres", "swdown", "difrad", "lwdown", "windspeed", "precip")
+    clim = {k: np.asarray(climdata[k], dtype=np.float64) for k in arr3}
+    wdir = np.asarray(climdata["winddir"], dtype=np.float64)
+    pnt = {k: np.asarray(pointm[k], dtype=np.float64) for k in ("Gp", "Tc", "RswabsG", "RlwabsG", "umu", "tr")}
+    p2 = {k: np.asarray(v, dtype=np.float64) for k, v in pointm2.items()}
+    wss = np.sqrt(np.asarray(wuv, dtype=np.float64) ** 2 + np.asarray(wvv, dtype=np.float64) ** 2)
+    n = subs.size
+    shape = z.shape + (n,)
+    Tc, Tg, sdepc, sden = (np.full(shape, np.nan) for _ in range(4))
+    sdepg = np.zeros(shape)
+    with np.errstate(invalid="ignore"):
+        pos = p2["snow"][p2["snow"] > 0]
+    msnow = np.nanmean(pos) if pos.size else np.nan
+    intfrac = canintfrac(vg["hgt"], vg["pai"], 2, msnow, np.nanmean(p2["tc"]), 0)
+    other["isnowdg"] = (1 - intfrac) * other["isnowdc"]
+
+    def resamplemelt(a, b):  # ref .resamplemelt (R/internal.R:2620-2624)
+        return resample_bilinear(dtmc.like(a[:, :, b].sum(axis=2)), dtm).matrix()
+
+    ped = 0
+    for day in range(n // 24):
+        s = slice(day * 24, day * 24 + 24)
+        first = int(subs[s.start])
+        if first - 1 > 1:
+            b = np.arange(ped + 1, first) - 1  # 0-based hours between the previous modelled day and this one
+            mu = meltmu2(other["skyview"], p2["sstemp"][:, :, b], p2["tc"][:, :, b])
+            melt = resamplemelt(p2["sublmelt"], b) + resamplemelt(p2["rainmelt"], b) + mu * resamplemelt(p2["tempmelt"], b)
+            snowsum = resamplemelt(p2["snow"], b)
+            balancec = snowsum / 1000 - melt
+            balanceg = (1 - intfrac) * snowsum / 1000 - np.exp(-vg["pai"]) * melt
+            sdec = resamplemelt(p2["sdenc"], b) / b.size
+            sdeg = resamplemelt(p2["sdeng"], b) / b.size
+            other["isnowdc"] = other["isnowdc"] + balancec * (1000 / sdec)
+            other["isnowdg"] = other["isnowdg"] + balanceg * (1000 / sdeg)
+        with np.errstate(invalid="ignore"):
+            other["isnowdc"] = np.where(other["isnowdc"] < 0, 0.0, other["isnowdc"])
+            other["isnowdg"] = np.where(other["isnowdg"] < 0, 0.0, other["isnowdg"])
+        smod = op({k: v[s] for k, v in ot.items()}, dict({k: v[:, :, s] for k, v in clim.items()}, winddir=wdir[s]),
+                  {k: v[:, :, s] for k, v in pnt.items()}, vg, other, snowenv)
+        dsnow = smod["sdepc"] - other["isnowdc"][:, :, None]
+        dsnowg = smod["sdepg"] - other["isnowdg"][:, :, None]
+        dsnowc = dsnow - dsnowg
+        dtms = dtm.like(z + sdepg[:, :, s.stop - 1])
+        tpr = 10 * np.mean(wss[s]) ** 0.5
+        af = int(round(tpr / dtm.res[0]))
+        tpi = _tpicalc(af, min(dtm.nrows, dtm.ncols), dtms, tfact)
+        dsnowg2 = dsnowg * tpi[:, :, None]
+        dsnowc2 = dsnowc + dsnowg2
+        Tc[:, :, s], Tg[:, :, s], sden[:, :, s] = smod["Tc"], smod["Tg"], smod["sden"]
+        with np.errstate(invalid="ignore"):
+            sdc = dsnowc2 + other["isnowdc"][:, :, None]
+            sdg = dsnowg2 + other["isnowdg"][:, :, None]
+            sdc = np.where(sdc < 0, 0.0, sdc)
+            sdg = np.where(sdg < 0, 0.0, sdg)
+        sdepc[:, :, s], sdepg[:, :, s] = sdc, sdg
+        ped = int(subs[s.stop - 1])
+        other["isnowdc"], other["isnowdg"] = sdc[:, :, 23], sdg[:, :, 23]
+    out = dict(Tc=Tc, Tg=Tg, groundsnowdepth=sdepg, totalSWE=sdepc * sden, snowden=sden, umu=pnt["umu"])
+    land = ~np.isnan(z)
+    return {k: np.where(land[:, :, None], v, np.nan) for k, v in out.items()}
+
+
 # ---------------------------------------------------------------------------------------------
 # runmicro(snow = TRUE), data.frame climate: .runmicrosnow1
 # ---------------------------------------------------------------------------------------------

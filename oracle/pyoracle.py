@@ -143,3 +143,19 @@ def meltmu(skyview, stemp, tc):
     if rc != 0:
         raise RuntimeError("ref_meltmu failed")
     return out
+
+
+def meltmu2(mu, stemp, tc):
+    """The compiled reference's meltmu2 (src/microclimfCpp.cpp:5495); stemp / tc are [rows, cols, n]."""
+    lib = _lib("ref")
+    m = np.asfortranarray(mu, dtype=np.float64)
+    st = np.asfortranarray(stemp, dtype=np.float64)
+    t = np.asfortranarray(tc, dtype=np.float64)
+    out = np.empty(m.shape, dtype=np.float64, order="F")
+    PD = C.POINTER(C.c_double)
+    lib.ref_meltmu2.argtypes = [PD, C.c_int32, C.c_int32, PD, PD, C.c_int32, PD]
+    rc = lib.ref_meltmu2(m.ctypes.data_as(PD), m.shape[0], m.shape[1], st.ctypes.data_as(PD), t.ctypes.data_as(PD), st.shape[2],
+                         out.ctypes.data_as(PD))
+    if rc != 0:
+        raise RuntimeError("ref_meltmu2 failed")
+    return out

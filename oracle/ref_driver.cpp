@@ -420,6 +420,27 @@ extern "C" int ref_meltmu(const double* skyview, int32_t rows, int32_t cols, con
     }
 }
 
+NumericMatrix meltmu2(NumericMatrix mu, NumericVector stemp, NumericVector tc);
+// meltmu2 (src/microclimfCpp.cpp:5495): stemp / tc are column-major [rows, cols, n] arrays
+extern "C" int ref_meltmu2(const double* mu, int32_t rows, int32_t cols, const double* stemp, const double* tc, int32_t n,
+                           double* out) {
+    try {
+        NumericMatrix m(rows, cols);
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) m[i] = mu[i];
+        const size_t len = (size_t)rows * cols * n;
+        NumericVector st(len), t(len);
+        for (size_t i = 0; i < len; ++i) { st[i] = stemp[i]; t[i] = tc[i]; }
+        IntegerVector dim = {rows, cols, n};
+        st.attr("dim") = dim;
+        t.attr("dim") = dim;
+        NumericMatrix r = meltmu2(m, st, t);
+        for (size_t i = 0; i < (size_t)rows * cols; ++i) out[i] = r[i];
+        return 0;
+    } catch (...) {
+        return 1;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Snow (SURVEY.md NEXT-3): the reference's gridmodelsnow1 / gridmicrosnow1 behind the product's structs
 // ---------------------------------------------------------------------------------------------

@@ -267,6 +267,9 @@ def test_quick_snow_model_helpers_match_reference_cpu():
     st, tc = rng.normal(-1, 3, 60), rng.normal(0, 4, 60)
     np.testing.assert_allclose(hostmodel.meltmu(sv, st, tc), pyoracle.meltmu(sv, st, tc), rtol=1e-13, equal_nan=True)
     assert np.array_equal(hostmodel.meltmu(sv, -np.abs(st), tc), pyoracle.meltmu(sv, -np.abs(st), tc))  # all ones
+    st3 = rng.normal(-1, 3, (9, 7, 40)); st3[1, 1, :] = -np.abs(st3[1, 1, :])   # a cell without positive degree-hours: 0.5
+    tc3 = rng.normal(0, 4, (9, 7, 40))
+    np.testing.assert_allclose(hostmodel.meltmu2(sv, st3, tc3), pyoracle.meltmu2(sv, st3, tc3), rtol=1e-13, equal_nan=True)
 
 
 @pytest.mark.gpu
@@ -306,3 +309,58 @@ def test_snowmodelq1_quick_driver_matches_reference_operator():
     assert a["Tc"].shape == (rows, cols, 72) and np.nanmax(a["totalSWE"]) > 0
     with pytest.raises(ValueError, match="sbtn"):
         hostmodel.snowmodelq1(weather, pmod, np.arange(1, 25), mk(z), vegp, soilc, **kw)
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_snowmodelq2_quick_driver_gridded_climate():
+    """hostmodel.snowmodelq2 (.snowmodelq2, R/internal.R:3017-3290): the quick model on fine-raster climate arrays with the
+    gap balances from coarse-grid point-model series (meltmu2, .resamplemelt); CUDA gridmodelsnow2 against the compiled
+    reference's in the same driver."""
+    from microclimf_b200 import hostmodel
+    from microclimf_b200.spatial import Raster, aggregate_mean
+    rows, cols, days = 20, 16, 9
+    T = 24 * days
+    s = synth.make_snow_inputs(rows, cols, T, seed=37)
+    clim, pointm, _ = _array_inputs(s, rows, cols)
+    rng = np.random.default_rng(10)
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    z = 280 + 30 * np.sin(ii / 4.0) * np.cos(jj / 3.0) + rng.normal(0, 0.5, (rows, cols))
+    z[-1, -2:] = np.nan
+    crs = ('PROJCRS["OSGB36 / British National Grid",BASEGEOGCRS["OSGB36",DATUM["Ordnance Survey of Great Britain 1936",'
+           'ELLIPSOID["Airy 1830",6377563.396,299.3249646]]],CONVERSION["British National Grid",METHOD["Transverse Mercator"],'
+           'PARAMETER["Latitude of natural origin",49],PARAMETER["Longitude of natural origin",-2],'
+           'PARAMETER["Scale factor at natural origin",0.9996012717],PARAMETER["False easting",400000],'
+           'PARAMETER["False northing",-100000]]]')
+    mk = lambda v: Raster(v, 170000.0, 170000.0 + cols * 10.0, 12000.0, 12000.0 + rows * 10.0, crs)  # noqa: E731
+    dtm = mk(z)
+    dtmc = aggregate_mean(mk(np.nan_to_num(z, nan=280.0)), 4)           # 5 x 4 coarse grid
+    cr, cc = dtmc.nrows, dtmc.ncols
+    hgt = np.nan_to_num(s["vegp"]["hgt"], nan=0.5)
+    vegp = {k: mk(np.nan_to_num(s["vegp"].get(k, hgt), nan=0.3)) for k in hostmodel.VEG_NAMES if k in s["vegp"] or k == "hgt"}
+    for k in hostmodel.VEG_NAMES:
+        vegp.setdefault(k, mk(np.full((rows, cols), 0.3)))
+    soilc = dict(soiltype=mk(np.full((rows, cols), 4.0)), groundr=mk(np.full((rows, cols), 0.15)))
+    tme = (np.datetime64("2023-01-10T00:00:00") + np.arange(T) * np.timedelta64(3600, "s")).astype("datetime64[s]")
+    sel_days = np.array([3, 6, 9])
+    subs = np.repeat((sel_days - 1) * 24, 24) + np.tile(np.arange(1, 25), sel_days.size)
+    ix = subs - 1
+    csub = {k: (v[:, :, ix] if np.ndim(v) == 3 else np.asarray(v)[ix]) for k, v in clim.items()}
+    psub = {k: v[:, :, ix] for k, v in pointm.items()}
+    tair = np.asarray(s["climdata"]["temp"])
+    coarse = lambda a, amp: a[None, None, :] + amp * rng.normal(0, 1, (cr, cc))[:, :, None]  # noqa: E731
+    pointm2 = dict(sstemp=np.minimum(clim["temp"] + 0.5, 1.0), tc=clim["temp"],
+                   sublmelt=np.abs(coarse(np.full(T, 2e-6), 2e-7)), tempmelt=np.abs(coarse(np.maximum(tair, 0) * 4e-5, 1e-6)),
+                   rainmelt=np.abs(coarse(np.full(T, 1e-6), 1e-7)),
+                   snow=np.where(coarse(tair, 0.3) > 2, 0.0, np.abs(coarse(np.asarray(s["climdata"]["precip"]), 0.05))),
+                   sdenc=coarse(np.full(T, 210.0), 5.0), sdeng=coarse(np.full(T, 260.0), 5.0))
+    wuv = np.asarray(s["climdata"]["windspeed"])[ix] * 0.6
+    wvv = np.asarray(s["climdata"]["windspeed"])[ix] * 0.5
+    args = (csub, psub, pointm2, tme[ix], subs, dtm, dtmc, vegp, soilc, np.full(T, 0.2), wuv, wvv)
+    kw = dict(snowenv="Maritime", snowinitd=0.12, zref=30.0)
+    a = hostmodel.snowmodelq2(*args, **kw)
+    b = hostmodel.snowmodelq2(*args, operator=pyoracle.gridmodelsnow2, **kw)
+    keys = ("Tc", "Tg", "groundsnowdepth", "totalSWE", "snowden")
+    ok, rows_ = parity.compare({k: a[k] for k in keys}, {k: b[k] for k in keys})
+    assert ok, "\n" + parity.fmt(rows_)
+    assert a["Tc"].shape == (rows, cols, 72) and np.nanmax(a["totalSWE"]) > 0 and np.isnan(a["Tc"][-1, -1]).all()
