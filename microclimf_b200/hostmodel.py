@@ -1224,6 +1224,50 @@ def snowmodelq2(climdata, pointm, pointm2, tme, subs, dtm, dtmc, vegp, soilc, sd
     return {k: np.where(land[:, :, None], v, np.nan) for k, v in out.items()}
 
 
+def runsnowmodel(weather, micropoint, pmod, vegp, soilc, dtm, snowenv: str = "Taiga", method: str = "fast", snowinitd: float = 0,
+                 snowinita: float = 0, zref: float = 2, stfact: float = 0.01, arrays=None, operator=None):
+    """ref runsnowmodel (R/Cppwrappers.R:718-760): the snow model behind `runmicro(snow = TRUE)`.  The point snow model is
+    upstream of this build, so its output travels as an argument: `pmod` = pointmodelsnow's list over the full series
+    (G, Tc, RswabsG, RlwabsG, umu, tr, sdepc, sdepg, and for the quick model sublmelt, tempmelt, rainmelt, sstemp, sdenc,
+    sdeng).
+
+    data.frame climate (`micropoint` a Micropoint): the full model (`snowmodel1`) when the point model covers every hour;
+    with a subset point model `method = "fast"` runs the quick model on the subset days (`snowmodelq1`), `"slow"` the
+    full model followed by `subsetsnowmodel` — exactly the reference's dispatch, including which zref each branch uses.
+    Gridded climate (`micropoint` a list): `arrays` holds the keyword arguments of `snowmodel2` / `snowmodelq2` that
+    `.snowmodel2` / `.snowmodelq2` build from the rasters (climdata, pointm, tme, sdept, wuv, wvv, ... — see those
+    functions); the dispatch is the same."""
+    vegp = _cleanvegp({k: as_raster(v) for k, v in vegp.items()})
+    if isinstance(micropoint, Micropoint):
+        g = lambda k: np.asarray(pmod[k], dtype=np.float64)  # noqa: E731
+        n = len(weather["temp"])
+        pointm = dict(Gp=g("G"), Tc=g("Tc"), RswabsG=g("RswabsG"), RlwabsG=g("RlwabsG"), umu=g("umu"), tr=g("tr"),
+                      sdepc=g("sdepc")[:n])
+        full = len(micropoint.subs) == len(micropoint.tmeorig)
+        if full:
+            return snowmodel1(weather, pointm, dtm, vegp, soilc, snowenv, snowinitd, snowinita, micropoint.zref, stfact,
+                              operator=operator)
+        if method == "fast":
+            return snowmodelq1(weather, pmod, micropoint.subs, dtm, vegp, soilc, snowenv, snowinitd, snowinita, zref, stfact,
+                               operator=operator)
+        smod = snowmodel1(weather, pointm, dtm, vegp, soilc, snowenv, snowinitd, snowinita, zref, stfact, operator=operator)
+        return subsetsnowmodel(smod, micropoint.subs)
+    if arrays is None:
+        raise ValueError("gridded climate: pass the prepared arrays of snowmodel2 / snowmodelq2 as `arrays`")
+    one = next(m for m in micropoint if m is not None)
+    kw = dict(arrays)
+    full = len(one.subs) == len(one.tmeorig)
+    if full:
+        return snowmodel2(dtm=dtm, vegp=vegp, soilc=soilc, snowenv=snowenv, snowinitd=snowinitd, snowinita=snowinita,
+                          zref=micropoint[0].zref if micropoint[0] is not None else one.zref, tfact=stfact, operator=operator, **kw)
+    if method == "fast":
+        return snowmodelq2(subs=one.subs, dtm=dtm, vegp=vegp, soilc=soilc, snowenv=snowenv, snowinitd=snowinitd,
+                           snowinita=snowinita, zref=zref, tfact=stfact, operator=operator, **kw)
+    smod = snowmodel2(dtm=dtm, vegp=vegp, soilc=soilc, snowenv=snowenv, snowinitd=snowinitd, snowinita=snowinita, zref=zref,
+                      tfact=stfact, operator=operator, **kw)
+    return subsetsnowmodel(smod, one.subs)
+
+
 # ---------------------------------------------------------------------------------------------
 # runmicro(snow = TRUE), data.frame climate: .runmicrosnow1
 # ---------------------------------------------------------------------------------------------

@@ -364,3 +364,52 @@ def test_snowmodelq2_quick_driver_gridded_climate():
     ok, rows_ = parity.compare({k: a[k] for k in keys}, {k: b[k] for k in keys})
     assert ok, "\n" + parity.fmt(rows_)
     assert a["Tc"].shape == (rows, cols, 72) and np.nanmax(a["totalSWE"]) > 0 and np.isnan(a["Tc"][-1, -1]).all()
+
+
+@pytest.mark.gpu
+def test_runsnowmodel_dispatch():
+    """runsnowmodel (R/Cppwrappers.R:718-760), data.frame climate: full point model -> snowmodel1; subset point model ->
+    the quick model (method "fast") or the full model followed by subsetsnowmodel ("slow")."""
+    from microclimf_b200 import hostmodel
+    from microclimf_b200.hostmodel import Micropoint
+    from microclimf_b200.spatial import Raster
+    rows, cols, days = 14, 12, 10
+    T = 24 * days
+    s = synth.make_snow_inputs(rows, cols, T, seed=41)
+    rng = np.random.default_rng(11)
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    z = 300 + 25 * np.sin(ii / 3.0) * np.cos(jj / 3.0) + rng.normal(0, 0.5, (rows, cols))
+    mk = lambda v: Raster(v, 0, cols * 10.0, 0, rows * 10.0, "")  # noqa: E731
+    hgt = np.nan_to_num(s["vegp"]["hgt"], nan=0.5)
+    vegp = {k: mk(np.nan_to_num(s["vegp"].get(k, hgt), nan=0.3)) for k in hostmodel.VEG_NAMES if k in s["vegp"] or k == "hgt"}
+    for k in hostmodel.VEG_NAMES:
+        vegp.setdefault(k, mk(np.full((rows, cols), 0.3)))
+    soilc = dict(soiltype=mk(np.full((rows, cols), 4.0)), groundr=mk(np.full((rows, cols), 0.15)))
+    tme = (np.datetime64("2023-01-10T00:00:00") + np.arange(T) * np.timedelta64(3600, "s")).astype("datetime64[s]")
+    weather = dict(s["climdata"], obs_time=tme)
+    p = s["pointm"]
+    tair = np.asarray(s["climdata"]["temp"])
+    pmod = dict(G=p["Gp"], Tc=p["Tc"], RswabsG=p["RswabsG"], RlwabsG=p["RlwabsG"], umu=p["umu"], tr=p["tr"],
+                sdepc=np.full(T + 1, 0.25), sdepg=np.full(T + 1, 0.2), sublmelt=np.full(T, 2e-6),
+                tempmelt=np.maximum(tair, 0) * 4e-5, rainmelt=np.full(T, 1e-6), sstemp=np.minimum(tair + 0.5, 1.0),
+                sdenc=np.full(T, 210.0), sdeng=np.full(T, 260.0))
+    mp_full = Micropoint(weather=weather, dfo={}, Tbz=None, lat=50.0, long=-5.0, zref=30.0, subs=np.arange(1, T + 1),
+                         tmeorig=tme, matemp=5.0)
+    sel_days = np.array([4, 8])
+    subs = np.repeat((sel_days - 1) * 24, 24) + np.tile(np.arange(1, 25), sel_days.size)
+    mp_sub = Micropoint(weather=weather, dfo={}, Tbz=None, lat=50.0, long=-5.0, zref=30.0, subs=subs, tmeorig=tme, matemp=5.0)
+    kw = dict(snowenv="Alpine", snowinitd=0.1, zref=30.0)
+    keys = ("Tc", "Tg", "groundsnowdepth", "totalSWE", "snowden")
+    same = lambda a, b: all(np.array_equal(a[k], b[k], equal_nan=True) for k in keys)  # noqa: E731
+    cv = hostmodel._cleanvegp(vegp)
+    pointm = dict(Gp=pmod["G"], Tc=pmod["Tc"], RswabsG=pmod["RswabsG"], RlwabsG=pmod["RlwabsG"], umu=pmod["umu"], tr=pmod["tr"],
+                  sdepc=pmod["sdepc"][:T])
+    full = hostmodel.runsnowmodel(weather, mp_full, pmod, vegp, soilc, mk(z), **kw)
+    want_full = hostmodel.snowmodel1(weather, pointm, mk(z), cv, soilc, "Alpine", 0.1, 0, 30.0, 0.01)
+    assert same(full, want_full) and full["Tc"].shape == (rows, cols, T)
+    fast = hostmodel.runsnowmodel(weather, mp_sub, pmod, vegp, soilc, mk(z), method="fast", **kw)
+    assert same(fast, hostmodel.snowmodelq1(weather, pmod, subs, mk(z), cv, soilc, "Alpine", 0.1, 0, 30.0, 0.01))
+    slow = hostmodel.runsnowmodel(weather, mp_sub, pmod, vegp, soilc, mk(z), method="slow", **kw)
+    assert same(slow, hostmodel.subsetsnowmodel(want_full, subs)) and slow["Tc"].shape == (rows, cols, 48)
+    with pytest.raises(ValueError, match="prepared arrays"):
+        hostmodel.runsnowmodel(weather, [mp_sub], pmod, vegp, soilc, mk(z))
