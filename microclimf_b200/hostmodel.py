@@ -1687,3 +1687,36 @@ def runbioclim(climdata, reqhgt, vegp, soilc, dtm, pointmodel, temp="air", zref=
              temp == "air")
     na = np.isnan(dtm_u.matrix())
     return {k: np.where(na, np.nan, v) for k, v in bio.items()}
+
+
+def runbioclim_a(micropointa, prech, tcmean, tme, reqhgt, vegp, soilc, dtm, dtmc, temp="air", runchecks=True, altcorrect=0,
+                 pai_a=None, tfact=1.5, out=(True,) * 19, operator=None):
+    """ref runbioclim with gridded climate and static vegetation -> .runbioclim2 (R/internal.R:1896-2081).
+
+    The point models are upstream of this build: `micropointa` is what `.biomicropoint` returns (:1921) — one Micropoint
+    for the 14 bioclim days (336 h) per cell of the coarse raster `dtmc`, None for sea cells.  `prech` and `tcmean` are
+    the space means of the climate array's precipitation and temperature for every hour of the full series and `tme`
+    its times (they choose the quarters, :1909-1917).  The coarse series go to the fused CUDA operator as they are
+    (interpolated in the kernels) instead of being expanded to [rows, cols, 336] arrays on the host.
+    Time-variant vegetation (`.runbioclim4`) is not built: a NotImplementedError says so."""
+    dtm_u, vegp_u, _ = _unpack(dtm, vegp, soilc)
+    if _vegpdmx(vegp_u) > 1:
+        raise NotImplementedError("runbioclim with gridded climate and time-variant vegetation (.runbioclim4) is not built")
+    ot_full = _obstime(np.asarray(tme).astype("datetime64[s]"))
+    months = sorted(set(ot_full["month"].tolist()))
+    pr, tc = np.asarray(prech, dtype=np.float64), np.asarray(tcmean, dtype=np.float64)
+    pmean = [np.nanmean(pr[ot_full["month"] == m]) for m in months]
+    tsum = [np.nansum(tc[ot_full["month"] == m]) for m in months]
+    wq, dq = _quarter(pmean, np.argmax), _quarter(pmean, np.argmin)
+    hq, cq = _quarter(tsum, np.argmax), _quarter(tsum, np.argmin)
+    call = prepare_model_a(micropointa, vegp, soilc, dtm, dtmc, reqhgt, runchecks, altcorrect, pai_a, tfact)
+    prob = call.problem()
+    if prob.tsteps != 336:
+        raise ValueError("micropointa must hold the 14 bioclim days (336 hours)")
+    month = np.asarray(_obstime(next(m for m in micropointa if m is not None).weather["obs_time"])["month"])
+    q = [(_getselq(x, month) - 1).astype(np.int32) for x in (wq, dq, hq, cq)]
+    fn = operator or api.run_bioclim_problem  # tests inject the reference's on the expanded arrays
+    bio = fn(prob, q[0], q[1], q[2], q[3], temp == "air", [bool(o) for o in out])
+    na = np.isnan(dtm_u.matrix())
+    return {k: np.where(na, np.nan, v) for k, v in bio.items()}
+

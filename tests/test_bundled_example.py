@@ -379,3 +379,36 @@ def test_gridded_climate_runmicro(altcorrect):
     assert np.array_equal(mout["Tz"], got["Tz"], equal_nan=True)
     with pytest.raises(ValueError, match="Require dtmc"):
         hostmodel.runmicro(mpa, 0.05, vegp, soilc, dtm)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("altcorrect", [0, 2])
+def test_runbioclim_gridded_climate(altcorrect):
+    """runbioclim with gridded climate, static vegetation (.runbioclim2, R/internal.R:1896-2081): the coarse series of the
+    14 bioclim days interpolated in the kernels + the 19 reductions, against the compiled reference's runbioclim2Cpp on
+    the [rows, cols, 336] arrays the R code would have expanded."""
+    from oracle import prep_oracle
+    dtm, vegp, soilc, mp, clim = load_example()
+    vegp1 = {k: (v.like(v.values[:, :, :1]) if v.values.shape[2] > 1 else v) for k, v in vegp.items()}   # static vegetation
+    vegp1 = _fill_reflectance(vegp1, dtm)
+    tme = np.asarray(clim["obs_time"]).astype("datetime64[s]")
+    selh, seld = hostmodel._biosel(tme, clim["temp"])
+    w336 = {k: np.asarray(v)[selh - 1] for k, v in clim.items()}
+    d_u, v_u, s_u = hostmodel._unpack(dtm, vegp1, soilc)
+    mp336 = _pointmodel336(w336, 0.05, d_u, v_u, s_u, 2, 2, None)
+    mpa, dtmc = _micropointa(mp336, dtm)
+
+    def ref_op(prob, wetq, dryq, hotq, colq, air, out):
+        return pyoracle.runbioclim(prep_oracle.materialise_coarse(prob), dict(wetq=wetq, dryq=dryq, hotq=hotq, colq=colq),
+                                   air=air, out_mask=out, kind="ref" if pyoracle.have_ref() else "oracle")
+
+    args = (mpa, clim["precip"], clim["temp"], tme, 0.05, vegp1, soilc, dtm, dtmc)
+    got = hostmodel.runbioclim_a(*args, altcorrect=altcorrect)
+    want = hostmodel.runbioclim_a(*args, altcorrect=altcorrect, operator=ref_op)
+    assert set(got) == {f"bio{i}" for i in range(1, 20)}
+    ok, rows = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rows)
+    land = ~np.isnan(dtm.matrix())
+    assert np.isfinite(got["bio1"][land]).all() and np.all(got["bio5"][land] >= got["bio6"][land])
+    with pytest.raises(NotImplementedError):
+        hostmodel.runbioclim_a(mpa, clim["precip"], clim["temp"], tme, 0.05, vegp, soilc, dtm, dtmc)
