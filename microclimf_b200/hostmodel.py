@@ -1690,18 +1690,17 @@ def runbioclim(climdata, reqhgt, vegp, soilc, dtm, pointmodel, temp="air", zref=
 
 
 def runbioclim_a(micropointa, prech, tcmean, tme, reqhgt, vegp, soilc, dtm, dtmc, temp="air", runchecks=True, altcorrect=0,
-                 pai_a=None, tfact=1.5, out=(True,) * 19, operator=None):
-    """ref runbioclim with gridded climate and static vegetation -> .runbioclim2 (R/internal.R:1896-2081).
+                 pai_a=None, tfact=1.5, out=(True,) * 19, vegpisannual=True, operator=None):
+    """ref runbioclim with gridded climate -> .runbioclim2 (static vegetation, R/internal.R:1896-2081) / .runbioclim4
+    (time-variant vegetation, :2200-2388).
 
     The point models are upstream of this build: `micropointa` is what `.biomicropoint` returns (:1921) — one Micropoint
     for the 14 bioclim days (336 h) per cell of the coarse raster `dtmc`, None for sea cells.  `prech` and `tcmean` are
     the space means of the climate array's precipitation and temperature for every hour of the full series and `tme`
     its times (they choose the quarters, :1909-1917).  The coarse series go to the fused CUDA operator as they are
-    (interpolated in the kernels) instead of being expanded to [rows, cols, 336] arrays on the host.
-    Time-variant vegetation (`.runbioclim4`) is not built: a NotImplementedError says so."""
-    dtm_u, vegp_u, _ = _unpack(dtm, vegp, soilc)
-    if _vegpdmx(vegp_u) > 1:
-        raise NotImplementedError("runbioclim with gridded climate and time-variant vegetation (.runbioclim4) is not built")
+    (interpolated in the kernels) instead of being expanded to [rows, cols, 336] arrays on the host."""
+    dtm_u, vegp_u, soilc_u = _unpack(dtm, vegp, soilc)
+    layered = _vegpdmx(vegp_u) > 1
     ot_full = _obstime(np.asarray(tme).astype("datetime64[s]"))
     months = sorted(set(ot_full["month"].tolist()))
     pr, tc = np.asarray(prech, dtype=np.float64), np.asarray(tcmean, dtype=np.float64)
@@ -1713,6 +1712,23 @@ def runbioclim_a(micropointa, prech, tcmean, tme, reqhgt, vegp, soilc, dtm, dtmc
     prob = call.problem()
     if prob.tsteps != 336:
         raise ValueError("micropointa must hold the 14 bioclim days (336 hours)")
+    if layered:
+        # .runbioclim4 (R/internal.R:2200-2388): the vegetation layer in force on each of the 14 days (.sortvegp2), one
+        # day-block per layer, foliage density per layer
+        vegp_c, dtm_c, soilc_c = _cleanvars(vegp_u, soilc_u, dtm_u)
+        if runchecks:
+            one = next(m for m in micropointa if m is not None)
+            vegp_c = checkinputs(one.weather, vegp_c, soilc_c, dtm_c, one.zref)["vegp"]
+        _, seld = _biosel(np.asarray(tme).astype("datetime64[s]"), tc)
+        vg = _sortvegp2(vegp_c, seld, vegpisannual, pr.size)
+        fd = _foliageden(reqhgt, vg["hgt"], vg["pai"], None if pai_a is None else as_raster(pai_a, dtm_u).values.squeeze())
+        vg["paia"], vg["leafden"] = fd["pai_a"], fd["leafden"]
+        prob.mode, prob.nlyr = 4, 14
+        prob.lyr_st = (np.arange(14) * 24).astype(np.int32)
+        prob.lyr_ed = (np.arange(14) * 24 + 23).astype(np.int32)
+        for k, v in vg.items():
+            prob.set(k, v)
+        prob.validate()
     month = np.asarray(_obstime(next(m for m in micropointa if m is not None).weather["obs_time"])["month"])
     q = [(_getselq(x, month) - 1).astype(np.int32) for x in (wq, dq, hq, cq)]
     fn = operator or api.run_bioclim_problem  # tests inject the reference's on the expanded arrays

@@ -384,9 +384,9 @@ def test_gridded_climate_runmicro(altcorrect):
 @pytest.mark.gpu
 @pytest.mark.parametrize("altcorrect", [0, 2])
 def test_runbioclim_gridded_climate(altcorrect):
-    """runbioclim with gridded climate, static vegetation (.runbioclim2, R/internal.R:1896-2081): the coarse series of the
-    14 bioclim days interpolated in the kernels + the 19 reductions, against the compiled reference's runbioclim2Cpp on
-    the [rows, cols, 336] arrays the R code would have expanded."""
+    """runbioclim with gridded climate (.runbioclim2 / .runbioclim4, R/internal.R:1896-2081, 2200-2388): the coarse series
+    of the 14 bioclim days interpolated in the kernels + the 19 reductions, against the compiled reference's
+    runbioclim2Cpp / runbioclim4Cpp on the [rows, cols, 336] arrays the R code would have expanded."""
     from oracle import prep_oracle
     dtm, vegp, soilc, mp, clim = load_example()
     vegp1 = {k: (v.like(v.values[:, :, :1]) if v.values.shape[2] > 1 else v) for k, v in vegp.items()}   # static vegetation
@@ -410,5 +410,11 @@ def test_runbioclim_gridded_climate(altcorrect):
     assert ok, "\n" + parity.fmt(rows)
     land = ~np.isnan(dtm.matrix())
     assert np.isfinite(got["bio1"][land]).all() and np.all(got["bio5"][land] >= got["bio6"][land])
-    with pytest.raises(NotImplementedError):
-        hostmodel.runbioclim_a(mpa, clim["precip"], clim["temp"], tme, 0.05, vegp, soilc, dtm, dtmc)
+    if altcorrect == 0:
+        # time-variant vegetation (.runbioclim4, R/internal.R:2200-2388): the bundled 12 layers -> 14 one-day layers
+        vegp12 = _fill_reflectance(vegp, dtm)
+        got4 = hostmodel.runbioclim_a(mpa, clim["precip"], clim["temp"], tme, 0.05, vegp12, soilc, dtm, dtmc)
+        want4 = hostmodel.runbioclim_a(mpa, clim["precip"], clim["temp"], tme, 0.05, vegp12, soilc, dtm, dtmc, operator=ref_op)
+        ok, rows = parity.compare(got4, want4)
+        assert ok, "\n" + parity.fmt(rows)
+        assert not np.allclose(got4["bio1"][land], got["bio1"][land])      # the seasonal layers matter
