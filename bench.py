@@ -366,6 +366,27 @@ def gpu_arm(args):
                   "d2h_bytes_per_step": sum(o.nbytes for o in pouts), "steps": esteps, "ms_per_step": 1e3 * p_s / esteps,
                   "pcie_gb_per_s": (h2d + sum(o.nbytes for o in pouts)) * esteps / p_s / 1e9,
                   "sample": "same tile through mcf_runmicro_packed: int16 outputs as the reference's writetonc stores them"}
+    # the same FP64 call into PAGEABLE result buffers — what R hands the library (its vectors are ordinary memory): served
+    # by the pool of copy threads with pinned slots.  N = 1 only; reported beside the pinned e2e.
+    e2e_pageable = None
+    if world == 1:
+        try:
+            import numpy as np
+            gouts = [np.empty(er * ec * et, dtype=np.float64) for _ in range(10)]
+            for _ in range(2):
+                api.run_problem(ep, out_buffers=gouts)
+            gsteps = max(1, min(args.steps, 3))
+            t0 = time.perf_counter()
+            for _ in range(gsteps):
+                api.run_problem(ep, out_buffers=gouts)
+            torch.cuda.synchronize()
+            g_s = time.perf_counter() - t0
+            e2e_pageable = {"value": float(er) * ec * et * gsteps / g_s, "unit": UNIT, "steps": gsteps,
+                            "ms_per_step": 1e3 * g_s / gsteps, "d2h_bytes_per_step": d2h,
+                            "sample": "same tile, result buffers in pageable host memory (as R's vectors are)"}
+            del gouts
+        except Exception as exc:  # an extra key: never let it take the benchmark down
+            e2e_pageable = {"error": repr(exc)}
     del pin_keep
 
     # ------------------------------------------------------------------ the optional FP32 build, same workload
@@ -417,7 +438,8 @@ def gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "e2e_packed": e2e_packed, "fp32": fp32,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "e2e_packed": e2e_packed, "e2e_pageable": e2e_pageable,
+            "fp32": fp32,
             "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "setup_seconds": t_gen,
         }
