@@ -15,6 +15,10 @@ result is 4.7 TB per variable and exists nowhere; the ring keeps the HBM write t
   roofline  : dominant kernel (k_grid) — algorithmic HBM bytes / CUDA-event launch time vs measured
               copy bandwidth; plus the FP64-pipe fraction (the binding roofline)
   cpu_baseline : the UNMODIFIED reference C++ (oracle/_ref) on the host cores, bounded sample
+  extra keys: e2e_packed (int16 sink through the same host call), e2e_pageable (pageable result buffers, N = 1),
+              fp32 (the optional FP32 build on the headline workload), clocks, gpu_launches
+
+stdout carries exactly ONE line (the JSON); everything else, NCCL's banner included, goes to stderr.
 
 `--impl reference` times only the reference CPU path (same metric / config), rank 0 only.
 """
