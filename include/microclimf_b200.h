@@ -210,7 +210,10 @@ int mcf_runbioclim(const mcf_problem* prob, const int32_t* wetq, int32_t nwetq, 
  * layer 1, ... which must be ascending and non-overlapping).  Hour k of the problem is written to
  * time slot ((k - hour0) mod ring_hours) of each output buffer, whose slot stride is rows*cols;
  * ring_hours >= 24 lets a caller reuse a small buffer as a ring (the output sink for rasters whose
- * full [rows, cols, tsteps] result exceeds HBM).  Window {0, -1, 0, tsteps} = the whole problem. */
+ * full [rows, cols, tsteps] result exceeds HBM).  Window {0, -1, 0, tsteps} = the whole problem.
+ * Preconditions (MCF_ERR_ARG otherwise): 0 <= hour0 <= first hour of block0, ring_hours >= 24.
+ * A PARTIAL window writes the hours of its day-blocks and nothing else: hours no block covers and outputs
+ * the requested height never produces are NA-filled only when the window is the whole problem. */
 typedef struct mcf_window {
     int32_t block0;
     int32_t nblocks; /* -1 = all remaining blocks */
@@ -263,7 +266,8 @@ int mcf_twi_partial(const double* twi, int64_t n, double tfact, double* sum, int
 /* ------------------------------------------------------------------------------------------- */
 int mcf_abi_version(void);
 /* The host-buffer entry points keep one grow-only device workspace between calls (allocating and
- * freeing tens of arrays per call costs more than the solve); this releases it. */
+ * freeing tens of arrays per call costs more than the solve); this releases it.  It belongs to the device
+ * that was current when it was allocated: mcf_set_device() to another device releases it first. */
 void mcf_release_workspace(void);
 int mcf_device_count(void);
 int mcf_set_device(int device);

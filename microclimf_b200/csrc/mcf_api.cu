@@ -471,24 +471,47 @@ Err prefill_whole(const Plan& pl, double* const out[MCF_NOUT], cudaStream_t st) 
     return Err();
 }
 
+// Resolve and validate a time window against the day-block list.  The kernels place hour k of the window in ring slot
+// (k - hour0) mod ring_hours with C++ '%', so hour0 must not lie beyond the window's first hour (a negative remainder
+// would index in front of the output buffers).
+Err resolve_window(const mcf_window* win, const std::vector<DayBlock>& blocks, int tsteps, int& b0, int& nb,
+                   long long& hour0, long long& ring) {
+    const int nblk = (int)blocks.size();
+    b0 = 0;
+    nb = nblk;
+    hour0 = 0;
+    ring = tsteps;
+    if (!win) return Err();
+    b0 = win->block0;
+    nb = win->nblocks < 0 ? nblk - b0 : win->nblocks;
+    hour0 = win->hour0;
+    ring = win->ring_hours;
+    if (b0 < 0 || nb < 0 || b0 + nb > nblk) return make_err(MCF_ERR_ARG, "window outside the %d day-blocks", nblk);
+    if (ring < 24) return make_err(MCF_ERR_ARG, "ring_hours must be >= 24");
+    if (hour0 < 0) return make_err(MCF_ERR_ARG, "window hour0 must be >= 0 (got %lld)", hour0);
+    if (nb > 0 && hour0 > blocks[b0].k0)
+        return make_err(MCF_ERR_ARG, "window hour0 (%lld) lies beyond the window's first hour (%d)", hour0, blocks[b0].k0);
+    return Err();
+}
+
 Err run_dev(const mcf_problem* p, double* const out[MCF_NOUT], const mcf_window* win, cudaStream_t st, int pack = 0) {
     Scratch sc(st);
     Plan pl;
     pl.pack = pack;
+    {   // argument errors are reported before any device work is queued
+        TRY(validate(p));
+        std::vector<DayBlock> blocks;
+        TRY(build_blocks(p, blocks));
+        int b0_, nb_;
+        long long h0_, ring_;
+        TRY(resolve_window(win, blocks, p->tsteps, b0_, nb_, h0_, ring_));
+    }
     TRY(plan_prepare(pl, p, sc, st));
     const int nblk = (int)pl.blocks.size();
     int b0 = 0, nb = nblk;
     long long hour0 = 0, ring = p->tsteps;
-    bool whole = true;
-    if (win) {
-        b0 = win->block0;
-        nb = win->nblocks < 0 ? nblk - b0 : win->nblocks;
-        hour0 = win->hour0;
-        ring = win->ring_hours;
-        if (b0 < 0 || nb < 0 || b0 + nb > nblk) return make_err(MCF_ERR_ARG, "window outside the %d day-blocks", nblk);
-        if (ring < 24) return make_err(MCF_ERR_ARG, "ring_hours must be >= 24");
-        whole = (b0 == 0 && nb == nblk && hour0 == 0 && ring >= p->tsteps);
-    }
+    TRY(resolve_window(win, pl.blocks, p->tsteps, b0, nb, hour0, ring));
+    const bool whole = !win || (b0 == 0 && nb == nblk && hour0 == 0 && ring >= p->tsteps);
     if (pl.rq == RQ_BELOW) {
         if (!whole) return make_err(MCF_ERR_ARG, "reqhgt < 0 needs the whole series in one window");
         TRY(prefill_whole(pl, out, st));
@@ -621,7 +644,12 @@ Err upload_problem(const mcf_problem* h, mcf_problem* d, DevCopy& dc) {
 struct StreamGuard {
     cudaStream_t s = nullptr;
     ~StreamGuard() {
-        if (s) cudaStreamDestroy(s);
+        if (!s) return;
+        // every exit path, errors included: nothing queued on the stream may still be using the workspace (or the
+        // caller's host buffers) once the call returns and g_ws_mu is released
+        (void)cudaStreamSynchronize(s);
+        (void)cudaStreamDestroy(s);
+        (void)cudaGetLastError();
     }
 };
 struct EventGuard {
@@ -783,7 +811,15 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT], int pack = 0) {
     size_t freeb = 0, totalb = 0;
     CU(cudaMemGetInfo(&freeb, &totalb));
     const size_t avail = freeb + g_ws.cap; // what a fresh reservation could use
-    bool fits = (double)in_bytes + (double)per_hour * T + (double)nreq * 256 < 0.55 * (double)avail;
+    // scratch the solve allocates beside inputs and outputs: the day stash, and for reqhgt < 0 the FP64 series the
+    // packed sink is packed from and the two expanded point-model series of coarse-grid climate (the ground-temperature
+    // chunk of plan_run_below sizes itself from what is left)
+    double scratch_bytes = 148.0 * 2 * 24 * kStashVars * kTile * sizeof(double);
+    if (rq == RQ_BELOW) {
+        if (pack && out[MCF_OUT_TZ]) scratch_bytes += (double)nc * T * sizeof(double);
+        if (hp->clim_rows > 0 && hp->p_Tg && hp->p_Tbp) scratch_bytes += 2.0 * (double)nc * T * sizeof(double);
+    }
+    bool fits = (double)in_bytes + (double)per_hour * T + (double)nreq * 256 + scratch_bytes < 0.55 * (double)avail;
     long long chunk_blocks = 0;
     // test hook: MCF_FORCE_STREAM_BLOCKS=n forces the streaming path with n day-blocks per device chunk
     const char* force = std::getenv("MCF_FORCE_STREAM_BLOCKS");
@@ -994,6 +1030,12 @@ int mcf_device_count(void) {
 }
 
 int mcf_set_device(int device) {
+    // The grow-only workspace and the pinned staging slots belong to the device that was current when they were
+    // allocated: give them back while that device is still current, so that the next host-buffer call carves its
+    // inputs and outputs from memory of the device it launches on.
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != device) mcf_release_workspace();
+    (void)cudaGetLastError();
     g_sm_count = 0;
     return cudaSetDevice(device) == cudaSuccess ? MCF_OK : MCF_ERR_CUDA;
 }
@@ -1048,17 +1090,9 @@ static Err run_dev_f32(const mcf_problem* p, float* const out[MCF_NOUT], const m
     Scratch sc(st);
     Plan pl;
     TRY(plan_prepare(pl, p, sc, st));
-    const int nblk = (int)pl.blocks.size();
-    int b0 = 0, nb = nblk;
+    int b0 = 0, nb = 0;
     long long hour0 = 0, ring = p->tsteps;
-    if (win) {
-        b0 = win->block0;
-        nb = win->nblocks < 0 ? nblk - b0 : win->nblocks;
-        hour0 = win->hour0;
-        ring = win->ring_hours;
-        if (b0 < 0 || nb < 0 || b0 + nb > nblk) return make_err(MCF_ERR_ARG, "window outside the %d day-blocks", nblk);
-        if (ring < 24) return make_err(MCF_ERR_ARG, "ring_hours must be >= 24");
-    }
+    TRY(resolve_window(win, pl.blocks, p->tsteps, b0, nb, hour0, ring));
     if (nb <= 0) return Err();
     char* hoursf = nullptr;
     CU(sc.alloc(&hoursf, (size_t)p->tsteps * hourrec_f32_bytes()));

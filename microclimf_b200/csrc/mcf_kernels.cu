@@ -689,6 +689,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 const int last_slot_wraps = (23 >= wrap_at);
                 o = last_slot_wraps ? (size_t)cell + (size_t)(23 - wrap_at) * a.ncells : o_first + (size_t)23 * a.ncells;
                 const double* st0 = stash + (size_t)23 * (kStashVars * kTile);
+                __syncwarp();
                 double radabs_n = ld_stash(&st0[0 * kTile]), surfwet_n = ld_stash(&st0[1 * kTile]);
                 double radCsw_n = ld_stash(&st0[2 * kTile]), Lhalf_n = ld_stash(&st0[3 * kTile]);
                 double soild_n = ld_stash(&st0[4 * kTile]), uf_n = ld_stash(&st0[5 * kTile]);
@@ -704,6 +705,11 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                         // the hour before, one iteration ahead (hour 0 re-reads itself, before its lines go: no branch
                         // in the loop body, which would cost the compiler its scheduling window)
                         const double* st = stash + (size_t)(hr > 0 ? hr - 1 : 0) * (kStashVars * kTile);
+                        // A stash line holds the values of 16 lanes and is discarded below by one of them, ordered only
+                        // behind that lane's own loaded registers.  Lanes may have diverged inside the previous hour's
+                        // physics: converge here, so that the loads are ONE warp instruction — when its result is
+                        // there for the discarding lane (next iteration) it is there for all 32
+                        __syncwarp();
                         radabs_n = ld_stash(&st[0 * kTile]);
                         surfwet_n = ld_stash(&st[1 * kTile]);
                         radCsw_n = ld_stash(&st[2 * kTile]);

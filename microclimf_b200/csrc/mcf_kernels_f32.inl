@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                 for (int hr = 23; hr >= 0; --hr) {
                     const HourRecF& h = slab_day[hr];
                     const float* st = stash + (size_t)hr * (kStashVars * kTileF);
+                    __syncwarp(); // one converged load instruction per line: complete for lane 0 = complete for all 32
                     const float radabs = ld_stash_f(&st[0 * kTileF]), surfwet = ld_stash_f(&st[1 * kTileF]);
                     const float radCsw = ld_stash_f(&st[2 * kTileF]), Lhalf = ld_stash_f(&st[3 * kTileF]);
                     const float soild = ld_stash_f(&st[4 * kTileF]);

@@ -198,6 +198,26 @@ def test_device_window_ring_matches_whole():
         np.testing.assert_array_equal(ring, whole[nm][:, :, 96:120])
 
 
+@pytest.mark.parametrize("window", [(0, 5, 24, 48), (2, 2, 49, 24), (1, 1, -1, 24), (0, 1, 0, 23), (5, 2, 120, 24)])
+def test_device_window_rejected_before_any_write(window):
+    """A window origin beyond the window's first hour would make the kernels' (k - hour0) % ring negative and index in
+    front of the output buffers: every sink rejects it (MCF_ERR_ARG) and leaves the buffers untouched."""
+    import torch
+
+    p = synth.make_problem(9, 7, 24 * 6, reqhgt=0.05, mode=1)
+    dp = p.to_device()
+    ring = max(window[3], 24)
+    outs = [torch.full((ring * p.ncells,), -1.0, dtype=torch.float64, device="cuda") for _ in range(10)]
+    outs16 = [torch.full((ring * p.ncells,), 7, dtype=torch.int16, device="cuda") for _ in range(10)]
+    outsf = [torch.full((ring * p.ncells,), -1.0, dtype=torch.float32, device="cuda") for _ in range(10)]
+    for fn, bufs in ((api.run_problem_dev, outs), (api.run_problem_packed_dev, outs16), (api.run_problem_f32_dev, outsf)):
+        with pytest.raises(_lib.McfError) as ei:
+            fn(dp, bufs, window=window)
+        assert ei.value.code == _abi.MCF_ERR_ARG
+    torch.cuda.synchronize()
+    assert all(bool((t == -1.0).all()) for t in outs + outsf) and all(bool((t == 7).all()) for t in outs16)
+
+
 @pytest.mark.parametrize("ring_hours,hour0", [(31, 48), (24, 37), (50, 0)])
 def test_device_window_ring_seam_inside_a_day(ring_hours, hour0):
     """A ring whose seam falls inside a day block (ring_hours not a multiple of 24, or a window origin that is not a
