@@ -194,7 +194,12 @@ int mcf_runmicro(const mcf_problem* prob, double* const out[MCF_NOUT], char* err
 /* runbioclimNCpp: tsteps must be 336 (14 days).  wetq/dryq/hotq/colq are 0-based hour indices
  * (src/microclimfCpp.cpp:3317-3360); `air` selects Tz (1) or tleaf (0).  bio[b] == NULL <=> out[b]
  * FALSE; each non-NULL buffer holds rows*cols doubles.  bio3 and bio7 are derived from bio2/5/6
- * computed internally, whether or not those outputs are requested. */
+ * computed internally, whether or not those outputs are requested.
+ * For reqhgt >= 0 the 19 reductions are accumulated inside the grid kernel while the 14 days are solved: the
+ * two [rows, cols, 336] arrays the reference materialises (src/microclimfCpp.cpp:3509-3515) never exist, so the
+ * raster size is bounded by the static layers alone.  Below ground the series needs the time-axis pass first
+ * and is reduced in chunks of cells (bounded scratch).  tsteps > 336 is accepted as the reference accepts it
+ * (soil statistics over all hours; hours no whole day covers make bio15 NA). */
 int mcf_runbioclim(const mcf_problem* prob, const int32_t* wetq, int32_t nwetq, const int32_t* dryq,
                    int32_t ndryq, const int32_t* hotq, int32_t nhotq, const int32_t* colq,
                    int32_t ncolq, int32_t air, double* const bio[MCF_NBIO], char* err, size_t errlen);
@@ -231,6 +236,24 @@ int mcf_runbioclim_dev(const mcf_problem* prob, const int32_t* wetq, int32_t nwe
                        const int32_t* dryq, int32_t ndryq, const int32_t* hotq, int32_t nhotq,
                        const int32_t* colq, int32_t ncolq, int32_t air, double* const bio[MCF_NBIO],
                        void* stream, char* err, size_t errlen);
+
+/* ------------------------------------------------------------------------------------------- */
+/* Summary sink: the hourly arrays of a large raster exist nowhere (config 4 of BASELINE.json: 4.7 TB per   */
+/* variable; the reference's runmicro_big, R/Cppwrappers.R:444-543, writes them tile by tile to disk).  These */
+/* entry points run the same solve and keep, per cell and requested output, the SUM, MINIMUM and MAXIMUM over */
+/* the computed hours of the window, accumulated inside the grid kernel; nothing hourly is stored.  NaN hours   */
+/* poison the sum and are ignored by the extremes; cells the reference skips (hgt NA) hold NA_real_; outputs     */
+/* the requested height never produces (tleaf / relhum at the surface) are NA.  reqhgt >= 0.                     */
+/* sum[v], mn[v], mx[v]: all three NULL (output not summarised) or all three [rows * cols].  accumulate != 0     */
+/* merges the window into what the buffers already hold (successive windows of one series); hours_done (may be   */
+/* NULL) receives the number of hours the call added.                                                            */
+/* ------------------------------------------------------------------------------------------- */
+int mcf_runmicro_summary_dev(const mcf_problem* prob, double* const sum[MCF_NOUT], double* const mn[MCF_NOUT],
+                             double* const mx[MCF_NOUT], const mcf_window* win, int32_t accumulate, int64_t* hours_done,
+                             void* stream, char* err, size_t errlen);
+/* HOST buffers, whole series: mean (= sum / hours_done), minimum and maximum per cell. */
+int mcf_runmicro_summary(const mcf_problem* prob, double* const mean[MCF_NOUT], double* const mn[MCF_NOUT],
+                         double* const mx[MCF_NOUT], int64_t* hours_done, char* err, size_t errlen);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Packed integer sink (SURVEY.md NEXT-4).  The reference stores hourly grids on disk as integers: */

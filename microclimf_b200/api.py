@@ -268,6 +268,51 @@ def run_problem_dev(p: GridProblem, out_tensors, window=None, stream=None) -> No
     del keep
 
 
+SUMMARY_STATS = ("mean", "min", "max")
+
+
+def run_summary(p: GridProblem, out: Optional[Sequence[bool]] = None):
+    """mcf_runmicro_summary on a host GridProblem: per-cell mean / minimum / maximum over the computed hours of each
+    requested output, reduced inside the grid kernel (nothing hourly is stored or copied).  Returns
+    ({name: {"mean" | "min" | "max": [rows, cols] array}}, hours)."""
+    L = _lib.lib()
+    out = [True] * _abi.MCF_NOUT if out is None else [bool(o) for o in out]
+    bufs = [[np.empty(p.ncells, dtype=np.float64) if o else None for o in out] for _ in range(3)]
+    ptrs = [_abi.OutPtrs(*[b.ctypes.data_as(_PD) if b is not None else None for b in bb]) for bb in bufs]
+    s, keep = p.as_struct()
+    hours = C.c_int64(0)
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runmicro_summary(C.byref(s), ptrs[0], ptrs[1], ptrs[2], C.byref(hours), err, 512), err)
+    del keep
+    res = {}
+    for v, nm in enumerate(_abi.OUT_NAMES):
+        if out[v]:
+            res[nm] = {st: bufs[k][v].reshape((p.rows, p.cols), order="F") for k, st in enumerate(SUMMARY_STATS)}
+    return res, int(hours.value)
+
+
+def run_summary_dev(p: GridProblem, sums, mins, maxs, window=None, accumulate: bool = False, stream=None) -> int:
+    """mcf_runmicro_summary_dev: device-resident problem; `sums`, `mins`, `maxs` are sequences of 10 CUDA float64
+    tensors [rows * cols] or None (all three or none per output).  Returns the hours the call added."""
+    import torch
+
+    L = _lib.lib()
+    st = torch.cuda.current_stream() if stream is None else stream
+    ptrs = [_abi.OutPtrs(*[C.cast(C.c_void_p(t.data_ptr()), _PD) if t is not None else None for t in tt])
+            for tt in (sums, mins, maxs)]
+    s, keep = p.as_struct()
+    w = None
+    if window is not None:
+        w = _abi.McfWindow(int(window[0]), int(window[1]), int(window[2]), int(window[3]))
+    hours = C.c_int64(0)
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runmicro_summary_dev(C.byref(s), ptrs[0], ptrs[1], ptrs[2], C.byref(w) if w is not None else None,
+                                          C.c_int32(1 if accumulate else 0), C.byref(hours), C.c_void_p(st.cuda_stream),
+                                          err, 512), err)
+    del keep
+    return int(hours.value)
+
+
 def run_bioclim_problem_dev(p: GridProblem, wetq, dryq, hotq, colq, air, bio_tensors, stream=None) -> None:
     import torch
 

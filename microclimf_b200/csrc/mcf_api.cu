@@ -301,6 +301,8 @@ void fill_common(const Plan& pl, GridArgs& a) {
     a.stash = pl.d_stash;
     a.pack = pl.pack;
     a.rows = p->rows;
+    a.out_stride = pl.ncells;
+    a.out_cell0 = 0;
     if (pl.arr == 2) {
         a.clim_rows = p->clim_rows;
         a.clim_cols = p->clim_cols;
@@ -317,14 +319,14 @@ void fill_common(const Plan& pl, GridArgs& a) {
     }
 }
 
-Err timed_grid_launch(const GridArgs& a, int arr, int rq, int grid, cudaStream_t st) {
+Err timed_grid_launch(const GridArgs& a, int arr, int rq, int grid, cudaStream_t st, int sink = -1) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_timing) {
         CU(cudaEventCreate(&e0));
         CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, st));
     }
-    CU(launch_grid(a, arr, rq, grid, st));
+    CU(launch_grid(a, arr, rq, grid, st, sink));
     count_launch();
     if (g_timing) {
         CU(cudaEventRecord(e1, st));
@@ -360,20 +362,28 @@ Err plan_run_window(const Plan& pl, double* const out[MCF_NOUT], int b0, int nb,
 }
 
 // Whole series for reqhgt < 0: grid kernel writes Tg into scratch per cell chunk, then the time-axis pass.
-Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cudaStream_t st) {
+// `bio` != NULL (runbioclim below ground): nothing hourly leaves the chunk — its below-ground Tz and soil moisture land
+// in two chunk-sized series ([tsteps][W], allocated here) and are reduced to the chunk's cells of the 19 summaries
+// before the next chunk reuses them, so the scratch is bounded whatever the raster size.
+Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cudaStream_t st, BioArgs* bio = nullptr) {
     const mcf_problem* p = pl.p;
     const int T = p->tsteps;
     const int numDays = T / 24;
     size_t freeb = 0, totalb = 0;
     CU(cudaMemGetInfo(&freeb, &totalb));
-    const size_t budget = std::max<size_t>(freeb / 4, (size_t)64 << 20);
+    size_t budget = std::max<size_t>(freeb / 4, (size_t)64 << 20);
+    if (bio) budget = std::min<size_t>(budget, (size_t)1 << 30) / 3;
     long long wmax = (long long)(budget / ((size_t)T * sizeof(double)));
     wmax = std::max<long long>(kTile, (wmax / kTile) * kTile);
     const int W = (int)std::min<long long>(wmax, ((pl.ncells + kTile - 1) / kTile) * kTile);
-    double *tg = nullptr, *dds = nullptr, *daily = nullptr;
+    double *tg = nullptr, *dds = nullptr, *daily = nullptr, *ctz = nullptr, *csm = nullptr;
     CU(sc.alloc(&tg, (size_t)T * W));
     CU(sc.alloc(&dds, W));
     CU(sc.alloc(&daily, (size_t)2 * std::max(numDays, 1) * W));
+    if (bio) {
+        CU(sc.alloc(&ctz, (size_t)T * W));
+        CU(sc.alloc(&csm, (size_t)T * W));
+    }
     const int nchunks = (pl.ncells + W - 1) / W;
     unsigned int* ctr = nullptr;
     CU(sc.alloc(&ctr, nchunks));
@@ -415,16 +425,27 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
             a.out[v] = out[v];
             if (out[v] && v != MCF_OUT_TZ && kernel_writes(pl.rq, v)) a.outmask |= 1u << v;
         }
+        if (bio) { // the chunk's soil moisture into its compact series; hours no day-block covers stay NA
+            CU(launch_fill_na(csm, (int64_t)T * W, st));
+            count_launch();
+            for (int v = 0; v < MCF_NOUT; ++v) a.out[v] = nullptr;
+            a.out[MCF_OUT_SOILM] = csm;
+            a.outmask = 1u << MCF_OUT_SOILM;
+            a.out_stride = W;
+            a.out_cell0 = c0;
+        }
         a.tile_counter = ctr + ch;
         a.tg_scratch = tg;
         a.dd_sum = dds;
         const int ntiles = (c1 - c0 + kTile - 1) / kTile;
         if (a.nblocks > 0) TRY(timed_grid_launch(a, pl.arr, pl.rq, std::min(pl.grid, ntiles), st));
-        if (out[MCF_OUT_TZ]) {
+        if (out[MCF_OUT_TZ] || bio) {
             BelowArgs b;
             std::memset(&b, 0, sizeof b);
             b.width = c1 - c0;
             b.ncells = pl.ncells;
+            b.tz_stride = bio ? W : pl.ncells;
+            b.tz_cell0 = bio ? c0 : 0;
             b.cell_begin = c0;
             b.tsteps = T;
             b.arr = pl.arr ? 1 : 0;
@@ -438,8 +459,18 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
             b.Tbp = tbp;
             b.hgt = p->hgt;
             b.daily = daily;
-            b.Tz = tz64 ? tz64 : out[MCF_OUT_TZ];
+            b.Tz = bio ? ctz : (tz64 ? tz64 : out[MCF_OUT_TZ]);
             CU(launch_below(b, st));
+            count_launch();
+        }
+        if (bio) {
+            BioArgs bb = *bio;
+            bb.width = c1 - c0;
+            bb.stride = W;
+            bb.Tz = ctz;
+            bb.soilm = csm;
+            bb.cell_begin = c0;
+            CU(launch_bioclim(bb, st));
             count_launch();
         }
     }
@@ -947,6 +978,23 @@ struct BioPatch {
     }
 };
 
+// Launch the grid kernel with a reducing sink over day-blocks [b0, b0 + nb) of the whole raster (reqhgt >= 0).
+Err plan_run_reduce(const Plan& pl, GridArgs& a, int sink, int b0, int nb, Scratch& sc, cudaStream_t st) {
+    if (nb <= 0) return Err();
+    a.cell_begin = 0;
+    a.cell_end = pl.ncells;
+    a.block0 = b0;
+    a.nblocks = nb;
+    a.hour0 = 0;
+    a.ring_hours = std::max(pl.p->tsteps, 24);
+    unsigned int* ctr = nullptr;
+    CU(sc.alloc(&ctr, 1));
+    CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
+    a.tile_counter = ctr;
+    const int ntiles = (pl.ncells + kTile - 1) / kTile;
+    return timed_grid_launch(a, pl.arr, pl.rq, std::min(pl.grid, ntiles), st, sink);
+}
+
 Err run_bioclim_dev(const mcf_problem* p, const int32_t* const q[4], const int32_t nq[4], int air,
                     double* const bio[MCF_NBIO], cudaStream_t st) {
     if (p->tsteps < 336) return make_err(MCF_ERR_ARG, "runbioclim needs the 14 selected days (336 hours), got %d", p->tsteps);
@@ -961,15 +1009,55 @@ Err run_bioclim_dev(const mcf_problem* p, const int32_t* const q[4], const int32
     TRY(plan_prepare(pl, &pp, sc, st));
     const int T = p->tsteps;
     const int nc = pl.ncells;
-    double *dTz = nullptr, *dsm = nullptr;
-    CU(sc.alloc(&dTz, (size_t)T * nc));
-    CU(sc.alloc(&dsm, (size_t)T * nc));
-    double* out[MCF_NOUT] = {nullptr};
-    out[air ? MCF_OUT_TZ : MCF_OUT_TLEAF] = dTz;
-    out[MCF_OUT_SOILM] = dsm;
-    TRY(prefill_whole(pl, out, st));
-    if (pl.rq == RQ_BELOW) TRY(plan_run_below(pl, out, sc, st));
-    else TRY(plan_run_window(pl, out, 0, (int)pl.blocks.size(), 0, T, sc, st));
+    uint32_t mask = 0;
+    for (int v = 0; v < MCF_NBIO; ++v)
+        if (bio[v]) mask |= 1u << v;
+    if (!mask) return Err();
+    // tleaf does not exist at or below the surface (ref :2300-2303): every cell keeps its NA fill (:3507-3508)
+    if (!air && pl.rq != RQ_ABOVE) {
+        for (int v = 0; v < MCF_NBIO; ++v)
+            if (bio[v]) {
+                CU(launch_fill_na(bio[v], nc, st));
+                count_launch();
+            }
+        return Err();
+    }
+    if (pl.rq != RQ_BELOW) {
+        // Fused: the 19 reductions are accumulated inside the grid kernel's day loop; no hourly series exists.
+        std::vector<char> covered(T, 0);
+        for (const DayBlock& b : pl.blocks)
+            for (int h = 0; h < 24; ++h) covered[b.k0 + h] = 1;
+        std::vector<uint32_t> qcnt(T, 0u);
+        uint32_t q_na = 0;
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < nq[i]; ++j) {
+                const int k = q[i][j];
+                if (!covered[k]) q_na |= 1u << i;
+                if (((qcnt[k] >> (8 * i)) & 255u) == 255u)
+                    return make_err(MCF_ERR_ARG, "quarter index vector %d repeats an hour more than 255 times", i);
+                qcnt[k] += 1u << (8 * i);
+            }
+        int soil_gap = 0;
+        for (int k = 0; k < T; ++k) soil_gap |= !covered[k];
+        uint32_t* d_qcnt = nullptr;
+        CU(sc.alloc(&d_qcnt, T));
+        // (pageable source: the copy is staged by the driver before the call returns)
+        CU(cudaMemcpyAsync(d_qcnt, qcnt.data(), (size_t)T * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        GridArgs a;
+        fill_common(pl, a);
+        for (int v = 0; v < MCF_NBIO; ++v) a.red[v] = bio[v];
+        a.red_mask = mask;
+        a.bio_air = air ? 1 : 0;
+        a.bio_soil_gap = soil_gap;
+        a.bio_q_na = q_na;
+        a.bio_qcnt = d_qcnt;
+        a.outmask = 0;
+        TRY(plan_run_reduce(pl, a, SINK_BIO, 0, (int)pl.blocks.size(), sc, st));
+        CU(cudaStreamSynchronize(st)); // qcnt lives on this frame
+        return Err();
+    }
+    // Below ground the series only exists after the time-axis pass over the whole year: chunks of cells, each reduced
+    // before the next one reuses the chunk's two series.
     int32_t* dq = nullptr;
     const int ntot = nq[0] + nq[1] + nq[2] + nq[3];
     CU(sc.alloc(&dq, ntot));
@@ -982,21 +1070,54 @@ Err run_bioclim_dev(const mcf_problem* p, const int32_t* const q[4], const int32
         b.nq[i] = nq[i];
         off += nq[i];
     }
-    b.width = nc;
     b.tsteps = T;
-    b.Tz = dTz;
-    b.soilm = dsm;
-    b.cell_begin = 0;
-    b.mask = 0;
-    for (int v = 0; v < MCF_NBIO; ++v) {
-        b.bio[v] = bio[v];
-        if (bio[v]) b.mask |= 1u << v;
-    }
-    CU(launch_bioclim(b, st));
-    count_launch();
+    b.mask = mask;
+    for (int v = 0; v < MCF_NBIO; ++v) b.bio[v] = bio[v];
+    double* out[MCF_NOUT] = {nullptr};
+    TRY(plan_run_below(pl, out, sc, st, &b));
     // the quarter index vectors are read from pageable host memory by the async copies above
     CU(cudaStreamSynchronize(st));
     return Err();
+}
+
+// Summary sink: per-cell sum / min / max over the window's hours of each requested output (reqhgt >= 0).
+Err run_summary_dev(const mcf_problem* p, double* const sum[MCF_NOUT], double* const mn[MCF_NOUT],
+                    double* const mx[MCF_NOUT], const mcf_window* win, int accumulate, int64_t* hours_done,
+                    cudaStream_t st) {
+    Scratch sc(st);
+    Plan pl;
+    TRY(plan_prepare(pl, p, sc, st));
+    if (pl.rq == RQ_BELOW)
+        return make_err(MCF_ERR_ARG, "the summary sink covers reqhgt >= 0 (below ground the series needs its time-axis pass)");
+    int b0 = 0, nb = 0;
+    long long hour0 = 0, ring = p->tsteps;
+    TRY(resolve_window(win, pl.blocks, p->tsteps, b0, nb, hour0, ring));
+    GridArgs a;
+    fill_common(pl, a);
+    a.outmask = 0;
+    for (int v = 0; v < MCF_NOUT; ++v) {
+        const int n = (sum[v] != nullptr) + (mn[v] != nullptr) + (mx[v] != nullptr);
+        if (n == 0) continue;
+        if (n != 3) return make_err(MCF_ERR_ARG, "summary output %d needs its sum, min and max buffers together", v);
+        if (!kernel_writes(pl.rq, v)) {
+            // never produced at this height (ref :2300-2303): NA, as the reference's array would be
+            if (!accumulate) {
+                CU(launch_fill_na(sum[v], pl.ncells, st));
+                CU(launch_fill_na(mn[v], pl.ncells, st));
+                CU(launch_fill_na(mx[v], pl.ncells, st));
+                count_launch(3);
+            }
+            continue;
+        }
+        a.outmask |= 1u << v;
+        a.red[v] = sum[v];
+        a.red[10 + v] = mn[v];
+        a.red[20 + v] = mx[v];
+    }
+    a.red_accumulate = accumulate ? 1 : 0;
+    if (hours_done) *hours_done = (int64_t)nb * 24;
+    if (!a.outmask) return Err();
+    return plan_run_reduce(pl, a, SINK_SUMMARY, b0, nb, sc, st);
 }
 
 } // namespace
@@ -1194,6 +1315,55 @@ int mcf_runbioclim(const mcf_problem* prob, const int32_t* wetq, int32_t nwetq, 
         for (int v = 0; v < MCF_NBIO; ++v)
             if (bio[v]) CU(cudaMemcpyAsync(bio[v], dbio[v], nc * sizeof(double), cudaMemcpyDeviceToHost, sg.s));
         CU(cudaStreamSynchronize(sg.s));
+        return Err();
+    };
+    return report(body(), err, errlen);
+}
+
+int mcf_runmicro_summary_dev(const mcf_problem* prob, double* const sum[MCF_NOUT], double* const mn[MCF_NOUT],
+                             double* const mx[MCF_NOUT], const mcf_window* win, int32_t accumulate, int64_t* hours_done,
+                             void* stream, char* err, size_t errlen) {
+    if (!sum || !mn || !mx) return report(make_err(MCF_ERR_ARG, "sum / min / max is NULL"), err, errlen);
+    return report(run_summary_dev(prob, sum, mn, mx, win, accumulate, hours_done, (cudaStream_t)stream), err, errlen);
+}
+
+int mcf_runmicro_summary(const mcf_problem* prob, double* const mean[MCF_NOUT], double* const mn[MCF_NOUT],
+                         double* const mx[MCF_NOUT], int64_t* hours_done, char* err, size_t errlen) {
+    auto body = [&]() -> Err {
+        if (!mean || !mn || !mx) return make_err(MCF_ERR_ARG, "mean / min / max is NULL");
+        TRY(validate(prob));
+        TRY(device_info());
+        std::lock_guard<std::mutex> ws_lock(g_ws_mu);
+        StreamGuard sg;
+        CU(cudaStreamCreateWithFlags(&sg.s, cudaStreamNonBlocking));
+        const size_t nc = (size_t)prob->rows * prob->cols;
+        DevCopy dc;
+        dc.stream = sg.s;
+        mcf_problem dp;
+        double* d[3][MCF_NOUT] = {{nullptr}};
+        double* const* h[3] = {mean, mn, mx};
+        for (int pass = 0; pass < 2; ++pass) { // sizing pass, then the real one
+            dc.sizing = (pass == 0);
+            TRY(upload_problem(prob, &dp, dc));
+            for (int v = 0; v < MCF_NOUT; ++v)
+                for (int k = 0; k < 3; ++k)
+                    if (h[k][v]) TRY(dc.dalloc(&d[k][v], nc));
+            if (pass == 0) TRY(dc.reserve(dc.need));
+        }
+        int64_t hours = 0;
+        TRY(run_summary_dev(&dp, d[0], d[1], d[2], nullptr, 0, &hours, sg.s));
+        std::vector<CopyJob> jobs;
+        for (int v = 0; v < MCF_NOUT; ++v)
+            for (int k = 0; k < 3; ++k)
+                if (h[k][v]) jobs.push_back(CopyJob{(char*)h[k][v], (const char*)d[k][v], nc * sizeof(double), nullptr});
+        CU(cudaStreamSynchronize(sg.s));
+        TRY(copy_back(jobs, sg.s));
+        if (hours_done) *hours_done = hours;
+        if (hours > 0)
+            for (int v = 0; v < MCF_NOUT; ++v)
+                if (mean[v])
+                    for (size_t i = 0; i < nc; ++i)
+                        if (!std::isnan(mean[v][i])) mean[v][i] /= (double)hours; // NA / NaN cells keep their bits
         return Err();
     };
     return report(body(), err, errlen);

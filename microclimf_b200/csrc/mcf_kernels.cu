@@ -96,10 +96,148 @@ __device__ __forceinline__ double pack_scale(int q) { return (q == 0 || q == 1 |
 // one output value: FP64 streaming store, or the packed int16 store when the launch asked for the packed sink
 // (PACK is a compile-time parameter of the grid kernel: a run-time test in front of every store splits the hour
 // loops into many small basic blocks and cost 16 % of the FP64 build's throughput)
-template <int Q, bool PACK>
-__device__ __forceinline__ void put(const GridArgs& a, size_t o, double v) {
-    if (PACK) reinterpret_cast<int16_t*>(a.out[Q])[o] = pack16(v, pack_scale(Q));
-    else __stcs(&a.out[Q][o], v);
+template <int Q, int SINK>
+__device__ __forceinline__ void put(const GridArgs& a, size_t o, double v, double* acc) {
+    if (SINK == SINK_PACK) reinterpret_cast<int16_t*>(a.out[Q])[o] = pack16(v, pack_scale(Q));
+    else if (SINK == SINK_F64) __stcs(&a.out[Q][o], v);
+    else if (SINK == SINK_SUMMARY) {
+        // running sum / minimum / maximum of output Q over the window's hours, in this thread's shared-memory slots
+        // (NaN poisons the sum and is ignored by the extremes, like R's mean() and the bioclim extremes)
+        double* s = acc + (size_t)Q * kTile;
+        const double sum = s[0], mn = s[(size_t)10 * kTile], mx = s[(size_t)20 * kTile];
+        s[0] = sum + v;
+        if (v < mn) s[(size_t)10 * kTile] = v;
+        if (v > mx) s[(size_t)20 * kTile] = v;
+    }
+    // SINK_BIO: the two series it needs are taken where they are produced
+}
+
+// ---------------------------------------------------------------------------------------------
+// SINK_BIO: runbioclimCpp's 19 reductions (ref :3245-3448, :3457-3560) accumulated while the days are solved.
+// The reference gathers each cell's 336-hour Tz (or tleaf) and soil-moisture series and reduces them afterwards; here
+// nothing hourly is ever stored.  Slots (shared memory, [slot][thread]): see the BIO_* enumeration in mcf_kernels.cuh.
+//   * sums run in this kernel's hour order (pass 2 walks each day backwards), the reference's in index order: rounding
+//     level differences only;
+//   * the 336-hour soil standard deviation (calc_std_dev :3227, two passes over the series) becomes one pass over the
+//     deviations d = s - K from the first hour's value K: (sum d^2 - (sum d)^2 / T) / (T - 1).  K is itself a sample
+//     (d = 0), so the subtracted term is at most T times the result: relative error <= ~T eps, no cancellation blow-up;
+//   * the 12 "monthly" means live in 12 slots and their standard deviation is formed at the end exactly as bioclim4 does.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bio_init(double* A) {
+    for (int s = 0; s < BIO_NSLOT; ++s) A[(size_t)s * kTile] = 0.0;
+    A[(size_t)BIO_B5 * kTile] = -273.15; // ref bioclim5 :3304
+    A[(size_t)BIO_B6 * kTile] = 273.15;  // ref bioclim6 :3314
+    A[(size_t)BIO_B14 * kTile] = 1.0;    // ref bioclim14 :3386 (bioclim13 starts from 0)
+}
+// soil moisture of hour k (pass 1)
+__device__ __forceinline__ void bio_soil(double* A, int k, bool first, uint32_t qc, double s) {
+    if (first) A[(size_t)BIO_K * kTile] = s;
+    const double d = s - A[(size_t)BIO_K * kTile];
+    A[(size_t)BIO_SD * kTile] += d;
+    A[(size_t)BIO_SD2 * kTile] += d * d;
+    if (s > A[(size_t)BIO_B13 * kTile]) A[(size_t)BIO_B13 * kTile] = s;
+    if (s < A[(size_t)BIO_B14 * kTile]) A[(size_t)BIO_B14 * kTile] = s;
+    if (k < 288) A[(size_t)BIO_M12 * kTile] += s;
+    if (qc) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t c = (qc >> (8 * q)) & 255u;
+            if (c) A[(size_t)(BIO_QS0 + q) * kTile] += (double)c * s;
+        }
+    }
+}
+// temperature of hour k (pass 2); day statistics are closed by bio_day_end
+__device__ __forceinline__ void bio_temp(double* A, int k, uint32_t qc, double t) {
+    if (k == 0) A[(size_t)BIO_TZ0 * kTile] = t;
+    if (k < 288) {
+        A[(size_t)BIO_S1 * kTile] += t;
+        A[(size_t)BIO_DSUM * kTile] += t;
+        if (t > A[(size_t)BIO_DMX * kTile]) A[(size_t)BIO_DMX * kTile] = t;
+        if (t < A[(size_t)BIO_DMN * kTile]) A[(size_t)BIO_DMN * kTile] = t;
+    } else if (k < 312) {
+        if (t > A[(size_t)BIO_B5 * kTile]) A[(size_t)BIO_B5 * kTile] = t;
+    } else if (k < 336) {
+        if (t < A[(size_t)BIO_B6 * kTile]) A[(size_t)BIO_B6 * kTile] = t;
+    }
+    if (qc) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t c = (qc >> (8 * q)) & 255u;
+            if (c) A[(size_t)(BIO_QT0 + q) * kTile] += (double)c * t;
+        }
+    }
+}
+__device__ __forceinline__ void bio_day_begin(double* A) {
+    A[(size_t)BIO_DMX * kTile] = -273.15; // ref bioclim2 :3264-3265
+    A[(size_t)BIO_DMN * kTile] = 273.15;
+    A[(size_t)BIO_DSUM * kTile] = 0.0;
+}
+__device__ __forceinline__ void bio_day_end(double* A, int k0) {
+    if (k0 < 288) {
+        A[(size_t)BIO_DTRSUM * kTile] += A[(size_t)BIO_DMX * kTile] - A[(size_t)BIO_DMN * kTile];
+        A[(size_t)(BIO_MON0 + k0 / 24) * kTile] = A[(size_t)BIO_DSUM * kTile] / 24;
+    }
+}
+__device__ void bio_finish(const GridArgs& a, const double* A, int cell, bool active) {
+    const double NA = na_real();
+    const uint32_t mk = a.red_mask;
+    if (!active || isnan(A[(size_t)BIO_TZ0 * kTile])) { // ref :3507-3508: the first hour is NA -> the cell keeps its NA fill
+        for (int b = 0; b < 19; ++b)
+            if (mk & (1u << b)) a.red[b][cell] = NA;
+        return;
+    }
+    const double bio1 = A[(size_t)BIO_S1 * kTile] / 288.0;
+    const double bio2 = A[(size_t)BIO_DTRSUM * kTile] / 12;
+    double mmean = 0.0;
+    for (int i = 0; i < 12; ++i) mmean += A[(size_t)(BIO_MON0 + i) * kTile];
+    mmean /= 12;
+    double ssd = 0.0;
+    for (int i = 0; i < 12; ++i) {
+        const double d = A[(size_t)(BIO_MON0 + i) * kTile] - mmean;
+        ssd += d * d;
+    }
+    const double bio4 = sqrt(ssd / 11) * 100.0;
+    const double bio5 = A[(size_t)BIO_B5 * kTile], bio6 = A[(size_t)BIO_B6 * kTile];
+    const double bio7 = bio5 - bio6;
+    if (mk & (1u << 0)) a.red[0][cell] = bio1;
+    if (mk & (1u << 1)) a.red[1][cell] = bio2;
+    if (mk & (1u << 2)) a.red[2][cell] = bio2 / bio7; // no x100, as the reference (:3534)
+    if (mk & (1u << 3)) a.red[3][cell] = bio4;
+    if (mk & (1u << 4)) a.red[4][cell] = bio5;
+    if (mk & (1u << 5)) a.red[5][cell] = bio6;
+    if (mk & (1u << 6)) a.red[6][cell] = bio7;
+    for (int q = 0; q < 4; ++q) { // quarter means: always divided by 72 (ref :3325 ...)
+        const bool qna = (a.bio_q_na >> q) & 1u;
+        if (mk & (1u << (7 + q))) a.red[7 + q][cell] = qna ? NA : A[(size_t)(BIO_QT0 + q) * kTile] / 72.0;
+        if (mk & (1u << (15 + q))) a.red[15 + q][cell] = qna ? NA : A[(size_t)(BIO_QS0 + q) * kTile] / 72.0;
+    }
+    const double m12 = A[(size_t)BIO_M12 * kTile] / 288.0;
+    const double T = (double)a.tsteps;
+    const double sd_ = A[(size_t)BIO_SD * kTile];
+    const double var = (A[(size_t)BIO_SD2 * kTile] - sd_ * sd_ / T) / (T - 1);
+    const double sd = a.bio_soil_gap ? NA : sqrt(var > 0.0 ? var : 0.0);
+    if (mk & (1u << 11)) a.red[11][cell] = m12;
+    if (mk & (1u << 12)) a.red[12][cell] = A[(size_t)BIO_B13 * kTile];
+    if (mk & (1u << 13)) a.red[13][cell] = A[(size_t)BIO_B14 * kTile];
+    if (mk & (1u << 14)) a.red[14][cell] = m12 / sd; // mean / sd, as the reference (:3402)
+}
+
+// SINK_SUMMARY: slots [stat][output], stat 0 sum, 1 minimum, 2 maximum
+__device__ __forceinline__ void summary_init(const GridArgs& a, double* A, int cell, bool load) {
+    for (int v = 0; v < kNOut; ++v) {
+        const bool on = (a.outmask >> v) & 1u;
+        const bool ld = load && on;
+        A[(size_t)v * kTile] = ld ? a.red[v][cell] : 0.0;
+        A[(size_t)(10 + v) * kTile] = ld ? a.red[10 + v][cell] : __longlong_as_double(0x7FF0000000000000LL);
+        A[(size_t)(20 + v) * kTile] = ld ? a.red[20 + v][cell] : __longlong_as_double(0xFFF0000000000000LL);
+    }
+}
+__device__ __forceinline__ void summary_finish(const GridArgs& a, const double* A, int cell, bool active) {
+    const double NA = na_real();
+    for (int v = 0; v < kNOut; ++v) {
+        if (!((a.outmask >> v) & 1u)) continue;
+        for (int st = 0; st < 3; ++st) a.red[st * 10 + v][cell] = active ? A[(size_t)(st * 10 + v) * kTile] : NA;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -485,7 +623,7 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
     h.windex = c.windex;
 }
 
-template <int ARR, int RQ, bool PACK, bool ALLOUT = false>
+template <int ARR, int RQ, int SINK, bool ALLOUT = false>
 #ifdef MCF_MAXNREG
 #define MCF_KGRID_BOUNDS __maxnreg__(MCF_MAXNREG)
 #else
@@ -505,8 +643,13 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
     __shared__ __align__(8) uint64_t full_bar[kStages];
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     __shared__ int s_tile;
+    // accumulators of the reducing sinks: [slot][thread], this thread's column (dynamic shared memory, absent otherwise)
+    extern __shared__ __align__(16) double acc_smem[];
+    constexpr bool PACK = (SINK == SINK_PACK);
+    constexpr bool REDUCE = (SINK == SINK_BIO || SINK == SINK_SUMMARY);
 
     const int tid = threadIdx.x;
+    double* const acc = REDUCE ? acc_smem + tid : nullptr;
     const int ntiles = (a.cell_end - a.cell_begin + kTile - 1) / kTile;
     double* const stash = a.stash + (size_t)blockIdx.x * (24 * kStashVars * kTile) + tid;
     unsigned int q0 = 0; // day number of the current tile's first day-block
@@ -561,6 +704,8 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
         CellInv v;
         int cur_lyr = -1;
         double ddsum = 0.0;
+        if (SINK == SINK_BIO) bio_init(acc);
+        if (SINK == SINK_SUMMARY) summary_init(a, acc, cc, a.red_accumulate != 0 && active);
 
         if (!ARR) {
             if (tid == 0)
@@ -587,11 +732,11 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
             }
 
             if (!active) {
-                if (valid) {
+                if (valid && !REDUCE) {
                     for (int hr = 0; hr < 24; ++hr) {
                         long long slot = slot0 + hr;
                         if (slot >= a.ring_hours) slot -= a.ring_hours;
-                        const size_t o = (size_t)slot * a.ncells + cell;
+                        const size_t o = (size_t)slot * a.out_stride + (cell - a.out_cell0);
 #pragma unroll
                         for (int q = 0; q < kNOut; ++q)
                             if (ALLOUT || (om & (1u << q))) {
@@ -604,7 +749,8 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 // ------------------------------------------------------------------ pass 1
                 // Output offset of the block's first hour; it advances by one time slot per hour and wraps
                 // at most once inside the block (ring_hours >= 24).
-                const size_t o_first = (size_t)slot0 * a.ncells + cell;
+                const size_t ocell = (size_t)(cell - a.out_cell0);
+                const size_t o_first = (size_t)slot0 * a.out_stride + ocell;
                 const long long wrap_at = a.ring_hours - slot0; // hour index at which the slot wraps to 0
                 double Rmx = -999.9, tmx = -999.0, tmn = 999.0;
                 // sector layers of the coming hour are fetched one hour ahead (modes 1/3: the sector indices
@@ -621,7 +767,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     HourRec hloc;
                     if (ARR) hour_from_arrays<ARR>(a, k, cell, sl, cl, lon, true, ccell, hloc);
                     const HourRec& h = ARR ? hloc : slab_day[hr];
-                    if (hr == wrap_at) o = cell;
+                    if (hr == wrap_at) o = ocell;
                     double ws, ha;
                     if (ARR) {
                         ws = __ldg(&a.wsa[(size_t)h.windex * a.ncells + cell]);
@@ -641,7 +787,8 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     if (ha > h.tan_sa) si = 0.0;
                     // distributed soil moisture
                     const double soild = soil_distribute(v, h.soilmp);
-                    if (ALLOUT || (om & (1u << 3))) put<3, PACK>(a, o, soild);
+                    if (ALLOUT || (om & (1u << 3))) put<3, SINK>(a, o, soild, acc);
+                    if (SINK == SINK_BIO) bio_soil(acc, k, bi == 0 && hr == 0, __ldg(&a.bio_qcnt[k]), soild);
                     // shortwave
                     Rad r;
                     if (h.Rsw > 0.0) {
@@ -649,16 +796,16 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     } else {
                         r.radGsw = 0.0; r.radCsw = 0.0; r.Rbdown = 0.0; r.Rddown = 0.0; r.Rdup = 0.0; r.Lhalf = 0.0;
                     }
-                    if (ALLOUT || (om & (1u << 5))) put<5, PACK>(a, o, r.Rbdown);
-                    if (ALLOUT || (om & (1u << 6))) put<6, PACK>(a, o, r.Rddown);
-                    if (ALLOUT || (om & (1u << 8))) put<8, PACK>(a, o, r.Rdup);
+                    if (ALLOUT || (om & (1u << 5))) put<5, SINK>(a, o, r.Rbdown, acc);
+                    if (ALLOUT || (om & (1u << 6))) put<6, SINK>(a, o, r.Rddown, acc);
+                    if (ALLOUT || (om & (1u << 8))) put<8, SINK>(a, o, r.Rdup, acc);
                     // longwave absorbed by the ground (ref :1165-1175); lwout = h.Rem
                     double radGlw;
                     if (v.pai > 0.0) radGlw = kEm * (v.trdif * v.svfa * h.Rlw + (1.0 - v.trdif) * h.Rem);
                     else radGlw = kEm * v.svfa * h.Rlw;
                     // wind
                     const Wind w = wind_hour(v, h.u2, h.umu, ws);
-                    if (ALLOUT || (om & (1u << 4))) put<4, PACK>(a, o, w.uz);
+                    if (ALLOUT || (om & (1u << 4))) put<4, SINK>(a, o, w.uz, acc);
                     // ground surface temperature with G = 0 (ref soiltempG0 :1262-1275)
                     const double radabs = r.radGsw + radGlw;
                     const double matric = -v.psie_abs * mexp_nc(-v.soilb * mlog(soild * v.inv_Smax));
@@ -679,15 +826,16 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     st_stash(&st[3 * kTile], r.Lhalf);
                     st_stash(&st[4 * kTile], soild);
                     st_stash(&st[5 * kTile], w.uf);
-                    o += a.ncells;
+                    o += a.out_stride;
                 }
                 // ------------------------------------------------------------------ pass 2
                 const double dtr = tmx - tmn;
+                if (SINK == SINK_BIO) bio_day_begin(acc);
                 // The hours of pass 2 are independent of each other, so it walks the day BACKWARDS: the stash is then
                 // read last-in-first-out (the lines written most recently are still in L2), and every line is
                 // discarded from L2 after its only read instead of being written back to DRAM behind the outputs.
                 const int last_slot_wraps = (23 >= wrap_at);
-                o = last_slot_wraps ? (size_t)cell + (size_t)(23 - wrap_at) * a.ncells : o_first + (size_t)23 * a.ncells;
+                o = last_slot_wraps ? ocell + (size_t)(23 - wrap_at) * a.out_stride : o_first + (size_t)23 * a.out_stride;
                 const double* st0 = stash + (size_t)23 * (kStashVars * kTile);
                 __syncwarp();
                 double radabs_n = ld_stash(&st0[0 * kTile]), surfwet_n = ld_stash(&st0[1 * kTile]);
@@ -760,17 +908,21 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     } else {
                         const double radClw = kEm * v.svfa * h.Rlw;
                         const Above tv = above_ground(v, h, dTmx, soild, Tg, G, w, radCsw, radClw, Lhalf);
-                        if (ALLOUT || (om & (1u << 0))) put<0, PACK>(a, o, (RQ == RQ_ABOVE) ? tv.Tz : Tg);
-                        if (ALLOUT || (om & (1u << 7))) put<7, PACK>(a, o, tv.lwdn);
-                        if (ALLOUT || (om & (1u << 9))) put<9, PACK>(a, o, tv.lwup);
+                        if (ALLOUT || (om & (1u << 0))) put<0, SINK>(a, o, (RQ == RQ_ABOVE) ? tv.Tz : Tg, acc);
+                        if (ALLOUT || (om & (1u << 7))) put<7, SINK>(a, o, tv.lwdn, acc);
+                        if (ALLOUT || (om & (1u << 9))) put<9, SINK>(a, o, tv.lwup, acc);
                         if (RQ == RQ_ABOVE) {
-                            if (ALLOUT || (om & (1u << 1))) put<1, PACK>(a, o, tv.tleaf);
-                            if (ALLOUT || (om & (1u << 2))) put<2, PACK>(a, o, tv.rh);
+                            if (ALLOUT || (om & (1u << 1))) put<1, SINK>(a, o, tv.tleaf, acc);
+                            if (ALLOUT || (om & (1u << 2))) put<2, SINK>(a, o, tv.rh, acc);
                         }
+                        if (SINK == SINK_BIO)
+                            bio_temp(acc, k, __ldg(&a.bio_qcnt[k]),
+                                     (RQ == RQ_ABOVE) ? (a.bio_air ? tv.Tz : tv.tleaf) : Tg);
                     }
-                    if (hr == wrap_at) o = (size_t)(a.ring_hours - 1) * a.ncells + cell; // back across the ring's seam
-                    else o -= a.ncells;
+                    if (hr == wrap_at) o = (size_t)(a.ring_hours - 1) * a.out_stride + ocell; // back across the ring's seam
+                    else o -= a.out_stride;
                 }
+                if (SINK == SINK_BIO) bio_day_end(acc, blk.k0);
             }
             if (!ARR) { // this warp is done with the stage: one arrival per warp
                 __syncwarp();
@@ -779,6 +931,8 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
         }
         q0 += (unsigned int)a.nblocks;
         if (RQ == RQ_BELOW && active) a.dd_sum[cell - a.cell_begin] = ddsum;
+        if (SINK == SINK_BIO && valid) bio_finish(a, acc, cell, active);
+        if (SINK == SINK_SUMMARY && valid) summary_finish(a, acc, cell, active);
     }
 }
 
@@ -787,11 +941,43 @@ int grid_blocks_per_sm(bool arr, int rq) {
     return arr ? (kMinBlocks > 1 ? kMinBlocks - 1 : 1) : kMinBlocks;
 }
 
-cudaError_t launch_grid(const GridArgs& a, int arr, int rq, int grid, cudaStream_t stream) {
-#define MCF_LAUNCH(ARR, RQ)                                                      \
-    do {                                                                         \
-        if (a.pack) k_grid<ARR, RQ, true><<<grid, kTile, 0, stream>>>(a);        \
-        else k_grid<ARR, RQ, false><<<grid, kTile, 0, stream>>>(a);              \
+// dynamic shared memory of the reducing sinks: kAccSlots doubles per thread
+constexpr size_t kAccBytes = (size_t)kAccSlots * kTile * sizeof(double);
+template <int ARR, int RQ, int SINK>
+static cudaError_t launch_reduce(const GridArgs& a, int grid, cudaStream_t stream) {
+    static bool configured = false; // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_grid<ARR, RQ, SINK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kAccBytes);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_grid<ARR, RQ, SINK, false><<<grid, kTile, kAccBytes, stream>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_grid(const GridArgs& a, int arr, int rq, int grid, cudaStream_t stream, int sink) {
+    if (sink < 0) sink = a.pack ? SINK_PACK : SINK_F64;
+    if (sink == SINK_BIO || sink == SINK_SUMMARY) {
+        if (rq == RQ_BELOW) return cudaErrorInvalidValue; // the below-ground series needs its time-axis pass first
+#define MCF_RED(ARR)                                                                               \
+    do {                                                                                           \
+        if (sink == SINK_BIO) {                                                                    \
+            if (rq == RQ_ABOVE) return launch_reduce<ARR, RQ_ABOVE, SINK_BIO>(a, grid, stream);    \
+            return launch_reduce<ARR, RQ_SURFACE, SINK_BIO>(a, grid, stream);                      \
+        }                                                                                          \
+        if (rq == RQ_ABOVE) return launch_reduce<ARR, RQ_ABOVE, SINK_SUMMARY>(a, grid, stream);    \
+        return launch_reduce<ARR, RQ_SURFACE, SINK_SUMMARY>(a, grid, stream);                      \
+    } while (0)
+        if (arr == 0) MCF_RED(0);
+        else if (arr == 1) MCF_RED(1);
+        else MCF_RED(2);
+#undef MCF_RED
+    }
+#define MCF_LAUNCH(ARR, RQ)                                                          \
+    do {                                                                             \
+        if (sink == SINK_PACK) k_grid<ARR, RQ, SINK_PACK><<<grid, kTile, 0, stream>>>(a); \
+        else k_grid<ARR, RQ, SINK_F64><<<grid, kTile, 0, stream>>>(a);               \
     } while (0)
 #define MCF_LAUNCH_RQ(ARR)                                 \
     do {                                                   \
@@ -801,8 +987,8 @@ cudaError_t launch_grid(const GridArgs& a, int arr, int rq, int grid, cudaStream
     } while (0)
     // every output requested, per-hour table, above ground, FP64 sink (the headline configuration): the ten mask tests
     // in front of the stores are compiled out
-    if (arr == 0 && rq == RQ_ABOVE && !a.pack && a.outmask == 0x3FFu) {
-        k_grid<0, RQ_ABOVE, false, true><<<grid, kTile, 0, stream>>>(a);
+    if (arr == 0 && rq == RQ_ABOVE && sink == SINK_F64 && a.outmask == 0x3FFu) {
+        k_grid<0, RQ_ABOVE, SINK_F64, true><<<grid, kTile, 0, stream>>>(a);
         return cudaGetLastError();
     }
     if (arr == 0) MCF_LAUNCH_RQ(0);
@@ -856,8 +1042,8 @@ __global__ void __launch_bounds__(128) k_below(const __grid_constant__ BelowArgs
     const int cell = a.cell_begin + c;
     const int T = a.tsteps;
     const int W = a.width;
-    double* Tz = a.Tz + cell;
-    const size_t S = (size_t)a.ncells;
+    double* Tz = a.Tz + (cell - a.tz_cell0);
+    const size_t S = (size_t)a.tz_stride;
     if (isnan(a.hgt[cell])) {
         const double NA = na_real();
         for (int k = 0; k < T; ++k) Tz[(size_t)k * S] = NA;
@@ -910,7 +1096,7 @@ __global__ void __launch_bounds__(128) k_below(const __grid_constant__ BelowArgs
         // incomplete time sequence (ref :1495-1536)
         const double* Tgp = a.arr ? a.Tgp + cell : a.Tgp;
         const double* Tbp = a.arr ? a.Tbp + cell : a.Tbp;
-        const size_t PS = a.arr ? S : 1;
+        const size_t PS = a.arr ? (size_t)a.ncells : 1;
         int mode = 0; // 0: Tz = Tg, 1: blend Tg/Tzd, 2: blend Tzd/mat, 3: mat
         double wgt = 0.0;
         if (nb > 1.0 && nb <= 24.0) {
@@ -977,7 +1163,7 @@ cudaError_t launch_below(const BelowArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(128) k_bioclim(const __grid_constant__ BioArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= a.width) return;
-    const int W = a.width, T = a.tsteps;
+    const int W = a.stride, T = a.tsteps;
     const double* Tz = a.Tz + c;
     const double* sm = a.soilm + c;
     const size_t oc = (size_t)a.cell_begin + c;

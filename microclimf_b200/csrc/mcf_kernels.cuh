@@ -35,6 +35,23 @@ struct DayBlock {
 
 enum { RQ_ABOVE = 0, RQ_SURFACE = 1, RQ_BELOW = 2 };
 
+// Where the hourly results of the grid kernel go (compile-time parameter of k_grid):
+//   SINK_F64     [rows, cols, T] FP64 arrays or a ring of time slots (the reference's return value)
+//   SINK_PACK    the same as writetonc's int16 (SURVEY.md NEXT-4)
+//   SINK_BIO     nowhere: the 19 bioclim reductions of runbioclimCpp (ref :3457-3560) are accumulated per cell in
+//                shared memory while the days are solved, and only the [rows, cols] summaries are written
+//   SINK_SUMMARY nowhere: per-cell sum / minimum / maximum over the window's hours of each requested output — the
+//                sink of runmicro_big for rasters whose hourly arrays exist nowhere
+enum { SINK_F64 = 0, SINK_PACK = 1, SINK_BIO = 2, SINK_SUMMARY = 3 };
+
+// accumulator slots per thread (shared memory, [slot][thread]) of the reducing sinks
+enum {
+    BIO_S1 = 0, BIO_DTRSUM, BIO_MON0, BIO_B5 = BIO_MON0 + 12, BIO_B6, BIO_QT0, BIO_TZ0 = BIO_QT0 + 4,
+    BIO_M12, BIO_B13, BIO_B14, BIO_K, BIO_SD, BIO_SD2, BIO_QS0, BIO_DMX = BIO_QS0 + 4, BIO_DMN, BIO_DSUM, BIO_NSLOT
+};
+constexpr int kSummarySlots = 30; // [stat 0 sum, 1 min, 2 max][output]
+constexpr int kAccSlots = (BIO_NSLOT > kSummarySlots) ? BIO_NSLOT : kSummarySlots;
+
 struct GridArgs {
     int32_t ncells;     // rows*cols of the problem = time-slot stride of every [rows, cols, n] array
     int32_t cell_begin; // cell range solved by this launch
@@ -75,10 +92,22 @@ struct GridArgs {
     const DayBlock* blocks;
     int32_t block0, nblocks;
     long long hour0, ring_hours;
-    // outputs
+    // outputs: hour slot s of cell c is element s * out_stride + (c - out_cell0) of each buffer (the whole raster:
+    // out_stride = ncells, out_cell0 = 0; a cell chunk with its own compact buffers: its width and first cell)
+    int32_t out_stride, out_cell0;
     double* out[kNOut];     // pack != 0: each is an int16_t* in disguise (the packed integer sink)
     uint32_t outmask;
     int32_t pack;
+    // reducing sinks.  SINK_BIO: red[b] = bio(b+1) [ncells] (NULL = not requested), red_mask = requested outputs;
+    // SINK_SUMMARY: red[stat * 10 + v] [ncells], stat 0 sum / 1 min / 2 max of output v over the window's hours,
+    // outmask = outputs summarised, red_accumulate != 0 merges into what the buffers hold (successive windows)
+    double* red[kSummarySlots];
+    uint32_t red_mask;
+    int32_t red_accumulate;
+    int32_t bio_air;            // 1: Tz, 0: tleaf (ref runbioclim1Cpp :3570-3590)
+    int32_t bio_soil_gap;       // some hour of [0, tsteps) is never computed: the 336-hour soil sd is NA
+    uint32_t bio_q_na;          // bit q: quarter q indexes an hour that is never computed (its sums are NA)
+    const uint32_t* bio_qcnt;   // [tsteps] multiplicity of hour k in wetq | dryq << 8 | hotq << 16 | colq << 24
     // scratch
     double* stash;          // [gridDim.x][24][kStashVars][kTile]
     unsigned int* tile_counter;
@@ -88,7 +117,8 @@ struct GridArgs {
 
 struct BelowArgs {
     int32_t width;  // cells in this chunk
-    int32_t ncells; // slot stride of Tz / Tgp / Tbp arrays
+    int32_t ncells; // slot stride of the Tgp / Tbp / hgt arrays
+    int32_t tz_stride, tz_cell0; // Tz: element k * tz_stride + (cell - tz_cell0)
     int32_t cell_begin;
     int32_t tsteps;
     int32_t arr;    // Tgp/Tbp are per-cell arrays (modes 2/4) or per-hour vectors
@@ -106,8 +136,9 @@ struct BelowArgs {
 
 struct BioArgs {
     int32_t width, tsteps;
-    const double* Tz;    // [tsteps][width]
-    const double* soilm; // [tsteps][width]
+    int32_t stride;      // hour stride of Tz / soilm (>= width)
+    const double* Tz;    // [tsteps][stride]
+    const double* soilm; // [tsteps][stride]
     const int32_t* q[4]; // wetq dryq hotq colq (device)
     int32_t nq[4];
     double* bio[19];     // each [ncells], written at cell_begin + c
@@ -127,7 +158,7 @@ cudaError_t launch_interp_coarse(const GridArgs& a, const double* coarse, double
 cudaError_t launch_twi_sum(const double* twi, int64_t n, double tfact, double* sum_count /* [2] */,
                            cudaStream_t stream);
 cudaError_t launch_grid(const GridArgs& a, int arr /* 0 table, 1 fine arrays, 2 coarse arrays */, int rq, int grid,
-                        cudaStream_t stream);
+                        cudaStream_t stream, int sink = -1 /* default: SINK_PACK if a.pack else SINK_F64 */);
 int grid_blocks_per_sm(bool arr, int rq);
 // FP32 build (modes 1/3, reqhgt >= 0): narrowed hour table, FP32 stash and outputs
 cudaError_t launch_narrow_hours(const HourRec* in, int n, void* out, cudaStream_t stream);

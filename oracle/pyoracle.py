@@ -19,6 +19,12 @@ from microclimf_b200.problem import GridProblem
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REF_PATH = os.path.join(_HERE, "_ref", "libmicroclimf_ref.so")
 ORACLE_PATH = os.path.join(_HERE, "liboracle.so")
+# kind "glue" is not a checker: it is the product entered through the Rcpp-typed binding (rglue/microclimf_glue.cpp
+# compiled against the Rcpp stand-in, driven by this directory's ref_driver.cpp with the reference's DataFrame / List
+# arguments).  It shares the calling code below so that the glue tests read like the reference-parity tests.
+GLUE_PATH = os.path.join(_HERE, "..", "rglue", "_build", "libmcf_glue_test.so")
+_PATHS = {"ref": REF_PATH, "oracle": ORACLE_PATH, "glue": GLUE_PATH}
+_PREFIX = {"ref": "ref_", "oracle": "oracle_", "glue": "glue_"}
 _libs = {}
 
 
@@ -30,11 +36,15 @@ def have_oracle() -> bool:
     return os.path.exists(ORACLE_PATH)
 
 
+def have_glue() -> bool:
+    return os.path.exists(GLUE_PATH)
+
+
 def _lib(kind: str):
     if kind not in _libs:
-        path = REF_PATH if kind == "ref" else ORACLE_PATH
+        path = _PATHS[kind]
         if not os.path.exists(path):
-            raise FileNotFoundError(f"{path} not built: run `make -C oracle` (or __graft_entry__.build())")
+            raise FileNotFoundError(f"{path} not built: run `make -C oracle` / `make -C rglue` (or __graft_entry__.build())")
         _libs[kind] = C.CDLL(path)
     return _libs[kind]
 
@@ -48,7 +58,7 @@ def _na_filled(n):
 def runmicro(prob: GridProblem, out_mask=None, kind: str = "oracle"):
     """Run the CPU checker; returns {name: array[rows, cols, tsteps] (Fortran order)}."""
     lib = _lib(kind)
-    fn = getattr(lib, "ref_runmicro" if kind == "ref" else "oracle_runmicro")
+    fn = getattr(lib, _PREFIX[kind] + "runmicro")
     fn.restype = C.c_int
     s, keep = prob.as_struct()
     out_mask = [True] * _abi.MCF_NOUT if out_mask is None else list(out_mask)
@@ -66,7 +76,7 @@ def runmicro(prob: GridProblem, out_mask=None, kind: str = "oracle"):
 
 def runbioclim(prob: GridProblem, quarters: dict, air: bool = True, out_mask=None, kind: str = "oracle"):
     lib = _lib(kind)
-    fn = getattr(lib, "ref_runbioclim" if kind == "ref" else "oracle_runbioclim")
+    fn = getattr(lib, _PREFIX[kind] + "runbioclim")
     fn.restype = C.c_int
     s, keep = prob.as_struct()
     out_mask = [True] * _abi.MCF_NBIO if out_mask is None else list(out_mask)
@@ -85,31 +95,31 @@ def runbioclim(prob: GridProblem, quarters: dict, air: bool = True, out_mask=Non
     return {nm: b.reshape((prob.rows, prob.cols), order="F") for nm, b in zip(_abi.BIO_NAMES, bufs) if b is not None}
 
 
-def gridmodelsnow1(obstime, climdata, pointm, vegp, other, snowenv="Alpine"):
+def gridmodelsnow1(obstime, climdata, pointm, vegp, other, snowenv="Alpine", kind="ref"):
     """The compiled reference's gridmodelsnow1 (src/microclimfCpp.cpp:4172) behind the product's snow structs."""
     from microclimf_b200 import snow
-    fn = _lib("ref").ref_gridmodelsnow
+    fn = getattr(_lib(kind), _PREFIX[kind] + "gridmodelsnow")
     fn.restype = C.c_int
     return snow.call_gridmodelsnow(fn, obstime, climdata, pointm, vegp, other, snowenv)
 
 
-def gridmicrosnow1(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out):
+def gridmicrosnow1(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out, kind="ref"):
     from microclimf_b200 import snow
-    fn = _lib("ref").ref_gridmicrosnow
+    fn = getattr(_lib(kind), _PREFIX[kind] + "gridmicrosnow")
     fn.restype = C.c_int
     return snow.call_gridmicrosnow(fn, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)
 
 
-def gridmodelsnow2(obstime, climdata, pointm, vegp, other, snowenv="Alpine"):
+def gridmodelsnow2(obstime, climdata, pointm, vegp, other, snowenv="Alpine", kind="ref"):
     from microclimf_b200 import snow
-    fn = _lib("ref").ref_gridmodelsnow2
+    fn = getattr(_lib(kind), _PREFIX[kind] + "gridmodelsnow2")
     fn.restype = C.c_int
     return snow.call_gridmodelsnow(fn, obstime, climdata, pointm, vegp, other, snowenv)
 
 
-def gridmicrosnow2(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out):
+def gridmicrosnow2(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out, kind="ref"):
     from microclimf_b200 import snow
-    fn = _lib("ref").ref_gridmicrosnow2
+    fn = getattr(_lib(kind), _PREFIX[kind] + "gridmicrosnow2")
     fn.restype = C.c_int
     return snow.call_gridmicrosnow(fn, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)
 

@@ -8,6 +8,10 @@
 //
 // Used by: tests/ (parity), tests/golden/make_golden.py (fixture generation), bench.py's
 // cpu_baseline / --impl reference legs.  Never by the product.
+//
+// Compiled a second time with -DMCF_GLUE_DRIVER (rglue/Makefile) it drives, with the very same DataFrame / List
+// arguments, the twelve functions of rglue/microclimf_glue.cpp — the Rcpp-typed binding a maintainer puts in the
+// reference's src/ — instead of the reference's own; the entry points are then called glue_* (tests/test_glue_gpu.py).
 #include <Rcpp.h>
 
 #include <cstdio>
@@ -16,7 +20,12 @@
 #include <vector>
 
 #include "microclimf_b200.h"
+#ifdef MCF_GLUE_DRIVER
+#define DRV(name) glue_##name
+#else
+#define DRV(name) ref_##name
 #include "microclimfheaders.h" // reference POD structs, included in place from /root/reference/src
+#endif
 
 using namespace Rcpp;
 
@@ -49,11 +58,13 @@ List runbioclim4Cpp(DataFrame obstime, List climdata, List pointm, List vegp, Li
                     NumericMatrix lats, NumericMatrix lons, double Sminp, double Smaxp, double tfact, double mat,
                     std::vector<bool> out, IntegerVector wetq, IntegerVector dryq, IntegerVector hotq,
                     IntegerVector colq, bool air);
+#ifndef MCF_GLUE_DRIVER
 solmodel solpositionCpp(double lat, double lon, int year, int month, int day, double lt);
 NumericVector clearskyradCpp(IntegerVector year, IntegerVector month, IntegerVector day, NumericVector lt, double lat,
                              double lon, NumericVector tc, NumericVector rh, NumericVector pk);
 std::vector<double> manCpp(std::vector<double> x, int n);
 double satvapCpp(double tc);
+#endif
 
 namespace {
 
@@ -85,7 +96,10 @@ struct Args {
     NumericMatrix lats, lons;
 };
 
-Args build(const mcf_problem* p) {
+// swap_types: store the integral-valued columns with the OTHER storage type than the reference reads them with (year /
+// month / day as doubles, hour and winddir as integers), as R data.frames often hold them: Rcpp's typed vectors coerce
+// on extraction, and so must any binding (tests/test_glue_gpu.py).
+Args build(const mcf_problem* p, bool swap_types = false) {
     Args a;
     const bool arrclim = (p->mode == 2 || p->mode == 4);
     const bool layered = (p->mode == 3 || p->mode == 4);
@@ -106,6 +120,17 @@ Args build(const mcf_problem* p) {
     a.climdata["lwdown"] = vec(p->lwdown, nclim);
     a.climdata["windspeed"] = vec(p->windspeed, nclim);
     a.climdata["winddir"] = vec(p->winddir, T);
+    if (swap_types) {
+        NumericVector y(T), m(T), d(T);
+        IntegerVector hr(T), wd(T);
+        for (int k = 0; k < T; ++k) {
+            y[k] = p->year[k]; m[k] = p->month[k]; d[k] = p->day[k];
+            hr[k] = (int)p->hour[k]; wd[k] = (int)p->winddir[k];
+        }
+        a.obstime["year"] = y; a.obstime["month"] = m; a.obstime["day"] = d;
+        a.obstime["hour"] = hr;
+        a.climdata["winddir"] = wd;
+    }
     a.pointm["soilm"] = vec(p->p_soilm, nclim);
     a.pointm["Tg"] = vec(p->p_Tg, nclim);
     a.pointm["Tbp"] = vec(p->p_Tbp, nclim);
@@ -171,9 +196,12 @@ const char* const kOutNames[MCF_NOUT] = {"Tz",       "tleaf",    "relhum",  "soi
 
 } // namespace
 
-extern "C" int ref_runmicro(const mcf_problem* p, double* const out[MCF_NOUT], char* err, size_t errlen) {
+static bool g_swap_types = false;
+extern "C" void DRV(set_swap_types)(int on) { g_swap_types = on != 0; }
+
+extern "C" int DRV(runmicro)(const mcf_problem* p, double* const out[MCF_NOUT], char* err, size_t errlen) {
     try {
-        Args a = build(p);
+        Args a = build(p, g_swap_types);
         std::vector<bool> o(MCF_NOUT);
         for (int v = 0; v < MCF_NOUT; ++v) o[v] = out[v] != nullptr;
         List res;
@@ -209,7 +237,7 @@ extern "C" int ref_runmicro(const mcf_problem* p, double* const out[MCF_NOUT], c
     return MCF_OK;
 }
 
-extern "C" int ref_runbioclim(const mcf_problem* p, const int32_t* wetq, int32_t nwetq, const int32_t* dryq,
+extern "C" int DRV(runbioclim)(const mcf_problem* p, const int32_t* wetq, int32_t nwetq, const int32_t* dryq,
                               int32_t ndryq, const int32_t* hotq, int32_t nhotq, const int32_t* colq, int32_t ncolq,
                               int32_t air, double* const bio[MCF_NBIO], char* err, size_t errlen) {
     try {
@@ -250,6 +278,7 @@ extern "C" int ref_runbioclim(const mcf_problem* p, const int32_t* wetq, int32_t
     return MCF_OK;
 }
 
+#ifndef MCF_GLUE_DRIVER
 // Small helpers of the reference exposed for fixture generation and unit checks of the restatement.
 extern "C" void ref_clearskyrad(int32_t n, const int32_t* year, const int32_t* month, const int32_t* day,
                                 const double* lt, double lat, double lon, const double* tc, const double* rh,
@@ -289,6 +318,7 @@ DataFrame pointmprocess(DataFrame pointvars, double zref, double h, double pai, 
                         double Mc);
 NumericMatrix flowaccCpp(NumericMatrix dm);
 
+#endif // !MCF_GLUE_DRIVER
 namespace {
 DataFrame obstime_df(int32_t n, const int32_t* year, const int32_t* month, const int32_t* day, const double* hour) {
     DataFrame o;
@@ -298,6 +328,7 @@ DataFrame obstime_df(int32_t n, const int32_t* year, const int32_t* month, const
     o["hour"] = vec(hour, n);
     return o;
 }
+#ifndef MCF_GLUE_DRIVER
 // weather: 9 columns of length n in the order temp, relhum, pres, swdown, difrad, lwdown, windspeed, winddir, precip
 const char* const kWeatherCols[9] = {"temp", "relhum", "pres", "swdown", "difrad", "lwdown", "windspeed", "winddir", "precip"};
 DataFrame weather_df(int32_t n, const double* w) {
@@ -305,7 +336,9 @@ DataFrame weather_df(int32_t n, const double* w) {
     for (int k = 0; k < 9; ++k) c[kWeatherCols[k]] = vec(w + (size_t)k * n, n);
     return c;
 }
+#endif
 } // namespace
+#ifndef MCF_GLUE_DRIVER
 
 // weatherhgtCpp: writes the adjusted temp / relhum / windspeed columns (3 x n)
 extern "C" int ref_weatherhgt(int32_t n, const int32_t* year, const int32_t* month, const int32_t* day,
@@ -441,6 +474,7 @@ extern "C" int ref_meltmu2(const double* mu, int32_t rows, int32_t cols, const d
     }
 }
 
+#endif // !MCF_GLUE_DRIVER
 // ---------------------------------------------------------------------------------------------
 // Snow (SURVEY.md NEXT-3): the reference's gridmodelsnow1 / gridmicrosnow1 behind the product's structs
 // ---------------------------------------------------------------------------------------------
@@ -465,7 +499,7 @@ DataFrame snow_clim_df(const mcf_snow_climate* c) {
 const char* const kSnowEnv[5] = {"Alpine", "Maritime", "Prairie", "Tundra", "Taiga"};
 } // namespace
 
-extern "C" int ref_gridmodelsnow(const mcf_snow_climate* c, const mcf_snow_point* pt, const mcf_snow_static* st,
+extern "C" int DRV(gridmodelsnow)(const mcf_snow_climate* c, const mcf_snow_point* pt, const mcf_snow_static* st,
                                  int32_t snowenv, double* const out3d[5], double* const out2d[4], char* err, size_t errlen) {
     try {
         const int n = c->tsteps, R = st->rows, C = st->cols;
@@ -502,7 +536,7 @@ extern "C" int ref_gridmodelsnow(const mcf_snow_climate* c, const mcf_snow_point
     }
 }
 
-extern "C" int ref_gridmicrosnow(double reqhgt, const mcf_snow_climate* c, const double* umu, const mcf_snow_state* sm,
+extern "C" int DRV(gridmicrosnow)(double reqhgt, const mcf_snow_climate* c, const double* umu, const mcf_snow_state* sm,
                                  const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err,
                                  size_t errlen) {
     try {
@@ -546,7 +580,7 @@ List gridmodelsnow2(DataFrame obstime, List climdata, List pointm, List vegp, Li
 List gridmicrosnow2(double reqhgt, DataFrame obstime, List climdata, List snowm, List micro, List vegp, List other, double mat,
                     std::vector<bool> out);
 
-extern "C" int ref_gridmodelsnow2(const mcf_snow_climate* c, const mcf_snow_point* pt, const mcf_snow_static* st,
+extern "C" int DRV(gridmodelsnow2)(const mcf_snow_climate* c, const mcf_snow_point* pt, const mcf_snow_static* st,
                                   int32_t snowenv, double* const out3d[5], double* const out2d[4], char* err, size_t errlen) {
     try {
         const int n = c->tsteps, R = st->rows, C = st->cols;
@@ -586,7 +620,7 @@ extern "C" int ref_gridmodelsnow2(const mcf_snow_climate* c, const mcf_snow_poin
     }
 }
 
-extern "C" int ref_gridmicrosnow2(double reqhgt, const mcf_snow_climate* c, const double* umu, const mcf_snow_state* sm,
+extern "C" int DRV(gridmicrosnow2)(double reqhgt, const mcf_snow_climate* c, const double* umu, const mcf_snow_state* sm,
                                   const mcf_snow_static* st, double mat, double* const micro[MCF_NOUT], char* err,
                                   size_t errlen) {
     try {
