@@ -23,8 +23,11 @@ ORACLE_PATH = os.path.join(_HERE, "liboracle.so")
 # compiled against the Rcpp stand-in, driven by this directory's ref_driver.cpp with the reference's DataFrame / List
 # arguments).  It shares the calling code below so that the glue tests read like the reference-parity tests.
 GLUE_PATH = os.path.join(_HERE, "..", "rglue", "_build", "libmcf_glue_test.so")
-_PATHS = {"ref": REF_PATH, "oracle": ORACLE_PATH, "glue": GLUE_PATH}
-_PREFIX = {"ref": "ref_", "oracle": "oracle_", "glue": "glue_"}
+# kind "patched": the reference's own translation unit after rglue/apply_glue.sh (its twelve grid functions removed, the
+# glue in their place) behind the full driver — what the R package's shared object holds after the change
+PATCHED_PATH = os.path.join(_HERE, "..", "rglue", "_build", "libmicroclimf_patched.so")
+_PATHS = {"ref": REF_PATH, "oracle": ORACLE_PATH, "glue": GLUE_PATH, "patched": PATCHED_PATH}
+_PREFIX = {"ref": "ref_", "oracle": "oracle_", "glue": "glue_", "patched": "ref_"}
 _libs = {}
 
 
@@ -38,6 +41,10 @@ def have_oracle() -> bool:
 
 def have_glue() -> bool:
     return os.path.exists(GLUE_PATH)
+
+
+def have_patched() -> bool:
+    return os.path.exists(PATCHED_PATH)
 
 
 def _lib(kind: str):
