@@ -105,6 +105,47 @@ def cpu_reference(nproc, rows, cols_per_proc, reps):
     return res[0][1], walls, float(nproc) * rows * cols_per_proc * 240
 
 
+def job_sink_check(p, summary, hours, pick):
+    """CPU leg (checker): the sampled cells `pick` of band problem `p` re-solved hour by hour by the compiled reference
+    as a len(pick) x 1 raster; mean / min / max of its arrays against what the job's summary sink holds."""
+    import numpy as np
+
+    from microclimf_b200 import _abi
+    from microclimf_b200.problem import OBSTIME_FIELDS, SERIES_FIELDS
+    from oracle import pyoracle
+
+    kind = "ref" if pyoracle.have_ref() else "oracle"
+    nc = p.ncells
+    sub = p._clone_meta()
+    sub.rows, sub.cols = len(pick), 1
+    sub.twi_mean = None if kind == "ref" else p.twi_mean
+    for name, arr in p.arrays.items():
+        a = np.asarray(arr)
+        ln = p.expected_len(name)
+        if name in OBSTIME_FIELDS or name == "winddir" or name in SERIES_FIELDS:
+            sub.arrays[name] = a
+        else:
+            sub.arrays[name] = np.ascontiguousarray(a.reshape(ln // nc, nc)[:, pick].ravel())
+    t0 = time.perf_counter()
+    want = pyoracle.runmicro(sub, kind=kind)
+    secs = time.perf_counter() - t0
+    worst, bad = 0.0, 0
+    for nm in _abi.OUT_NAMES:
+        w = want[nm][:, 0, :hours]
+        na = np.isnan(w[:, 0])
+        with np.errstate(invalid="ignore"):
+            stats = {"mean": w.sum(axis=1) / hours, "min": w.min(axis=1), "max": w.max(axis=1)}
+        for st, wv in stats.items():
+            g = summary[nm][st].ravel(order="F")[pick]
+            bad += int((np.isnan(g) != na).sum())
+            m = ~na
+            if m.any():
+                worst = max(worst, float((np.abs(g[m] - wv[m]) / (1e-6 + 1e-6 * np.abs(wv[m]))).max()))
+    return {"cells": int(len(pick)), "hours": int(hours), "checker": "unmodified reference C++ (oracle/_ref)" if kind == "ref"
+            else "C restatement (oracle/)", "max_err_over_tol": worst, "nan_mismatches": bad, "ok": bool(worst <= 1.0 and bad == 0),
+            "tolerance": "1e-6 abs + 1e-6 rel on mean / min / max of each of the 10 outputs", "checker_seconds": secs}
+
+
 def host_cores():
     try:
         return max(1, len(os.sched_getaffinity(0)))
@@ -218,6 +259,10 @@ def gpu_arm(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the grid solver has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # every pinned allocation below (torch's and the library's staging slots) is first-touched after this: the rank sits
+    # on the CPUs, and prefers the memory, of the socket its GPU hangs off (microclimf_b200/numa.py; best effort)
+    from microclimf_b200 import numa
+    numa_rep = numa.bind_to_gpu(local_rank) if not args.no_numa else {"disabled": True}
     L = _lib.lib()
     if L.mcf_set_device(local_rank) != 0:
         raise SystemExit("mcf_set_device failed")
@@ -313,6 +358,28 @@ def gpu_arm(args):
                                     "fp64_instr_per_cell_hour_ncu": pm.get("fp64_instr_per_cell_hour"),
                                     "flop_source": pm.get("source", "profiles/")}
 
+    # ------------------------------------------------------------------ what the box can copy: all ranks at once
+    # Plain cudaMemcpyAsync of a pinned 1 GiB buffer per rank, device -> host, every rank at the same time: the ceiling
+    # of the host-buffer path (80 B per cell-hour of FP64 results) at this N, independent of the solver.
+    def copy_ceiling(nbytes=1 << 30, reps=4):
+        dbuf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        hbuf = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        hbuf.copy_(dbuf, non_blocking=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            hbuf.copy_(dbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        del dbuf, hbuf
+        return nbytes * reps * world / dt / 1e9
+
+    d2h_ceiling = copy_ceiling()
+
     # ------------------------------------------------------------------ e2e through the host-buffer C ABI
     e2e = None
     er, ec, et = args.e2e_rows, args.e2e_cols, args.e2e_hours
@@ -348,6 +415,9 @@ def gpu_arm(args):
            # bytes over PCIe per second of the whole call: the host-buffer path is bound by the link (80 B per cell-hour
            # of FP64 results), not by the kernels
            "pcie_gb_per_s": (h2d + d2h) * esteps / e_s / 1e9,
+           # aggregate over all ranks of plain pinned cudaMemcpyAsync device -> host, all ranks copying at once: what the
+           # box itself can move at this N (the ceiling of pcie_gb_per_s), and where this rank's pinned memory lives
+           "d2h_ceiling_gb_per_s": d2h_ceiling, "numa": numa_rep,
            "sample": f"{er}x{ec} cells x {et} h per GPU through mcf_runmicro (pinned host buffers, all 10 outputs "
                      f"copied back; timed with the host clock around the blocking call)"}
     # the same call with the packed integer sink (writetonc's x100 / x1 int16 packing done by the kernels, SURVEY.md
@@ -392,6 +462,114 @@ def gpu_arm(args):
         except Exception as exc:  # an extra key: never let it take the benchmark down
             e2e_pageable = {"error": repr(exc)}
     del pin_keep
+
+    # ------------------------------------------------------------------ the whole job, end to end
+    # BASELINE configs[3] to completion: every rank solves ALL 8760 hours of its 8192 x 1024 band (N = 8: the 8192 x 8192
+    # raster) through the host-buffer API with the SUMMARY sink — per-cell mean / min / max of the 10 outputs over the year,
+    # reduced inside the grid kernel (mcf_runmicro_summary): host statics in, 30 [rows, cols] rasters out, nothing hourly
+    # is stored anywhere (the hourly arrays would be 4.7 TB per variable).  Wall clock around the blocking call, max over
+    # ranks.  At N = 1 the CPU leg re-solves sampled cells of the band with the compiled reference and compares them with
+    # what the sink holds (job["sink_check"]).
+    job = None
+    if not args.no_job:
+        try:
+            jp = hp
+            pick = None
+            if rank == 0 and world == 1 and not args.no_cpu:
+                rng = np.random.default_rng(5)
+                pick = np.sort(rng.choice(ncells, 256, replace=False))
+                tw = np.log(np.asarray(hp.arrays["twi"])[pick]) / hp.tfact
+                tw = tw[~np.isnan(tw)]
+                acc = 0.0
+                for x_ in tw:  # the reference sums sequentially (src/microclimfCpp.cpp:993-1004)
+                    acc += float(x_)
+                jp = hp.replace(twi_mean=acc / len(tw))  # any mean is a legitimate band input; the sample's lets the
+                #                                          unmodified reference reproduce it from the sample alone
+            barrier()
+            t0 = time.perf_counter()
+            jres, jhours = api.run_summary(jp)
+            j_s = time.perf_counter() - t0
+            if dist is not None:
+                t = torch.tensor([j_s], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                j_s = float(t.item())
+            job = {"workload": f"{rows}x{cols * world} raster x {jhours} h = {world} band(s) of {rows}x{cols}, one per GPU, whole "
+                               f"series in one call of mcf_runmicro_summary (host statics in, per-cell mean/min/max of the 10 "
+                               f"outputs out)", "wall_s": j_s, "hours": jhours, "cell_hours": float(ncells) * jhours * world,
+                   "value": float(ncells) * jhours * world / j_s, "unit": UNIT, "sink": "summary (30 rasters per band)",
+                   "h2d_bytes_per_gpu": int(ncells * BYTES_PER_CELL_STATIC + 25 * 8 * T), "d2h_bytes_per_gpu": int(30 * 8 * ncells)}
+            if pick is not None:
+                job["sink_check"] = job_sink_check(jp, jres, jhours, pick)
+            del jres
+        except Exception as exc:  # an extra key: never let it take the headline down
+            job = {"error": repr(exc)[:300]}
+
+    # ------------------------------------------------------------------ BASELINE configs[2] and [4] (N = 1 only)
+    # Parity cases of the headline metric's definition, timed like `value` (CUDA events, inputs resident in HBM) so that
+    # their numbers come from the driver's own run: runbioclim on a 2048 x 2048 raster (336 h, the 19 reductions fused into
+    # the grid kernel) and runmicro with gridded climate on a 4096 x 4096 raster (climate on a 41 x 41 grid interpolated
+    # in the kernel, 240 h into a 24-h ring) plus the snow-pack operator on a bounded tile through its host-buffer entry.
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = {}
+        del outs
+        torch.cuda.empty_cache()
+
+        def ev_timed(fn, reps):
+            fn()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(reps):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / reps
+
+        try:
+            days, q = synth.bioclim_days()
+            bp = synth.make_problem(2048, 2048, 336, reqhgt=REQHGT, mode=1, day_list=days, seed=77)
+            bdp = bp.to_device()
+            bio = [torch.empty(bp.ncells, dtype=torch.float64, device="cuda") for _ in range(19)]
+            bms = ev_timed(lambda: api.run_bioclim_problem_dev(bdp, q["wetq"], q["dryq"], q["hotq"], q["colq"], True, bio), 3)
+            t0 = time.perf_counter()
+            api.run_bioclim_problem(bp, q["wetq"], q["dryq"], q["hotq"], q["colq"], air=True)
+            bh = time.perf_counter() - t0
+            configs["bioclim_2048"] = {
+                "workload": "BASELINE configs[2]: runbioclim1Cpp on a synthetic 2048x2048 raster, 14 days x 24 h, air, 19 outputs",
+                "value": bp.ncells * 336 / (bms * 1e-3), "unit": UNIT, "ms": bms,
+                "sink": "19 [rows, cols] rasters; the reductions run inside the grid kernel (no [rows, cols, 336] scratch)",
+                "e2e_value": bp.ncells * 336 / bh, "e2e_ms": bh * 1e3,
+                "e2e_note": "mcf_runbioclim on pageable host buffers: 1.8 GB of statics up, 19 rasters back"}
+            del bp, bdp, bio
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            configs["bioclim_2048"] = {"error": repr(exc)[:300]}
+        try:
+            cp = synth.make_coarse_problem(4096, 4096, 240, reqhgt=REQHGT, mode=2, crows=41, ccols=41, altcorrect=2)
+            cdp = cp.to_device()
+            couts = [torch.empty(24 * cp.ncells, dtype=torch.float64, device="cuda") for _ in range(10)]
+            cms = ev_timed(lambda: api.run_problem_dev(cdp, couts, window=(0, 10, 0, 24)), 2)
+            configs["gridded_snow_4096"] = {
+                "workload": "BASELINE configs[4]: runmicro2Cpp semantics on a synthetic 4096x4096 raster x 240 h, climate and "
+                            "point model on a 41x41 grid interpolated per cell-hour in the kernel (altcorrect 2), 10 outputs",
+                "value": cp.ncells * 240 / (cms * 1e-3), "unit": UNIT, "ms": cms, "sink": "24-h FP64 ring in HBM"}
+            del cp, cdp, couts
+            torch.cuda.empty_cache()
+            from microclimf_b200 import snow
+            sn = synth.make_snow_inputs(1024, 1024, 120)
+            snow.gridmodelsnow1(sn["obstime"], sn["climdata"], sn["pointm"], sn["vegp"], sn["other"], "Alpine")
+            t0 = time.perf_counter()
+            snow.gridmodelsnow1(sn["obstime"], sn["climdata"], sn["pointm"], sn["vegp"], sn["other"], "Alpine")
+            ss = time.perf_counter() - t0
+            configs["gridded_snow_4096"]["snow"] = {
+                "workload": "gridmodelsnow1 (hourly snow-pack recurrence) on a 1024x1024 tile x 120 h through mcf_gridmodelsnow, "
+                            "host buffers (5 [rows, cols, hours] arrays back)",
+                "value": 1024 * 1024 * 120 / ss, "unit": UNIT, "ms": ss * 1e3}
+            del sn
+        except Exception as exc:
+            configs.setdefault("gridded_snow_4096", {})["error"] = repr(exc)[:300]
+        outs = [torch.empty(ring_hours * ncells, dtype=torch.float64, device="cuda") for _ in range(10)]
 
     # ------------------------------------------------------------------ the optional FP32 build, same workload
     # (north_star: within 0.05 degC / 0.5 % radiation; tests/test_f32_gpu.py).  Reported beside the FP64 headline.
@@ -443,7 +621,7 @@ def gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "e2e_packed": e2e_packed, "e2e_pageable": e2e_pageable,
-            "fp32": fp32,
+            "fp32": fp32, "job": job, "configs": configs,
             "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "setup_seconds": t_gen,
         }
@@ -487,6 +665,9 @@ def main():
     ap.add_argument("--e2e-cols", dest="e2e_cols", type=int, default=1024)
     ap.add_argument("--e2e-hours", dest="e2e_hours", type=int, default=120)
     ap.add_argument("--no-cpu", dest="no_cpu", action="store_true")
+    ap.add_argument("--no-job", dest="no_job", action="store_true", help="skip the whole-year summary-sink job")
+    ap.add_argument("--no-configs", dest="no_configs", action="store_true", help="skip the configs[2] / configs[4] timings")
+    ap.add_argument("--no-numa", dest="no_numa", action="store_true", help="do not bind the rank next to its GPU")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

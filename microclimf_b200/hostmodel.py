@@ -743,13 +743,48 @@ def _checkbiginputs(dtm, vegp, soilc):
 
 
 def runmicro_big(micropoint, reqhgt, pathout, vegp, soilc, dtm, dtmc=None, altcorrect=0, tilesize=None, toverlap=0,
-                 writeasnc=False, runchecks=True, pai_a=None, tfact=1.5, out=(True,) * 10):
+                 writeasnc=False, runchecks=True, pai_a=None, tfact=1.5, out=(True,) * 10, gpus=None, sink=None,
+                 window_days=5):
     """ref runmicro_big (R/Cppwrappers.R:444-543): whole-area terrain layers once, then the model tile by
     tile, one file per tile in `<pathout>microut/` (`area_RR_CC.npz`, the analogue of the reference's RDS;
     `writeasnc = TRUE` stores writetonc's x100 integer packing, produced by the kernels' packed sink).
-    Returns the list of files written."""
+    Returns the list of files written.
+
+    `gpus = N` (an addition; the reference's arguments are unchanged) replaces the tile loop by ONE COLUMN BAND PER GPU
+    (bigrun.py: one process per GPU, statics distributed over NCCL, the whole-raster twi mean all-reduced, no collective
+    during the solve).  `sink` then says what becomes of the hourly results: "packed" (default with `writeasnc`):
+    writetonc's integers, one `area_<band>_<window>.nc` per band and `window_days`-day window; "summary" (default
+    otherwise): per-cell mean / min / max of every requested output over the series, reduced inside the kernel and
+    returned as {name: {stat: [rows, cols]}} — the sink for rasters whose hourly arrays exist nowhere; "arrays": the
+    [rows, cols, hours] arrays themselves (small rasters).  The tile-size heuristic and `toverlap` do not apply (bands
+    need no overlap: cells are independent).  Unlike the tile loop, which subtracts each tile's own mean of
+    log(twi)/tfact (src/microclimfCpp.cpp:993-1004 sees one tile), the band run subtracts the whole area's mean — the
+    untiled result."""
     dtm, vegp, soilc = _unpack(dtm, vegp, soilc)
     _checkbiginputs(dtm, vegp, soilc)
+    if gpus is not None:
+        if not isinstance(micropoint, Micropoint):
+            raise ValueError("runmicro_big(gpus = N) takes a data.frame-climate micropoint (runpointmodel)")
+        from . import bigrun
+
+        def fill0_(r):
+            m = r.matrix().copy()
+            m[np.isnan(m)] = 0.0
+            return mask(r.like(m), dtm)
+
+        slr, apr = fill0_(terrain(dtm, "slope")), fill0_(terrain(dtm, "aspect"))
+        twi = _topidx(dtm)
+        hor, svfa = api.horizon(dtm.matrix(), dtm.res[0], want_svf=True)
+        wsa = _windsheltera(dtm.like(dtm.matrix() + vegp["hgt"].matrix()), 8, None)
+        call = prepare_model(micropoint, vegp, soilc, dtm, reqhgt, runchecks, pai_a, tfact, out, slr, apr, hor, twi, wsa,
+                             svf=svfa)
+        root = call.problem()
+        root.tme = np.asarray(micropoint.weather["obs_time"])
+        sink = sink or ("packed" if writeasnc else "summary")
+        res = bigrun.run_local(root, int(gpus), sink=sink, out=call.args["out"], pathout=os.path.join(pathout, "microut"),
+                               window_days=int(window_days), dtm=dtm)
+        res["tme"] = root.tme
+        return res
     if tilesize is None:
         nt = len(micropoint.weather["temp"])
         osize = math.sqrt(20000000 / nt) - 2 * toverlap
