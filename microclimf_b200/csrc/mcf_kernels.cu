@@ -689,6 +689,9 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
 
         // cell skip rule: first vegetation layer's hgt is NA (ref :2182-2183, :2765-2766)
         const bool active = valid && !isnan(__ldg(&a.veg[0][cc]));
+        // lanes of this warp that take the solving branch below (the warp is converged here, behind the CTA barrier):
+        // the mask of every __syncwarp inside that branch — skipped cells never arrive at them
+        const unsigned amask = __ballot_sync(0xffffffffu, active);
         const double tmean = a.has_tadd_mean ? a.tadd_mean : a.dscal[1] / a.dscal[2];
         const double tadd = log(__ldg(&a.soil[11][cc])) / a.tfact - tmean;
         double lat = a.lat, lon = 0.0, dTmx = -0.6273 * a.dscal[0] + 49.79;
@@ -837,7 +840,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 const int last_slot_wraps = (23 >= wrap_at);
                 o = last_slot_wraps ? ocell + (size_t)(23 - wrap_at) * a.out_stride : o_first + (size_t)23 * a.out_stride;
                 const double* st0 = stash + (size_t)23 * (kStashVars * kTile);
-                __syncwarp();
+                __syncwarp(amask);
                 double radabs_n = ld_stash(&st0[0 * kTile]), surfwet_n = ld_stash(&st0[1 * kTile]);
                 double radCsw_n = ld_stash(&st0[2 * kTile]), Lhalf_n = ld_stash(&st0[3 * kTile]);
                 double soild_n = ld_stash(&st0[4 * kTile]), uf_n = ld_stash(&st0[5 * kTile]);
@@ -856,8 +859,8 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                         // A stash line holds the values of 16 lanes and is discarded below by one of them, ordered only
                         // behind that lane's own loaded registers.  Lanes may have diverged inside the previous hour's
                         // physics: converge here, so that the loads are ONE warp instruction — when its result is
-                        // there for the discarding lane (next iteration) it is there for all 32
-                        __syncwarp();
+                        // there for the discarding lane (next iteration) it is there for every lane that loaded
+                        __syncwarp(amask);
                         radabs_n = ld_stash(&st[0 * kTile]);
                         surfwet_n = ld_stash(&st[1 * kTile]);
                         radCsw_n = ld_stash(&st[2 * kTile]);

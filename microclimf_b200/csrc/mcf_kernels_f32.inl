@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
         const bool valid = cell < a.cell_end;
         const int cc = valid ? cell : a.cell_end - 1;
         const bool active = valid && !isnan(__ldg(&a.veg[0][cc]));
+        const unsigned amask = __ballot_sync(0xffffffffu, active); // lanes taking the solving branch (converged here)
         const double tmean = a.has_tadd_mean ? a.tadd_mean : a.dscal[1] / a.dscal[2];
         const double tadd = log(__ldg(&a.soil[11][cc])) / a.tfact - tmean;
         const float dTmx = (float)(-0.6273 * a.dscal[0] + 49.79);
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                 for (int hr = 23; hr >= 0; --hr) {
                     const HourRecF& h = slab_day[hr];
                     const float* st = stash + (size_t)hr * (kStashVars * kTileF);
-                    __syncwarp(); // one converged load instruction per line: complete for lane 0 = complete for all 32
+                    __syncwarp(amask); // one converged load instruction per line: complete for its first lane = complete for all
                     const float radabs = ld_stash_f(&st[0 * kTileF]), surfwet = ld_stash_f(&st[1 * kTileF]);
                     const float radCsw = ld_stash_f(&st[2 * kTileF]), Lhalf = ld_stash_f(&st[3 * kTileF]);
                     const float soild = ld_stash_f(&st[4 * kTileF]);
