@@ -323,6 +323,23 @@ int mcf_horizon(const double* dtm, int32_t rows, int32_t cols, double reso, int3
 int mcf_windcoef(const double* dsm, int32_t rows, int32_t cols, double reso, double hgt, int32_t ndir,
                  const double* direction_deg, double* index, double* blend8, char* err, size_t errlen);
 
+/* .windsheltera (R/internal.R:970-991) as ONE call, everything on the device: .windcoef in 16 directions at height
+ * `hgt`, each direction smoothed by terra::aggregate(fact = s, fun = "mean") + terra::resample (bilinear, :979-981;
+ * s <= 1: no smoothing), blended to 8 sectors (:983-989).  wsa8 is [rows, cols, 8].  The terra steps are restated from
+ * their published definitions (parity unpinned: no R here). */
+int mcf_windshelter(const double* dsm, int32_t rows, int32_t cols, double reso, double hgt, int32_t s, double* wsa8,
+                    char* err, size_t errlen);
+
+/* terra::terrain(dtm, v = "slope" / "aspect") (R/internal.R:1124-1129, R/Cppwrappers.R:483-484): Horn's 8-neighbour
+ * finite difference, degrees; NaN on the edge and beside missing cells (terra: NA); aspect = downslope bearing clockwise
+ * from north, 90 on flat ground.  Either output may be NULL.  Row 0 of the matrix is the raster's northern edge. */
+int mcf_slope_aspect(const double* dtm, int32_t rows, int32_t cols, double xres, double yres, double* slope, double* aspect,
+                     char* err, size_t errlen);
+
+/* .topidx (R/internal.R:861-874): a / tan(B) with B the Horn slope (device kernel) floored at atan(0.02 / mean(res)) and
+ * missing slopes replaced by the median, a = (flowaccCpp + 1) x cell area floored at 1 (host sweep), NaN where dtm is. */
+int mcf_topidx(const double* dtm, int32_t rows, int32_t cols, double xres, double yres, double* twi, char* err, size_t errlen);
+
 /* flowaccCpp (src/microclimfCpp.cpp:5368-5414, with flowdirCpp :5326-5366): D8 flow accumulation of a
  * [rows, cols] elevation matrix, the input of .topidx (R/internal.R:861-874).  HOST code (one sequential
  * sweep over the cells sorted by elevation); NaN cells receive (double)INT_MIN as in the reference. */

@@ -51,6 +51,12 @@ def lib() -> C.CDLL:
         L.mcf_horizon.restype = C.c_int
         L.mcf_windcoef.argtypes = [pd, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, pd, pd, pd, C.c_char_p, C.c_size_t]
         L.mcf_windcoef.restype = C.c_int
+        L.mcf_windshelter.argtypes = [pd, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, pd, C.c_char_p, C.c_size_t]
+        L.mcf_windshelter.restype = C.c_int
+        L.mcf_slope_aspect.argtypes = [pd, C.c_int32, C.c_int32, C.c_double, C.c_double, pd, pd, C.c_char_p, C.c_size_t]
+        L.mcf_slope_aspect.restype = C.c_int
+        L.mcf_topidx.argtypes = [pd, C.c_int32, C.c_int32, C.c_double, C.c_double, pd, C.c_char_p, C.c_size_t]
+        L.mcf_topidx.restype = C.c_int
         L.mcf_flowacc.argtypes = [pd, C.c_int32, C.c_int32, pd, C.c_char_p, C.c_size_t]
         L.mcf_flowacc.restype = C.c_int
         L.mcf_math_eval.argtypes = [C.c_int, pd, pd, C.c_int64, pd, C.c_char_p, C.c_size_t]

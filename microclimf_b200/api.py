@@ -409,3 +409,43 @@ def flowacc(dtm):
     err = C.create_string_buffer(512)
     _lib.check(L.mcf_flowacc(flat.ctypes.data_as(_PD), rows, cols, fa.ctypes.data_as(_PD), err, 512), err)
     return fa.reshape((rows, cols), order="F")
+
+
+def slope_aspect(dtm, xres: float, yres: float):
+    """terra::terrain(v = "slope") / (v = "aspect") of a [rows, cols] elevation matrix (row 0 = north), degrees, NaN where
+    terra leaves NA (R/internal.R:1124-1129): Horn's stencil on the GPU."""
+    L = _lib.lib()
+    d = np.asarray(dtm, dtype=np.float64)
+    rows, cols = d.shape
+    flat = np.ascontiguousarray(d.ravel(order="F"))
+    sl, asp = np.empty(rows * cols), np.empty(rows * cols)
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_slope_aspect(flat.ctypes.data_as(_PD), rows, cols, float(xres), float(yres), sl.ctypes.data_as(_PD),
+                                  asp.ctypes.data_as(_PD), err, 512), err)
+    return sl.reshape((rows, cols), order="F"), asp.reshape((rows, cols), order="F")
+
+
+def windshelter(dsm, reso: float, hgt: float, s: int = 10):
+    """.windsheltera (R/internal.R:970-991) in one call on the GPU: 16 x .windcoef, block-mean + bilinear smoothing of each
+    direction (fact = s), 16 -> 8 blend.  Returns wsa[rows, cols, 8]."""
+    L = _lib.lib()
+    d = np.asarray(dsm, dtype=np.float64)
+    rows, cols = d.shape
+    flat = np.ascontiguousarray(d.ravel(order="F"))
+    out = np.empty(rows * cols * 8)
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_windshelter(flat.ctypes.data_as(_PD), rows, cols, float(reso), float(hgt), int(s),
+                                 out.ctypes.data_as(_PD), err, 512), err)
+    return out.reshape((rows, cols, 8), order="F")
+
+
+def topidx(dtm, xres: float, yres: float):
+    """.topidx (R/internal.R:861-874) of a [rows, cols] elevation matrix (NaN = NA)."""
+    L = _lib.lib()
+    d = np.asarray(dtm, dtype=np.float64)
+    rows, cols = d.shape
+    flat = np.ascontiguousarray(d.ravel(order="F"))
+    out = np.empty(rows * cols)
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_topidx(flat.ctypes.data_as(_PD), rows, cols, float(xres), float(yres), out.ctypes.data_as(_PD), err, 512), err)
+    return out.reshape((rows, cols), order="F")

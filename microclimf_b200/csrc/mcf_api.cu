@@ -1451,6 +1451,132 @@ int mcf_windcoef(const double* dsm, int32_t rows, int32_t cols, double reso, dou
     return report(terrain_stencil(dsm, rows, cols, reso, ndir, direction_deg, true, hgt, index, nullptr, blend8), err, errlen);
 }
 
+// .windsheltera (R/internal.R:970-991) end to end on the device: .windcoef in 16 directions, each smoothed by
+// terra::aggregate(fact = s, mean) + terra::resample(bilinear) (:979-981; s <= 1 skips the smoothing), blended to the 8
+// sectors the solver indexes (:983-989).  Only the [rows, cols, 8] result crosses PCIe.
+int mcf_windshelter(const double* dsm, int32_t rows, int32_t cols, double reso, double hgt, int32_t s, double* wsa8,
+                    char* err, size_t errlen) {
+    auto body = [&]() -> Err {
+        if (!dsm || !wsa8 || rows <= 0 || cols <= 0 || !(reso > 0)) return make_err(MCF_ERR_ARG, "bad argument");
+        TRY(device_info());
+        std::lock_guard<std::mutex> ws_lock(g_ws_mu);
+        const size_t nc = (size_t)rows * cols;
+        std::vector<double> offs((size_t)16 * 20);
+        for (int a = 0; a < 16; ++a) {
+            const double azi = (a * 22.5) * (3.14159265358979323846 / 180);
+            for (int st = 1; st <= 10; ++st) {
+                offs[((size_t)a * 10 + st - 1) * 2 + 0] = 101 - std::cos(azi) * (double)(st * st);
+                offs[((size_t)a * 10 + st - 1) * 2 + 1] = 101 + std::sin(azi) * (double)(st * st);
+            }
+        }
+        const int fact = s > 1 ? s : 1;
+        const size_t onc = (size_t)((rows + fact - 1) / fact) * ((cols + fact - 1) / fact);
+        DevCopy dc;
+        const double *d_dsm = nullptr, *d_offs = nullptr;
+        double *d_scaled = nullptr, *d_idx = nullptr, *d_coarse = nullptr, *d_smooth = nullptr, *d_b8 = nullptr;
+        for (int pass = 0; pass < 2; ++pass) {
+            dc.sizing = (pass == 0);
+            TRY(dc.up(dsm, nc, &d_dsm));
+            TRY(dc.up(offs.data(), offs.size(), &d_offs));
+            TRY(dc.dalloc(&d_scaled, nc));
+            TRY(dc.dalloc(&d_idx, nc * 16));
+            if (fact > 1) {
+                TRY(dc.dalloc(&d_coarse, onc * 16));
+                TRY(dc.dalloc(&d_smooth, nc * 16));
+            }
+            TRY(dc.dalloc(&d_b8, nc * 8));
+            if (pass == 0) TRY(dc.reserve(dc.need));
+        }
+        CU(launch_scale_dtm(d_dsm, (int64_t)nc, reso, d_scaled, nullptr));
+        CU(launch_horizon(d_scaled, rows, cols, 16, d_offs, hgt / reso, true, d_idx, nullptr));
+        count_launch(2);
+        const double* blend_in = d_idx;
+        if (fact > 1) {
+            CU(launch_smooth(d_idx, rows, cols, 16, fact, d_coarse, d_smooth, nullptr));
+            count_launch(2);
+            blend_in = d_smooth;
+        }
+        CU(launch_blend16to8(blend_in, (int64_t)nc, d_b8, nullptr));
+        count_launch();
+        CU(cudaMemcpyAsync(wsa8, d_b8, nc * 8 * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+        CU(cudaStreamSynchronize(nullptr));
+        return Err();
+    };
+    return report(body(), err, errlen);
+}
+
+// terra::terrain(v = "slope") and (v = "aspect") of the DTM (R/internal.R:1124-1129; R/Cppwrappers.R:483-484), degrees,
+// NaN on the raster's edge and beside missing cells as terra leaves NA there.  Either output may be NULL.
+int mcf_slope_aspect(const double* dtm, int32_t rows, int32_t cols, double xres, double yres, double* slope, double* aspect,
+                     char* err, size_t errlen) {
+    auto body = [&]() -> Err {
+        if (!dtm || rows <= 0 || cols <= 0 || !(xres > 0) || !(yres > 0)) return make_err(MCF_ERR_ARG, "bad argument");
+        TRY(device_info());
+        std::lock_guard<std::mutex> ws_lock(g_ws_mu);
+        const size_t nc = (size_t)rows * cols;
+        DevCopy dc;
+        const double* d_dtm = nullptr;
+        double *d_sl = nullptr, *d_as = nullptr;
+        for (int pass = 0; pass < 2; ++pass) {
+            dc.sizing = (pass == 0);
+            TRY(dc.up(dtm, nc, &d_dtm));
+            if (slope) TRY(dc.dalloc(&d_sl, nc));
+            if (aspect) TRY(dc.dalloc(&d_as, nc));
+            if (pass == 0) TRY(dc.reserve(dc.need));
+        }
+        CU(launch_horn(d_dtm, rows, cols, xres, yres, d_sl, d_as, nullptr));
+        count_launch();
+        if (slope) CU(cudaMemcpyAsync(slope, d_sl, nc * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+        if (aspect) CU(cudaMemcpyAsync(aspect, d_as, nc * sizeof(double), cudaMemcpyDeviceToHost, nullptr));
+        CU(cudaStreamSynchronize(nullptr));
+        return Err();
+    };
+    return report(body(), err, errlen);
+}
+
+// .topidx (R/internal.R:861-874): topographic wetness index a / tan(B), B = Horn slope (device) floored at
+// atan(0.02 / mean(res)) with missing slopes replaced by the median, a = (flow accumulation + 1) x cell area floored at 1
+// (flowaccCpp: the sequential sweep of mcf_flowacc, host), masked by the DTM.
+int mcf_topidx(const double* dtm, int32_t rows, int32_t cols, double xres, double yres, double* twi, char* err, size_t errlen) {
+    auto body = [&]() -> Err {
+        if (!dtm || !twi || rows <= 0 || cols <= 0 || !(xres > 0) || !(yres > 0)) return make_err(MCF_ERR_ARG, "bad argument");
+        const size_t nc = (size_t)rows * cols;
+        std::vector<double> B(nc), fa(nc);
+        char e2[256];
+        if (mcf_slope_aspect(dtm, rows, cols, xres, yres, B.data(), nullptr, e2, sizeof e2) != MCF_OK)
+            return make_err(MCF_ERR_CUDA, "%s", e2);
+        if (mcf_flowacc(dtm, rows, cols, fa.data(), e2, sizeof e2) != MCF_OK) return make_err(MCF_ERR_ARG, "%s", e2);
+        const double minslope = std::atan(0.02 / (0.5 * (xres + yres)));
+        const double torad = 3.14159265358979323846 / 180.0;
+        std::vector<double> finite;
+        finite.reserve(nc);
+        for (size_t i = 0; i < nc; ++i) {
+            double b = B[i] * torad; // terrain(unit = "radians")
+            if (b < minslope) b = minslope;
+            B[i] = b;
+            if (!std::isnan(b)) finite.push_back(b);
+        }
+        double med = std::nan("");
+        if (!finite.empty()) { // R's median: mean of the two middle values for an even count
+            const size_t m = finite.size() / 2;
+            std::nth_element(finite.begin(), finite.begin() + m, finite.end());
+            med = finite[m];
+            if (finite.size() % 2 == 0) {
+                const double lo = *std::max_element(finite.begin(), finite.begin() + m);
+                med = 0.5 * (lo + med);
+            }
+        }
+        for (size_t i = 0; i < nc; ++i) {
+            const double b = std::isnan(B[i]) ? med : B[i];
+            double a = (fa[i] + 1) * xres * yres;
+            if (a < 1) a = 1;
+            twi[i] = std::isnan(dtm[i]) ? std::nan("") : a / std::tan(b);
+        }
+        return Err();
+    };
+    return report(body(), err, errlen);
+}
+
 // flowdirCpp + flowaccCpp (src/microclimfCpp.cpp:5326-5414): D8 flow direction to the lowest of the 3x3
 // neighbourhood (first minimum in column-major scan order, the cell itself included) and accumulation by one
 // sweep over the cells in decreasing (elevation, row * cols + col) order.  A sequential sorted sweep over the

@@ -178,6 +178,10 @@ cudaError_t launch_horizon(const double* d, int rows, int cols, int ndir, const 
                            double* out, cudaStream_t st);
 cudaError_t launch_skyview(const double* hor, int64_t nc, int ndir, double* svf, cudaStream_t st);
 cudaError_t launch_blend16to8(const double* a, int64_t nc, double* out, cudaStream_t st);
+cudaError_t launch_horn(const double* z, int rows, int cols, double dx, double dy, double* slope, double* aspect,
+                        cudaStream_t st);
+// block mean over fact x fact cells into `coarse` ([ceil(rows/fact), ceil(cols/fact), nl]), then bilinear back to `out`
+cudaError_t launch_smooth(const double* src, int rows, int cols, int nl, int fact, double* coarse, double* out, cudaStream_t st);
 cudaError_t launch_math_eval(int fn, const double* x, const double* y, int64_t n, double* out, cudaStream_t stream);
 cudaError_t launch_fp64_peak(double* sink, int grid, int iters, cudaStream_t stream);
 

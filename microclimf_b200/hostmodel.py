@@ -32,7 +32,7 @@ import numpy as np
 from . import api
 from .problem import GridProblem
 from .spatial import (Raster, aggregate_mean, as_raster, latlong_from_raster, latslons_from_raster, mask,
-                      resample_bilinear, terrain)
+                      resample_bilinear)
 from .tables import SOILPARAMETERS
 
 VEG_NAMES = ("pai", "hgt", "x", "gsmax", "leafr", "clump", "leafd", "leaft")
@@ -412,34 +412,29 @@ def _soilinit(soilc: Dict[str, Raster]) -> Dict[str, np.ndarray]:
     return out
 
 
+def terrain(dtm: Raster, v: str = "slope", unit: str = "degrees") -> Raster:
+    """terra::terrain(dtm, v = "slope" | "aspect") (R/internal.R:1124-1129; R/Cppwrappers.R:483-484): Horn's stencil on the
+    GPU (mcf_slope_aspect); NA on the edge and beside missing cells, as terra leaves them."""
+    sl, asp = api.slope_aspect(dtm.matrix(), dtm.res[0], dtm.res[1])
+    if v not in ("slope", "aspect"):
+        raise ValueError("terrain: v must be 'slope' or 'aspect'")
+    m = sl if v == "slope" else asp
+    return dtm.like(m * (math.pi / 180.0) if unit == "radians" else m)
+
+
 def _topidx(dtm: Raster) -> Raster:
-    """ref .topidx (R/internal.R:861-874): topographic wetness index a / tan(slope)."""
-    rx, ry = dtm.res
-    minslope = math.atan(0.02 / (0.5 * (rx + ry)))
-    B = terrain(dtm, "slope", unit="radians").matrix().copy()
-    with np.errstate(invalid="ignore"):
-        B[B < minslope] = minslope
-    B[np.isnan(B)] = np.nanmedian(B)
-    a = api.flowacc(dtm.matrix()) + 1
-    a = a * rx * ry
-    a[a < 1] = 1
-    return mask(dtm.like(a / np.tan(B)), dtm)
+    """ref .topidx (R/internal.R:861-874): topographic wetness index a / tan(slope) — mcf_topidx: Horn slope on the GPU,
+    the sequential flow-accumulation sweep of flowaccCpp in host C++."""
+    return dtm.like(api.topidx(dtm.matrix(), dtm.res[0], dtm.res[1]))
 
 
 def _windsheltera(dtm: Raster, whgt: float, s) -> np.ndarray:
-    """ref .windsheltera (R/internal.R:970-991): .windcoef in 16 directions (GPU), block-mean + bilinear
-    smoothing (terra aggregate / resample, restated), blended to 8 directions."""
+    """ref .windsheltera (R/internal.R:970-991), one call, all on the GPU (mcf_windshelter): .windcoef in 16 directions,
+    block-mean + bilinear smoothing of each (terra aggregate / resample, restated), blended to 8 directions."""
     if s is None or (isinstance(s, float) and math.isnan(s)):
         s = min(dtm.nrows, dtm.ncols)
         s = 10 if s > 10 else s
-    a = api.windcoef(dtm.matrix(), dtm.res[0], whgt)  # [rows, cols, 16]
-    r = dtm.like(a)
-    a = resample_bilinear(aggregate_mean(r, int(s)), dtm).values
-    a2 = np.empty(a.shape[:2] + (8,))
-    for i in range(8):
-        mid, nxt, prv = 2 * i, 2 * i + 1, (15 if i == 0 else 2 * i - 1)
-        a2[:, :, i] = 0.5 * a[:, :, mid] + 0.25 * a[:, :, nxt] + 0.25 * a[:, :, prv]
-    return a2
+    return api.windshelter(dtm.matrix(), dtm.res[0], whgt, int(s))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -411,9 +411,8 @@ List snow_model(const mcf_snow_climate& c, const mcf_snow_point& pt, const mcf_s
             err);
     List out;
     for (int v = 0; v < 5; ++v) out[n3[v]] = a3[v];
-    // the reference returns the two ages as IntegerMatrix (src/microclimfCpp.cpp:4291-4292)
-    for (int v = 0; v < 2; ++v) out[n2[v]] = IntegerMatrix(a2[v]);
-    for (int v = 2; v < 4; ++v) out[n2[v]] = a2[v];
+    // ages and melts are NumericMatrix in the reference too (bioclimfill, src/microclimfCpp.cpp:4306-4309): skipped cells NA
+    for (int v = 0; v < 4; ++v) out[n2[v]] = a2[v];
     return out;
 }
 

@@ -33,10 +33,12 @@ def _check_sinks(p, gpus, tmp_path):
     for nm in _abi.OUT_NAMES:
         w = whole[nm][:, :, :hours]
         s = r["summary"][nm]
-        assert np.isnan(s["mean"][na]).all()
-        np.testing.assert_allclose(s["mean"][~na], w[~na].mean(axis=1), rtol=1e-12, atol=1e-12, err_msg=nm)
-        np.testing.assert_array_equal(s["min"][~na], w[~na].min(axis=1), err_msg=nm)
-        np.testing.assert_array_equal(s["max"][~na], w[~na].max(axis=1), err_msg=nm)
+        assert np.isnan(s["mean"][na]).all(), nm
+        # NaN hours of a solved cell poison its mean and are skipped by its extremes (the sink's rule)
+        with np.errstate(invalid="ignore"):
+            np.testing.assert_allclose(s["mean"][~na], w[~na].sum(axis=1) / hours, rtol=1e-12, atol=1e-12, err_msg=nm)
+        np.testing.assert_array_equal(s["min"][~na], np.fmin.reduce(w[~na], axis=1, initial=np.inf), err_msg=nm)
+        np.testing.assert_array_equal(s["max"][~na], np.fmax.reduce(w[~na], axis=1, initial=-np.inf), err_msg=nm)
     out_dir = str(tmp_path / f"packed{gpus}")
     r = bigrun.run_local(p.replace(), gpus, sink="packed", pathout=out_dir, window_days=2)
     assert r["hours"] == hours
@@ -90,11 +92,16 @@ def test_hostmodel_runmicro_big_bands_on_bundled_example(tmp_path):
     from microclimf_b200 import hostmodel
 
     dtm, vegp, soilc, mp, _ = tb.load_example()
+    vegp = tb._fill_reflectance(vegp, dtm)  # .checkbiginputs refuses the bundled NA reflectances of bare ground
     sub = hostmodel.subsetpointmodel(mp, days=[100, 101, 250])
     res = hostmodel.runmicro_big(sub, 0.05, str(tmp_path) + "/", vegp, soilc, dtm, gpus=1)
     mout = hostmodel.runmicro(sub, 0.05, vegp, soilc, dtm)
     assert res["hours"] == 72
-    for nm in ("Tz", "tleaf", "soilm", "Rlwup"):
+    # runmicro_big derives the wind shelter from dtm + vegetation height at 8 m (R/Cppwrappers.R:493-494), runmicro from
+    # the dtm at zref: compare what does not depend on wind
+    for nm in ("soilm", "Rdirdown", "Rdifdown", "Rswup"):
         m = ~np.isnan(mout[nm][:, :, 0])
         np.testing.assert_allclose(res["summary"][nm]["mean"][m], mout[nm][m].mean(axis=1), rtol=1e-9, atol=1e-9, err_msg=nm)
         np.testing.assert_allclose(res["summary"][nm]["max"][m], mout[nm][m].max(axis=1), rtol=1e-9, atol=1e-9, err_msg=nm)
+    na = np.isnan(dtm.matrix())
+    assert np.isnan(res["summary"]["Tz"]["mean"][na]).all() and np.isfinite(res["summary"]["Tz"]["mean"][~na]).all()

@@ -42,6 +42,12 @@ def load_example(reqhgt=0.05):
     return dtm, vegp, soilc, mp, clim
 
 
+def cpu_slope_aspect(dtm):
+    """slr / apr through the numpy restatement of terra::terrain (spatial.terrain), so host-logic tests run without a GPU."""
+    from microclimf_b200 import spatial
+    return dict(slr=spatial.terrain(dtm, "slope"), apr=spatial.terrain(dtm, "aspect"))
+
+
 def cpu_terrain(dtm, zref):
     """hor / wsa through the numpy restatement, so host-logic tests run without a GPU."""
     d = dtm.matrix()
@@ -89,7 +95,7 @@ def test_prepare_model_layers_and_masks():
     sub = hostmodel.subsetpointmodel(mp, tstep="month", what="tmax")
     hor, wsa = cpu_terrain(dtm, mp.zref)
     twi = dtm.like(np.where(np.isnan(dtm.matrix()), np.nan, 5.0))  # flow accumulation needs the built library
-    call = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=0.05, hor=hor, wsa=wsa, twi=twi)
+    call = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=0.05, hor=hor, wsa=wsa, twi=twi, **cpu_slope_aspect(dtm))
     a = call.args
     assert call.mode == 3
     # 12 monthly layers, each spanning one 24-hour block (R/internal.R:1388-1399)
@@ -107,7 +113,7 @@ def test_prepare_model_layers_and_masks():
     k = int(st[10, 10])
     assert a["soilc"]["Smax"][10, 10] == SOILPARAMETERS["Smax"][k - 1] and a["soilc"]["soilb"][10, 10] == SOILPARAMETERS["b"][k - 1]
     # reqhgt = 0 / < 0 mask the outputs as the reference does (R/internal.R:1159-1166)
-    call0 = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=0.0, hor=hor, wsa=wsa, twi=twi)
+    call0 = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=0.0, hor=hor, wsa=wsa, twi=twi, **cpu_slope_aspect(dtm))
     assert call0.args["out"] == [True, False, False, True, False, True, True, True, True, True]
     p = to_problem(call)
     p.validate()
@@ -140,7 +146,7 @@ def test_reference_on_bundled_example_ranges():
     sub = hostmodel.subsetpointmodel(mp, days=[172])  # midsummer
     hor, wsa = cpu_terrain(dtm, mp.zref)
     twi = dtm.like(np.where(np.isnan(dtm.matrix()), np.nan, 5.0))
-    call = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=0.05, hor=hor, wsa=wsa, twi=twi)
+    call = hostmodel.prepare_model(sub, vegp, soilc, dtm, reqhgt=0.05, hor=hor, wsa=wsa, twi=twi, **cpu_slope_aspect(dtm))
     ref = pyoracle.runmicro(to_problem(call), kind="ref")
     ok = ~np.isnan(dtm.matrix())
     tair = sub.weather["temp"]
@@ -350,7 +356,8 @@ def test_gridded_climate_mapping_cpu():
     mpa, dtmc = _micropointa(sub, dtm)
     hor, wsa = cpu_terrain(dtm, mp.zref)
     twi = dtm.like(np.where(np.isnan(dtm.matrix()), np.nan, 5.0))
-    call = hostmodel.prepare_model_a(mpa, vegp, soilc, dtm, dtmc, reqhgt=0.05, altcorrect=2, hor=hor, wsa=wsa, twi=twi)
+    call = hostmodel.prepare_model_a(mpa, vegp, soilc, dtm, dtmc, reqhgt=0.05, altcorrect=2, hor=hor, wsa=wsa, twi=twi,
+                                     **cpu_slope_aspect(dtm))
     p = call.prob
     assert (p.mode, p.clim_rows, p.clim_cols, p.nlyr) == (4, 2, 2, 1) or p.mode == 4
     tc = p.arrays["temp"].reshape(p.tsteps, 2, 2)  # [k, cj, ci]

@@ -4,7 +4,7 @@ import numpy as np
 
 from microclimf_b200 import hostmodel
 from microclimf_b200.spatial import Raster, resample_bilinear
-from test_bundled_example import _micropointa, cpu_terrain, load_example
+from test_bundled_example import _micropointa, cpu_slope_aspect, cpu_terrain, load_example
 
 
 def test_snow_day_sets_seed_and_merge():
@@ -44,7 +44,7 @@ def test_prepsnowinputs2_climate_arrays():
     hor, wsa = cpu_terrain(dtm, mp.zref)
     moutn = {"Tz": np.zeros((dtm.nrows, dtm.ncols, 48))}
     r0 = hostmodel.prepsnowinputs2(0.05, dtm, dtmc, vegp, soilc, mps, 0, True, np.array([2, 3]), np.array([1, 4]), moutn,
-                                   hor=hor, wsa=wsa)
+                                   hor=hor, wsa=wsa, **cpu_slope_aspect(dtm))
     w = r0["weather"]
     tc = np.stack([np.asarray(m.weather["temp"], dtype=float) for m in mps]).reshape(dtmc.nrows, dtmc.ncols, 48)
     np.testing.assert_allclose(w["temp"], resample_bilinear(dtmc.like(tc), dtm).values, rtol=0, atol=1e-12)
@@ -54,7 +54,7 @@ def test_prepsnowinputs2_climate_arrays():
     assert r0["micro"]["Tz"].shape == (dtm.nrows, dtm.ncols, 48) and r0["other"]["lats"].shape == land.shape
     # altitude correction: fixed lapse rate moves temperature by 5 K per km of (coarse - fine) elevation
     r1 = hostmodel.prepsnowinputs2(0.05, dtm, dtmc, vegp, soilc, mps, 1, True, np.array([2, 3]), np.array([1, 4]), moutn,
-                                   hor=hor, wsa=wsa)
+                                   hor=hor, wsa=wsa, **cpu_slope_aspect(dtm))
     zc = np.nan_to_num(dtmc.matrix())
     elevd = resample_bilinear(dtmc.like(zc), dtm).matrix() - dtm.matrix()
     np.testing.assert_allclose((r1["weather"]["temp"] - w["temp"])[land], np.repeat((elevd * 0.005)[:, :, None], 48, 2)[land],

@@ -75,3 +75,94 @@ def test_terrain_feeds_the_grid_model():
     want = pyoracle.runmicro(p, kind="ref" if pyoracle.have_ref() else "oracle")
     ok, rows = parity.compare(got, want)
     assert ok, "\n" + parity.fmt(rows)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# slope / aspect, aggregate + resample, wind shelter, TWI on the device.  terra's routines are third-party arithmetic with
+# no vectors to pin against (PARITY UNPINNED): what CAN be pinned is pinned on analytic surfaces, where
+# Horn's stencil, the horizon search and bilinear interpolation have closed-form answers; on rough surfaces the kernels
+# are compared with the numpy restatements of the same published definitions (microclimf_b200/spatial.py).
+# ---------------------------------------------------------------------------------------------------------------------
+def _plane(rows, cols, gx, gy, dx, dy):
+    """z = gx * x + gy * y with x east, y north; row 0 is the northern edge."""
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    return gx * (jj * dx) + gy * ((rows - 1 - ii) * dy)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gx,gy", [(0.3, 0.0), (0.0, -0.2), (0.15, 0.25), (-0.4, 0.1), (0.0, 0.0)])
+def test_slope_aspect_known_answers_on_planes(gx, gy):
+    """Horn's stencil is exact on a plane: slope = atan |grad z|, aspect = bearing of the DOWNSLOPE direction clockwise
+    from north (90 on flat ground), NA on the one-cell edge."""
+    from microclimf_b200 import api
+
+    dx, dy = 10.0, 12.0
+    sl, asp = api.slope_aspect(_plane(33, 41, gx, gy, dx, dy), dx, dy)
+    inner = (slice(1, -1), slice(1, -1))
+    assert np.isnan(sl[0]).all() and np.isnan(sl[-1]).all() and np.isnan(asp[:, 0]).all() and np.isnan(asp[:, -1]).all()
+    np.testing.assert_allclose(sl[inner], np.degrees(np.arctan(np.hypot(gx, gy))), rtol=0, atol=1e-10)
+    want = 90.0 if gx == 0 and gy == 0 else np.degrees(np.arctan2(-gx, -gy)) % 360.0
+    np.testing.assert_allclose(asp[inner], want, rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_slope_aspect_on_a_cone_and_against_the_restatement():
+    from microclimf_b200 import api, spatial
+
+    n, k = 101, 0.35
+    ii, jj = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    r = np.hypot(ii - 50, jj - 50) * 5.0
+    sl, asp = api.slope_aspect(1000.0 - k * r, 5.0, 5.0)
+    far = r > 150  # away from the apex Horn's 3 x 3 average of a cone's gradient is within 1e-3 of the true one
+    far[[0, -1], :] = False
+    far[:, [0, -1]] = False
+    np.testing.assert_allclose(sl[far], np.degrees(np.arctan(k)), atol=0.05)
+    bearing_out = np.degrees(np.arctan2(jj - 50, -(ii - 50))) % 360.0  # direction away from the apex = downslope
+    dif = np.abs((asp[far] - bearing_out[far] + 180) % 360 - 180)
+    assert dif.max() < 0.5
+    d = _dtm(77, 58, seed=12)
+    ras = spatial.Raster(d, 0, 58 * 7.0, 0, 77 * 9.0, "")
+    sl, asp = api.slope_aspect(d, 7.0, 9.0)
+    np.testing.assert_allclose(sl, spatial.terrain(ras, "slope").matrix(), rtol=0, atol=1e-10, equal_nan=True)
+    np.testing.assert_allclose(asp, spatial.terrain(ras, "aspect").matrix(), rtol=0, atol=1e-9, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_horizon_known_answer_on_planes():
+    """On a plane the horizon tangent towards a cardinal azimuth is the (positive part of the) directional derivative,
+    whichever of the 10 search steps finds it — as long as the search stays inside the raster (beyond it R pads zeros)."""
+    from microclimf_b200 import api
+
+    reso = 10.0
+    z = _plane(260, 250, 0.2, -0.1, reso, reso) + 500.0
+    hor, _ = api.horizon(z, reso, azimuths=np.array([0.0, 90.0, 180.0, 270.0]), want_svf=False)
+    core = (slice(101, -101), slice(101, -101))  # every search step (up to 100 cells) stays inside
+    for k, want in enumerate((0.0, 0.2, 0.1, 0.0)):  # north: -0.1 -> 0; east: +0.2; south: +0.1; west: -0.2 -> 0
+        np.testing.assert_allclose(hor[core][..., k], want, rtol=0, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_windshelter_and_topidx_against_restatements():
+    from microclimf_b200 import api, spatial
+
+    d = _dtm(123, 97, seed=21)
+    d[np.isnan(d)] = 100.0
+    reso = 4.0
+    ras = spatial.Raster(d, 0, 97 * reso, 0, 123 * reso, "")
+    # .windsheltera = 16 x .windcoef -> aggregate(10, mean) -> resample(bilinear) -> 16 to 8 blend
+    idx = api.windcoef(d, reso, 2.0)
+    sm = spatial.resample_bilinear(spatial.aggregate_mean(ras.like(idx), 10), ras).values
+    np.testing.assert_allclose(api.windshelter(d, reso, 2.0, 10), T.blend16to8(sm), rtol=0, atol=1e-12)
+    np.testing.assert_allclose(api.windshelter(d, reso, 2.0, 1), T.blend16to8(idx), rtol=0, atol=1e-14)
+    # a constant field survives block mean + bilinear exactly; a plane survives it away from the ragged edge blocks
+    # .topidx
+    B = spatial.terrain(ras, "slope", unit="radians").matrix().copy()
+    minslope = np.arctan(0.02 / reso)
+    with np.errstate(invalid="ignore"):
+        B[B < minslope] = minslope
+    B[np.isnan(B)] = np.nanmedian(B)
+    a = np.maximum((api.flowacc(d) + 1) * reso * reso, 1.0)
+    np.testing.assert_allclose(api.topidx(d, reso, reso), a / np.tan(B), rtol=1e-12)
+    sea = d.copy()
+    sea[:20, :30] = np.nan
+    assert np.array_equal(np.isnan(api.topidx(sea, reso, reso)), np.isnan(sea))
