@@ -139,7 +139,7 @@ def scatter_problem(root: "GridProblem | None", src: int = 0, group=None):
                                                           "clim_cols", "clim_row0", "clim_drow", "clim_col0", "clim_dcol",
                                                           "altcorrect")},
                     lyr_st=None if root.lyr_st is None else np.asarray(root.lyr_st), lyr_ed=None if root.lyr_ed is None
-                    else np.asarray(root.lyr_ed), ranges=rngs,
+                    else np.asarray(root.lyr_ed), ranges=rngs, twi_mean=root.twi_mean,
                     ints={n: np.asarray(root.arrays[n]) for n in ("year", "month", "day")},
                     replicated=[(n, int(np.asarray(root.arrays[n]).size)) for n in replicated if n not in ("year", "month", "day")],
                     banded=[(n, root.expected_len(n) // root.ncells) for n in root.arrays
@@ -154,6 +154,7 @@ def scatter_problem(root: "GridProblem | None", src: int = 0, group=None):
     b = GP(**{**f, "cols": c1 - c0})
     b.clim_col0 = f["clim_col0"] + f["clim_dcol"] * c0
     b.lyr_st, b.lyr_ed = meta["lyr_st"], meta["lyr_ed"]
+    b.twi_mean = meta["twi_mean"]  # a caller-supplied whole-raster mean travels with the problem
     for n, a in meta["ints"].items():
         b.arrays[n] = np.ascontiguousarray(a, dtype=np.int32)
     for n, ln in meta["replicated"]:

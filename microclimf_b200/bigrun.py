@@ -186,7 +186,8 @@ def run_spmd(root: Optional[GridProblem], sink: str = "summary", out: Sequence[b
     rank, world = bands.rank_world(group)
     t0 = time.perf_counter()
     band, (c0, c1), (R, C) = bands.scatter_problem(root, 0, group)
-    band.twi_mean = _twi_mean(band, group)
+    if band.twi_mean is None:  # else: the caller's mean (e.g. this raster is itself part of a larger area)
+        band.twi_mean = _twi_mean(band, group)
     on_gpu = bands.collective_device(group) == "cuda" or (world == 1 and torch.cuda.is_available())
     if world == 1 and on_gpu:
         band = band.to_device("cuda")

@@ -97,6 +97,7 @@ def _worker_plane(rank, world, port, q):
             root = synth.make_problem(7, 11, 72, reqhgt=0.05, mode=mode, nlyr=3) if rank == 0 else None
             band, (c0, c1), (R, C) = bands.scatter_problem(root, 0)
             assert (R, C) == (7, 11) and band.cols == c1 - c0 and band.rows == 7
+            assert band.twi_mean is None
             band.twi_mean = bigrun._twi_mean(band)
             hb = band._clone_meta()
             hb.arrays = {n: (a.numpy() if hasattr(a, "numpy") else a) for n, a in band.arrays.items()}
