@@ -414,10 +414,13 @@ def gpu_arm(args):
            "d2h_bytes_per_step": d2h, "steps": esteps, "ms_per_step": 1e3 * e_s / esteps,
            # bytes over PCIe per second of the whole call: the host-buffer path is bound by the link (80 B per cell-hour
            # of FP64 results), not by the kernels
-           "pcie_gb_per_s": (h2d + d2h) * esteps / e_s / 1e9,
+           "pcie_gb_per_s": (h2d + d2h) * esteps * world / e_s / 1e9, "pcie_gb_per_s_per_gpu": (h2d + d2h) * esteps / e_s / 1e9,
            # aggregate over all ranks of plain pinned cudaMemcpyAsync device -> host, all ranks copying at once: what the
-           # box itself can move at this N (the ceiling of pcie_gb_per_s), and where this rank's pinned memory lives
-           "d2h_ceiling_gb_per_s": d2h_ceiling, "numa": numa_rep,
+           # box itself can move at this N — the ceiling of pcie_gb_per_s (both are whole-box figures) — and where this
+           # rank's pinned memory lives.  The FP64 sink moves 80 B per cell-hour, so e2e <= ceiling / 80 B whatever the
+           # kernels do; the sinks that scale are the ones that move less (e2e_packed: 20 B; job: 240 B per CELL).
+           "d2h_ceiling_gb_per_s": d2h_ceiling, "frac_of_d2h_ceiling": d2h * esteps * world / e_s / 1e9 / d2h_ceiling,
+           "numa": numa_rep,
            "sample": f"{er}x{ec} cells x {et} h per GPU through mcf_runmicro (pinned host buffers, all 10 outputs "
                      f"copied back; timed with the host clock around the blocking call)"}
     # the same call with the packed integer sink (writetonc's x100 / x1 int16 packing done by the kernels, SURVEY.md
@@ -438,7 +441,7 @@ def gpu_arm(args):
         p_s = float(t.item())
     e2e_packed = {"value": float(er) * ec * et * esteps * world / p_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                   "d2h_bytes_per_step": sum(o.nbytes for o in pouts), "steps": esteps, "ms_per_step": 1e3 * p_s / esteps,
-                  "pcie_gb_per_s": (h2d + sum(o.nbytes for o in pouts)) * esteps / p_s / 1e9,
+                  "pcie_gb_per_s": (h2d + sum(o.nbytes for o in pouts)) * esteps * world / p_s / 1e9,
                   "sample": "same tile through mcf_runmicro_packed: int16 outputs as the reference's writetonc stores them"}
     # the same FP64 call into PAGEABLE result buffers — what R hands the library (its vectors are ordinary memory): served
     # by the pool of copy threads with pinned slots.  N = 1 only; reported beside the pinned e2e.
