@@ -443,6 +443,30 @@ def gpu_arm(args):
                   "d2h_bytes_per_step": sum(o.nbytes for o in pouts), "steps": esteps, "ms_per_step": 1e3 * p_s / esteps,
                   "pcie_gb_per_s": (h2d + sum(o.nbytes for o in pouts)) * esteps * world / p_s / 1e9,
                   "sample": "same tile through mcf_runmicro_packed: int16 outputs as the reference's writetonc stores them"}
+    # the FP32 build through the same host path (mcf_runmicro_f32): 40 instead of 80 bytes per cell-hour over PCIe
+    e2e_f32 = None
+    try:
+        fouts_t = [torch.empty(er * ec * et, dtype=torch.float32).pin_memory() for _ in range(10)]
+        fouts = [t_.numpy() for t_ in fouts_t]
+        for _ in range(2):
+            api.run_problem_f32(ep, out_buffers=fouts)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            api.run_problem_f32(ep, out_buffers=fouts)
+        torch.cuda.synchronize()
+        f_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([f_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            f_s = float(t.item())
+        e2e_f32 = {"value": float(er) * ec * et * esteps * world / f_s, "unit": UNIT, "dtype": "f32", "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": sum(o.nbytes for o in fouts), "steps": esteps, "ms_per_step": 1e3 * f_s / esteps,
+                   "pcie_gb_per_s": (h2d + sum(o.nbytes for o in fouts)) * esteps * world / f_s / 1e9,
+                   "sample": "same tile through mcf_runmicro_f32 (the optional FP32 build, float outputs)"}
+        del fouts_t, fouts
+    except Exception as exc:
+        e2e_f32 = {"error": repr(exc)[:200]}
     # the same FP64 call into PAGEABLE result buffers — what R hands the library (its vectors are ordinary memory): served
     # by the pool of copy threads with pinned slots.  N = 1 only; reported beside the pinned e2e.
     e2e_pageable = None
@@ -623,7 +647,7 @@ def gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "e2e_packed": e2e_packed, "e2e_pageable": e2e_pageable,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args), "e2e": e2e, "e2e_packed": e2e_packed, "e2e_f32": e2e_f32, "e2e_pageable": e2e_pageable,
             "fp32": fp32, "job": job, "configs": configs,
             "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clk, "setup_seconds": t_gen,

@@ -271,13 +271,17 @@ int mcf_runmicro_packed_dev(const mcf_problem* prob, int16_t* const out[MCF_NOUT
                             void* stream, char* err, size_t errlen);
 
 /* ------------------------------------------------------------------------------------------- */
-/* FP32 build (BASELINE north_star: "an optional FP32 build must stay within 0.05 degC and 0.5 %      */
-/* radiation").  Device buffers, modes 1/3 (per-hour forcing), reqhgt >= 0.  `prob` is the FP64 problem  */
-/* of mcf_runmicro_dev; the hour loops run in FP32 (SFU transcendentals), per-cell invariants in FP64;   */
-/* outputs are float arrays (quiet NaN in skipped cells), window / ring as for mcf_runmicro_dev.          */
-/* ------------------------------------------------------------------------------------------- */
+/* FP32 build (BASELINE north_star: "an optional FP32 build must stay within 0.05 degC and 0.5 % radiation").  `prob` is
+ * the FP64 problem of mcf_runmicro[_dev] — every mode (data.frame, fine-array and coarse-grid climate, layered
+ * vegetation) and every height.  The hour loops run in FP32 (SFU transcendentals); per-cell invariants, the per-cell-hour
+ * assembly of array climate (interpolation, altitude correction, solar position) and the below-ground time-axis pass stay
+ * FP64.  Outputs are float arrays (quiet NaN where the FP64 entry points write NA_real_): 40 instead of 80 bytes per
+ * cell-hour in HBM and over PCIe.  Window / ring as for mcf_runmicro_dev. */
 int mcf_runmicro_f32_dev(const mcf_problem* prob, float* const out[MCF_NOUT], const mcf_window* win, void* stream,
                          char* err, size_t errlen);
+/* HOST buffers: the same host path as mcf_runmicro (one upload, windowed copy-back overlapping the kernels, pageable
+ * destinations served by the pinned-slot copy pool), moving half the bytes. */
+int mcf_runmicro_f32(const mcf_problem* prob, float* const out[MCF_NOUT], char* err, size_t errlen);
 
 /* sum and count of log(twi)/tfact over the non-NaN cells of a HOST twi buffer holding n cells
  * (the two numbers the bands all-reduce before calling with has_twi_mean = 1). */

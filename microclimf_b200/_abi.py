@@ -66,5 +66,5 @@ EXPORTED_SYMBOLS = (
     "mcf_runmicro", "mcf_runbioclim", "mcf_runmicro_dev", "mcf_runbioclim_dev", "mcf_twi_partial",
     "mcf_abi_version", "mcf_device_count", "mcf_set_device", "mcf_launch_count", "mcf_launch_count_reset",
     "mcf_kernel_time", "mcf_kernel_time_reset", "mcf_kernel_timing_enable", "mcf_fp64_peak", "mcf_math_eval", "mcf_release_workspace", "mcf_horizon", "mcf_windcoef", "mcf_flowacc", "mcf_runmicro_packed", "mcf_runmicro_packed_dev", "mcf_gridmodelsnow", "mcf_gridmicrosnow", "mcf_gridmodelsnow2", "mcf_gridmicrosnow2", "mcf_runmicro_f32_dev",
-    "mcf_runmicro_summary", "mcf_runmicro_summary_dev", "mcf_windshelter", "mcf_slope_aspect", "mcf_topidx",
+    "mcf_runmicro_summary", "mcf_runmicro_summary_dev", "mcf_windshelter", "mcf_slope_aspect", "mcf_topidx", "mcf_runmicro_f32",
 )

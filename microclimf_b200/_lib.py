@@ -71,6 +71,8 @@ def lib() -> C.CDLL:
         L.mcf_runmicro_packed_dev.restype = C.c_int
         L.mcf_runmicro_f32_dev.argtypes = [pp, _abi.OutPtrsF, pw, C.c_void_p, C.c_char_p, C.c_size_t]
         L.mcf_runmicro_f32_dev.restype = C.c_int
+        L.mcf_runmicro_f32.argtypes = [pp, _abi.OutPtrsF, C.c_char_p, C.c_size_t]
+        L.mcf_runmicro_f32.restype = C.c_int
         L.mcf_runmicro_summary.argtypes = [pp, _abi.OutPtrs, _abi.OutPtrs, _abi.OutPtrs, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]
         L.mcf_runmicro_summary.restype = C.c_int
         L.mcf_runmicro_summary_dev.argtypes = [pp, _abi.OutPtrs, _abi.OutPtrs, _abi.OutPtrs, pw, C.c_int32, C.POINTER(C.c_int64),

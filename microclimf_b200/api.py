@@ -161,6 +161,29 @@ def run_problem_f32_dev(p: GridProblem, out_tensors, window=None, stream=None) -
     del keep
 
 
+def run_problem_f32(p: GridProblem, out: Optional[Sequence[bool]] = None, out_buffers=None) -> Dict[str, np.ndarray]:
+    """mcf_runmicro_f32: the FP32 build through the host-buffer path; float32 arrays [rows, cols, tsteps] (NaN = NA)."""
+    L = _lib.lib()
+    n = p.ncells * p.tsteps
+    if out_buffers is not None:
+        bufs = list(out_buffers)
+        for b in bufs:
+            if b is not None and (b.dtype != np.float32 or b.size != n or not b.flags.c_contiguous):
+                raise ValueError("each output buffer must be a contiguous float32 array of rows*cols*tsteps")
+    else:
+        out = [True] * _abi.MCF_NOUT if out is None else [bool(o) for o in out]
+        bufs = [np.empty(n, dtype=np.float32) if o else None for o in out]
+    if len(bufs) != _abi.MCF_NOUT:
+        raise ValueError("10 outputs expected")
+    PF = C.POINTER(C.c_float)
+    ptrs = _abi.OutPtrsF(*[b.ctypes.data_as(PF) if b is not None else None for b in bufs])
+    s, keep = p.as_struct()
+    err = C.create_string_buffer(512)
+    _lib.check(L.mcf_runmicro_f32(C.byref(s), ptrs, err, 512), err)
+    del keep
+    return {nm: b.reshape((p.rows, p.cols, p.tsteps), order="F") for nm, b in zip(_abi.OUT_NAMES, bufs) if b is not None}
+
+
 def run_bioclim_problem(p: GridProblem, wetq, dryq, hotq, colq, air: bool = True,
                         out: Optional[Sequence[bool]] = None) -> Dict[str, np.ndarray]:
     L = _lib.lib()

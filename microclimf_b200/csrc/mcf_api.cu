@@ -215,7 +215,12 @@ struct Plan {
     double* d_mxtc_cell = nullptr;
     double* d_stash = nullptr;
     int grid = 0;
-    int pack = 0; // outputs are int16 (the packed integer sink): out[v] pointers are int16_t* in disguise
+    // element type of the outputs: 0 FP64; 1 int16 (the packed integer sink); 2 FP32 (the FP32 build: k_grid_f32).
+    // out[v] pointers are int16_t* / float* in disguise for 1 / 2.
+    int pack = 0;
+    char* d_hoursf = nullptr;  // FP32 build, modes 1/3: the narrowed hour table
+    float* d_stashf = nullptr; // FP32 build: its day stash
+    int tile() const { return pack == 2 ? f32_tile() : kTile; }
 };
 
 void fill_common(const Plan& pl, GridArgs& a);
@@ -261,6 +266,16 @@ Err plan_prepare(Plan& pl, const mcf_problem* p, Scratch& sc, cudaStream_t st) {
     if (!p->has_twi_mean) {
         CU(launch_twi_sum(p->twi, pl.ncells, p->tfact, pl.d_scal + 1, st));
         count_launch(2);
+    }
+    if (pl.pack == 2) { // FP32 build: its own CTA shape, stash and (modes 1/3) narrowed hour table
+        pl.grid = g_sm_count * f32_blocks_per_sm();
+        CU(sc.alloc(&pl.d_stashf, (size_t)pl.grid * 24 * kStashVars * f32_tile()));
+        if (!pl.arr) {
+            CU(sc.alloc(&pl.d_hoursf, (size_t)T * hourrec_f32_bytes()));
+            CU(launch_narrow_hours(pl.d_hours, T, pl.d_hoursf, st));
+            count_launch();
+        }
+        return Err();
     }
     pl.grid = g_sm_count * grid_blocks_per_sm(pl.arr != 0, pl.rq);
     CU(sc.alloc(&pl.d_stash, (size_t)pl.grid * 24 * kStashVars * kTile));
@@ -319,14 +334,23 @@ void fill_common(const Plan& pl, GridArgs& a) {
     }
 }
 
-Err timed_grid_launch(const GridArgs& a, int arr, int rq, int grid, cudaStream_t st, int sink = -1) {
+// one launch of the grid kernel of the plan's build over cells [a.cell_begin, a.cell_end), timed if timing is on
+Err timed_grid_launch(const Plan& pl, const GridArgs& a, cudaStream_t st, int sink = -1) {
+    const int ntiles = (a.cell_end - a.cell_begin + pl.tile() - 1) / pl.tile();
+    const int grid = std::min(pl.grid, ntiles);
+    if (grid <= 0) return Err();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_timing) {
         CU(cudaEventCreate(&e0));
         CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, st));
     }
-    CU(launch_grid(a, arr, rq, grid, st, sink));
+    if (pl.pack == 2) {
+        if (sink >= 0) return make_err(MCF_ERR_ARG, "the reducing sinks run in the FP64 build");
+        CU(launch_grid_f32(a, pl.d_hoursf, reinterpret_cast<float* const*>(a.out), pl.d_stashf, pl.arr, pl.rq, grid, st));
+    } else {
+        CU(launch_grid(a, pl.arr, pl.rq, grid, st, sink));
+    }
     count_launch();
     if (g_timing) {
         CU(cudaEventRecord(e1, st));
@@ -357,8 +381,7 @@ Err plan_run_window(const Plan& pl, double* const out[MCF_NOUT], int b0, int nb,
     CU(sc.alloc(&ctr, 1));
     CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
     a.tile_counter = ctr;
-    const int ntiles = (pl.ncells + kTile - 1) / kTile;
-    return timed_grid_launch(a, pl.arr, pl.rq, std::min(pl.grid, ntiles), st);
+    return timed_grid_launch(pl, a, st);
 }
 
 // Whole series for reqhgt < 0: grid kernel writes Tg into scratch per cell chunk, then the time-axis pass.
@@ -374,8 +397,9 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
     size_t budget = std::max<size_t>(freeb / 4, (size_t)64 << 20);
     if (bio) budget = std::min<size_t>(budget, (size_t)1 << 30) / 3;
     long long wmax = (long long)(budget / ((size_t)T * sizeof(double)));
-    wmax = std::max<long long>(kTile, (wmax / kTile) * kTile);
-    const int W = (int)std::min<long long>(wmax, ((pl.ncells + kTile - 1) / kTile) * kTile);
+    const long long tl = pl.tile();
+    wmax = std::max<long long>(tl, (wmax / tl) * tl);
+    const int W = (int)std::min<long long>(wmax, ((pl.ncells + tl - 1) / tl) * tl);
     double *tg = nullptr, *dds = nullptr, *daily = nullptr, *ctz = nullptr, *csm = nullptr;
     CU(sc.alloc(&tg, (size_t)T * W));
     CU(sc.alloc(&dds, W));
@@ -392,7 +416,7 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
     if (p->year[0] % 4 == 0) hiy = 366 * 24; // ref :2171-2172
     // packed sink: the time-axis pass produces FP64; it lands in a scratch series and is packed afterwards
     double* tz64 = nullptr;
-    if (pl.pack && out[MCF_OUT_TZ]) CU(sc.alloc(&tz64, (size_t)T * pl.ncells));
+    if (pl.pack && out[MCF_OUT_TZ] && !bio) CU(sc.alloc(&tz64, (size_t)T * pl.ncells));
     // coarse-grid climate: the time-axis pass reads the point model's Tg / Tbz per cell-hour; expand them once
     const double *tgp = p->p_Tg, *tbp = p->p_Tbp;
     if (pl.arr == 2 && out[MCF_OUT_TZ] && tgp && tbp) {
@@ -437,8 +461,7 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
         a.tile_counter = ctr + ch;
         a.tg_scratch = tg;
         a.dd_sum = dds;
-        const int ntiles = (c1 - c0 + kTile - 1) / kTile;
-        if (a.nblocks > 0) TRY(timed_grid_launch(a, pl.arr, pl.rq, std::min(pl.grid, ntiles), st));
+        if (a.nblocks > 0) TRY(timed_grid_launch(pl, a, st));
         if (out[MCF_OUT_TZ] || bio) {
             BelowArgs b;
             std::memset(&b, 0, sizeof b);
@@ -475,7 +498,8 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
         }
     }
     if (tz64) {
-        CU(launch_pack16(tz64, reinterpret_cast<int16_t*>(out[MCF_OUT_TZ]), (int64_t)T * pl.ncells, 100.0, st));
+        if (pl.pack == 2) CU(launch_narrow32(tz64, reinterpret_cast<float*>(out[MCF_OUT_TZ]), (int64_t)T * pl.ncells, st));
+        else CU(launch_pack16(tz64, reinterpret_cast<int16_t*>(out[MCF_OUT_TZ]), (int64_t)T * pl.ncells, 100.0, st));
         count_launch();
     }
     return Err();
@@ -494,7 +518,8 @@ Err prefill_whole(const Plan& pl, double* const out[MCF_NOUT], cudaStream_t st) 
         const bool written = kernel_writes(pl.rq, v);
         const bool all_hours = (pl.rq == RQ_BELOW && v == MCF_OUT_TZ); // the time-axis pass writes every hour
         if (!written || (gaps && !all_hours)) {
-            if (pl.pack) CU(launch_fill16(reinterpret_cast<int16_t*>(out[v]), (int64_t)T * pl.ncells, (int16_t)-9999, st));
+            if (pl.pack == 1) CU(launch_fill16(reinterpret_cast<int16_t*>(out[v]), (int64_t)T * pl.ncells, (int16_t)-9999, st));
+            else if (pl.pack == 2) CU(launch_fill32(reinterpret_cast<float*>(out[v]), (int64_t)T * pl.ncells, st));
             else CU(launch_fill_na(out[v], (int64_t)T * pl.ncells, st));
             count_launch();
         }
@@ -802,9 +827,14 @@ Err stage_copies(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream, b
 Err copy_back(const std::vector<CopyJob>& jobs, cudaStream_t direct_stream) { return stage_copies(jobs, direct_stream, false); }
 
 void host_fill_na(double* p, size_t n, int pack) {
-    if (pack) {
+    if (pack == 1) {
         int16_t* q = reinterpret_cast<int16_t*>(p);
         for (size_t i = 0; i < n; ++i) q[i] = (int16_t)-9999;
+        return;
+    }
+    if (pack == 2) {
+        uint32_t* q = reinterpret_cast<uint32_t*>(p);
+        for (size_t i = 0; i < n; ++i) q[i] = 0x7FC00000u; // quiet NaN: FP32 has no NA payload convention
         return;
     }
     const uint64_t bits = MCF_NA_REAL_BITS;
@@ -814,7 +844,7 @@ void host_fill_na(double* p, size_t n, int pack) {
 
 // `pack`: out[v] are int16_t* (packed integer sink), else double*; esz = bytes per output element
 Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT], int pack = 0) {
-    const size_t esz = pack ? sizeof(int16_t) : sizeof(double);
+    const size_t esz = pack == 1 ? sizeof(int16_t) : (pack == 2 ? sizeof(float) : sizeof(double));
     TRY(validate(hp));
     TRY(device_info());
     std::lock_guard<std::mutex> ws_lock(g_ws_mu);
@@ -848,6 +878,7 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT], int pack = 0) {
     double scratch_bytes = 148.0 * 2 * 24 * kStashVars * kTile * sizeof(double);
     if (rq == RQ_BELOW) {
         if (pack && out[MCF_OUT_TZ]) scratch_bytes += (double)nc * T * sizeof(double);
+        if (pack == 2) scratch_bytes += 148.0 * 24 * kStashVars * f32_tile() * sizeof(float);
         if (hp->clim_rows > 0 && hp->p_Tg && hp->p_Tbp) scratch_bytes += 2.0 * (double)nc * T * sizeof(double);
     }
     bool fits = (double)in_bytes + (double)per_hour * T + (double)nreq * 256 + scratch_bytes < 0.55 * (double)avail;
@@ -991,8 +1022,7 @@ Err plan_run_reduce(const Plan& pl, GridArgs& a, int sink, int b0, int nb, Scrat
     CU(sc.alloc(&ctr, 1));
     CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
     a.tile_counter = ctr;
-    const int ntiles = (pl.ncells + kTile - 1) / kTile;
-    return timed_grid_launch(a, pl.arr, pl.rq, std::min(pl.grid, ntiles), st, sink);
+    return timed_grid_launch(pl, a, st, sink);
 }
 
 Err run_bioclim_dev(const mcf_problem* p, const int32_t* const q[4], const int32_t nq[4], int air,
@@ -1203,61 +1233,17 @@ int mcf_runmicro(const mcf_problem* prob, double* const out[MCF_NOUT], char* err
     return report(run_host(prob, out), err, errlen);
 }
 
-// FP32 build (north_star: optional, within 0.05 degC / 0.5 % radiation): modes 1/3, reqhgt >= 0, device buffers.
-// Inputs are the FP64 problem; the hour loops, the day stash and the outputs are FP32.
-static Err run_dev_f32(const mcf_problem* p, float* const out[MCF_NOUT], const mcf_window* win, cudaStream_t st) {
-    if (p && (p->mode == 2 || p->mode == 4)) return make_err(MCF_ERR_ARG, "the FP32 build covers modes 1 and 3 (per-hour forcing table)");
-    if (p && p->reqhgt < 0) return make_err(MCF_ERR_ARG, "the FP32 build covers reqhgt >= 0");
-    Scratch sc(st);
-    Plan pl;
-    TRY(plan_prepare(pl, p, sc, st));
-    int b0 = 0, nb = 0;
-    long long hour0 = 0, ring = p->tsteps;
-    TRY(resolve_window(win, pl.blocks, p->tsteps, b0, nb, hour0, ring));
-    if (nb <= 0) return Err();
-    char* hoursf = nullptr;
-    CU(sc.alloc(&hoursf, (size_t)p->tsteps * hourrec_f32_bytes()));
-    CU(launch_narrow_hours(pl.d_hours, p->tsteps, hoursf, st));
-    count_launch();
-    const int grid_max = g_sm_count * f32_blocks_per_sm();
-    float* stashf = nullptr;
-    CU(sc.alloc(&stashf, (size_t)grid_max * 24 * kStashVars * f32_tile()));
-    GridArgs a;
-    fill_common(pl, a);
-    a.cell_begin = 0;
-    a.cell_end = pl.ncells;
-    a.block0 = b0;
-    a.nblocks = nb;
-    a.hour0 = hour0;
-    a.ring_hours = ring;
-    a.outmask = 0;
-    for (int v = 0; v < MCF_NOUT; ++v)
-        if (out[v] && kernel_writes(pl.rq, v)) a.outmask |= 1u << v;
-    unsigned int* ctr = nullptr;
-    CU(sc.alloc(&ctr, 1));
-    CU(cudaMemsetAsync(ctr, 0, sizeof(unsigned int), st));
-    a.tile_counter = ctr;
-    const int ntiles = (pl.ncells + f32_tile() - 1) / f32_tile();
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (g_timing) {
-        CU(cudaEventCreate(&e0));
-        CU(cudaEventCreate(&e1));
-        CU(cudaEventRecord(e0, st));
-    }
-    CU(launch_grid_f32(a, hoursf, out, stashf, pl.rq, std::min(grid_max, ntiles), st));
-    count_launch();
-    if (g_timing) {
-        CU(cudaEventRecord(e1, st));
-        std::lock_guard<std::mutex> lk(g_time_mu);
-        g_events.emplace_back(e0, e1);
-    }
-    return Err();
-}
-
+// FP32 build (north_star: optional, within 0.05 degC / 0.5 % radiation): every mode and height, device or host buffers.
+// Inputs are the FP64 problem; the hour loops, the day stash and the outputs are FP32 (Plan::pack == 2).
 int mcf_runmicro_f32_dev(const mcf_problem* prob, float* const out[MCF_NOUT], const mcf_window* win, void* stream, char* err,
                          size_t errlen) {
     if (!out) return report(make_err(MCF_ERR_ARG, "out is NULL"), err, errlen);
-    return report(run_dev_f32(prob, out, win, (cudaStream_t)stream), err, errlen);
+    return report(run_dev(prob, reinterpret_cast<double* const*>(out), win, (cudaStream_t)stream, 2), err, errlen);
+}
+
+int mcf_runmicro_f32(const mcf_problem* prob, float* const out[MCF_NOUT], char* err, size_t errlen) {
+    if (!out) return report(make_err(MCF_ERR_ARG, "out is NULL"), err, errlen);
+    return report(run_host(prob, reinterpret_cast<double* const*>(out), 2), err, errlen);
 }
 
 // Packed integer sink (SURVEY.md NEXT-4): the same solve, results stored as writetonc stores them

@@ -960,7 +960,7 @@ static cudaError_t launch_reduce(const GridArgs& a, int grid, cudaStream_t strea
 }
 
 cudaError_t launch_grid(const GridArgs& a, int arr, int rq, int grid, cudaStream_t stream, int sink) {
-    if (sink < 0) sink = a.pack ? SINK_PACK : SINK_F64;
+    if (sink < 0) sink = (a.pack == 1) ? SINK_PACK : SINK_F64;
     if (sink == SINK_BIO || sink == SINK_SUMMARY) {
         if (rq == RQ_BELOW) return cudaErrorInvalidValue; // the below-ground series needs its time-axis pass first
 #define MCF_RED(ARR)                                                                               \

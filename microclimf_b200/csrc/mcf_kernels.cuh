@@ -165,8 +165,10 @@ cudaError_t launch_narrow_hours(const HourRec* in, int n, void* out, cudaStream_
 size_t hourrec_f32_bytes();
 int f32_blocks_per_sm();
 int f32_tile();
-cudaError_t launch_grid_f32(const GridArgs& a, const void* hoursf, float* const outf[kNOut], float* stashf, int rq, int grid,
-                            cudaStream_t stream);
+cudaError_t launch_grid_f32(const GridArgs& a, const void* hoursf, float* const outf[kNOut], float* stashf, int arr, int rq,
+                            int grid, cudaStream_t stream);
+cudaError_t launch_narrow32(const double* src, float* dst, int64_t n, cudaStream_t stream);
+cudaError_t launch_fill32(float* p, int64_t n, cudaStream_t stream);
 cudaError_t launch_below(const BelowArgs& a, cudaStream_t stream);
 cudaError_t launch_bioclim(const BioArgs& a, cudaStream_t stream);
 cudaError_t launch_fill_na(double* p, int64_t n, cudaStream_t stream);

@@ -2,11 +2,16 @@
 //
 // BASELINE north_star: "an optional FP32 build must stay within 0.05 degC and 0.5 % radiation".  Same execution model as
 // k_grid (persistent 384-thread CTAs, one thread per cell, TMA-fed hour-table ring, two 24-hour passes per cell-day), for
-// the per-hour-table modes (1/3) and reqhgt >= 0.  What differs:
+// all four drivers and every height.  What differs:
 //   * the hour loops run in FP32 with SFU transcendentals (mcf_physics_f32.cuh, generated from the FP64 physics);
 //   * per-cell invariants are still computed in FP64 (cell_setup: two-stream solution, logarithms) and narrowed once;
 //   * static inputs stay FP64 in HBM (they are R's arrays), the hour table is narrowed once per launch (k_narrow_hours),
-//     the day stash and the outputs are FP32: 40 algorithmic bytes per cell-hour instead of 80.
+//     the day stash and the outputs are FP32: 40 algorithmic bytes per cell-hour instead of 80;
+//   * array climate (modes 2/4, ARR = 1 fine arrays / 2 coarse grid): the hour record of a cell-hour is assembled in FP64
+//     exactly as k_grid assembles it (hour_from_arrays: interpolation, altitude correction, solar position are
+//     cancellation-prone) and narrowed; the physics that consumes it is FP32;
+//   * below ground (RQ_BELOW): the ground temperature series and the damping depths leave the kernel in FP64 for the
+//     time-axis pass (k_below accumulates in FP64); its result is narrowed to FP32 afterwards.
 // (mcf_physics_f32.cuh is included at the top of mcf_kernels.cu)
 
 #ifndef MCF_F32_TILE
@@ -43,7 +48,7 @@ __device__ __forceinline__ void discard_line_f(const float* p, float loaded) {
     asm volatile("discard.global.L2 [%0], 128; // after %1" ::"l"(p), "f"(loaded) : "memory");
 }
 
-template <int RQ>
+template <int ARR, int RQ>
 __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_constant__ GridArgsF af) {
     using f32::HourRecF;
     const GridArgs& a = af.g;
@@ -56,7 +61,7 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
     const int ntiles = (a.cell_end - a.cell_begin + kTileF - 1) / kTileF;
     float* const stash = af.stashf + (size_t)blockIdx.x * (24 * kStashVars * kTileF) + tid;
     unsigned int q0 = 0;
-    if (tid == 0) {
+    if (!ARR && tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kTileF / 32);
@@ -86,25 +91,37 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
         const unsigned amask = __ballot_sync(0xffffffffu, active); // lanes taking the solving branch (converged here)
         const double tmean = a.has_tadd_mean ? a.tadd_mean : a.dscal[1] / a.dscal[2];
         const double tadd = log(__ldg(&a.soil[11][cc])) / a.tfact - tmean;
-        const float dTmx = (float)(-0.6273 * a.dscal[0] + 49.79);
+        double lat = a.lat, lon = 0.0, sl = 0.0, cl = 1.0;
+        float dTmx = (float)(-0.6273 * a.dscal[0] + 49.79);
+        CoarseCell ccell;
+        if (ARR == 2) coarse_setup(a, cc, ccell);
+        if (ARR) { // modes 2/4: per-cell latitude / longitude and series maximum of tc (ref :2458, :2467-2471)
+            lat = __ldg(&a.lats[cc]);
+            lon = __ldg(&a.lons[cc]);
+            dTmx = (float)(-0.6273 * __ldg(&a.mxtc_cell[cc]) + 49.79);
+            sincos(lat * kPi / 180.0, &sl, &cl);
+        }
         f32::CellInvF v;
         int cur_lyr = -1;
-        if (tid == 0)
+        double ddsum = 0.0;
+        if (!ARR && tid == 0)
             for (int bi = 0; bi < kAhead && bi < a.nblocks; ++bi) issue_fill(q0 + bi, bi);
         for (int bi = 0; bi < a.nblocks; ++bi) {
             const DayBlock blk = a.blocks[a.block0 + bi];
             const unsigned int q = q0 + bi;
             const int buf = (int)(q % kStages);
             const HourRecF* const slab_day = &slab_ring[buf][0];
-            if (tid == 0 && bi + kAhead < a.nblocks) issue_fill(q + kAhead, bi + kAhead);
-            mbar_wait(&full_bar[buf], (q / kStages) & 1u);
+            if (!ARR) {
+                if (tid == 0 && bi + kAhead < a.nblocks) issue_fill(q + kAhead, bi + kAhead);
+                mbar_wait(&full_bar[buf], (q / kStages) & 1u);
+            }
             const long long slot0 = ((long long)blk.k0 - a.hour0) % a.ring_hours;
             if (blk.lyr != cur_lyr) {
                 cur_lyr = blk.lyr;
                 CellIn ci;
                 load_cell(a, cc, cur_lyr, tadd, ci);
                 CellInv v64;
-                cell_setup(ci, a.reqhgt2, a.zref, a.lat, v64); // FP64: once per cell and layer
+                cell_setup(ci, a.reqhgt2, a.zref, lat, v64); // FP64: once per cell and layer
                 f32::narrow(v64, v);
             }
             if (!active) {
@@ -122,18 +139,36 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                 const size_t o_first = (size_t)slot0 * a.ncells + cell;
                 const long long wrap_at = a.ring_hours - slot0;
                 float Rmx = -999.9f, tmx = -999.0f, tmn = 999.0f;
-                float ws_n = (float)__ldg(&a.wsa[(size_t)slab_day[0].windex * a.ncells + cell]);
-                float ha_n = (float)__ldg(&a.hor[(size_t)slab_day[0].sindex * a.ncells + cell]);
+                float ws_n = 0.0f, ha_n = 0.0f;
+                if (!ARR) {
+                    ws_n = (float)__ldg(&a.wsa[(size_t)slab_day[0].windex * a.ncells + cell]);
+                    ha_n = (float)__ldg(&a.hor[(size_t)slab_day[0].sindex * a.ncells + cell]);
+                }
                 size_t o = o_first;
 #pragma unroll 1
                 for (int hr = 0; hr < 24; ++hr) {
-                    const HourRecF& h = slab_day[hr];
+                    HourRecF hloc;
+                    if (ARR) {
+                        HourRec h64{};
+                        hour_from_arrays<ARR>(a, blk.k0 + hr, cell, sl, cl, lon, true, ccell, h64);
+                        f32::narrow(h64, hloc);
+                    }
+                    const HourRecF& h = ARR ? hloc : slab_day[hr];
                     if (hr == wrap_at) o = cell;
-                    const float ws = ws_n, ha = ha_n;
-                    const HourRecF& hn = slab_day[hr < 23 ? hr + 1 : 23];
-                    ws_n = (float)__ldg(&a.wsa[(size_t)hn.windex * a.ncells + cell]);
-                    ha_n = (float)__ldg(&a.hor[(size_t)hn.sindex * a.ncells + cell]);
-                    float si = h.cosz * v.cs + h.sinz * (h.cosazi * v.ssca + h.sinazi * v.sssa);
+                    float ws, ha;
+                    if (ARR) {
+                        ws = (float)__ldg(&a.wsa[(size_t)h.windex * a.ncells + cell]);
+                        ha = (float)__ldg(&a.hor[(size_t)h.sindex * a.ncells + cell]);
+                    } else {
+                        ws = ws_n;
+                        ha = ha_n;
+                        const HourRecF& hn = slab_day[hr < 23 ? hr + 1 : 23];
+                        ws_n = (float)__ldg(&a.wsa[(size_t)hn.windex * a.ncells + cell]);
+                        ha_n = (float)__ldg(&a.hor[(size_t)hn.sindex * a.ncells + cell]);
+                    }
+                    float si;
+                    if (ARR && h.zend > 90.0f) si = 0.0f; // shadowmask = false in modes 2/4
+                    else si = h.cosz * v.cs + h.sinz * (h.cosazi * v.ssca + h.sinazi * v.sssa);
                     if (si < 0.0f) si = 0.0f;
                     if (ha > h.tan_sa) si = 0.0f;
                     const float soild = f32::soil_distribute(v, h.soilmp);
@@ -178,7 +213,13 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                 o = (23 >= wrap_at) ? (size_t)cell + (size_t)(23 - wrap_at) * a.ncells : o_first + (size_t)23 * a.ncells;
 #pragma unroll 1
                 for (int hr = 23; hr >= 0; --hr) {
-                    const HourRecF& h = slab_day[hr];
+                    HourRecF hloc;
+                    if (ARR) {
+                        HourRec h64{};
+                        hour_from_arrays<ARR>(a, blk.k0 + hr, cell, sl, cl, lon, false, ccell, h64);
+                        f32::narrow(h64, hloc);
+                    }
+                    const HourRecF& h = ARR ? hloc : slab_day[hr];
                     const float* st = stash + (size_t)hr * (kStashVars * kTileF);
                     __syncwarp(amask); // one converged load instruction per line: complete for its first lane = complete for all
                     const float radabs = ld_stash_f(&st[0 * kTileF]), surfwet = ld_stash_f(&st[1 * kTileF]);
@@ -203,8 +244,9 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                     const float c2 = 1.06f * v.rho * soild;
                     const float kcon = v.c1 + c2 * soild - (v.c1 - v.c4) * f32::fexp(-f32::pow4(v.c3 * soild));
                     const float kap = f32::fdiv(kcon, cs * ph);
+                    const float kap2 = kap * (float)(2.0 / kOmdy);
                     float iDD;
-                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(iDD) : "f"(kap * (float)(2.0 / kOmdy)));
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(iDD) : "f"(kap2));
                     const float dtR = dtr * h.inv_dtrp;
                     const float Gmu = dtR * (kcon * h.muGp_kp) * iDD;
                     float G = h.Gp * Gmu;
@@ -212,24 +254,57 @@ __global__ void __launch_bounds__(kTileF, MCF_F32_MINB) k_grid_f32(const __grid_
                     if (G < -0.6f * Rmx) G = -0.6f * Rmx;
                     float m_unused;
                     const float Tg = f32::pm_ts(h, dTmx, radabs, w.gHa, w.gHa, G, surfwet, m_unused);
-                    const float radClw = f32::kEm * v.svfa * h.Rlw;
-                    const f32::Above tv = f32::above_ground(v, h, dTmx, soild, Tg, G, w, radCsw, radClw, Lhalf);
-                    if (om & (1u << 0)) __stcs(&af.outf[0][o], (RQ == RQ_ABOVE) ? tv.Tz : Tg);
-                    if (om & (1u << 7)) __stcs(&af.outf[7][o], tv.lwdn);
-                    if (om & (1u << 9)) __stcs(&af.outf[9][o], tv.lwup);
-                    if (RQ == RQ_ABOVE) {
-                        if (om & (1u << 1)) __stcs(&af.outf[1][o], tv.tleaf);
-                        if (om & (1u << 2)) __stcs(&af.outf[2][o], tv.rh);
+                    if (RQ == RQ_BELOW) {
+                        // the time-axis pass runs in FP64 over the whole series: ground temperature and damping depth
+                        a.tg_scratch[(size_t)(blk.k0 + hr) * (a.cell_end - a.cell_begin) + (cell - a.cell_begin)] = (double)Tg;
+                        ddsum += (double)(kap2 * iDD); // sqrt(x) = x rsqrt(x)
+                    } else {
+                        const float radClw = f32::kEm * v.svfa * h.Rlw;
+                        const f32::Above tv = f32::above_ground(v, h, dTmx, soild, Tg, G, w, radCsw, radClw, Lhalf);
+                        if (om & (1u << 0)) __stcs(&af.outf[0][o], (RQ == RQ_ABOVE) ? tv.Tz : Tg);
+                        if (om & (1u << 7)) __stcs(&af.outf[7][o], tv.lwdn);
+                        if (om & (1u << 9)) __stcs(&af.outf[9][o], tv.lwup);
+                        if (RQ == RQ_ABOVE) {
+                            if (om & (1u << 1)) __stcs(&af.outf[1][o], tv.tleaf);
+                            if (om & (1u << 2)) __stcs(&af.outf[2][o], tv.rh);
+                        }
                     }
                     if (hr == wrap_at) o = (size_t)(a.ring_hours - 1) * a.ncells + cell; // back across the ring's seam
                     else o -= a.ncells;
                 }
             }
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty_bar[buf]);
+            if (!ARR) {
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&empty_bar[buf]);
+            }
         }
         q0 += (unsigned int)a.nblocks;
+        if (RQ == RQ_BELOW && active) a.dd_sum[cell - a.cell_begin] = ddsum;
     }
+}
+
+// FP64 -> FP32 (the below-ground Tz, which the time-axis pass produces in FP64); NA / NaN -> quiet NaN
+__global__ void k_narrow32(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+cudaError_t launch_narrow32(const double* src, float* dst, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_narrow32<<<(int)blocks, 256, 0, stream>>>(src, dst, n);
+    return cudaGetLastError();
+}
+__global__ void k_fill32(float* __restrict__ p, int64_t n) {
+    const float NA = __int_as_float(0x7FC00000);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = NA;
+}
+cudaError_t launch_fill32(float* p, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_fill32<<<(int)blocks, 256, 0, stream>>>(p, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_narrow_hours(const HourRec* in, int n, void* out, cudaStream_t stream) {
@@ -240,14 +315,22 @@ size_t hourrec_f32_bytes() { return sizeof(f32::HourRecF); }
 int f32_blocks_per_sm() { return MCF_F32_MINB; }
 int f32_tile() { return kTileF; }
 
-cudaError_t launch_grid_f32(const GridArgs& a, const void* hoursf, float* const outf[kNOut], float* stashf, int rq, int grid,
-                            cudaStream_t stream) {
+cudaError_t launch_grid_f32(const GridArgs& a, const void* hoursf, float* const outf[kNOut], float* stashf, int arr, int rq,
+                            int grid, cudaStream_t stream) {
     GridArgsF af;
     af.g = a;
     af.hoursf = (const f32::HourRecF*)hoursf;
     for (int i = 0; i < kNOut; ++i) af.outf[i] = outf[i];
     af.stashf = stashf;
-    if (rq == RQ_ABOVE) k_grid_f32<RQ_ABOVE><<<grid, kTileF, 0, stream>>>(af);
-    else k_grid_f32<RQ_SURFACE><<<grid, kTileF, 0, stream>>>(af);
+#define MCF_F32_RQ(ARR)                                                                          \
+    do {                                                                                         \
+        if (rq == RQ_ABOVE) k_grid_f32<ARR, RQ_ABOVE><<<grid, kTileF, 0, stream>>>(af);          \
+        else if (rq == RQ_SURFACE) k_grid_f32<ARR, RQ_SURFACE><<<grid, kTileF, 0, stream>>>(af); \
+        else k_grid_f32<ARR, RQ_BELOW><<<grid, kTileF, 0, stream>>>(af);                         \
+    } while (0)
+    if (arr == 0) MCF_F32_RQ(0);
+    else if (arr == 1) MCF_F32_RQ(1);
+    else MCF_F32_RQ(2);
+#undef MCF_F32_RQ
     return cudaGetLastError();
 }

@@ -67,11 +67,43 @@ def test_fp32_seasons_and_latitudes():
         check(run_f32(p), pyoracle.runmicro(p, kind=KIND))
 
 
-def test_fp32_rejects_unsupported():
-    from microclimf_b200._lib import McfError
-    p = synth.make_problem(8, 8, 24, reqhgt=-0.1, mode=1)
-    with pytest.raises(McfError):
-        run_f32(p, [True] + [False] * 9)
-    p = synth.make_problem(8, 8, 24, reqhgt=0.05, mode=2)
-    with pytest.raises(McfError):
-        run_f32(p)
+@pytest.mark.parametrize("mode", [2, 4])
+@pytest.mark.parametrize("reqhgt", [0.05, 0.0, 5.0])
+def test_fp32_array_climate(mode, reqhgt):
+    """modes 2/4 (fine [rows, cols, hours] arrays): the hour record of each cell-hour is assembled in FP64 and narrowed."""
+    p = synth.make_problem(29, 23, 24 * 3, reqhgt=reqhgt, mode=mode, nlyr=2)
+    mask = [True] * 10 if reqhgt > 0 else [True, False, False, True, False, True, True, True, True, True]
+    check(run_f32(p, mask), pyoracle.runmicro(p, out_mask=mask, kind=KIND))
+
+
+@pytest.mark.parametrize("altcorrect", [0, 2])
+def test_fp32_coarse_grid_climate(altcorrect):
+    """coarse-grid climate interpolated in the kernel (ABI 2) against the FP64 reference on the expanded arrays."""
+    from oracle import prep_oracle
+    p = synth.make_coarse_problem(27, 21, 24 * 3, reqhgt=0.05, mode=2, crows=4, ccols=3, altcorrect=altcorrect)
+    want = pyoracle.runmicro(prep_oracle.materialise_coarse(p), kind=KIND)
+    check(run_f32(p), want)
+
+
+@pytest.mark.parametrize("mode,reqhgt,complete", [(1, -0.05, True), (1, -0.6, True), (3, -0.1, False), (2, -0.2, True)])
+def test_fp32_below_ground(mode, reqhgt, complete):
+    """reqhgt < 0: FP32 hour loops feed the FP64 time-axis pass (rolling means over the stored ground temperatures);
+    the window length n = round(-118.35 z / mean damping depth) may differ by one hour from the FP64 build's."""
+    p = synth.make_problem(21, 17, 24 * 6, reqhgt=reqhgt, mode=mode, nlyr=2, complete=complete)
+    mask = [True, False, False, True, False, False, False, False, False, False]
+    check(run_f32(p, mask), pyoracle.runmicro(p, out_mask=mask, kind=KIND))
+
+
+def test_fp32_host_entry_point_matches_device_entry_point():
+    """mcf_runmicro_f32 (host buffers, windowed copy-back) == mcf_runmicro_f32_dev, bit for bit; hours beyond the whole
+    days are NaN."""
+    p = synth.make_problem(37, 19, 24 * 5 + 5, reqhgt=0.05, mode=1)
+    dev = run_f32(p)
+    host = api.run_problem_f32(p)
+    for nm in _abi.OUT_NAMES:
+        assert host[nm].dtype == np.float32
+        np.testing.assert_array_equal(host[nm].astype(np.float64), dev[nm], err_msg=nm)
+        assert np.isnan(host[nm][:, :, 120:]).all()
+    pb = synth.make_problem(9, 8, 24 * 4, reqhgt=-0.1, mode=1)
+    hb = api.run_problem_f32(pb, out=[True, False, False, True] + [False] * 6)
+    check({k: v.astype(np.float64) for k, v in hb.items()}, pyoracle.runmicro(pb, out_mask=[True, False, False, True] + [False] * 6, kind=KIND))
