@@ -199,6 +199,9 @@ Err device_info() {
     return Err();
 }
 
+// MCF_NO_PAIR=1 in the environment keeps every launch on k_grid (A/B measurements of the two builds)
+const bool g_use_pair = [] { const char* e = std::getenv("MCF_NO_PAIR"); return !(e && e[0] == '1'); }();
+
 void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 // A prepared problem on the device: everything a window launch needs.
@@ -220,7 +223,9 @@ struct Plan {
     int pack = 0;
     char* d_hoursf = nullptr;  // FP32 build, modes 1/3: the narrowed hour table
     float* d_stashf = nullptr; // FP32 build: its day stash
-    int tile() const { return pack == 2 ? f32_tile() : kTile; }
+    // below ground the FP32 build runs the FP64 hour loops (see mcf_kernels_f32.inl) and narrows its outputs
+    bool f32_kernel() const { return pack == 2 && rq != RQ_BELOW; }
+    int tile() const { return f32_kernel() ? f32_tile() : kTile; }
 };
 
 void fill_common(const Plan& pl, GridArgs& a);
@@ -267,7 +272,7 @@ Err plan_prepare(Plan& pl, const mcf_problem* p, Scratch& sc, cudaStream_t st) {
         CU(launch_twi_sum(p->twi, pl.ncells, p->tfact, pl.d_scal + 1, st));
         count_launch(2);
     }
-    if (pl.pack == 2) { // FP32 build: its own CTA shape, stash and (modes 1/3) narrowed hour table
+    if (pl.f32_kernel()) { // FP32 build: its own CTA shape, stash and (modes 1/3) narrowed hour table
         pl.grid = g_sm_count * f32_blocks_per_sm();
         CU(sc.alloc(&pl.d_stashf, (size_t)pl.grid * 24 * kStashVars * f32_tile()));
         if (!pl.arr) {
@@ -278,7 +283,8 @@ Err plan_prepare(Plan& pl, const mcf_problem* p, Scratch& sc, cudaStream_t st) {
         return Err();
     }
     pl.grid = g_sm_count * grid_blocks_per_sm(pl.arr != 0, pl.rq);
-    CU(sc.alloc(&pl.d_stash, (size_t)pl.grid * 24 * kStashVars * kTile));
+    // one scratch serves both builds of the FP64 kernel (k_grid's day stash; k_grid_pair's stash + reduction exchange)
+    CU(sc.alloc(&pl.d_stash, (size_t)pl.grid * std::max((size_t)24 * kStashVars * kTile, pair_scratch_doubles())));
     return Err();
 }
 
@@ -336,8 +342,12 @@ void fill_common(const Plan& pl, GridArgs& a) {
 
 // one launch of the grid kernel of the plan's build over cells [a.cell_begin, a.cell_end), timed if timing is on
 Err timed_grid_launch(const Plan& pl, const GridArgs& a, cudaStream_t st, int sink = -1) {
-    const int ntiles = (a.cell_end - a.cell_begin + pl.tile() - 1) / pl.tile();
-    const int grid = std::min(pl.grid, ntiles);
+    // the pair build (two threads per cell, invariants in shared memory) serves the per-hour-table drivers above ground
+    const int eff_sink = sink >= 0 ? sink : (a.pack == 1 ? SINK_PACK : SINK_F64);
+    const bool pair = !pl.f32_kernel() && g_use_pair && pair_eligible(pl.arr, pl.rq, eff_sink);
+    const int tl = pair ? pair_tile() : pl.tile();
+    const int ntiles = (a.cell_end - a.cell_begin + tl - 1) / tl;
+    const int grid = std::min(pair ? g_sm_count : pl.grid, ntiles);
     if (grid <= 0) return Err();
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (g_timing) {
@@ -345,9 +355,11 @@ Err timed_grid_launch(const Plan& pl, const GridArgs& a, cudaStream_t st, int si
         CU(cudaEventCreate(&e1));
         CU(cudaEventRecord(e0, st));
     }
-    if (pl.pack == 2) {
+    if (pl.f32_kernel()) {
         if (sink >= 0) return make_err(MCF_ERR_ARG, "the reducing sinks run in the FP64 build");
         CU(launch_grid_f32(a, pl.d_hoursf, reinterpret_cast<float* const*>(a.out), pl.d_stashf, pl.arr, pl.rq, grid, st));
+    } else if (pair) {
+        CU(launch_grid_pair(a, pl.rq, grid, st, sink));
     } else {
         CU(launch_grid(a, pl.arr, pl.rq, grid, st, sink));
     }
@@ -417,6 +429,16 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
     // packed sink: the time-axis pass produces FP64; it lands in a scratch series and is packed afterwards
     double* tz64 = nullptr;
     if (pl.pack && out[MCF_OUT_TZ] && !bio) CU(sc.alloc(&tz64, (size_t)T * pl.ncells));
+    // FP32 build: the hour loops run in FP64 below ground (mcf_kernels_f32.inl); what pass 1 writes (soil moisture, wind,
+    // shortwave streams) lands in FP64 scratch series, NA where no day-block covers the hour, and is narrowed afterwards
+    double* f64s[MCF_NOUT] = {};
+    if (pl.pack == 2 && !bio)
+        for (int v = 0; v < MCF_NOUT; ++v)
+            if (out[v] && v != MCF_OUT_TZ && kernel_writes(pl.rq, v)) {
+                CU(sc.alloc(&f64s[v], (size_t)T * pl.ncells));
+                CU(launch_fill_na(f64s[v], (int64_t)T * pl.ncells, st));
+                count_launch();
+            }
     // coarse-grid climate: the time-axis pass reads the point model's Tg / Tbz per cell-hour; expand them once
     const double *tgp = p->p_Tg, *tbp = p->p_Tbp;
     if (pl.arr == 2 && out[MCF_OUT_TZ] && tgp && tbp) {
@@ -446,7 +468,7 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
         a.ring_hours = T;
         a.outmask = 0;
         for (int v = 0; v < MCF_NOUT; ++v) {
-            a.out[v] = out[v];
+            a.out[v] = f64s[v] ? f64s[v] : out[v];
             if (out[v] && v != MCF_OUT_TZ && kernel_writes(pl.rq, v)) a.outmask |= 1u << v;
         }
         if (bio) { // the chunk's soil moisture into its compact series; hours no day-block covers stay NA
@@ -502,6 +524,11 @@ Err plan_run_below(const Plan& pl, double* const out[MCF_NOUT], Scratch& sc, cud
         else CU(launch_pack16(tz64, reinterpret_cast<int16_t*>(out[MCF_OUT_TZ]), (int64_t)T * pl.ncells, 100.0, st));
         count_launch();
     }
+    for (int v = 0; v < MCF_NOUT; ++v)
+        if (f64s[v]) {
+            CU(launch_narrow32(f64s[v], reinterpret_cast<float*>(out[v]), (int64_t)T * pl.ncells, st));
+            count_launch();
+        }
     return Err();
 }
 
@@ -878,7 +905,9 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT], int pack = 0) {
     double scratch_bytes = 148.0 * 2 * 24 * kStashVars * kTile * sizeof(double);
     if (rq == RQ_BELOW) {
         if (pack && out[MCF_OUT_TZ]) scratch_bytes += (double)nc * T * sizeof(double);
-        if (pack == 2) scratch_bytes += 148.0 * 24 * kStashVars * f32_tile() * sizeof(float);
+        if (pack == 2) // FP32 build below ground: FP64 series of whatever pass 1 writes, narrowed afterwards
+            for (int v = 0; v < MCF_NOUT; ++v)
+                if (out[v] && v != MCF_OUT_TZ && kernel_writes(rq, v)) scratch_bytes += (double)nc * T * sizeof(double);
         if (hp->clim_rows > 0 && hp->p_Tg && hp->p_Tbp) scratch_bytes += 2.0 * (double)nc * T * sizeof(double);
     }
     bool fits = (double)in_bytes + (double)per_hour * T + (double)nreq * 256 + scratch_bytes < 0.55 * (double)avail;

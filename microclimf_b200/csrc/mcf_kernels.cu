@@ -804,19 +804,19 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     if (ALLOUT || (om & (1u << 8))) put<8, SINK>(a, o, r.Rdup, acc);
                     // longwave absorbed by the ground (ref :1165-1175); lwout = h.Rem
                     double radGlw;
-                    if (v.pai > 0.0) radGlw = kEm * (v.trdif * v.svfa * h.Rlw + (1.0 - v.trdif) * h.Rem);
-                    else radGlw = kEm * v.svfa * h.Rlw;
+                    if (v.pai > 0.0) radGlw = kL.em * (v.trdif * v.svfa * h.Rlw + (1.0 - v.trdif) * h.Rem);
+                    else radGlw = kL.em * v.svfa * h.Rlw;
                     // wind
                     const Wind w = wind_hour(v, h.u2, h.umu, ws);
                     if (ALLOUT || (om & (1u << 4))) put<4, SINK>(a, o, w.uz, acc);
                     // ground surface temperature with G = 0 (ref soiltempG0 :1262-1275)
                     const double radabs = r.radGsw + radGlw;
                     const double matric = -v.psie_abs * mexp_nc(-v.soilb * mlog(soild * v.inv_Smax));
-                    double surfwet = mexp_lo((0.018 * matric) * h.invRT);
+                    double surfwet = mexp_lo((kL.wet_a * matric) * h.invRT);
                     if (surfwet > 1.0) surfwet = 1.0;
                     double m_unused;
                     const double Tg0 = pm_ts(h, dTmx, radabs, w.gHa, w.gHa, 0.0, surfwet, m_unused);
-                    const double Rnet = radabs - kEm * kSb * radem4(Tg0);
+                    const double Rnet = radabs - kL.emsb * radem4(Tg0);
                     const double Rval = fabs(Rnet);
                     if (Rmx < Rval) Rmx = Rval;
                     if (tmx < Tg0) tmx = Tg0;
@@ -884,32 +884,32 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     w.uz = w.uf * v.uz_coef;
                     if (w.uz > h.u2) w.uz = h.u2;
                     w.gHa = w.uf * v.gHa_coef;
-                    if (w.gHa < 0.0001) w.gHa = 0.0001;
+                    if (w.gHa < kL.gha_lo) w.gHa = kL.gha_lo;
                     soild_n = soild_n2;
                     uf_n = uf_n2;
                     // soil conductivity and damping depth (ref soilcondCpp :1249-1260)
-                    const double cs = (2400 * v.rho / 2.64 + 4180.0 * soild);
+                    const double cs = (v.cs0 + 4180.0 * soild);
                     const double ph = (v.rho * (1.0 - soild) + soild) * 1000.0;
-                    const double c2 = 1.06 * v.rho * soild;
-                    const double kcon = v.c1 + c2 * soild - (v.c1 - v.c4) * mexp_lo(-pow4(v.c3 * soild));
+                    const double c2 = kL.c2_a * v.rho * soild;
+                    const double kcon = v.c1 + c2 * soild - v.c14 * mexp_lo(-pow4(v.c3 * soild));
                     const double kap = mdiv(kcon, cs * ph);
                     // damping depth DD = sqrt(2 kap / omega): only its reciprocal enters the heat flux, the depth
                     // itself is needed for the below-ground pass alone
-                    const double iDD = mrsqrt(kap * (2.0 / kOmdy));
-                    const double DD = (RQ == RQ_BELOW) ? msqrt(kap * (2.0 / kOmdy)) : 0.0;
+                    const double iDD = mrsqrt(kap * kL.two_omdy);
+                    const double DD = (RQ == RQ_BELOW) ? msqrt(kap * kL.two_omdy) : 0.0;
                     // ground heat flux scaled from the point model (ref soiltemp_hrCpp :1277-1296)
                     const double dtR = dtr * h.inv_dtrp;
                     const double Gmu = dtR * (kcon * h.muGp_kp) * iDD;
                     double G = h.Gp * Gmu;
-                    if (G > 0.6 * Rmx) G = 0.6 * Rmx;
-                    if (G < -0.6 * Rmx) G = -0.6 * Rmx;
+                    if (G > kL.g_cap * Rmx) G = kL.g_cap * Rmx;
+                    if (G < -kL.g_cap * Rmx) G = -kL.g_cap * Rmx;
                     double m_unused;
                     const double Tg = pm_ts(h, dTmx, radabs, w.gHa, w.gHa, G, surfwet, m_unused);
                     if (RQ == RQ_BELOW) {
                         a.tg_scratch[(size_t)k * (a.cell_end - a.cell_begin) + (cell - a.cell_begin)] = Tg;
                         ddsum += DD;
                     } else {
-                        const double radClw = kEm * v.svfa * h.Rlw;
+                        const double radClw = kL.em * v.svfa * h.Rlw;
                         const Above tv = above_ground(v, h, dTmx, soild, Tg, G, w, radCsw, radClw, Lhalf);
                         if (ALLOUT || (om & (1u << 0))) put<0, SINK>(a, o, (RQ == RQ_ABOVE) ? tv.Tz : Tg, acc);
                         if (ALLOUT || (om & (1u << 7))) put<7, SINK>(a, o, tv.lwdn, acc);
@@ -1347,5 +1347,6 @@ cudaError_t launch_fp64_peak(double* sink, int grid, int iters, cudaStream_t str
 }
 
 #include "mcf_kernels_f32.inl"
+#include "mcf_kernels_pair.inl"
 
 } // namespace mcf

@@ -160,6 +160,11 @@ cudaError_t launch_twi_sum(const double* twi, int64_t n, double tfact, double* s
 cudaError_t launch_grid(const GridArgs& a, int arr /* 0 table, 1 fine arrays, 2 coarse arrays */, int rq, int grid,
                         cudaStream_t stream, int sink = -1 /* default: SINK_PACK if a.pack else SINK_F64 */);
 int grid_blocks_per_sm(bool arr, int rq);
+// the pair build of the FP64 kernel (mcf_kernels_pair.inl): two threads per cell, per-cell invariants in shared memory
+bool pair_eligible(int arr, int rq, int sink);
+int pair_tile();
+size_t pair_scratch_doubles(); // per CTA: day stash + reduction exchange
+cudaError_t launch_grid_pair(const GridArgs& a, int rq, int grid, cudaStream_t stream, int sink = -1);
 // FP32 build (modes 1/3, reqhgt >= 0): narrowed hour table, FP32 stash and outputs
 cudaError_t launch_narrow_hours(const HourRec* in, int n, void* out, cudaStream_t stream);
 size_t hourrec_f32_bytes();

@@ -10,8 +10,11 @@
 //   * array climate (modes 2/4, ARR = 1 fine arrays / 2 coarse grid): the hour record of a cell-hour is assembled in FP64
 //     exactly as k_grid assembles it (hour_from_arrays: interpolation, altitude correction, solar position are
 //     cancellation-prone) and narrowed; the physics that consumes it is FP32;
-//   * below ground (RQ_BELOW): the ground temperature series and the damping depths leave the kernel in FP64 for the
-//     time-axis pass (k_below accumulates in FP64); its result is narrowed to FP32 afterwards.
+//   * below ground (RQ_BELOW) this kernel is not used: the time-axis pass is DISCONTINUOUS in its inputs (a rolling mean
+//     over n = round(-118.35 z / mean damping depth) hours, ref Tbelowgroundv :1481-1482; a ratio of daily ranges in the
+//     incomplete branch, :1511) and single-precision ground temperatures / damping depths flip n or move the ratio in a
+//     few cells per thousand by 0.1-0.25 degC (measured, tools/diag_f32_below.py).  The FP32 build therefore runs the
+//     FP64 hour loops there (a pass that has no canopy physics and is cheap) and narrows Tz and soil moisture to FP32.
 // (mcf_physics_f32.cuh is included at the top of mcf_kernels.cu)
 
 #ifndef MCF_F32_TILE
@@ -326,7 +329,7 @@ cudaError_t launch_grid_f32(const GridArgs& a, const void* hoursf, float* const 
     do {                                                                                         \
         if (rq == RQ_ABOVE) k_grid_f32<ARR, RQ_ABOVE><<<grid, kTileF, 0, stream>>>(af);          \
         else if (rq == RQ_SURFACE) k_grid_f32<ARR, RQ_SURFACE><<<grid, kTileF, 0, stream>>>(af); \
-        else k_grid_f32<ARR, RQ_BELOW><<<grid, kTileF, 0, stream>>>(af);                         \
+        else return cudaErrorInvalidValue; /* below ground the FP32 build runs the FP64 hour loops (mcf_api.cu) */ \
     } while (0)
     if (arr == 0) MCF_F32_RQ(0);
     else if (arr == 1) MCF_F32_RQ(1);

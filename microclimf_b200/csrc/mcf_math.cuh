@@ -157,14 +157,43 @@ __device__ const double2 kLogTab[64] = { // {1 / c_j, log c_j}, c_j = 1 + (j + 0
     {0.5059288537549407, 0.6813592248079031}, {0.5019607843137255, 0.689233281238809},
 };
 
+// Where the two tables are read from (template parameter TAB of the functions below):
+//   0  global memory through the read-only path (__ldg): L1-resident in kernels that leave the L1 its capacity;
+//   1  the first 12 KB of the kernel's DYNAMIC shared memory, which the kernel has filled with math_tables_to_smem():
+//      conflict-free replicas — the 2^(j/32) table [32][16 copies] of doubles (a 64-bit LDS is served per half-warp: lane
+//      c reads copy c & 15, 16 distinct bank pairs) and the {1/c, log c} table [64][8 copies] of double2 (a 128-bit LDS is
+//      served per quarter-warp: lane c reads copy c & 7).  For kernels whose shared-memory carve-out leaves a 28 KB L1,
+//      where the data-dependent __ldg gathers miss (k_grid_pair: 7 % of its stall samples, profiles/r02_kpair_v2).
+extern __shared__ __align__(128) unsigned char mcf_dyn_smem[]; // every extern __shared__ array of a kernel starts here
+constexpr int kMathSmemExpBytes = 32 * 16 * 8, kMathSmemLogBytes = 64 * 8 * 16;
+constexpr int kMathSmemBytes = kMathSmemExpBytes + kMathSmemLogBytes;
+template <int TAB>
+__device__ __forceinline__ double exp_tab_entry(int j) {
+    if (TAB == 0) return __ldg(&kExpTab[j]);
+    return reinterpret_cast<const double*>(mcf_dyn_smem)[(j << 4) | (threadIdx.x & 15)];
+}
+template <int TAB>
+__device__ __forceinline__ double2 log_tab_entry(int j) {
+    if (TAB == 0) return __ldg(&kLogTab[j]);
+    return reinterpret_cast<const double2*>(mcf_dyn_smem + kMathSmemExpBytes)[(j << 3) | (threadIdx.x & 7)];
+}
+// all threads of the CTA; the caller synchronises afterwards
+__device__ __forceinline__ void math_tables_to_smem() {
+    double* e = reinterpret_cast<double*>(mcf_dyn_smem);
+    for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) e[i] = kExpTab[i >> 4];
+    double2* l = reinterpret_cast<double2*>(mcf_dyn_smem + kMathSmemExpBytes);
+    for (int i = threadIdx.x; i < 64 * 8; i += blockDim.x) l[i] = kLogTab[i >> 3];
+}
+
 // exp(r) 2^(k/32) for |r| <= ln2/64
+template <int TAB = 0>
 __device__ __forceinline__ double exp_tab(double r, int k) {
     const double r2 = r * r;
     const double a = fma(r, kMathC[21], 0.5);
     const double b = fma(r, kMathC[23], kMathC[22]);
     const double c = fma(r2, b, a);
     const double p = fma(r2, c, r + 1.0);
-    const double t = __ldg(&kExpTab[k & 31]);
+    const double t = exp_tab_entry<TAB>(k & 31);
     return __hiloint2double(__double2hiint(t * p) + ((k >> 5) << 20), __double2loint(t * p));
 }
 
@@ -188,6 +217,7 @@ __device__ __forceinline__ double scale2(double p, int k) {
 }
 
 // exp(x) for |x| <= 700 (no range clamps: out-of-range or non-finite x gives garbage or NaN, never a trap)
+template <int TAB = 0>
 __device__ __forceinline__ double mexp_nc(double x) {
 #ifndef MCF_MATH_POLY
     const double t = fma(x, kMathC[24], kMagic); // round(32 x / ln2) lands in the low word
@@ -195,7 +225,7 @@ __device__ __forceinline__ double mexp_nc(double x) {
     const double kf = t - kMagic;
     // one-constant reduction (exact product inside the FMA): error |k| * 2.4e-18 in r, <= 8e-14 relative for |x| <= 700
     const double r = fma(kf, -kMathC[25], x);
-    return exp_tab(r, k);
+    return exp_tab<TAB>(r, k);
 #else
     const double t = fma(x, kMathC[10], kMagic); // round-to-nearest integer lands in the low word
     const int k = __double2loint(t);
@@ -207,25 +237,28 @@ __device__ __forceinline__ double mexp_nc(double x) {
 #endif
 }
 // exp(x) for x <= 700: arguments below -708 (including -inf) return exp(-708) ~ 3e-308
+template <int TAB = 0>
 __device__ __forceinline__ double mexp_lo(double x) {
     x = (x < -708.0) ? -708.0 : x;
-    return mexp_nc(x);
+    return mexp_nc<TAB>(x);
 }
 // exp(x), any x
+template <int TAB = 0>
 __device__ __forceinline__ double mexp(double x) {
     x = (x < -708.0) ? -708.0 : x;
     x = (x > 709.0) ? 709.0 : x;
-    return mexp_nc(x);
+    return mexp_nc<TAB>(x);
 }
 
 // 2^x for |x| <= 1000 (no clamps)
+template <int TAB = 0>
 __device__ __forceinline__ double mexp2_nc(double x) {
 #ifndef MCF_MATH_POLY
     const double t = fma(x, 32.0, kMagic);
     const int k = __double2loint(t);
     const double kf = t - kMagic;
     const double r = fma(kf, -0.03125, x) * kMathC[13]; // (x - k/32) ln2, the subtraction is exact
-    return exp_tab(r, k);
+    return exp_tab<TAB>(r, k);
 #else
     const double t = x + kMagic;
     const int k = __double2loint(t);
@@ -234,18 +267,20 @@ __device__ __forceinline__ double mexp2_nc(double x) {
     return scale2(exp_poly(r), k);
 #endif
 }
+template <int TAB = 0>
 __device__ __forceinline__ double mexp2(double x) {
     x = (x < -1021.0) ? -1021.0 : x;
     x = (x > 1023.0) ? 1023.0 : x;
-    return mexp2_nc(x);
+    return mexp2_nc<TAB>(x);
 }
 
+template <int TAB = 0>
 __device__ __forceinline__ double mlog(double x) {
 #ifndef MCF_MATH_POLY
     const int hi = __double2hiint(x);
     const int e = (hi >> 20) - 1023;
     const double m = __hiloint2double((hi & 0x000FFFFF) | 0x3FF00000, __double2loint(x)); // mantissa in [1, 2)
-    const double2 tc = __ldg(&kLogTab[(hi >> 14) & 63]);                                    // {1 / c_j, log c_j}
+    const double2 tc = log_tab_entry<TAB>((hi >> 14) & 63);                                  // {1 / c_j, log c_j}
     const double r = fma(m, tc.x, -1.0); // m / c_j - 1, |r| < 2^-7 (single rounding)
     const double r2 = r * r;
     // log1p(r) = r + r^2 (-1/2 + r/3 - r^2/4 + r^3/5 - r^4/6), Estrin form
@@ -315,6 +350,7 @@ __device__ __forceinline__ void msincos(double x, double* sn, double* cs) {
 }
 
 // x^y for x > 0, |y log x| <= 700
-__device__ __forceinline__ double mpow(double x, double y) { return mexp_nc(y * mlog(x)); }
+template <int TAB = 0>
+__device__ __forceinline__ double mpow(double x, double y) { return mexp_nc<TAB>(y * mlog<TAB>(x)); }
 
 } // namespace mcf

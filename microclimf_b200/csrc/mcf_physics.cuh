@@ -65,22 +65,47 @@ struct __align__(16) HourRec {
 static_assert(sizeof(HourRec) == 320, "HourRec must be 320 bytes");
 
 // ---------------------------------------------------------------------------------------------
+// FP64 literals of the hour loops.  An FP64 immediate whose low 32 bits are not zero is materialised by two UMOVs (or two
+// IMAD.MOVs) at every use: 65 + 31 of the 1,414 instructions per cell-hour (profiles/r02_kpair_v3.txt).  From constant
+// memory the same values are plain c[bank][offset] operands of the DFMA / DMUL / DSETP that use them.  Values as the
+// reference writes them (compile-time folded exactly as the expressions they replace).
+// ---------------------------------------------------------------------------------------------
+#define MCF_LITS(X)                                                                                                    \
+    X(kelvin, 273.15) X(em, 0.97) X(emsb, 0.97 * 5.67e-8) X(emhalf, 0.97 * 0.5) X(th_hi, 0.9999) X(th_lo, 0.0001)      \
+    X(ws_lo, 0.05) X(uf_lo, 0.001) X(gha_lo, 0.0001) X(cpa, 29.3) X(tr_hi, 0.999) X(alb_lo, 0.01) X(theta_m, 0.365)    \
+    X(pct, 0.01) X(et_lo, 0.001) X(plf_a, 0.8753) X(plf_b, 1.7126) X(gs_na, 9999.99) X(gh_a, 0.135) X(gh_b, 1.4)        \
+    X(gs_cap, 999.99) X(hlf_a, 1.09767) X(hlf_b, 0.2672778) X(gmin_a, 0.0463) X(gmin_b, 0.2) X(gmin_lo, 0.05)          \
+    X(r_lo, 0.001) X(cp, 29.3 * 43.0) X(inv_cp, 1.0 / (29.3 * 43.0)) X(sv_a, 17.27) X(sv_b, 237.3) X(sv_c, 0.61078)     \
+    X(wet_a, 0.018) X(c2_a, 1.06) X(two_omdy, 2.0 / ((2.0 * 3.14159265358979323846) / (24.0 * 3600.0))) X(g_cap, 0.6)
+struct PhysLit {
+#define X(n, v) double n;
+    MCF_LITS(X)
+#undef X
+};
+__constant__ PhysLit kL = {
+#define X(n, v) v,
+    MCF_LITS(X)
+#undef X
+};
+
+// ---------------------------------------------------------------------------------------------
 // helpers
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double sq(double x) { return x * x; }
 __device__ __forceinline__ double pow4(double x) { double y = x * x; return y * y; }
-__device__ __forceinline__ double radem4(double tc) { return pow4(tc + 273.15); } // ref radem :24
+__device__ __forceinline__ double radem4(double tc) { return pow4(tc + kL.kelvin); } // ref radem :24
 
 // ref satvapCpp :480-490
 __device__ __forceinline__ double satvap(double tc) {
     return (tc > 0) ? 0.61078 * exp(17.27 * tc / (tc + 237.3)) : 0.61078 * exp(21.875 * tc / (tc + 265.5));
 }
 // same, through the branch-free mexp / mrcp (hot loops; tc + 237.3 and tc + 265.5 never vanish)
+template <int TAB = 0>
 __device__ __forceinline__ double satvap_m(double tc) {
     const bool w = tc > 0;
-    const double a = w ? 17.27 : 21.875;
-    const double b = w ? 237.3 : 265.5;
-    return 0.61078 * mexp_nc(a * tc * mrcp(tc + b)); // |argument| < 20 for any air / surface temperature
+    const double a = w ? kL.sv_a : 21.875;
+    const double b = w ? kL.sv_b : 265.5;
+    return kL.sv_c * mexp_nc<TAB>(a * tc * mrcp(tc + b)); // |argument| < 20 for any air / surface temperature
 }
 __device__ __forceinline__ double latent(double tc) { // ref :1227-1232
     return (tc >= 0) ? 45068.7 - 42.8428 * tc : 51078.69 - 4.338 * tc - 0.06367 * tc * tc;
@@ -191,6 +216,7 @@ struct CellInv {
     double uz_coef;  // uz = uf * uz_coef (before the uref cap)
     // soil thermal (ref soilpfun :628, soilcondCpp :1249) and hydraulic
     double c1, c3, c4, rho, Smax, psie_abs, soilb;
+    double cs0, c14; // 2400 rho / 2.64 (volumetric heat capacity of the solids, ref soilcondCpp :1251) and c1 - c4
     // stomata (ref stomparamsCpp :391-440, stomcondCpp :442-458)
     double gsmax, Rsmx, inv02Rsmx, psiw0, kk, rat, inv_stomden; // 1/(exp(-kk*psiw0)-1)
     // canopy / above-ground temperature model (ref TVabove :1298, TVbelow :1381, leaftemp :1333)
@@ -207,6 +233,69 @@ struct CellInv {
     double Hf500;         // mincondCpp's Hf for rs = 500 (gs = 0: every night hour)
     // reciprocals of cell invariants (IEEE division, once per cell)
     double inv_rge, inv_Smax, inv_kden, inv_leafd, inv_hgt, inv_a2h;
+};
+
+// The fields of CellInv the hour loops read (the rest only feeds cell_setup itself), as an X-macro: the pair kernel
+// (k_grid_pair, mcf_kernels_pair.inl) keeps them in SHARED memory, [field][cell], instead of ~150 registers per thread.
+#define MCF_INV_D(X)                                                                                                   \
+    X(cs) X(ssca) X(sssa) X(svfa) X(Smin) X(rge) X(Etadd) X(x) X(pai) X(pait) X(paiaa) X(om) X(omp) X(a) X(gma)        \
+    X(Jdel) X(h) X(gref) X(u1) X(u2) X(S1) X(invS1) X(invD1) X(invD2) X(logclump) X(loggi) X(trdn) X(trdu) X(amx)      \
+    X(albd) X(Rddn_g) X(Rdup_z) X(Rddn_z) X(Ehm) X(Ehp) X(trdif) X(ufs_coef) X(gHa_coef) X(uz_coef) X(c1) X(c3) X(c4)  \
+    X(rho) X(cs0) X(c14) X(psie_abs) X(soilb) X(gsmax) X(Rsmx) X(inv02Rsmx) X(psiw0) X(kk) X(rat) X(inv_stomden) X(one_m_lnr)        \
+    X(e_mpai) X(shade_fac) X(e_paia) X(e_paig) X(leafden) X(nearcoef) X(inth_h) X(inth_z) X(zq) X(hmz) X(Hf0)          \
+    X(Hf500) X(inv_rge) X(inv_Smax) X(inv_kden) X(inv_leafd) X(inv_hgt) X(inv_a2h)
+enum {
+#define X(n) INVD_##n,
+    MCF_INV_D(X)
+#undef X
+    kInvD
+};
+// A CellInv whose fields live in shared memory: member `n` reads element [INVD_n][this thread's cell] where it is used.
+// The physics templates take either this or the register-resident CellInv.
+template <int F, int STRIDE>
+struct InvD {
+    const double* b;
+    __device__ __forceinline__ operator double() const { return b[F * STRIDE]; }
+};
+template <int SHIFT, int MASK> // the three small integers share one word per cell
+struct InvI {
+    const int* b;
+    __device__ __forceinline__ operator int() const { return (b[0] >> SHIFT) & MASK; }
+};
+template <int STRIDE>
+struct CellInvS {
+#define X(n) InvD<INVD_##n, STRIDE> n;
+    MCF_INV_D(X)
+#undef X
+    InvI<0, 3> xflag;
+    InvI<2, 1> prof_above;
+    InvI<3, 1> above;
+    __device__ __forceinline__ CellInvS(const double* d, const int* i)
+        :
+#define X(n) n{d},
+          MCF_INV_D(X)
+#undef X
+          xflag{i}, prof_above{i}, above{i} {}
+    // cell_setup's result -> this thread's column (d, i as above, writable)
+    static __device__ __forceinline__ void store(const CellInv& v, double* d, int* i) {
+#define X(n) d[INVD_##n * STRIDE] = v.n;
+        MCF_INV_D(X)
+#undef X
+        i[0] = v.xflag | (v.prof_above << 2) | (v.above << 3);
+    }
+};
+// which copy of the math tables the physics templates read (mcf_math.cuh): shared-memory replicas next to shared-memory
+// invariants (the kernel has then given most of the L1 away), the global tables otherwise
+template <class V>
+struct MathTab {
+    static constexpr int value = 0;
+};
+#ifndef MCF_PAIR_SMEM_TABLES
+#define MCF_PAIR_SMEM_TABLES 1
+#endif
+template <int STRIDE>
+struct MathTab<CellInvS<STRIDE>> {
+    static constexpr int value = MCF_PAIR_SMEM_TABLES;
 };
 
 // ref zeroplanedisCpp :294
@@ -342,6 +431,8 @@ static __device__ __noinline__ void cell_setup(const CellIn& c, double reqhgt2, 
     v.c3 = 1.0 + 2.6 * pow(c.Mc, -0.5);
     v.c4 = 0.03 + 0.7 * frs * frs;
     v.rho = c.rho;
+    v.cs0 = 2400 * c.rho / 2.64;
+    v.c14 = v.c1 - v.c4;
     v.Smax = c.Smax;
     v.psie_abs = fabs(c.psie);
     v.soilb = c.soilb;
@@ -415,10 +506,11 @@ constexpr int kStashVars = 4;
 #endif
 
 // ref soildCpp :1021-1032, closed form of logistic(logit(theta) + tadd)
-__device__ __forceinline__ double soil_distribute(const CellInv& v, double soilmp) {
+template <class V>
+__device__ __forceinline__ double soil_distribute(const V& v, double soilmp) {
     double theta = (soilmp - v.Smin) * v.inv_rge;
-    if (theta > 0.9999) theta = 0.9999;
-    if (theta < 0.0001) theta = 0.0001;
+    if (theta > kL.th_hi) theta = kL.th_hi;
+    if (theta < kL.th_lo) theta = kL.th_lo;
     double sm = mdiv(theta, theta + (1.0 - theta) * v.Etadd); // divisor in (0, max(1, Etadd)]
     return sm * v.rge + v.Smin;
 }
@@ -427,17 +519,18 @@ struct Wind {
     double uf, uz, gHa;
 };
 // ref windCpp :1189-1218 with the cell-invariant logarithms folded
-__device__ __forceinline__ Wind wind_hour(const CellInv& v, double u2, double umu, double ws) {
+template <class V>
+__device__ __forceinline__ Wind wind_hour(const V& v, double u2, double umu, double ws) {
     Wind w;
     if (isnan(ws)) ws = 1.0;
-    if (ws < 0.05) ws = 0.05;
+    if (ws < kL.ws_lo) ws = kL.ws_lo;
     double ufs = u2 * v.ufs_coef;
     w.uf = ufs * umu * ws;
-    if (w.uf < 0.001) w.uf = 0.001;
+    if (w.uf < kL.uf_lo) w.uf = kL.uf_lo;
     w.uz = w.uf * v.uz_coef;
     if (w.uz > u2) w.uz = u2;
     w.gHa = w.uf * v.gHa_coef;
-    if (w.gHa < 0.0001) w.gHa = 0.0001;
+    if (w.gHa < kL.gha_lo) w.gHa = kL.gha_lo;
     return w;
 }
 
@@ -450,7 +543,7 @@ __device__ __forceinline__ double pm_ts(const HourRec& h, double dTmx, double Ra
     double gHr = gHa + h.gr4;
     double m = h.la * (gV * h.inv_pk);
     double L = m * (h.es - h.ea) * surfwet;
-    double dT = mdiv(Rabs - h.Rem - L - G, 29.3 * gHr + m * h.De); // divisor > 0
+    double dT = mdiv(Rabs - h.Rem - L - G, kL.cpa * gHr + m * h.De); // divisor > 0
     if (dT > dTmx) dT = dTmx;
     if (dT > 80.0) dT = 80.0;
     double Ts = dT + h.tc;
@@ -464,7 +557,9 @@ struct Rad {
 };
 
 // ref cankCpp :104-132 + twostreamdirCpp :164-185 + twostreamCpp :1086-1163 (shortwave part, Rsw > 0)
-__device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, double si) {
+template <class V>
+__device__ __forceinline__ Rad shortwave(const V& v, const HourRec& h, double si) {
+    constexpr int MT = MathTab<V>::value;
     Rad o;
     const double Rsw = h.Rsw, Rdif = h.Rdif;
     const double cosz = h.cosz;
@@ -485,7 +580,7 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
         double sig = kd * kd + v.gma * v.gma - apg * apg;
         double ss = 0.5 * (v.om + v.Jdel * mrcp(kd)) * kd;
         double sstr = v.om * kd - ss;
-        double S2 = mexp_lo(-kd * v.pait);
+        double S2 = mexp_lo<MT>(-kd * v.pait);
         double p5 = -ss * (apg - kd) - v.gma * sstr;
         double isig = mrcp(sig);
         double p5s = p5 * isig;
@@ -499,17 +594,17 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
         double p9 = -v.invD2 * ((p8s * v.invS1) * (v.u2 + v.h) + v3);
         double p10 = v.invD2 * ((p8s * v.S1) * (v.u2 - v.h) + v3);
         // gap transmissions
-        double trbn = mexp_lo(Kc * v.logclump); // clump == 0: logclump = -inf, mexp -> 3e-308 (the reference: 0)
-        if (trbn > 0.999) trbn = 0.999;
+        double trbn = mexp_lo<MT>(Kc * v.logclump); // clump == 0: logclump = -inf, mexp -> 3e-308 (the reference: 0)
+        if (trbn > kL.tr_hi) trbn = kL.tr_hi;
         if (trbn < 0.0) trbn = 0.0;
-        double trb = mexp_lo(Kc * v.loggi);
-        if (trb > 0.999) trb = 0.999;
+        double trb = mexp_lo<MT>(Kc * v.loggi);
+        if (trb > kL.tr_hi) trb = kL.tr_hi;
         if (trb < 0.0) trb = 0.0;
-        double S2a = mexp_lo(-kd * v.paiaa);
+        double S2a = mexp_lo<MT>(-kd * v.paiaa);
         // black-sky albedo
         double albb = (1.0 - v.trdn * trbn) * (p5s + p6 + p7) + v.trdn * trbn * v.gref;
         if (albb > v.amx) albb = v.amx;
-        if (albb < 0.01) albb = 0.01;
+        if (albb < kL.alb_lo) albb = kL.alb_lo;
         double Rdbdn_g = (1.0 - trbn) * (p8s * S2 + p9 * v.S1 + p10 * v.invS1);
         if (Rdbdn_g > v.amx) Rdbdn_g = v.amx;
         if (Rdbdn_g < 0.0) Rdbdn_g = 0.0;
@@ -550,22 +645,26 @@ __device__ __forceinline__ Rad shortwave(const CellInv& v, const HourRec& h, dou
 
 // Soil-moisture limitation of stomatal conductance: the theta-only factor of stomcondCpp (:450-455),
 // gs2 = mu * gsmax.  Shared by the (up to) three stomcondCpp calls of one cell-hour.
-__device__ __forceinline__ double stom_gs2(const CellInv& v, double theta) {
-    double thetan = v.rat * theta + (1 - v.rat) * kThetaM;
+template <class V>
+__device__ __forceinline__ double stom_gs2(const V& v, double theta) {
+    constexpr int MT = MathTab<V>::value;
+    double thetan = v.rat * theta + (1 - v.rat) * kL.theta_m;
     double Se = thetan * v.inv_Smax;
     if (Se > 1.0) Se = 1.0;
-    double psiw = -v.psie_abs * mexp_nc(-v.soilb * mlog(Se)) * 0.01; // pow(Se, -b), Se in (0, 1]
+    double psiw = -v.psie_abs * mexp_nc<MT>(-v.soilb * mlog<MT>(Se)) * kL.pct; // pow(Se, -b), Se in (0, 1]
     if (psiw < v.psiw0) psiw = v.psiw0;
-    double mu = 1.0 - (mexp_nc(-v.kk * psiw) - 1.0) * v.inv_stomden;
+    double mu = 1.0 - (mexp_nc<MT>(-v.kk * psiw) - 1.0) * v.inv_stomden;
     return mu * v.gsmax;
 }
 // ref stomcondCpp :442-458 given gs2
-__device__ __forceinline__ double stomcond(const CellInv& v, double Rswabs, double gs2) {
+template <class V>
+__device__ __forceinline__ double stomcond(const V& v, double Rswabs, double gs2) {
+    constexpr int MT = MathTab<V>::value;
     if (Rswabs <= 0.0) return 0.0;
     // Rswabs >= Rsmx (always the case for sunlit leaves: kq is ~6000) clamps the exponent to 0 and
     // 2^0 = 1 exactly, so the exponential is only evaluated below saturation
     double gs = v.gsmax;
-    if (Rswabs < v.Rsmx) gs = v.gsmax * mexp2_nc(-(v.Rsmx - Rswabs) * v.inv02Rsmx); // argument in (-5, 0)
+    if (Rswabs < v.Rsmx) gs = v.gsmax * mexp2_nc<MT>(-(v.Rsmx - Rswabs) * v.inv02Rsmx); // argument in (-5, 0)
     if (gs > gs2) gs = gs2;
     return gs;
 }
@@ -575,16 +674,18 @@ struct Above {
 };
 
 // ref TVaboveground :1411-1472 (with TVabove :1298, leaftemp :1333, TVbelow :1381, rhcanopy :1365)
-__device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h, double dTmx, double soilm, double Tg,
+template <class V>
+__device__ __forceinline__ Above above_ground(const V& v, const HourRec& h, double dTmx, double soilm, double Tg,
                                               double G, const Wind& w, double radCsw, double radClw, double Lhalf) {
+    constexpr int MT = MathTab<V>::value;
     Above out;
     const double tc = h.tc, ea = h.ea, Rlw = h.Rlw;
     // ground and surface wetness
-    double esTg = satvap_m(Tg);
+    double esTg = satvap_m<MT>(Tg);
     double eT = esTg - ea;
-    if (eT < 0.001) eT = 0.001;
-    double plf = 0.8753 - 1.7126 * mlog(eT);
-    double gwet = mrcp(1.0 + mexp_nc(-plf)); // plf in [-6, 13]
+    if (eT < kL.et_lo) eT = kL.et_lo;
+    double plf = kL.plf_a - kL.plf_b * mlog<MT>(eT);
+    double gwet = mrcp(1.0 + mexp_nc<MT>(-plf)); // plf in [-6, 13]
     double surfwet = (soilm - v.Smin) * v.inv_rge;
     if (surfwet > gwet) gwet = surfwet;
     // canopy conductance (ref canopycondCpp :460-477) with k from the degrees-as-radians cankCpp call
@@ -594,7 +695,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
     // leaf reflectance / transmittance NA (bare cells of real rasters keep NA there, R/internal.R:1052-1058):
     // canopycondCpp skips its body and returns Gs = 9999.99 (ref :463-464), whatever pai is
     const bool om_na = isnan(v.omp);
-    double gS = om_na ? 9999.99 : 0.0;
+    double gS = om_na ? kL.gs_na : 0.0;
     if (v.pai != 0.0 && !om_na) { // pai == 0: Rshade_abs is 0/0 = NaN in the reference, so gS is NaN and gV stays 0
         double kq = msqrt(v.x * v.x + h.kq_tan * h.kq_tan) * v.inv_kden;
         kq = (v.xflag == 1) ? h.kq1 : kq;
@@ -610,7 +711,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             // the zenith-in-degrees argument is clamped, i.e. almost always)
             const double kp_ = kq * v.pai;
             double esun = 0.0;
-            if (kp_ < 700.0) esun = mexp_nc(-kp_);
+            if (kp_ < 700.0) esun = mexp_nc<MT>(-kp_);
             double P_sun = (1.0 - esun) * mrcp(kq);
             double P_shade = v.pai - P_sun;
             gs2 = stom_gs2(v, soilm);
@@ -628,7 +729,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
     double Rabs = radCsw + radClw;
     double m;
     double Tcan = pm_ts(h, dTmx, Rabs, w.gHa, gV, G, surfwet, m);
-    double esTcan = satvap_m(Tcan);
+    double esTcan = satvap_m<MT>(Tcan);
     double ez;
     if (v.above) {
         // ref TVabove :1298-1313 at reqhgt
@@ -640,30 +741,30 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             ez = ea + (esTcan - ea) * surfwet;
         }
         out.tleaf = Tcan;
-        out.lwup = kEm * kSb * radem4(Tcan);
+        out.lwup = kL.emsb * radem4(Tcan);
         out.lwdn = Rlw;
     } else {
-        double pmH = 29.3 * w.gHa * (Tcan - tc);
+        double pmH = kL.cpa * w.gHa * (Tcan - tc);
         double pmL = m * (esTcan - ea) * surfwet;
         double pmmu = h.pmmu;
         // ---- leaf temperature (ref leaftemp :1333-1364)
-        double lwcan = kEm * kSb * radem4(Tcan);
-        double lwgro = kEm * kSb * radem4(Tg);
+        double lwcan = kL.emsb * radem4(Tcan);
+        double lwgro = kL.emsb * radem4(Tg);
         out.lwup = v.e_paig * lwgro + (1 - v.e_paig) * lwcan;
         out.lwdn = v.e_paia * Rlw + (1 - v.e_paia) * lwcan;
-        double lwabs = kEm * 0.5 * (out.lwup + out.lwdn);
+        double lwabs = kL.emhalf * (out.lwup + out.lwdn);
         // radLsw / radLpar are set to 0, not computed, at night and for pai == 0 (ref twostreamCpp :1147-1163): with NA
         // leaf reflectance the product (1 - om) * 0 would be NaN where the reference has 0
         const bool lit = (h.Rsw > 0.0) && (v.pai > 0.0);
         const double radLsw = lit ? (1.0 - v.om) * Lhalf : 0.0;
         double leafabs = radLsw + lwabs;
-        double gh = 0.135 * msqrt(w.uz * v.inv_leafd) * 1.4;
+        double gh = kL.gh_a * msqrt(w.uz * v.inv_leafd) * kL.gh_b;
         double Rnetl = leafabs - lwcan;
         // leaftemp calls mincondCpp twice (gs = 999.99, then the stomatal gs; ref :1348, :1354) and keeps the larger
         // gmin.  gmin = 0.0463 (|Hf| |Rnet| / leafd)^0.2 is monotone in |Hf|, so one power of the larger |Hf| gives
         // max(gmin1, gmin2) exactly; at night (gs = 0, rs = 500) the second |Hf| is a constant.
         double Hfmag = fabs(v.Hf0);
-        const bool stom = v.gsmax < 999.99;
+        const bool stom = v.gsmax < kL.gs_cap;
         double gs = 0.0;
         if (stom) {
             double radLpar = lit ? (1.0 - v.omp) * Lhalf : 0.0;
@@ -675,15 +776,15 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             if (gs > 0.0) {
                 double rs = mrcp(gs);
                 if (rs > 500.0) rs = 500.0;
-                const double Hlf = 1.09767 * mpow(rs, 0.2672778);
-                Hf2 = -mrcp(1.0 + mexp_nc(2.0 - Hlf));
+                const double Hlf = kL.hlf_a * mpow<MT>(rs, kL.hlf_b);
+                Hf2 = -mrcp(1.0 + mexp_nc<MT>(2.0 - Hlf));
             }
             const double m2 = fabs(Hf2);
             if (Hfmag < m2) Hfmag = m2;
         }
-        // H == 0: mlog(0) ~ -709, so the power is ~1e-62 instead of 0; either way gmin takes its floor
-        double gmin = 0.0463 * mpow((Hfmag * fabs(Rnetl)) * v.inv_leafd, 0.2);
-        if (gmin < 0.05) gmin = 0.05;
+        // H == 0: mlog<MT>(0) ~ -709, so the power is ~1e-62 instead of 0; either way gmin takes its floor
+        double gmin = kL.gmin_a * mpow<MT>((Hfmag * fabs(Rnetl)) * v.inv_leafd, kL.gmin_b);
+        if (gmin < kL.gmin_lo) gmin = kL.gmin_lo;
         if (gh < gmin) gh = gmin;
         double gVl = gh;
         if (stom) {
@@ -692,8 +793,8 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         }
         double ml;
         double tleaf = pm_ts(h, dTmx, leafabs, gh, gVl, 0.0, surfwet, ml);
-        double esTl = satvap_m(tleaf);
-        double lfH = 29.3 * gh * (tleaf - tc);
+        double esTl = satvap_m<MT>(tleaf);
+        double lfH = kL.cpa * gh * (tleaf - tc);
         double lfL = ml * (esTl - ea) * surfwet;
         out.tleaf = tleaf;
         // ---- canopy-top state (ref TVabove at hgt, :1449)
@@ -708,9 +809,9 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         // ---- diffusivities (ref TVbelow :1385-1390, rhcanopy :1365-1380)
         double mu_r = v.inv_a2h * mrcp(w.uf); // (uf / a2h) / uf^2
         double Rc = v.inth_h * mu_r;
-        if (Rc < 0.001) Rc = 0.001;
+        if (Rc < kL.r_lo) Rc = kL.r_lo;
         double Rz = v.inth_z * mu_r;
-        if (Rz < 0.001) Rz = 0.001;
+        if (Rz < kL.r_lo) Rz = kL.r_lo;
         double iKc = Rc * v.inv_hgt; // 1 / Kc
         double Kc = mrcp(iKc);
         double Kg = mrcp(Rz * v.zq);
@@ -718,7 +819,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
         double iK = mrcp(Kg + Kh + Kc);
         // ---- temperature below canopy (ref :1447-1453)
         {
-            const double cp = 29.3 * 43.0;
+            const double cp = kL.cp;
             double Flux = pmH * v.e_mpai;
             double SH = Th * cp;
             double SG = Tg * cp;
@@ -728,7 +829,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             double nearf = v.nearcoef * (lfH * v.leafden);
             if (fabs(nearf) > mxnear) nearf = (nearf > 0.0) ? mxnear : -mxnear;
             if (isnan(nearf)) nearf = 0;
-            out.Tz = (nearf + farg) * (1.0 / cp);
+            out.Tz = (nearf + farg) * kL.inv_cp;
         }
         // ---- vapour pressure below canopy (ref :1455-1460)
         {
@@ -744,7 +845,7 @@ __device__ __forceinline__ Above above_ground(const CellInv& v, const HourRec& h
             ez = (nearf + farg) * h.inv_pmmu;
         }
     }
-    out.rh = mdiv(ez, satvap_m(out.Tz)) * 100.0;
+    out.rh = mdiv(ez, satvap_m<MT>(out.Tz)) * 100.0;
     if (out.rh > 100.0) out.rh = 100.0;
     // limits (ref :1467-1470; std::max/min over {tleaf, tc, Tg, Tcan} with their NaN-ignoring fold order)
     double tmx = out.tleaf;

@@ -41,8 +41,10 @@ def _check_sinks(p, gpus, tmp_path):
         # NaN hours of a solved cell poison its mean and are skipped by its extremes (the sink's rule)
         with np.errstate(invalid="ignore"):
             np.testing.assert_allclose(s["mean"][~na], w[~na].sum(axis=1) / hours, rtol=1e-12, atol=1e-12, err_msg=nm)
-        np.testing.assert_array_equal(s["min"][~na], np.fmin.reduce(w[~na], axis=1, initial=np.inf), err_msg=nm)
-        np.testing.assert_array_equal(s["max"][~na], np.fmax.reduce(w[~na], axis=1, initial=-np.inf), err_msg=nm)
+        # the reducing sinks run in the register build of the grid kernel (k_grid), the hourly arrays come from the pair
+        # build (k_grid_pair): same physics source, different FMA contraction, so the extremes agree to rounding
+        np.testing.assert_allclose(s["min"][~na], np.fmin.reduce(w[~na], axis=1, initial=np.inf), rtol=1e-12, atol=1e-12, err_msg=nm)
+        np.testing.assert_allclose(s["max"][~na], np.fmax.reduce(w[~na], axis=1, initial=-np.inf), rtol=1e-12, atol=1e-12, err_msg=nm)
     out_dir = str(tmp_path / f"packed{gpus}")
     r = bigrun.run_local(p.replace(), gpus, sink="packed", pathout=out_dir, window_days=2)
     assert r["hours"] == hours

@@ -87,11 +87,13 @@ def test_fp32_coarse_grid_climate(altcorrect):
 
 @pytest.mark.parametrize("mode,reqhgt,complete", [(1, -0.05, True), (1, -0.6, True), (3, -0.1, False), (2, -0.2, True)])
 def test_fp32_below_ground(mode, reqhgt, complete):
-    """reqhgt < 0: FP32 hour loops feed the FP64 time-axis pass (rolling means over the stored ground temperatures);
-    the window length n = round(-118.35 z / mean damping depth) may differ by one hour from the FP64 build's."""
+    """reqhgt < 0: the time-axis pass is discontinuous in its inputs (rolling-mean length n = round(-118.35 z / mean
+    damping depth); a ratio of daily ranges when the series is incomplete), so the FP32 build runs the FP64 hour loops
+    there and narrows: Tz and soil moisture agree with the FP64 reference to single-precision rounding."""
     p = synth.make_problem(21, 17, 24 * 6, reqhgt=reqhgt, mode=mode, nlyr=2, complete=complete)
     mask = [True, False, False, True, False, False, False, False, False, False]
-    check(run_f32(p, mask), pyoracle.runmicro(p, out_mask=mask, kind=KIND))
+    worst = check(run_f32(p, mask), pyoracle.runmicro(p, out_mask=mask, kind=KIND))
+    assert worst["Tz"][0] < 1e-4 and worst["soilm"][0] < 1e-6, worst
 
 
 def test_fp32_host_entry_point_matches_device_entry_point():

@@ -27,7 +27,7 @@ for vals in rows[2:]:
     st = {k[len("smsp__pcsamp_warps_issue_stalled_"):]: g(k) for k in d if k.startswith("smsp__pcsamp_warps_issue_stalled_") and not k.endswith("_not_issued")}
     tot = sum(st.values())
     print("  stall samples:", ", ".join(f"{k} {100*v/tot:.1f}%" for k, v in sorted(st.items(), key=lambda kv: -kv[1])[:8]))
-    if ch:
+    if ch and "sm__sass_thread_inst_executed_op_dfma_pred_on.sum" in d:
         wi = g("smsp__inst_executed.sum")
         f = {k: g(f"sm__sass_thread_inst_executed_op_{k}_pred_on.sum") for k in ("dfma", "dadd", "dmul", "fp64")}
         print(f"  per cell-hour: warp-level instr x32 = {wi*32/ch:.0f}, fp64 instr {f['fp64']/ch:.0f} (dfma {f['dfma']/ch:.0f} dadd {f['dadd']/ch:.0f} dmul {f['dmul']/ch:.0f}), "

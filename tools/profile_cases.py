@@ -19,7 +19,8 @@ if which == "bio":
     for _ in range(3):
         api.run_bioclim_problem_dev(dp, q["wetq"], q["dryq"], q["hotq"], q["colq"], True, bio)
 else:
-    p = synth.make_problem(2048, 512, 48, reqhgt=0.05, mode=1)
+    hours = 240 if which == "headline10" else 48  # headline10: ten days per tile (tile set-up amortised as in the bench)
+    p = synth.make_problem(2048, 512, hours, reqhgt=0.05, mode=1)
     dp = p.to_device()
     if which == "summary":
         s = [[torch.empty(p.ncells, dtype=torch.float64, device="cuda") for _ in range(10)] for _ in range(3)]
@@ -28,6 +29,6 @@ else:
     else:
         o = [torch.empty(24 * p.ncells, dtype=torch.float64, device="cuda") for _ in range(10)]
         for _ in range(3):
-            api.run_problem_dev(dp, o, window=(0, 2, 0, 24))
+            api.run_problem_dev(dp, o, window=(0, hours // 24, 0, 24))
 torch.cuda.synchronize()
 print("done", which)
