@@ -623,6 +623,9 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
     h.windex = c.windex;
 }
 
+constexpr int kGridTab = MathTab<CellInv>::value;          // which copy of the math tables k_grid's physics reads
+constexpr size_t kGridTabBytes = kGridTab ? kMathSmemBytes : 0;
+
 template <int ARR, int RQ, int SINK, bool ALLOUT = false>
 #ifdef MCF_MAXNREG
 #define MCF_KGRID_BOUNDS __maxnreg__(MCF_MAXNREG)
@@ -644,7 +647,8 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
     __shared__ __align__(8) uint64_t empty_bar[kStages];
     __shared__ int s_tile;
     // accumulators of the reducing sinks: [slot][thread], this thread's column (dynamic shared memory, absent otherwise)
-    extern __shared__ __align__(16) double acc_smem[];
+    // dynamic shared memory: the math-table replicas (mcf_math.cuh, TAB = 1) first, then the reducing sinks' accumulators
+    double* const acc_smem = reinterpret_cast<double*>(mcf_dyn_smem + kGridTabBytes);
     constexpr bool PACK = (SINK == SINK_PACK);
     constexpr bool REDUCE = (SINK == SINK_BIO || SINK == SINK_SUMMARY);
 
@@ -664,6 +668,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
         }
     }
     static_assert(kStashVars == 6, "pass 2 takes six variables per cell-hour from the day stash");
+    if (kGridTab) math_tables_to_smem(); // ordered before their first use by the tile loop's __syncthreads
     const uint32_t om = a.outmask;
     const double NA = na_real();
 
@@ -811,8 +816,8 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     if (ALLOUT || (om & (1u << 4))) put<4, SINK>(a, o, w.uz, acc);
                     // ground surface temperature with G = 0 (ref soiltempG0 :1262-1275)
                     const double radabs = r.radGsw + radGlw;
-                    const double matric = -v.psie_abs * mexp_nc(-v.soilb * mlog(soild * v.inv_Smax));
-                    double surfwet = mexp_lo((kL.wet_a * matric) * h.invRT);
+                    const double matric = -v.psie_abs * mexp_nc<kGridTab>(-v.soilb * mlog<kGridTab>(soild * v.inv_Smax));
+                    double surfwet = mexp_lo<kGridTab>((kL.wet_a * matric) * h.invRT);
                     if (surfwet > 1.0) surfwet = 1.0;
                     double m_unused;
                     const double Tg0 = pm_ts(h, dTmx, radabs, w.gHa, w.gHa, 0.0, surfwet, m_unused);
@@ -891,7 +896,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                     const double cs = (v.cs0 + 4180.0 * soild);
                     const double ph = (v.rho * (1.0 - soild) + soild) * 1000.0;
                     const double c2 = kL.c2_a * v.rho * soild;
-                    const double kcon = v.c1 + c2 * soild - v.c14 * mexp_lo(-pow4(v.c3 * soild));
+                    const double kcon = v.c1 + c2 * soild - v.c14 * mexp_lo<kGridTab>(-pow4(v.c3 * soild));
                     const double kap = mdiv(kcon, cs * ph);
                     // damping depth DD = sqrt(2 kap / omega): only its reciprocal enters the heat flux, the depth
                     // itself is needed for the below-ground pass alone
@@ -945,7 +950,7 @@ int grid_blocks_per_sm(bool arr, int rq) {
 }
 
 // dynamic shared memory of the reducing sinks: kAccSlots doubles per thread
-constexpr size_t kAccBytes = (size_t)kAccSlots * kTile * sizeof(double);
+constexpr size_t kAccBytes = kGridTabBytes + (size_t)kAccSlots * kTile * sizeof(double);
 template <int ARR, int RQ, int SINK>
 static cudaError_t launch_reduce(const GridArgs& a, int grid, cudaStream_t stream) {
     static bool configured = false; // per instantiation
@@ -979,8 +984,8 @@ cudaError_t launch_grid(const GridArgs& a, int arr, int rq, int grid, cudaStream
     }
 #define MCF_LAUNCH(ARR, RQ)                                                          \
     do {                                                                             \
-        if (sink == SINK_PACK) k_grid<ARR, RQ, SINK_PACK><<<grid, kTile, 0, stream>>>(a); \
-        else k_grid<ARR, RQ, SINK_F64><<<grid, kTile, 0, stream>>>(a);               \
+        if (sink == SINK_PACK) k_grid<ARR, RQ, SINK_PACK><<<grid, kTile, kGridTabBytes, stream>>>(a); \
+        else k_grid<ARR, RQ, SINK_F64><<<grid, kTile, kGridTabBytes, stream>>>(a);               \
     } while (0)
 #define MCF_LAUNCH_RQ(ARR)                                 \
     do {                                                   \
@@ -991,7 +996,7 @@ cudaError_t launch_grid(const GridArgs& a, int arr, int rq, int grid, cudaStream
     // every output requested, per-hour table, above ground, FP64 sink (the headline configuration): the ten mask tests
     // in front of the stores are compiled out
     if (arr == 0 && rq == RQ_ABOVE && sink == SINK_F64 && a.outmask == 0x3FFu) {
-        k_grid<0, RQ_ABOVE, SINK_F64, true><<<grid, kTile, 0, stream>>>(a);
+        k_grid<0, RQ_ABOVE, SINK_F64, true><<<grid, kTile, kGridTabBytes, stream>>>(a);
         return cudaGetLastError();
     }
     if (arr == 0) MCF_LAUNCH_RQ(0);

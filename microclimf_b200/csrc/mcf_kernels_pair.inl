@@ -23,11 +23,15 @@
 constexpr int kPairCells = MCF_PAIR_CELLS;  // cells per tile
 constexpr int kPairThreads = 2 * kPairCells;
 constexpr int kPairStages = MCF_PAIR_STAGES;
+#ifndef MCF_PAIR_UNROLL1
+#define MCF_PAIR_UNROLL1 1
+#endif
+constexpr int kPairUnroll1 = MCF_PAIR_UNROLL1; // hours of pass 1 in flight per thread (2: spills at 128 registers)
 static_assert(kPairCells % 32 == 0 && kPairCells / 32 <= 15, "one named barrier per warp pair (ids 1..15)");
 
 // dynamic shared memory of the pair kernel
 constexpr size_t kPairRingBytes = sizeof(HourRec) * 24 * kPairStages;
-constexpr size_t kPairInvDBytes = sizeof(double) * kInvD * kPairCells;
+constexpr size_t kPairInvDBytes = sizeof(double) * 2 * ((kInvD + 1) / 2) * kPairCells; // [field pair][cell][2]
 constexpr size_t kPairInvIBytes = sizeof(int) * kPairCells; // the three small integers of CellInv packed into one word
 constexpr int kPairTab = MathTab<CellInvS<kPairCells>>::value;
 constexpr size_t kPairTabBytes = kPairTab ? kMathSmemBytes : 0; // math-table replicas, at offset 0 (mcf_math.cuh, TAB = 1)
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
     double* const scratch = a.stash + (size_t)blockIdx.x * kPairScratchDoubles;
     double* const stash = scratch + ci;
     double* const xch = scratch + kPairStashDoubles + ci;
-    const CellInvS<kPairCells> v(inv_d + ci, inv_i + ci);
+    const CellInvS<kPairCells> v(inv_d + kInvCellStep * ci, inv_i + ci);
     unsigned int q0 = 0;
 
     if (tid == 0) {
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
                     CellInv vr;
                     load_cell(a, cc, cur_lyr, tadd, cin);
                     cell_setup(cin, a.reqhgt2, a.zref, a.lat, vr);
-                    CellInvS<kPairCells>::store(vr, inv_d + ci, inv_i + ci);
+                    CellInvS<kPairCells>::store(vr, inv_d + kInvCellStep * ci, inv_i + ci);
                 }
                 pair_sync(bar_id);
             }
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
                 double ws_n = ld_sector(&a.wsa[(size_t)slab_day[half].windex * a.ncells + cell]);
                 double ha_n = ld_sector(&a.hor[(size_t)slab_day[half].sindex * a.ncells + cell]);
                 ws_n = settle(ws_n, zero), ha_n = settle(ha_n, zero); // as for the stash loads of pass 2, below
-#pragma unroll 1
+#pragma unroll(kPairUnroll1)
                 for (int hr = half; hr < 24; hr += 2) {
                     const HourRec& h = slab_day[hr];
                     size_t o = o_first + (size_t)hr * a.out_stride;

@@ -236,14 +236,17 @@ struct CellInv {
 };
 
 // The fields of CellInv the hour loops read (the rest only feeds cell_setup itself), as an X-macro: the pair kernel
-// (k_grid_pair, mcf_kernels_pair.inl) keeps them in SHARED memory, [field][cell], instead of ~150 registers per thread.
+// (k_grid_pair, mcf_kernels_pair.inl) keeps them in SHARED memory instead of ~150 registers per thread.  Layout
+// [field pair][cell][2]: fields 2i and 2i + 1 of a cell are one aligned 16-byte element, and the list is ordered so that
+// neighbours are used together — the compiler then fetches a pair with one LDS.128 (a quarter-warp's 8 cells are 128
+// contiguous bytes: conflict-free).
 #define MCF_INV_D(X)                                                                                                   \
-    X(cs) X(ssca) X(sssa) X(svfa) X(Smin) X(rge) X(Etadd) X(x) X(pai) X(pait) X(paiaa) X(om) X(omp) X(a) X(gma)        \
-    X(Jdel) X(h) X(gref) X(u1) X(u2) X(S1) X(invS1) X(invD1) X(invD2) X(logclump) X(loggi) X(trdn) X(trdu) X(amx)      \
-    X(albd) X(Rddn_g) X(Rdup_z) X(Rddn_z) X(Ehm) X(Ehp) X(trdif) X(ufs_coef) X(gHa_coef) X(uz_coef) X(c1) X(c3) X(c4)  \
-    X(rho) X(cs0) X(c14) X(psie_abs) X(soilb) X(gsmax) X(Rsmx) X(inv02Rsmx) X(psiw0) X(kk) X(rat) X(inv_stomden) X(one_m_lnr)        \
-    X(e_mpai) X(shade_fac) X(e_paia) X(e_paig) X(leafden) X(nearcoef) X(inth_h) X(inth_z) X(zq) X(hmz) X(Hf0)          \
-    X(Hf500) X(inv_rge) X(inv_Smax) X(inv_kden) X(inv_leafd) X(inv_hgt) X(inv_a2h)
+    X(cs) X(ssca) X(sssa) X(svfa) X(Smin) X(inv_rge) X(Etadd) X(rge) X(pai) X(x) X(inv_kden) X(a) X(gma) X(om)         \
+    X(Jdel) X(pait) X(u1) X(h) X(invD1) X(invS1) X(S1) X(u2) X(gref) X(invD2) X(logclump) X(loggi) X(paiaa) X(trdn)    \
+    X(amx) X(Ehm) X(Ehp) X(trdu) X(Rddn_g) X(albd) X(Rddn_z) X(Rdup_z) X(trdif) X(ufs_coef) X(uz_coef) X(gHa_coef)     \
+    X(psie_abs) X(soilb) X(inv_Smax) X(rho) X(cs0) X(c1) X(c14) X(c3) X(omp) X(shade_fac) X(rat) X(psiw0) X(kk)        \
+    X(inv_stomden) X(gsmax) X(Rsmx) X(inv02Rsmx) X(one_m_lnr) X(e_paig) X(e_paia) X(inv_leafd) X(Hf0) X(Hf500)         \
+    X(inv_a2h) X(inth_h) X(inth_z) X(inv_hgt) X(zq) X(hmz) X(e_mpai) X(nearcoef) X(leafden) X(c4)
 enum {
 #define X(n) INVD_##n,
     MCF_INV_D(X)
@@ -252,10 +255,19 @@ enum {
 };
 // A CellInv whose fields live in shared memory: member `n` reads element [INVD_n][this thread's cell] where it is used.
 // The physics templates take either this or the register-resident CellInv.
+#ifndef MCF_INV_PAIRED
+#define MCF_INV_PAIRED 0
+#endif
+// element index of field F in a thread's view of the table (the thread's base pointer carries its cell)
+template <int F, int STRIDE>
+__device__ __forceinline__ constexpr int inv_index() {
+    return MCF_INV_PAIRED ? (F >> 1) * (2 * STRIDE) + (F & 1) : F * STRIDE;
+}
+constexpr int kInvCellStep = MCF_INV_PAIRED ? 2 : 1; // doubles between neighbouring cells
 template <int F, int STRIDE>
 struct InvD {
     const double* b;
-    __device__ __forceinline__ operator double() const { return b[F * STRIDE]; }
+    __device__ __forceinline__ operator double() const { return b[inv_index<F, STRIDE>()]; }
 };
 template <int SHIFT, int MASK> // the three small integers share one word per cell
 struct InvI {
@@ -278,7 +290,7 @@ struct CellInvS {
           xflag{i}, prof_above{i}, above{i} {}
     // cell_setup's result -> this thread's column (d, i as above, writable)
     static __device__ __forceinline__ void store(const CellInv& v, double* d, int* i) {
-#define X(n) d[INVD_##n * STRIDE] = v.n;
+#define X(n) d[inv_index<INVD_##n, STRIDE>()] = v.n;
         MCF_INV_D(X)
 #undef X
         i[0] = v.xflag | (v.prof_above << 2) | (v.above << 3);
@@ -289,6 +301,13 @@ struct CellInvS {
 template <class V>
 struct MathTab {
     static constexpr int value = 0;
+};
+#ifndef MCF_GRID_SMEM_TABLES
+#define MCF_GRID_SMEM_TABLES 0
+#endif
+template <>
+struct MathTab<CellInv> { // k_grid: the register build of the grid kernel
+    static constexpr int value = MCF_GRID_SMEM_TABLES;
 };
 #ifndef MCF_PAIR_SMEM_TABLES
 #define MCF_PAIR_SMEM_TABLES 1
@@ -812,11 +831,17 @@ __device__ __forceinline__ Above above_ground(const V& v, const HourRec& h, doub
         if (Rc < kL.r_lo) Rc = kL.r_lo;
         double Rz = v.inth_z * mu_r;
         if (Rz < kL.r_lo) Rz = kL.r_lo;
-        double iKc = Rc * v.inv_hgt; // 1 / Kc
-        double Kc = mrcp(iKc);
-        double Kg = mrcp(Rz * v.zq);
-        double Kh = mrcp((Rc - Rz) * v.hmz); // Rc == Rz: NaN here, inf / inf = NaN in the reference
-        double iK = mrcp(Kg + Kh + Kc);
+        // The reference weights ground, canopy-top and canopy sources with the conductances Kg, Kh, Kc and divides by their
+        // sum (four divisions in a row).  With the resistances A = 1/Kc, B = 1/Kg, C = 1/Kh the normalised weights are
+        // AC, AB, BC over AB + AC + BC: one reciprocal, all terms positive (no cancellation).  C == 0 (both resistance
+        // integrals at their floor): Kh = 1/0 = inf and the reference's inf / inf is NaN — kept.
+        const double iKc = Rc * v.inv_hgt;          // A
+        const double rB = Rz * v.zq;                // B
+        const double rC = (Rc - Rz) * v.hmz;        // C
+        const double wAB = iKc * rB, wAC = iKc * rC, wBC = rB * rC;
+        double iden = mrcp(wAB + wAC + wBC);
+        if (rC == 0.0) iden = (double)NAN;
+        const double wG = wAC * iden, wH = wAB * iden, wC = wBC * iden;
         // ---- temperature below canopy (ref :1447-1453)
         {
             const double cp = kL.cp;
@@ -825,7 +850,7 @@ __device__ __forceinline__ Above above_ground(const V& v, const HourRec& h, doub
             double SG = Tg * cp;
             double mxnear = fabs(tleaf - Th) * cp;
             double SC = SH + Flux * iKc;
-            double farg = (Kg * SG + Kh * SH + Kc * SC) * iK;
+            double farg = wG * SG + wH * SH + wC * SC;
             double nearf = v.nearcoef * (lfH * v.leafden);
             if (fabs(nearf) > mxnear) nearf = (nearf > 0.0) ? mxnear : -mxnear;
             if (isnan(nearf)) nearf = 0;
@@ -838,7 +863,7 @@ __device__ __forceinline__ Above above_ground(const V& v, const HourRec& h, doub
             double SG = esTg * gwet * pmmu;
             double mxnear = fabs(esTl - eh) * pmmu;
             double SC = SH + Flux * iKc;
-            double farg = (Kg * SG + Kh * SH + Kc * SC) * iK;
+            double farg = wG * SG + wH * SH + wC * SC;
             double nearf = v.nearcoef * (lfL * v.leafden);
             if (fabs(nearf) > mxnear) nearf = (nearf > 0.0) ? mxnear : -mxnear;
             if (isnan(nearf)) nearf = 0;

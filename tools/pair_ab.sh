@@ -8,6 +8,6 @@ import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$label', '%.3e c-h/s' % d['value'], 'kernel ms %.2f' % d['roofline']['avg_launch_ms'], 'clk', d['clocks']['sm_mhz'])"
 }
 run k_grid MCF_NO_PAIR=1
-run pair320 MCF_NO_PAIR=0
-for v in "$@"; do run $v MCF_LIB_PATH=$PWD/variants/lib_$v.so; done
+run pair MCF_NO_PAIR=0
+for v in "$@"; do n=${v%:nopair}; if [ "$n" != "$v" ]; then run $v MCF_NO_PAIR=1 MCF_LIB_PATH=$PWD/variants/lib_$n.so; else run $v MCF_LIB_PATH=$PWD/variants/lib_$v.so; fi; done
 run k_grid_again MCF_NO_PAIR=1
