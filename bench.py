@@ -12,7 +12,7 @@ result is 4.7 TB per variable and exists nowhere; the ring keeps the HBM write t
   value     : device-timed whole-job cell-hours/s, inputs resident in HBM (mcf_runmicro_dev)
   e2e       : the same metric through the host-buffer C ABI (mcf_runmicro): pinned host inputs are
               uploaded and all outputs copied back to host inside the timed region, on a bounded tile
-  roofline  : dominant kernel (k_grid) — algorithmic HBM bytes / CUDA-event launch time vs measured
+  roofline  : dominant kernel (k_grid_pair, the pair build of the grid kernel) — algorithmic HBM bytes / CUDA-event launch time vs measured
               copy bandwidth; plus the FP64-pipe fraction (the binding roofline)
   cpu_baseline : the UNMODIFIED reference C++ (oracle/_ref) on the host cores, bounded sample
   extra keys: e2e_packed (int16 sink through the same host call), e2e_pageable (pageable result buffers, N = 1),
@@ -43,9 +43,7 @@ REQHGT = 0.05
 # algorithmic HBM bytes: 8 B x 10 outputs per cell-hour + 440 B of static layers per cell
 BYTES_PER_CELL_HOUR = 80.0
 BYTES_PER_CELL_STATIC = 440.0
-# FP64 flop per cell-hour executed by k_grid<false, RQ_ABOVE> on this workload: measured with ncu
-# (profiles/); DFMA counted as 2.
-FLOP_PER_CELL_HOUR = None  # filled from profiles/fp64_ops.json when present
+# FP64 flop per cell-hour of the dominant kernel: measured with ncu, read from profiles/kgrid_metrics.json
 
 
 def workload_config(args):
@@ -328,7 +326,7 @@ def gpu_arm(args):
     k_avg_ms = kms / max(kn, 1)
     bytes_launch = cell_hours_step * BYTES_PER_CELL_HOUR + ncells * BYTES_PER_CELL_STATIC
     achieved = bytes_launch / (k_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_grid<ARR=0,RQ_ABOVE,PACK=false,ALLOUT=true>", "achieved": achieved, "peak": peaks["hbm_gbs"],
+    roofline = {"bound": "hbm", "kernel": "k_grid_pair<RQ_ABOVE,SINK_F64,ALLOUT=true>", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": k_avg_ms, "launches": kn, "kernel_share_of_step": kms / ms,
                 "algorithmic_bytes_per_launch": bytes_launch}
@@ -337,7 +335,7 @@ def gpu_arm(args):
         with open(prof) as f:
             pm = json.load(f)
         # DRAM bytes per launch from the committed ncu capture: of a launch of exactly this size when the workload is the
-        # default one (profiles/r01_dram_benchwindow_v10.csv), else the per-cell-hour figure of the 48-hour profile window
+        # default one (profiles/r02_dram_benchwindow.csv), else the per-cell-hour figure of the 240-hour profile window
         per_ch = pm.get("dram_bytes_per_cell_hour", 0)
         if (args.rows, args.band_cols, args.win_days) == (8192, 1024, 30):
             per_ch = pm.get("dram_bytes_per_cell_hour_bench_window", per_ch)
