@@ -1,8 +1,9 @@
 // microclimf_b200 — sm_100a kernels of the grid solver.
 //
 // Execution model:
-//   * one thread per raster cell, kTile = 128 cells per CTA; persistent CTAs (a multiple of the SM
-//     count) pull 128-cell tiles from an atomic counter;
+//   * k_grid: one thread per raster cell, kTile = 384 cells per CTA; persistent CTAs (one per SM) pull tiles from an
+//     atomic counter.  k_grid_pair (mcf_kernels_pair.inl, the headline path): two threads per cell, invariants in
+//     shared memory;
 //   * cells are the fastest axis of every array (R layout), so each warp reads its statics and writes
 //     each output hour as one contiguous 256-byte segment (streaming stores, the outputs are
 //     write-once);
@@ -621,6 +622,15 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
     h.pmmu = h.la * (43.0 * h.inv_pk);
     h.inv_pmmu = mrcp(h.pmmu);
     h.windex = c.windex;
+}
+
+// x, through an integer instruction the compiler cannot remove (`zero` is 0 at run time only): the hardware has to wait
+// for a pending load of x HERE.  ptxas gives the stash loads in front of pass 2 and the look-ahead loads inside its loop
+// the same scoreboard; the loop's first consumer then waits on it for the entry path, i.e. in every iteration on the
+// look-ahead loads it has just issued.  Consuming the prologue values before the loop retires the scoreboard.  (Used by
+// k_grid_pair, where it is worth 2 %; the same treatment of k_grid's pass 2 measured nothing: 72.5 vs 71.4-72.5 ms.)
+__device__ __forceinline__ double settle(double x, int zero) {
+    return __hiloint2double(__double2hiint(x) ^ zero, __double2loint(x) ^ zero);
 }
 
 constexpr int kGridTab = MathTab<CellInv>::value;          // which copy of the math tables k_grid's physics reads

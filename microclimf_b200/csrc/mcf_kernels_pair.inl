@@ -56,12 +56,6 @@ __device__ __forceinline__ double ld_xch(const double* p) {
     return v;
 }
 
-// x, through an integer instruction the compiler cannot remove (`zero` is 0 at run time only): the hardware has to wait
-// for a pending load of x HERE
-__device__ __forceinline__ double settle(double x, int zero) {
-    return __hiloint2double(__double2hiint(x) ^ zero, __double2loint(x) ^ zero);
-}
-
 template <int RQ, int SINK, bool ALLOUT>
 __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_constant__ GridArgs a) {
     static_assert(RQ != RQ_BELOW && (SINK == SINK_F64 || SINK == SINK_PACK), "pair kernel: hourly sinks, reqhgt >= 0");
