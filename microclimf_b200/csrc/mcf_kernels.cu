@@ -963,12 +963,14 @@ int grid_blocks_per_sm(bool arr, int rq) {
 constexpr size_t kAccBytes = kGridTabBytes + (size_t)kAccSlots * kTile * sizeof(double);
 template <int ARR, int RQ, int SINK>
 static cudaError_t launch_reduce(const GridArgs& a, int grid, cudaStream_t stream) {
-    static bool configured = false; // per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_grid<ARR, RQ, SINK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kAccBytes);
+    static bool configured[64] = {}; // per instantiation and device (the opt-in is per device)
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        e = cudaFuncSetAttribute(k_grid<ARR, RQ, SINK, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAccBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     k_grid<ARR, RQ, SINK, false><<<grid, kTile, kAccBytes, stream>>>(a);
     return cudaGetLastError();

@@ -317,12 +317,16 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
 
 template <int RQ, int SINK, bool ALLOUT>
 static cudaError_t launch_pair_t(const GridArgs& a, int grid, cudaStream_t stream) {
-    static bool configured = false; // per instantiation
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_grid_pair<RQ, SINK, ALLOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kPairSmemBytes);
+    // the opt-in is per device and per function: remembered per (instantiation, device) so that a process that moves
+    // between devices (mcf_set_device) configures each of them
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+        e = cudaFuncSetAttribute(k_grid_pair<RQ, SINK, ALLOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);
         if (e != cudaSuccess) return e;
-        configured = true;
+        if (dev >= 0 && dev < 64) configured[dev] = true;
     }
     k_grid_pair<RQ, SINK, ALLOUT><<<grid, kPairThreads, kPairSmemBytes, stream>>>(a);
     return cudaGetLastError();
