@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import parity
-from microclimf_b200 import api, synth
+from microclimf_b200 import _abi, api, synth
 from oracle import prep_oracle, pyoracle
 
 KIND = "ref" if pyoracle.have_ref() else "oracle"
@@ -33,6 +33,23 @@ def test_coarse_problem_layout_cpu():
         bad = synth.make_coarse_problem(8, 8, 24, mode=2)
         del bad.arrays["relhum"]
         bad.validate()
+
+
+def test_sampled_expansion_equals_sample_of_expansion_cpu():
+    """materialise_coarse(p, pick) — what the raster-size test feeds the checker — is the sampled full expansion."""
+    p = synth.make_coarse_problem(19, 13, 48, mode=2, crows=4, ccols=3, altcorrect=2)
+    pick = np.array([0, 5, 18, 19, 100, 246])
+    full = prep_oracle.materialise_coarse(p)
+    sub = prep_oracle.materialise_coarse(p, pick)
+    assert (sub.rows, sub.cols) == (len(pick), 1) and not sub.coarse
+    nc = p.ncells
+    for n, a in sub.arrays.items():
+        ln = full.expected_len(n)
+        f = np.asarray(full.arrays[n])
+        if ln % nc == 0 and ln >= nc and ln != p.tsteps:
+            np.testing.assert_array_equal(a, f.reshape(ln // nc, nc)[:, pick].ravel(), err_msg=n)
+        else:
+            np.testing.assert_array_equal(a, f, err_msg=n)
 
 
 def _check(p, out_mask=None):
@@ -88,3 +105,38 @@ def test_coarse_climate_packed_sink():
     pk = api.run_problem_packed(p)
     for k in fp:
         assert np.array_equal(pk[k], packing_oracle.pack(k, fp[k])), k
+
+
+@pytest.mark.gpu
+def test_config5_raster_size_sampled_against_reference():
+    """BASELINE configs[4]: gridded climate on a 4096 x 4096 raster (41 x 41 climate grid, altcorrect 2), device-resident,
+    one day.  The reference's host-side expansion would be 15 arrays x 16.8 M cells x 24 h; here 300 sampled cells are
+    expanded by the numpy restatement of `.runmodel2Cpp` (oracle/prep_oracle.materialise_coarse with `pick`) and solved
+    by the CPU checker as a 300 x 1 raster with the sample's own twi mean (tests/sampling.py); every other cell must be
+    NA exactly where the raster is NA and finite elsewhere."""
+    import torch
+
+    import sampling
+    from oracle import prep_oracle
+
+    rows = cols = 4096
+    T = 24
+    p = synth.make_coarse_problem(rows, cols, T, reqhgt=0.05, mode=2, crows=41, ccols=41, altcorrect=2, seed=11)
+    pick = sampling.pick_cells(p, 300, seed=8)
+    p.twi_mean = sampling.sample_twi_mean(p, pick)
+    dp = p.to_device()
+    nc = p.ncells
+    outs = [torch.empty(T * nc, dtype=torch.float64, device="cuda") for _ in range(10)]
+    api.run_problem_dev(dp, outs)
+    torch.cuda.synchronize()
+    sub = prep_oracle.materialise_coarse(p, pick)
+    want = pyoracle.runmicro(sub, kind=KIND)
+    na = torch.from_numpy(np.isnan(np.asarray(p.arrays["hgt"])[:nc])).cuda()
+    idx = torch.from_numpy(pick).cuda()
+    got = {}
+    for nm, o in zip(_abi.OUT_NAMES, outs):
+        full = o.view(T, nc)
+        assert bool(torch.isnan(full[:, na]).all()) and bool(torch.isfinite(full[:, ~na]).all()), nm
+        got[nm] = np.ascontiguousarray(full[:, idx].cpu().numpy().T).reshape(len(pick), 1, T)
+    ok, rws = parity.compare(got, want)
+    assert ok, "\n" + parity.fmt(rws)
