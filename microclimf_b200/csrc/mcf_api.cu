@@ -217,6 +217,7 @@ struct Plan {
     double* d_scal = nullptr;      // [0] mxtc, [1] twi sum, [2] twi count, then reduction scratch
     double* d_mxtc_cell = nullptr;
     double* d_stash = nullptr;
+    double* d_cpack = nullptr;     // coarse-grid climate: one 128-byte record per (hour, coarse node), see k_pack_coarse
     int grid = 0;
     // element type of the outputs: 0 FP64; 1 int16 (the packed integer sink); 2 FP32 (the FP32 build: k_grid_f32).
     // out[v] pointers are int16_t* / float* in disguise for 1 / 2.
@@ -263,6 +264,11 @@ Err plan_prepare(Plan& pl, const mcf_problem* p, Scratch& sc, cudaStream_t st) {
             GridArgs ga;
             fill_common(pl, ga);
             CU(launch_mxtc_cell_coarse(ga, pl.d_mxtc_cell, st));
+            if (!pl.f32_kernel()) { // the FP64 grid kernel reads the coarse series as packed node records
+                CU(sc.alloc(&pl.d_cpack, coarse_pack_doubles(ga)));
+                CU(launch_pack_coarse(ga, pl.d_cpack, st));
+                count_launch();
+            }
         } else {
             CU(launch_mxtc_cell(p->temp, pl.ncells, T, pl.d_mxtc_cell, st));
         }
@@ -337,6 +343,7 @@ void fill_common(const Plan& pl, GridArgs& a) {
         a.wv = p->wv;
         a.elevd = p->elevd;
         a.pfac = p->pfac;
+        a.cpack = pl.d_cpack;
     }
 }
 
@@ -359,7 +366,7 @@ Err timed_grid_launch(const Plan& pl, const GridArgs& a, cudaStream_t st, int si
         if (sink >= 0) return make_err(MCF_ERR_ARG, "the reducing sinks run in the FP64 build");
         CU(launch_grid_f32(a, pl.d_hoursf, reinterpret_cast<float* const*>(a.out), pl.d_stashf, pl.arr, pl.rq, grid, st));
     } else if (pair) {
-        CU(launch_grid_pair(a, pl.rq, grid, st, sink));
+        CU(launch_grid_pair(a, pl.arr, pl.rq, grid, st, sink));
     } else {
         CU(launch_grid(a, pl.arr, pl.rq, grid, st, sink));
     }
@@ -903,6 +910,7 @@ Err run_host(const mcf_problem* hp, double* const out[MCF_NOUT], int pack = 0) {
     // packed sink is packed from and the two expanded point-model series of coarse-grid climate (the ground-temperature
     // chunk of plan_run_below sizes itself from what is left)
     double scratch_bytes = 148.0 * 2 * 24 * kStashVars * kTile * sizeof(double);
+    if (hp->clim_rows > 0) scratch_bytes += (double)T * hp->clim_rows * hp->clim_cols * 16 * sizeof(double); // packed node records
     if (rq == RQ_BELOW) {
         if (pack && out[MCF_OUT_TZ]) scratch_bytes += (double)nc * T * sizeof(double);
         if (pack == 2) // FP32 build below ground: FP64 series of whatever pass 1 writes, narrowed afterwards

@@ -508,10 +508,15 @@ __device__ __forceinline__ double cinterp(const double* __restrict__ A, size_t k
 // air temperature, vapour pressures and pressure of one cell-hour as .runmodel2Cpp derives them
 // (R/internal.R:1219-1245; .satvap :501, .dewpoint :509, .lapserate :546): es / ea / tdew from the UNCORRECTED
 // temperature, then the altitude correction of pressure and temperature
+__device__ __forceinline__ void coarse_air_from(const GridArgs& a, const CoarseCell& c, double tc0, double rh, double pk0,
+                                                double& tc, double& es, double& ea, double& tdew, double& pk);
 __device__ __forceinline__ void coarse_air(const GridArgs& a, size_t koff, const CoarseCell& c, double& tc, double& es,
                                            double& ea, double& tdew, double& pk) {
-    const double tc0 = cinterp(a.clim[0], koff, c);
-    const double rh = cinterp(a.relhum, koff, c);
+    coarse_air_from(a, c, cinterp(a.clim[0], koff, c), cinterp(a.relhum, koff, c), cinterp(a.clim[4], koff, c), tc, es, ea,
+                    tdew, pk);
+}
+__device__ __forceinline__ void coarse_air_from(const GridArgs& a, const CoarseCell& c, double tc0, double rh, double pk0,
+                                                double& tc, double& es, double& ea, double& tdew, double& pk) {
     es = satvap_m(tc0);
     ea = es * rh / 100;
     const double lg = (ea > 0.0) ? mlog(ea) : log(ea); // rh == 0: -inf, as R's log(0)
@@ -519,7 +524,7 @@ __device__ __forceinline__ void coarse_air(const GridArgs& a, size_t koff, const
     double Td = mrcp(1 / 273.15 - (461.5 * mrcp((2.501 * 1000000) - (2340 * tc0))) * (lg - (-0.4923310411298262))) - 273.15;
     const double Tf = mrcp(1 / 273.15 - (461.5 / (2.834 * 1000000)) * (lg - (-0.49301845011612494))) - 273.15;
     tdew = (Td < 0) ? Tf : Td;
-    pk = cinterp(a.clim[4], koff, c) * c.pfac;
+    pk = pk0 * c.pfac;
     tc = tc0;
     if (a.altcorrect == 1) {
         tc = c.elevd * (5.0 / 1000) + tc0;
@@ -532,10 +537,44 @@ __device__ __forceinline__ void coarse_air(const GridArgs& a, size_t koff, const
     }
 }
 
-template <int ARR>
+// The 14 coarse series of one (hour, coarse node) as ONE 128-byte record (k_pack_coarse): the four corner records of a
+// cell-hour are four cache lines instead of 2 lines x 15 arrays, neighbouring cells read the same records, and a pair of
+// series comes with one 128-bit load.  Order: temp relhum | pres swdown | difrad lwdown | wu wv | soilm G | umu kp | muGp dtrp.
+constexpr int kCoarseRec = 16; // doubles per record (14 used)
+__device__ __forceinline__ double2 cinterp2(const double2* __restrict__ rec, int i, const CoarseCell& c) {
+    const double2 a00 = __ldg(rec + (size_t)c.o00 * (kCoarseRec / 2) + i), a01 = __ldg(rec + (size_t)c.o01 * (kCoarseRec / 2) + i);
+    const double2 a10 = __ldg(rec + (size_t)c.o10 * (kCoarseRec / 2) + i), a11 = __ldg(rec + (size_t)c.o11 * (kCoarseRec / 2) + i);
+    double2 r;
+    {
+        const double top = a00.x * (1.0 - c.wx) + a01.x * c.wx, bot = a10.x * (1.0 - c.wx) + a11.x * c.wx;
+        r.x = top * (1.0 - c.wy) + bot * c.wy;
+    }
+    {
+        const double top = a00.y * (1.0 - c.wx) + a01.y * c.wx, bot = a10.y * (1.0 - c.wx) + a11.y * c.wx;
+        r.y = top * (1.0 - c.wy) + bot * c.wy;
+    }
+    return r;
+}
+
+template <int ARR, bool PACKED = false>
 __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int cell, double sl, double cl, double lon,
                                                  bool full, const CoarseCell& cc, HourRec& h) {
-    if (ARR == 2) {
+    if (ARR == 2 && PACKED) {
+        const double2* rec = reinterpret_cast<const double2*>(a.cpack) + (size_t)k * (size_t)(a.clim_rows * a.clim_cols) * (kCoarseRec / 2);
+        const double2 t_rh = cinterp2(rec, 0, cc), p_sw = cinterp2(rec, 1, cc), df_lw = cinterp2(rec, 2, cc);
+        const double2 w = cinterp2(rec, 3, cc), sm_g = cinterp2(rec, 4, cc), um_kp = cinterp2(rec, 5, cc), mg_dt = cinterp2(rec, 6, cc);
+        coarse_air_from(a, cc, t_rh.x, t_rh.y, p_sw.x, h.tc, h.es, h.ea, h.tdew, h.pk);
+        h.Rsw = p_sw.y;
+        h.Rdif = df_lw.x;
+        h.Rlw = df_lw.y;
+        h.u2 = msqrt(w.x * w.x + w.y * w.y); // R/internal.R:1259
+        h.soilmp = sm_g.x;
+        h.Gp = sm_g.y;
+        h.umu = um_kp.x;
+        h.kp = um_kp.y;
+        h.muGp = mg_dt.x;
+        h.dtrp = mg_dt.y;
+    } else if (ARR == 2) {
         const size_t ko = (size_t)k * (size_t)(a.clim_rows * a.clim_cols);
         coarse_air(a, ko, cc, h.tc, h.es, h.ea, h.tdew, h.pk);
         h.Rsw = cinterp(a.clim[5], ko, cc);
@@ -783,7 +822,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 for (int hr = 0; hr < 24; ++hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
-                    if (ARR) hour_from_arrays<ARR>(a, k, cell, sl, cl, lon, true, ccell, hloc);
+                    if (ARR) hour_from_arrays<ARR, true>(a, k, cell, sl, cl, lon, true, ccell, hloc);
                     const HourRec& h = ARR ? hloc : slab_day[hr];
                     if (hr == wrap_at) o = ocell;
                     double ws, ha;
@@ -863,7 +902,7 @@ __global__ void MCF_KGRID_BOUNDS k_grid(const __grid_constant__ GridArgs a) {
                 for (int hr = 23; hr >= 0; --hr) {
                     const int k = blk.k0 + hr;
                     HourRec hloc;
-                    if (ARR) hour_from_arrays<ARR>(a, k, cell, sl, cl, lon, false, ccell, hloc);
+                    if (ARR) hour_from_arrays<ARR, true>(a, k, cell, sl, cl, lon, false, ccell, hloc);
                     const HourRec& h = ARR ? hloc : slab_day[hr];
                     const double radabs = radabs_n, surfwet = surfwet_n, radCsw = radCsw_n, Lhalf = Lhalf_n;
                     double soild_n2, uf_n2;
@@ -1016,6 +1055,27 @@ cudaError_t launch_grid(const GridArgs& a, int arr, int rq, int grid, cudaStream
     else MCF_LAUNCH_RQ(2);
 #undef MCF_LAUNCH_RQ
 #undef MCF_LAUNCH
+    return cudaGetLastError();
+}
+
+// coarse series [clim_rows, clim_cols, tsteps] x 14 -> records [tsteps][node][kCoarseRec] (see cinterp2)
+__global__ void k_pack_coarse(const __grid_constant__ GridArgs a, double* __restrict__ out, int64_t n /* tsteps * nodes */) {
+    const double* src[14] = {a.clim[0], a.relhum, a.clim[4], a.clim[5], a.clim[6], a.clim[7], a.wu, a.wv,
+                             a.pnt[0], a.pnt[1], a.pnt[2], a.pnt[3], a.pnt[4], a.pnt[5]};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double2* o = reinterpret_cast<double2*>(out + i * kCoarseRec);
+#pragma unroll
+        for (int v = 0; v < 7; ++v) o[v] = make_double2(__ldg(src[2 * v] + i), __ldg(src[2 * v + 1] + i));
+        o[7] = make_double2(0.0, 0.0);
+    }
+}
+size_t coarse_pack_doubles(const GridArgs& a) { return (size_t)a.tsteps * a.clim_rows * a.clim_cols * kCoarseRec; }
+cudaError_t launch_pack_coarse(const GridArgs& a, double* out, cudaStream_t stream) {
+    const int64_t n = (int64_t)a.tsteps * a.clim_rows * a.clim_cols;
+    if (n <= 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_pack_coarse<<<(int)blocks, 256, 0, stream>>>(a, out, n);
     return cudaGetLastError();
 }
 

@@ -83,6 +83,8 @@ struct GridArgs {
     const double* wv;
     const double* elevd;     // [ncells] (altcorrect != 0)
     const double* pfac;      // [ncells] (altcorrect != 0)
+    const double* cpack;     // [tsteps][clim_rows * clim_cols][16]: the 14 coarse series as one 128-byte record per
+                             // (hour, node), built once per call by k_pack_coarse (k_grid reads these, not clim[] / pnt[])
     // statics
     const double* veg[10];  // hgt pai x gsmax leafr leaft clump leafd paia leafden   [nlyr * ncells]
     const double* soil[13]; // Smin Smax gref soilb Psie Vq Vm Mc rho slope aspect twi svfa
@@ -153,6 +155,8 @@ cudaError_t launch_prep_hours(const int32_t* year, const int32_t* month, const i
                               cudaStream_t stream);
 cudaError_t launch_mxtc_cell(const double* tc, int ncells, int tsteps, double* mxtc_cell, cudaStream_t stream);
 cudaError_t launch_mxtc_cell_coarse(const GridArgs& a, double* mxtc_cell, cudaStream_t stream);
+size_t coarse_pack_doubles(const GridArgs& a);
+cudaError_t launch_pack_coarse(const GridArgs& a, double* out, cudaStream_t stream);
 // coarse [clim_rows, clim_cols, tsteps] -> fine [ncells, tsteps] with the grid kernel's own interpolation
 cudaError_t launch_interp_coarse(const GridArgs& a, const double* coarse, double* fine, cudaStream_t stream);
 cudaError_t launch_twi_sum(const double* twi, int64_t n, double tfact, double* sum_count /* [2] */,
@@ -164,7 +168,7 @@ int grid_blocks_per_sm(bool arr, int rq);
 bool pair_eligible(int arr, int rq, int sink);
 int pair_tile();
 size_t pair_scratch_doubles(); // per CTA: day stash + reduction exchange
-cudaError_t launch_grid_pair(const GridArgs& a, int rq, int grid, cudaStream_t stream, int sink = -1);
+cudaError_t launch_grid_pair(const GridArgs& a, int arr, int rq, int grid, cudaStream_t stream, int sink = -1);
 // FP32 build (modes 1/3, reqhgt >= 0): narrowed hour table, FP32 stash and outputs
 cudaError_t launch_narrow_hours(const HourRec* in, int n, void* out, cudaStream_t stream);
 size_t hourrec_f32_bytes();

@@ -56,7 +56,7 @@ __device__ __forceinline__ double ld_xch(const double* p) {
     return v;
 }
 
-template <int RQ, int SINK, bool ALLOUT>
+template <int ARR, int RQ, int SINK, bool ALLOUT>
 __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_constant__ GridArgs a) {
     static_assert(RQ != RQ_BELOW && (SINK == SINK_F64 || SINK == SINK_PACK), "pair kernel: hourly sinks, reqhgt >= 0");
     unsigned char* const pair_smem = mcf_dyn_smem + kPairTabBytes;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
     const CellInvS<kPairCells> v(inv_d + kInvCellStep * ci, inv_i + ci);
     unsigned int q0 = 0;
 
-    if (tid == 0) {
+    if (!ARR && tid == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], kPairThreads / 32);
@@ -112,10 +112,19 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
         const int cc = valid ? cell : a.cell_end - 1;
         const bool active = valid && !isnan(__ldg(&a.veg[0][cc])); // ref :2182-2183, :2765-2766
         const unsigned amask = __ballot_sync(0xffffffffu, active);
-        const double dTmx = -0.6273 * a.dscal[0] + 49.79;
+        double lat = a.lat, lon = 0.0, dTmx = -0.6273 * a.dscal[0] + 49.79;
+        double sl = 0.0, cl = 1.0; // sin / cos of the cell's latitude (modes 2/4)
+        CoarseCell ccell;
+        if (ARR == 2) coarse_setup(a, cc, ccell);
+        if (ARR) {
+            lat = __ldg(&a.lats[cc]);
+            lon = __ldg(&a.lons[cc]);
+            dTmx = -0.6273 * __ldg(&a.mxtc_cell[cc]) + 49.79;
+            sincos(lat * kPi / 180.0, &sl, &cl);
+        }
         int cur_lyr = -1;
 
-        if (tid == 0)
+        if (!ARR && tid == 0)
             for (int bi = 0; bi < kAhead && bi < a.nblocks; ++bi) issue_fill(q0 + bi, bi);
 
         for (int bi = 0; bi < a.nblocks; ++bi) {
@@ -123,8 +132,10 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
             const unsigned int q = q0 + bi;
             const int buf = (int)(q % kStages);
             const HourRec* const slab_day = &slab_ring[buf][0];
-            if (tid == 0 && bi + kAhead < a.nblocks) issue_fill(q + kAhead, bi + kAhead);
-            mbar_wait(&full_bar[buf], (q / kStages) & 1u);
+            if (!ARR) {
+                if (tid == 0 && bi + kAhead < a.nblocks) issue_fill(q + kAhead, bi + kAhead);
+                mbar_wait(&full_bar[buf], (q / kStages) & 1u);
+            }
 
             if (blk.lyr != cur_lyr) { // uniform over the CTA: the work list is the launch's
                 if (cur_lyr >= 0) pair_sync(bar_id); // the partner is done with the previous layer's invariants
@@ -135,7 +146,7 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
                     CellIn cin;
                     CellInv vr;
                     load_cell(a, cc, cur_lyr, tadd, cin);
-                    cell_setup(cin, a.reqhgt2, a.zref, a.lat, vr);
+                    cell_setup(cin, a.reqhgt2, a.zref, lat, vr);
                     CellInvS<kPairCells>::store(vr, inv_d + kInvCellStep * ci, inv_i + ci);
                 }
                 pair_sync(bar_id);
@@ -163,22 +174,33 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
                 }
             } else {
                 // ------------------------------------------------------------------ pass 1 (this half's hours)
-                double ws_n = ld_sector(&a.wsa[(size_t)slab_day[half].windex * a.ncells + cell]);
-                double ha_n = ld_sector(&a.hor[(size_t)slab_day[half].sindex * a.ncells + cell]);
-                ws_n = settle(ws_n, zero), ha_n = settle(ha_n, zero); // as for the stash loads of pass 2, below
+                double ws_n = 0.0, ha_n = 0.0;
+                if (!ARR) {
+                    ws_n = ld_sector(&a.wsa[(size_t)slab_day[half].windex * a.ncells + cell]);
+                    ha_n = ld_sector(&a.hor[(size_t)slab_day[half].sindex * a.ncells + cell]);
+                    ws_n = settle(ws_n, zero), ha_n = settle(ha_n, zero); // as for the stash loads of pass 2, below
+                }
 #pragma unroll(kPairUnroll1)
                 for (int hr = half; hr < 24; hr += 2) {
-                    const HourRec& h = slab_day[hr];
+                    HourRec hloc;
+                    if (ARR) hour_from_arrays<ARR>(a, blk.k0 + hr, cell, sl, cl, lon, true, ccell, hloc);
+                    const HourRec& h = ARR ? hloc : slab_day[hr];
                     size_t o = o_first + (size_t)hr * a.out_stride;
                     if (hr >= wrap_at) o -= o_unwrap;
-                    const double ws = ws_n, ha = ha_n;
-                    {
+                    double ws, ha;
+                    if (ARR) {
+                        ws = ld_sector(&a.wsa[(size_t)h.windex * a.ncells + cell]);
+                        ha = ld_sector(&a.hor[(size_t)h.sindex * a.ncells + cell]);
+                    } else {
+                        ws = ws_n, ha = ha_n;
                         const HourRec& hn = slab_day[hr < 22 ? hr + 2 : hr];
                         ws_n = ld_sector(&a.wsa[(size_t)hn.windex * a.ncells + cell]);
                         ha_n = ld_sector(&a.hor[(size_t)hn.sindex * a.ncells + cell]);
                     }
-                    // terrain-adjusted solar index with horizon shading (ref :2218-2223)
-                    double si = h.cosz * v.cs + h.sinz * (h.cosazi * v.ssca + h.sinazi * v.sssa);
+                    // terrain-adjusted solar index with horizon shading (ref :2218-2223 / :2499-2504)
+                    double si;
+                    if (ARR && h.zend > 90.0) si = 0.0; // shadowmask = false in modes 2/4
+                    else si = h.cosz * v.cs + h.sinz * (h.cosazi * v.ssca + h.sinazi * v.sssa);
                     if (si < 0.0) si = 0.0;
                     if (ha > h.tan_sa) si = 0.0;
                     const double soild = soil_distribute(v, h.soilmp);
@@ -249,7 +271,9 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
                 Lhalf_n = settle(Lhalf_n, zero), soild_n = settle(soild_n, zero), uf_n = settle(uf_n, zero);
 #pragma unroll 1
                 for (int hr = hlast; hr >= 0; hr -= 2) {
-                    const HourRec& h = slab_day[hr];
+                    HourRec hloc;
+                    if (ARR) hour_from_arrays<ARR>(a, blk.k0 + hr, cell, sl, cl, lon, false, ccell, hloc);
+                    const HourRec& h = ARR ? hloc : slab_day[hr];
                     size_t o = o_first + (size_t)hr * a.out_stride;
                     if (hr >= wrap_at) o -= o_unwrap;
                     const double radabs = radabs_n, surfwet = surfwet_n, radCsw = radCsw_n, Lhalf = Lhalf_n;
@@ -308,14 +332,16 @@ __global__ void __launch_bounds__(kPairThreads, 1) k_grid_pair(const __grid_cons
                     }
                 }
             }
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&empty_bar[buf]);
+            if (!ARR) {
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(&empty_bar[buf]);
+            }
         }
         q0 += (unsigned int)a.nblocks;
     }
 }
 
-template <int RQ, int SINK, bool ALLOUT>
+template <int ARR, int RQ, int SINK, bool ALLOUT>
 static cudaError_t launch_pair_t(const GridArgs& a, int grid, cudaStream_t stream) {
     // the opt-in is per device and per function: remembered per (instantiation, device) so that a process that moves
     // between devices (mcf_set_device) configures each of them
@@ -324,23 +350,37 @@ static cudaError_t launch_pair_t(const GridArgs& a, int grid, cudaStream_t strea
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
     if (dev < 0 || dev >= 64 || !configured[dev]) {
-        e = cudaFuncSetAttribute(k_grid_pair<RQ, SINK, ALLOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);
+        e = cudaFuncSetAttribute(k_grid_pair<ARR, RQ, SINK, ALLOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPairSmemBytes);
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) configured[dev] = true;
     }
-    k_grid_pair<RQ, SINK, ALLOUT><<<grid, kPairThreads, kPairSmemBytes, stream>>>(a);
+    k_grid_pair<ARR, RQ, SINK, ALLOUT><<<grid, kPairThreads, kPairSmemBytes, stream>>>(a);
     return cudaGetLastError();
 }
 int pair_tile() { return kPairCells; }
 size_t pair_scratch_doubles() { return kPairScratchDoubles; }
-bool pair_eligible(int arr, int rq, int sink) { return arr == 0 && rq != RQ_BELOW && (sink == SINK_F64 || sink == SINK_PACK); }
-cudaError_t launch_grid_pair(const GridArgs& a, int rq, int grid, cudaStream_t stream, int sink) {
-    if (sink < 0) sink = (a.pack == 1) ? SINK_PACK : SINK_F64;
+#ifndef MCF_PAIR_ARR
+#define MCF_PAIR_ARR 0 // 1: array climate (modes 2/4) also runs the pair build
+#endif
+bool pair_eligible(int arr, int rq, int sink) {
+    return (arr == 0 || MCF_PAIR_ARR) && rq != RQ_BELOW && (sink == SINK_F64 || sink == SINK_PACK);
+}
+template <int ARR>
+static cudaError_t launch_pair_arr(const GridArgs& a, int rq, int grid, cudaStream_t stream, int sink) {
     if (rq == RQ_ABOVE) {
-        if (sink == SINK_F64 && a.outmask == 0x3FFu) return launch_pair_t<RQ_ABOVE, SINK_F64, true>(a, grid, stream);
-        if (sink == SINK_F64) return launch_pair_t<RQ_ABOVE, SINK_F64, false>(a, grid, stream);
-        return launch_pair_t<RQ_ABOVE, SINK_PACK, false>(a, grid, stream);
+        if (ARR == 0 && sink == SINK_F64 && a.outmask == 0x3FFu) return launch_pair_t<0, RQ_ABOVE, SINK_F64, true>(a, grid, stream);
+        if (sink == SINK_F64) return launch_pair_t<ARR, RQ_ABOVE, SINK_F64, false>(a, grid, stream);
+        return launch_pair_t<ARR, RQ_ABOVE, SINK_PACK, false>(a, grid, stream);
     }
-    if (sink == SINK_F64) return launch_pair_t<RQ_SURFACE, SINK_F64, false>(a, grid, stream);
-    return launch_pair_t<RQ_SURFACE, SINK_PACK, false>(a, grid, stream);
+    if (sink == SINK_F64) return launch_pair_t<ARR, RQ_SURFACE, SINK_F64, false>(a, grid, stream);
+    return launch_pair_t<ARR, RQ_SURFACE, SINK_PACK, false>(a, grid, stream);
+}
+cudaError_t launch_grid_pair(const GridArgs& a, int arr, int rq, int grid, cudaStream_t stream, int sink) {
+    if (sink < 0) sink = (a.pack == 1) ? SINK_PACK : SINK_F64;
+#if MCF_PAIR_ARR
+    if (arr == 1) return launch_pair_arr<1>(a, rq, grid, stream, sink);
+    if (arr == 2) return launch_pair_arr<2>(a, rq, grid, stream, sink);
+#endif
+    if (arr != 0) return cudaErrorInvalidValue;
+    return launch_pair_arr<0>(a, rq, grid, stream, sink);
 }
