@@ -274,8 +274,9 @@ int mcf_runmicro_packed_dev(const mcf_problem* prob, int16_t* const out[MCF_NOUT
 /* FP32 build (BASELINE north_star: "an optional FP32 build must stay within 0.05 degC and 0.5 % radiation").  `prob` is
  * the FP64 problem of mcf_runmicro[_dev] — every mode (data.frame, fine-array and coarse-grid climate, layered
  * vegetation) and every height.  The hour loops run in FP32 (SFU transcendentals); per-cell invariants, the per-cell-hour
- * assembly of array climate (interpolation, altitude correction, solar position) and the below-ground time-axis pass stay
- * FP64.  Outputs are float arrays (quiet NaN where the FP64 entry points write NA_real_): 40 instead of 80 bytes per
+ * assembly of array climate (interpolation, altitude correction, solar position) and everything below ground stay FP64
+ * (reqhgt < 0: the time-axis pass is discontinuous in its inputs — a rolling mean over round(-118.35 z / mean damping
+ * depth) hours — so its ground temperatures and damping depths are computed in FP64 and only the results are narrowed).  Outputs are float arrays (quiet NaN where the FP64 entry points write NA_real_): 40 instead of 80 bytes per
  * cell-hour in HBM and over PCIe.  Window / ring as for mcf_runmicro_dev. */
 int mcf_runmicro_f32_dev(const mcf_problem* prob, float* const out[MCF_NOUT], const mcf_window* win, void* stream,
                          char* err, size_t errlen);
