@@ -1,18 +1,25 @@
 // microclimf_b200 — the pair build of the grid kernel (included by mcf_kernels.cu, inside namespace mcf).
 //
-// k_grid keeps the ~75 per-cell invariants of a vegetation layer (CellInv) in registers: 168 registers per thread,
-// 12 warps per SM, and a dependent FP64 chain per warp that the schedulers cannot cover (stall `wait` 40 %, FP64 pipe
-// 42 % busy, profiles/r02_kgrid_headline.txt).  This build trades registers for warps:
-//   * the invariants live in SHARED memory, [field][cell] (conflict-free: a warp's 32 cells are 32 consecutive words
-//     pairs), written once per tile and layer by cell_setup and read where they are used (CellInvS, mcf_physics.cuh);
-//   * TWO threads per cell: the hours of both passes of a day (ref src/microclimfCpp.cpp:2214-2262, :2264-2305) are
-//     independent of each other within the pass, so the thread of half p takes the hours hr = p, p + 2, ... in both
-//     passes — its day stash stays private — and the only exchange per cell-day is the daily reduction
-//     (Rmx, tmx, tmn; ref :2196-2263) between the two partner WARPS: three doubles through an L2-resident scratch and
-//     one 64-thread named barrier (bar.sync 1 + warp-pair, 64);
-//   * kPairCells cells x 2 = 640 threads per CTA at <= 96 registers: 20 warps per SM instead of 12.
+// k_grid keeps the ~75 per-cell invariants of a vegetation layer (CellInv) in registers: 168 registers per thread + spills,
+// 12 warps per SM, and a dependent FP64 chain per warp that the schedulers cannot cover (stall `wait` 42 %, FP64 pipe
+// 46 % busy, profiles/r02_kgrid_headline10.txt).  This build trades registers for shared memory and warps:
+//   * the invariants live in SHARED memory, [field][cell] (a warp's 32 cells are 256 contiguous bytes per field:
+//     conflict-free), written once per tile and layer by cell_setup and read where they are used through the proxy type
+//     CellInvS (mcf_physics.cuh), which the physics templates take in place of the register struct;
+//   * TWO threads per cell: the hours of a day are independent of each other within each of the reference's two passes
+//     (ref src/microclimfCpp.cpp:2214-2262, :2264-2305), so the thread of half p takes the hours hr = p, p + 2, ... of BOTH
+//     passes — its day stash stays private — and the only exchange per cell-day is the daily reduction (Rmx, tmx, tmn;
+//     ref :2196-2263) between the two partner WARPS: three doubles through an L2-resident scratch and one 64-thread
+//     named barrier (bar.sync 1 + warp pair, 64);
+//   * 256 cells x 2 = 512 threads per CTA at 128 registers: 16 warps per SM (measured best: 320 cells / 96 registers and
+//     192 cells / 168 registers are 10 % and 7 % slower);
+//   * the two math tables of mcf_math.cuh as conflict-free shared-memory replicas (TAB = 1): with 196 KB of the SM carved
+//     out for shared memory the __ldg gathers of the tables miss what is left of the L1.
 // Same tile counter, TMA-fed hour-table ring (full / empty mbarriers), stash policy and output layout as k_grid.
-// Instantiated for the per-hour-table drivers (modes 1/3), reqhgt >= 0, FP64 and packed sinks; everything else runs k_grid.
+// Serves the per-hour-table drivers (modes 1/3), reqhgt >= 0, FP64 and packed sinks: the headline path.  Everything else
+// runs k_grid: the reducing sinks need the shared memory for their accumulators, array climate needs the registers for
+// its per-thread hour record (-DMCF_PAIR_ARR=1 builds it here too: measured slower), below ground has no canopy physics.
+// FP64 pipe 54 % busy, 1.54e10 cell-hours/s per B200 (k_grid: 1.32e10); profiles/r02_kpair_headline10.txt.
 
 #ifndef MCF_PAIR_CELLS
 #define MCF_PAIR_CELLS 256
@@ -31,7 +38,7 @@ static_assert(kPairCells % 32 == 0 && kPairCells / 32 <= 15, "one named barrier 
 
 // dynamic shared memory of the pair kernel
 constexpr size_t kPairRingBytes = sizeof(HourRec) * 24 * kPairStages;
-constexpr size_t kPairInvDBytes = sizeof(double) * 2 * ((kInvD + 1) / 2) * kPairCells; // [field pair][cell][2]
+constexpr size_t kPairInvDBytes = sizeof(double) * 2 * ((kInvD + 1) / 2) * kPairCells; // [field][cell] (MCF_INV_PAIRED: [field pair][cell][2])
 constexpr size_t kPairInvIBytes = sizeof(int) * kPairCells; // the three small integers of CellInv packed into one word
 constexpr int kPairTab = MathTab<CellInvS<kPairCells>>::value;
 constexpr size_t kPairTabBytes = kPairTab ? kMathSmemBytes : 0; // math-table replicas, at offset 0 (mcf_math.cuh, TAB = 1)
