@@ -1391,7 +1391,9 @@ def runmicrosnow1(micropoint: Micropoint, reqhgt, vegp, soilc, dtm, smod, runche
     micros = _seed_snow_micro(moutn, snowdays, nosnowdays)
     smods = subsetsnowmodel(smod, ai)
     outm = _snow_out_mask(out, reqhgt, micros)
-    mouts = op(reqhgt, obstime, climdata, smods, micros, vg, other, micropoint.matemp, outm)
+    # `micros` was seeded just above and is ours: the product operator may update it in place (no host copies)
+    kw = {} if snow_operator is not None else {"copy": False}
+    mouts = op(reqhgt, obstime, climdata, smods, micros, vg, other, micropoint.matemp, outm, **kw)
     if not nosnowdays.size:
         return mouts
     return _merge_snow_days(moutn, mouts, snowdays, nosnowdays)
@@ -1579,7 +1581,8 @@ def runmicrosnow2(micropoint, reqhgt, vegp, soilc, dtm, dtmc, smod, altcorrect=0
                           slr, apr, hor, svf, wsa, pai_a)
     smods = subsetsnowmodel(smod, _hours_of_days(snowdays))
     outm = _snow_out_mask(out, reqhgt, sin["micro"])
-    mouts = op(reqhgt, sin["obstime"], sin["weather"], smods, sin["micro"], sin["vegp"], sin["other"], matemp, outm)
+    kw = {} if snow_operator is not None else {"copy": False}  # sin["micro"] is ours (prepsnowinputs2 built it): update in place
+    mouts = op(reqhgt, sin["obstime"], sin["weather"], smods, sin["micro"], sin["vegp"], sin["other"], matemp, outm, **kw)
     if not nosnowdays.size:
         return mouts
     return _merge_snow_days(moutn, mouts, snowdays, nosnowdays)

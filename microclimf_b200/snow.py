@@ -129,13 +129,15 @@ def call_gridmodelsnow(fn, obstime, climdata, pointm, vegp, other, snowenv):
     return out
 
 
-def call_gridmicrosnow(fn, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out):
+def call_gridmicrosnow(fn, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out, copy=True):
     keep = []
     c, st, s = pack_climate(obstime, climdata, keep), pack_state(snowm, keep), pack_static(vegp, other, keep)
     umu = _f(climdata["umu"])
     bufs = []
     for nm, o in zip(_abi.OUT_NAMES, out):
-        bufs.append(_f(micro[nm]).copy() if o else None)
+        # the C entry point works IN PLACE, as the reference does on its arguments; `copy` keeps the caller's arrays intact
+        # (R semantics) at the price of a host copy of every requested array
+        bufs.append((_f(micro[nm]).copy() if copy else _f(micro[nm])) if o else None)
     err = C.create_string_buffer(512)
     rc = fn(C.c_double(reqhgt), C.byref(c), umu.ctypes.data_as(_PD), C.byref(st), C.byref(s), C.c_double(mat),
             _abi.OutPtrs(*[b.ctypes.data_as(_PD) if b is not None else None for b in bufs]), err, C.c_size_t(512))
@@ -151,11 +153,14 @@ def gridmodelsnow1(obstime, climdata, pointm, vegp, other, snowenv: str = "Alpin
     return call_gridmodelsnow(L.mcf_gridmodelsnow, obstime, climdata, pointm, vegp, other, snowenv)
 
 
-def gridmicrosnow1(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out: Sequence[bool]) -> Dict[str, np.ndarray]:
-    """src/microclimfCpp.cpp:4894 — microclimate on snow-covered cell-hours, overwriting `micro`'s arrays (copies)."""
+def gridmicrosnow1(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out: Sequence[bool],
+                   copy: bool = True) -> Dict[str, np.ndarray]:
+    """src/microclimfCpp.cpp:4894 — microclimate on snow-covered cell-hours.  `copy=True` (default) leaves `micro`'s arrays
+    untouched and returns updated copies; `copy=False` updates F-contiguous float64 arrays in place, as the C entry point
+    does (no host copies: the call is then bound by the 200 bytes per cell-hour that cross PCIe)."""
     L = _lib.lib()
     _bind(L)
-    return call_gridmicrosnow(L.mcf_gridmicrosnow, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)
+    return call_gridmicrosnow(L.mcf_gridmicrosnow, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out, copy)
 
 
 def gridmodelsnow2(obstime, climdata, pointm, vegp, other, snowenv: str = "Alpine") -> Dict[str, np.ndarray]:
@@ -165,9 +170,10 @@ def gridmodelsnow2(obstime, climdata, pointm, vegp, other, snowenv: str = "Alpin
     return call_gridmodelsnow(L.mcf_gridmodelsnow2, obstime, climdata, pointm, vegp, other, snowenv)
 
 
-def gridmicrosnow2(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out: Sequence[bool]) -> Dict[str, np.ndarray]:
+def gridmicrosnow2(reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out: Sequence[bool],
+                   copy: bool = True) -> Dict[str, np.ndarray]:
     """src/microclimfCpp.cpp:5059 — snow microclimate, array climate (climdata$prec, climdata$umu arrays; other$lat / lon
     matrices, passed here as other["lats"] / other["lons"])."""
     L = _lib.lib()
     _bind(L)
-    return call_gridmicrosnow(L.mcf_gridmicrosnow2, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out)
+    return call_gridmicrosnow(L.mcf_gridmicrosnow2, reqhgt, obstime, climdata, snowm, micro, vegp, other, mat, out, copy)

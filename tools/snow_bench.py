@@ -20,6 +20,11 @@ for rep in range(2):
     t2 = time.perf_counter()
     snow.gridmicrosnow1(0.05, s["obstime"], s["climdata"], snowm, micro, s["vegp"], s["other"], 3.0, [True] * 10)
     t3 = time.perf_counter()
+for rep in range(2):
+    t4 = time.perf_counter()
+    snow.gridmicrosnow1(0.05, s["obstime"], s["climdata"], snowm, micro, s["vegp"], s["other"], 3.0, [True] * 10, copy=False)
+    t5 = time.perf_counter()
 ch = n * n * T
 print(json.dumps({"cells": n * n, "hours": T, "gridmodelsnow1_host_cell_hours_per_s": ch / (t1 - t0), "gridmicrosnow1_host_cell_hours_per_s": ch / (t3 - t2),
+                  "gridmicrosnow1_host_inplace_cell_hours_per_s": ch / (t5 - t4),
                   "snow_covered_fraction": float((snowm["totalSWE"] > 0).mean())}))
