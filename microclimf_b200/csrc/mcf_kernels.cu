@@ -624,14 +624,16 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
         h.coszc = up ? coh : kCosHalfPi;
         h.k1 = mrcp(2.0 * h.coszc);
         double sazi = c.cd * stt * isinz; // ref :61 with cos(hh) = sin(zenith)
-        const double num = sl * c.cd * ctt - cl * c.sd; // sign of the reference's cazi (:62-64)
-        double sqt = 1.0 - sazi * sazi;
-        if (sqt < 0.0) sqt = 0.0;
+        const double num = sl * c.cd * ctt - cl * c.sd; // numerator of the reference's cazi (:62-64)
         if (sazi > 1.0) sazi = 1.0;
         if (sazi < -1.0) sazi = -1.0;
-        const double ca = msqrt(sqt);
         h.sinazi = -sazi;
-        h.cosazi = (num < 0.0) ? ca : -ca;
+        // The reference forms |cos(azimuth)| as sqrt(1 - sazi^2) (through atan, :65-70) and takes the sign from cazi.  With
+        // the sun near due east / west (sazi -> +-1) that difference amplifies the 1e-12 of the fast reciprocal in sazi
+        // to 2e-6 of cos(azimuth) — and, on steep north- or south-facing slopes where the solar index is that cosine,
+        // beyond the parity bar (four cells in 9,700 fuzzed problems, profiles/r02_fuzz.txt).  cazi's own numerator gives
+        // the same quantity without the cancellation: cos(azimuth) = -num / cos(hh) = -num / sin(zenith).
+        h.cosazi = -num * isinz;
         h.sindex = azimuth_sector(h.sinazi, h.cosazi);
         h.Rbeam0 = mdiv(h.Rsw - h.Rdif, coh);
     }
