@@ -620,7 +620,7 @@ __device__ __forceinline__ void hour_from_arrays(const GridArgs& a, int k, int c
         const double isinz = mrcp(sinz);
         h.sinz = sinz;
         h.tan_sa = coh * isinz; // tan(pi/2 - zenith), ref :2504
-        h.tanzc = up ? sinz * mrcp(coh) : kTanHalfPi;
+        h.tanzc = up ? sinz * mrcp2(coh) : kTanHalfPi; // feeds kd (see shortwave): full precision
         h.coszc = up ? coh : kCosHalfPi;
         h.k1 = mrcp(2.0 * h.coszc);
         double sazi = c.cd * stt * isinz; // ref :61 with cos(hh) = sin(zenith)

@@ -47,6 +47,14 @@ __device__ __forceinline__ double mrcp(double x) {
     double e = fma(-x, r, 1.0);
     return fma(r, e, r);          // one Newton step: <= 2^-40 ~ 1e-12
 }
+// 1 / x to ~1 ulp (two Newton steps): for the few quotients whose error a later cancellation amplifies
+__device__ __forceinline__ double mrcp2(double x) {
+    double r = rcp_seed(x);
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
 // a / b
 __device__ __forceinline__ double mdiv(double a, double b) { return a * mrcp(b); }
 

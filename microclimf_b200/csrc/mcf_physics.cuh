@@ -589,7 +589,10 @@ __device__ __forceinline__ Rad shortwave(const V& v, const HourRec& h, double si
         k = (v.xflag == 3) ? 1.0 : k;
         k = (v.xflag == 2) ? h.tanzc : k;
         if (k > 6000.0) k = 6000.0;
-        const double isi = mrcp(si); // NaN for si == 0: both uses are replaced below, as the reference's inf is
+        // full-precision reciprocal: kd = k cos(z) / si enters sig = kd^2 + gma^2 - (a + gma)^2 below, which vanishes at
+        // kd = h (the two-stream solution's removable singularity) — near it the 1e-12 of the one-step reciprocal was
+        // amplified beyond the parity bar (1 value in 8,000 fuzzed problems, profiles/r02_fuzz.txt)
+        const double isi = mrcp2(si); // NaN for si == 0: both uses are replaced below, as the reference's inf is
         double kd = k * h.coszc * isi;
         if (si == 0) kd = 1.0;
         double Kc = isi;
@@ -597,11 +600,11 @@ __device__ __forceinline__ Rad shortwave(const V& v, const HourRec& h, double si
         // direct-beam two-stream parameters
         const double apg = v.a + v.gma;
         double sig = kd * kd + v.gma * v.gma - apg * apg;
-        double ss = 0.5 * (v.om + v.Jdel * mrcp(kd)) * kd;
+        double ss = 0.5 * (v.om + v.Jdel * mrcp2(kd)) * kd;
         double sstr = v.om * kd - ss;
         double S2 = mexp_lo<MT>(-kd * v.pait);
         double p5 = -ss * (apg - kd) - v.gma * sstr;
-        double isig = mrcp(sig);
+        double isig = mrcp2(sig); // p5 .. p10 are differences of large terms for thin canopies: keep their inputs at 1 ulp
         double p5s = p5 * isig;
         double v1 = ss - p5s * (apg + kd);
         double v2 = ss - v.gma - p5s * (v.u1 + kd);
