@@ -326,7 +326,7 @@ def gpu_arm(args):
     k_avg_ms = kms / max(kn, 1)
     bytes_launch = cell_hours_step * BYTES_PER_CELL_HOUR + ncells * BYTES_PER_CELL_STATIC
     achieved = bytes_launch / (k_avg_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_grid_pair<RQ_ABOVE,SINK_F64,ALLOUT=true>", "achieved": achieved, "peak": peaks["hbm_gbs"],
+    roofline = {"bound": "hbm", "kernel": "k_grid_pair<ARR=0,RQ_ABOVE,SINK_F64,ALLOUT=true>", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": k_avg_ms, "launches": kn, "kernel_share_of_step": kms / ms,
                 "algorithmic_bytes_per_launch": bytes_launch}
